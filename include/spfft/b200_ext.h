@@ -1,0 +1,77 @@
+/* spfft/b200_ext.h -- entry points this build adds to the SpFFT C ABI.
+ *
+ * They cover what the reference expresses through MPI (absent here: the distributed transform is
+ * sharded over the GPUs of one NVSwitch box and exchanges over NCCL / NVLink peer memory), plus
+ * inspection hooks the parity tests and the benchmark need. Plain pointers and sizes only.
+ * Everything returns an SpfftError (spfft/errors.h).
+ */
+#ifndef SPFFT_B200_EXT_H
+#define SPFFT_B200_EXT_H
+#include "spfft/config.h"
+#include "spfft/errors.h"
+#include "spfft/grid.h"
+#include "spfft/grid_float.h"
+#include "spfft/transform.h"
+#include "spfft/transform_float.h"
+#include "spfft/types.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- plan inspection (host only, no GPU needed) -------------------------------------------- */
+
+/* The index conversion every transform performs at creation, exposed so that tests can compare it
+ * bit for bit with the reference's convert_index_triplets (src/compression/indices.hpp:120-186).
+ * triplets: 3*numValues ints. valueIndices: numValues ints out. stickIndices: up to
+ * min(numValues, dimX*dimY) ints out. Either output may be NULL. Errors as the reference:
+ * SPFFT_INVALID_PARAMETER_ERROR (numValues > dimX*dimY*dimZ), SPFFT_INVALID_INDICES_ERROR. */
+SPFFT_EXPORT SpfftError spfft_b200_convert_index_triplets(int hermitianSymmetry, int dimX,
+                                                          int dimY, int dimZ, int numValues,
+                                                          const int* triplets, int* valueIndices,
+                                                          int* stickIndices, int* numSticks);
+
+/* Pointers (owned by the transform, host memory) to the two reference-defined index maps of an
+ * existing transform: valueIndices[numValues] = stick*dimZ + z, stickIndices[numSticks] = x*dimY+y
+ * ascending. Mirrors Parameters::local_value_indices / z_stick_xy_indices
+ * (src/parameters/parameters.hpp). */
+SPFFT_EXPORT SpfftError spfft_b200_transform_index_maps(SpfftTransform transform,
+                                                        const int** valueIndices, int* numValues,
+                                                        const int** stickIndices, int* numSticks);
+SPFFT_EXPORT SpfftError spfft_b200_float_transform_index_maps(SpfftFloatTransform transform,
+                                                              const int** valueIndices,
+                                                              int* numValues,
+                                                              const int** stickIndices,
+                                                              int* numSticks);
+
+/* ---- execution control / measurement ------------------------------------------------------- */
+
+/* The CUDA stream (cudaStream_t) a transform enqueues its kernels on; the reference keeps it
+ * private (src/execution/execution_gpu.cpp:53). Needed to time kernels with CUDA events. */
+SPFFT_EXPORT SpfftError spfft_b200_transform_stream(SpfftTransform transform, void** stream);
+SPFFT_EXPORT SpfftError spfft_b200_float_transform_stream(SpfftFloatTransform transform,
+                                                          void** stream);
+
+/* Per-kernel device timing. With profiling enabled every stage kernel of a transform call is
+ * bracketed by CUDA events on the transform's stream; after the call has completed,
+ * *_stage_times returns, for the most recent backward or forward call, the number of stages,
+ * their names (static strings) and milliseconds. maxStages bounds the output arrays.
+ * Takes the place of the reference's host-side rt_graph timers (src/timing/timing.hpp:34-62). */
+SPFFT_EXPORT SpfftError spfft_b200_transform_set_profiling(SpfftTransform transform, int enable);
+SPFFT_EXPORT SpfftError spfft_b200_transform_stage_times(SpfftTransform transform, int maxStages,
+                                                         int* numStages, const char** names,
+                                                         float* milliseconds);
+SPFFT_EXPORT SpfftError spfft_b200_float_transform_set_profiling(SpfftFloatTransform transform,
+                                                                 int enable);
+SPFFT_EXPORT SpfftError spfft_b200_float_transform_stage_times(SpfftFloatTransform transform,
+                                                               int maxStages, int* numStages,
+                                                               const char** names,
+                                                               float* milliseconds);
+
+/* Number of kernels this library has launched since it was loaded (all transforms). */
+SPFFT_EXPORT SpfftError spfft_b200_kernel_launch_count(long long int* count);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

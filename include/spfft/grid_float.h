@@ -1,0 +1,24 @@
+/* spfft/grid_float.h -- C API, float. See spfft/detail/*.inc for the documented declarations. */
+#ifndef SPFFT_GRID_FLOAT_H
+#define SPFFT_GRID_FLOAT_H
+#include "spfft/config.h"
+#include "spfft/errors.h"
+#include "spfft/types.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+typedef void* SpfftFloatGrid;
+#define SPFFT_FN(name) spfft_float_##name
+#define SPFFT_GRID_T SpfftFloatGrid
+#define SPFFT_TRANSFORM_T SpfftFloatTransform
+#define SPFFT_REAL float
+#include "spfft/detail/grid_api.inc"
+#undef SPFFT_FN
+#undef SPFFT_GRID_T
+#undef SPFFT_TRANSFORM_T
+#undef SPFFT_REAL
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,24 @@
+/* spfft/multi_transform_float.h -- C API, float. See spfft/detail/*.inc for the documented declarations. */
+#ifndef SPFFT_MULTI_TRANSFORM_FLOAT_H
+#define SPFFT_MULTI_TRANSFORM_FLOAT_H
+#include "spfft/config.h"
+#include "spfft/errors.h"
+#include "spfft/types.h"
+#include "spfft/transform_float.h"
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SPFFT_FN(name) spfft_float_##name
+#define SPFFT_GRID_T SpfftFloatGrid
+#define SPFFT_TRANSFORM_T SpfftFloatTransform
+#define SPFFT_REAL float
+#include "spfft/detail/multi_transform_api.inc"
+#undef SPFFT_FN
+#undef SPFFT_GRID_T
+#undef SPFFT_TRANSFORM_T
+#undef SPFFT_REAL
+#ifdef __cplusplus
+}
+#endif
+#endif

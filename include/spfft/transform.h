@@ -1,0 +1,24 @@
+/* spfft/transform.h -- C API, double. See spfft/detail/*.inc for the documented declarations. */
+#ifndef SPFFT_TRANSFORM_H
+#define SPFFT_TRANSFORM_H
+#include "spfft/config.h"
+#include "spfft/errors.h"
+#include "spfft/types.h"
+#include "spfft/grid.h"
+#ifdef __cplusplus
+extern "C" {
+#endif
+typedef void* SpfftTransform;
+#define SPFFT_FN(name) spfft_##name
+#define SPFFT_GRID_T SpfftGrid
+#define SPFFT_TRANSFORM_T SpfftTransform
+#define SPFFT_REAL double
+#include "spfft/detail/transform_api.inc"
+#undef SPFFT_FN
+#undef SPFFT_GRID_T
+#undef SPFFT_TRANSFORM_T
+#undef SPFFT_REAL
+#ifdef __cplusplus
+}
+#endif
+#endif

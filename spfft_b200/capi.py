@@ -1,0 +1,299 @@
+"""ctypes binding of the SpFFT C ABI (include/spfft/{grid,transform,multi_transform}[_float].h).
+
+The binding is library-agnostic: it drives ``libspfft_b200.so`` (this repo's product) and -- in
+the tests and the CPU-baseline leg of bench.py -- the reference host library compiled under
+``oracle/_ref`` through the *same* entry points, which is what "drop-in" means here.
+
+Class and method names mirror the reference's C++ API (include/spfft/grid.hpp:49-203,
+include/spfft/transform.hpp:56-315): Grid.create_transform, Transform.backward / forward /
+space_domain_data / clone / local_z_length ...  Errors raise SpfftError carrying the C error code
+(include/spfft/errors.h:37-125).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+# include/spfft/types.h
+SPFFT_EXCH_DEFAULT = 0
+SPFFT_EXCH_BUFFERED = 1
+SPFFT_EXCH_BUFFERED_FLOAT = 2
+SPFFT_EXCH_COMPACT_BUFFERED = 3
+SPFFT_EXCH_COMPACT_BUFFERED_FLOAT = 4
+SPFFT_EXCH_UNBUFFERED = 5
+SPFFT_PU_HOST = 1
+SPFFT_PU_GPU = 2
+SPFFT_INDEX_TRIPLETS = 0
+SPFFT_TRANS_C2C = 0
+SPFFT_TRANS_R2C = 1
+SPFFT_NO_SCALING = 0
+SPFFT_FULL_SCALING = 1
+SPFFT_EXEC_SYNCHRONOUS = 0
+SPFFT_EXEC_ASYNCHRONOUS = 1
+
+# include/spfft/errors.h
+ERROR_NAMES = [
+    "SPFFT_SUCCESS", "SPFFT_UNKNOWN_ERROR", "SPFFT_INVALID_HANDLE_ERROR", "SPFFT_OVERFLOW_ERROR",
+    "SPFFT_ALLOCATION_ERROR", "SPFFT_INVALID_PARAMETER_ERROR", "SPFFT_DUPLICATE_INDICES_ERROR",
+    "SPFFT_INVALID_INDICES_ERROR", "SPFFT_MPI_SUPPORT_ERROR", "SPFFT_MPI_ERROR",
+    "SPFFT_MPI_PARAMETER_MISMATCH_ERROR", "SPFFT_HOST_EXECUTION_ERROR", "SPFFT_FFTW_ERROR",
+    "SPFFT_GPU_ERROR", "SPFFT_GPU_PRECEDING_ERROR", "SPFFT_GPU_SUPPORT_ERROR",
+    "SPFFT_GPU_ALLOCATION_ERROR", "SPFFT_GPU_LAUNCH_ERROR", "SPFFT_GPU_NO_DEVICE_ERROR",
+    "SPFFT_GPU_INVALID_VALUE_ERROR", "SPFFT_GPU_INVALID_DEVICE_PTR_ERROR", "SPFFT_GPU_COPY_ERROR",
+    "SPFFT_GPU_FFT_ERROR",
+]
+for _i, _n in enumerate(ERROR_NAMES):
+    globals()[_n] = _i
+
+
+class SpfftError(RuntimeError):
+    def __init__(self, code: int, where: str = ""):
+        self.code = code
+        name = ERROR_NAMES[code] if 0 <= code < len(ERROR_NAMES) else f"error {code}"
+        super().__init__(f"{name} ({code}) in {where}")
+
+
+def _ptr(x):
+    """Raw address of a numpy array / torch tensor / int / None."""
+    if x is None:
+        return C.c_void_p(None)
+    if isinstance(x, int):
+        return C.c_void_p(x)
+    if isinstance(x, np.ndarray):
+        return C.c_void_p(x.ctypes.data)
+    if hasattr(x, "data_ptr"):
+        return C.c_void_p(x.data_ptr())
+    if isinstance(x, C.c_void_p):
+        return x
+    raise TypeError(f"cannot take the address of {type(x)}")
+
+
+class SpfftLib:
+    """One loaded shared library exporting the SpFFT C ABI."""
+
+    def __init__(self, path: str):
+        if not os.path.exists(path):
+            raise FileNotFoundError(
+                f"{path} not found -- build it first (python -c 'import __graft_entry__ as g; "
+                f"g.build()'); there is no fallback implementation")
+        self.path = path
+        self.lib = C.CDLL(path, mode=C.RTLD_GLOBAL if "b200" in os.path.basename(path) else 0)
+
+    def call(self, name: str, *args):
+        fn = getattr(self.lib, name)
+        fn.restype = C.c_int
+        err = fn(*args)
+        if err != 0:
+            raise SpfftError(err, name)
+
+    def has(self, name: str) -> bool:
+        return hasattr(self.lib, name)
+
+
+class Grid:
+    """spfft::Grid / spfft::GridFloat (include/spfft/grid.hpp:49-203)."""
+
+    def __init__(self, lib: SpfftLib, max_dim_x, max_dim_y, max_dim_z, max_num_local_z_columns,
+                 processing_unit=SPFFT_PU_GPU, max_num_threads=-1, single=False):
+        self.lib = lib
+        self.single = single
+        self._sfx = "_float" if single else ""
+        self.handle = C.c_void_p()
+        lib.call("spfft" + self._sfx + "_grid_create", C.byref(self.handle), int(max_dim_x),
+                 int(max_dim_y), int(max_dim_z), int(max_num_local_z_columns),
+                 int(processing_unit), int(max_num_threads))
+
+    def _get_int(self, what):
+        v = C.c_int()
+        self.lib.call(f"spfft{self._sfx}_grid_{what}", self.handle, C.byref(v))
+        return v.value
+
+    def max_dim_x(self): return self._get_int("max_dim_x")
+    def max_dim_y(self): return self._get_int("max_dim_y")
+    def max_dim_z(self): return self._get_int("max_dim_z")
+    def max_num_local_z_columns(self): return self._get_int("max_num_local_z_columns")
+    def max_local_z_length(self): return self._get_int("max_local_z_length")
+    def processing_unit(self): return self._get_int("processing_unit")
+    def device_id(self): return self._get_int("device_id")
+    def num_threads(self): return self._get_int("num_threads")
+
+    def create_transform(self, processing_unit, transform_type, dim_x, dim_y, dim_z,
+                         local_z_length, indices, index_format=SPFFT_INDEX_TRIPLETS,
+                         num_local_elements=None):
+        return Transform(self.lib, grid=self, processing_unit=processing_unit,
+                         transform_type=transform_type, dim_x=dim_x, dim_y=dim_y, dim_z=dim_z,
+                         local_z_length=local_z_length, indices=indices,
+                         index_format=index_format, single=self.single,
+                         num_local_elements=num_local_elements)
+
+    def destroy(self):
+        if self.handle:
+            self.lib.call("spfft" + self._sfx + "_grid_destroy", self.handle)
+            self.handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.destroy()
+        except Exception:
+            pass
+
+
+class Transform:
+    """spfft::Transform / spfft::TransformFloat (include/spfft/transform.hpp:56-315)."""
+
+    def __init__(self, lib: SpfftLib, grid=None, processing_unit=SPFFT_PU_GPU,
+                 transform_type=SPFFT_TRANS_C2C, dim_x=0, dim_y=0, dim_z=0, local_z_length=None,
+                 indices=None, index_format=SPFFT_INDEX_TRIPLETS, max_num_threads=-1,
+                 single=False, num_local_elements=None, _handle=None):
+        self.lib = lib
+        self.single = single
+        self._sfx = "_float" if single else ""
+        self.real_t = np.float32 if single else np.float64
+        self.cplx_t = np.complex64 if single else np.complex128
+        self.handle = C.c_void_p()
+        if _handle is not None:
+            self.handle = _handle
+            return
+        idx = None
+        n = 0
+        if indices is not None:
+            idx = np.ascontiguousarray(np.asarray(indices, dtype=np.int32).reshape(-1))
+            n = idx.size // 3
+        if num_local_elements is not None:
+            n = int(num_local_elements)
+        iptr = idx.ctypes.data_as(C.POINTER(C.c_int)) if idx is not None and idx.size else None
+        if grid is not None:
+            if local_z_length is None:
+                local_z_length = dim_z
+            lib.call("spfft" + self._sfx + "_transform_create", C.byref(self.handle), grid.handle,
+                     int(processing_unit), int(transform_type), int(dim_x), int(dim_y), int(dim_z),
+                     int(local_z_length), int(n), int(index_format), iptr)
+        else:
+            lib.call("spfft" + self._sfx + "_transform_create_independent", C.byref(self.handle),
+                     int(max_num_threads), int(processing_unit), int(transform_type), int(dim_x),
+                     int(dim_y), int(dim_z), int(n), int(index_format), iptr)
+
+    # ---- getters ----
+    def _get_int(self, what):
+        v = C.c_int()
+        self.lib.call(f"spfft{self._sfx}_transform_{what}", self.handle, C.byref(v))
+        return v.value
+
+    def _get_ll(self, what):
+        v = C.c_longlong()
+        self.lib.call(f"spfft{self._sfx}_transform_{what}", self.handle, C.byref(v))
+        return v.value
+
+    def dim_x(self): return self._get_int("dim_x")
+    def dim_y(self): return self._get_int("dim_y")
+    def dim_z(self): return self._get_int("dim_z")
+    def local_z_length(self): return self._get_int("local_z_length")
+    def local_z_offset(self): return self._get_int("local_z_offset")
+    def local_slice_size(self): return self._get_int("local_slice_size")
+    def num_local_elements(self): return self._get_int("num_local_elements")
+    def global_size(self): return self._get_ll("global_size")
+    def num_global_elements(self): return self._get_ll("num_global_elements")
+    def device_id(self): return self._get_int("device_id")
+    def num_threads(self): return self._get_int("num_threads")
+    def execution_mode(self): return self._get_int("execution_mode")
+
+    def set_execution_mode(self, mode):
+        self.lib.call(f"spfft{self._sfx}_transform_set_execution_mode", self.handle, int(mode))
+
+    def clone(self):
+        h = C.c_void_p()
+        self.lib.call(f"spfft{self._sfx}_transform_clone", self.handle, C.byref(h))
+        return Transform(self.lib, single=self.single, _handle=h)
+
+    # ---- data ----
+    def space_domain_data(self, location) -> int:
+        """Raw address of the internal space-domain buffer at `location`."""
+        p = C.c_void_p()
+        self.lib.call(f"spfft{self._sfx}_transform_get_space_domain", self.handle, int(location),
+                      C.byref(p))
+        return p.value or 0
+
+    def space_domain_host_view(self, transform_type) -> np.ndarray:
+        """numpy view (z_local, y, x) of the internal HOST space-domain buffer."""
+        addr = self.space_domain_data(SPFFT_PU_HOST)
+        nz, ny, nx = self.local_z_length(), self.dim_y(), self.dim_x()
+        n = nz * ny * nx
+        if transform_type == SPFFT_TRANS_R2C:
+            buf = (C.c_float if self.single else C.c_double) * n
+            return np.frombuffer(buf.from_address(addr), dtype=self.real_t).reshape(nz, ny, nx)
+        buf = (C.c_float if self.single else C.c_double) * (2 * n)
+        return np.frombuffer(buf.from_address(addr), dtype=self.real_t).view(self.cplx_t).reshape(
+            nz, ny, nx)
+
+    def backward(self, input_values, output_location) -> None:
+        self.lib.call(f"spfft{self._sfx}_transform_backward", self.handle, _ptr(input_values),
+                      int(output_location))
+
+    def backward_ptr(self, input_values, output) -> None:
+        self.lib.call(f"spfft{self._sfx}_transform_backward_ptr", self.handle, _ptr(input_values),
+                      _ptr(output))
+
+    def forward(self, input_location, output_values, scaling=SPFFT_NO_SCALING) -> None:
+        self.lib.call(f"spfft{self._sfx}_transform_forward", self.handle, int(input_location),
+                      _ptr(output_values), int(scaling))
+
+    def forward_ptr(self, input_space, output_values, scaling=SPFFT_NO_SCALING) -> None:
+        self.lib.call(f"spfft{self._sfx}_transform_forward_ptr", self.handle, _ptr(input_space),
+                      _ptr(output_values), int(scaling))
+
+    def destroy(self):
+        if self.handle:
+            self.lib.call(f"spfft{self._sfx}_transform_destroy", self.handle)
+            self.handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.destroy()
+        except Exception:
+            pass
+
+
+def _ptr_array(objs):
+    arr = (C.c_void_p * len(objs))()
+    for i, o in enumerate(objs):
+        arr[i] = _ptr(o)
+    return arr
+
+
+def _int_array(vals):
+    arr = (C.c_int * len(vals))()
+    for i, v in enumerate(vals):
+        arr[i] = int(v)
+    return arr
+
+
+def multi_transform_backward(transforms, inputs, output_locations):
+    """spfft_multi_transform_backward (include/spfft/multi_transform.h:74-82)."""
+    t0 = transforms[0]
+    hs = (C.c_void_p * len(transforms))(*[t.handle for t in transforms])
+    t0.lib.call(f"spfft{t0._sfx}_multi_transform_backward", len(transforms), hs,
+                _ptr_array(inputs), _int_array(output_locations))
+
+
+def multi_transform_backward_ptr(transforms, inputs, outputs):
+    t0 = transforms[0]
+    hs = (C.c_void_p * len(transforms))(*[t.handle for t in transforms])
+    t0.lib.call(f"spfft{t0._sfx}_multi_transform_backward_ptr", len(transforms), hs,
+                _ptr_array(inputs), _ptr_array(outputs))
+
+
+def multi_transform_forward(transforms, input_locations, outputs, scalings):
+    """spfft_multi_transform_forward (include/spfft/multi_transform.h:49-60)."""
+    t0 = transforms[0]
+    hs = (C.c_void_p * len(transforms))(*[t.handle for t in transforms])
+    t0.lib.call(f"spfft{t0._sfx}_multi_transform_forward", len(transforms), hs,
+                _int_array(input_locations), _ptr_array(outputs), _int_array(scalings))
+
+
+def multi_transform_forward_ptr(transforms, inputs, outputs, scalings):
+    t0 = transforms[0]
+    hs = (C.c_void_p * len(transforms))(*[t.handle for t in transforms])
+    t0.lib.call(f"spfft{t0._sfx}_multi_transform_forward_ptr", len(transforms), hs,
+                _ptr_array(inputs), _ptr_array(outputs), _int_array(scalings))

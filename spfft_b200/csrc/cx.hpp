@@ -1,0 +1,81 @@
+// cx.hpp -- minimal complex value type + the host/device portability macros used by the stage
+// kernel bodies.
+//
+// The stage bodies (fft_tile.hpp, stage_kernels.hpp) are written once and compiled two ways:
+//   * by nvcc for sm_100a: a "phase" is the code between two __syncthreads(), `tid` is threadIdx.x
+//   * by g++ for the CPU-side unit tests (tests/emu): a "phase" is a loop over all thread ids.
+// The second build exists only so that index arithmetic can be unit-tested without a GPU; it is
+// never linked into libspfft_b200.so and is not a fallback path.
+#pragma once
+
+#if defined(__CUDACC__) && !defined(SB_EMULATE)
+#define SB_HD __host__ __device__ __forceinline__
+#define SB_DEV __device__ __forceinline__
+#define SB_ON_GPU 1
+#define SB_PHASE_BEGIN                 \
+  {                                    \
+    const int tid = (int)threadIdx.x;  \
+    const int nthr = (int)blockDim.x;
+#define SB_PHASE_END \
+  }                  \
+  __syncthreads();
+#else
+#define SB_HD inline
+#define SB_DEV inline
+#define SB_ON_GPU 0
+#define SB_PHASE_BEGIN                                \
+  for (int tid = 0; tid < ctx.nthreads; ++tid) {      \
+    const int nthr = ctx.nthreads;
+#define SB_PHASE_END }
+#endif
+
+namespace sb {
+
+template <typename T>
+struct alignas(2 * sizeof(T)) cx {
+  T x, y;
+};
+
+template <typename T>
+SB_HD cx<T> mk(T x, T y) {
+  cx<T> r;
+  r.x = x;
+  r.y = y;
+  return r;
+}
+template <typename T>
+SB_HD cx<T> operator+(cx<T> a, cx<T> b) {
+  return mk<T>(a.x + b.x, a.y + b.y);
+}
+template <typename T>
+SB_HD cx<T> operator-(cx<T> a, cx<T> b) {
+  return mk<T>(a.x - b.x, a.y - b.y);
+}
+template <typename T>
+SB_HD cx<T> operator*(cx<T> a, cx<T> b) {
+  return mk<T>(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+template <typename T>
+SB_HD cx<T> operator*(T s, cx<T> a) {
+  return mk<T>(s * a.x, s * a.y);
+}
+template <typename T>
+SB_HD cx<T> conj(cx<T> a) {
+  return mk<T>(a.x, -a.y);
+}
+// multiply by +i (BWD) or -i (forward): the sign of the DFT exponent
+template <bool BWD, typename T>
+SB_HD cx<T> mul_si(cx<T> a) {
+  return BWD ? mk<T>(-a.y, a.x) : mk<T>(a.y, -a.x);
+}
+template <typename T>
+SB_HD bool nonzero(cx<T> a) {
+  return a.x != T(0) || a.y != T(0);
+}
+
+// Execution context: empty on the GPU, carries the emulated block size on the CPU.
+struct Ctx {
+  int nthreads;
+};
+
+}  // namespace sb

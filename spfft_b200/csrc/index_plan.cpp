@@ -1,0 +1,287 @@
+// index_plan.cpp -- see index_plan.hpp.
+#include "index_plan.hpp"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <numeric>
+
+#include "spfft/exceptions.hpp"
+
+namespace spfft {
+namespace b200 {
+
+namespace {
+inline int storage_index(int dim, int idx) { return idx < 0 ? idx + dim : idx; }
+}  // namespace
+
+// Same results as the reference's std::map based routine (indices.hpp:120-186), computed with a
+// presence table + prefix sum: O(Ne + Nx*Ny) instead of O(Ne log Ns).
+void convert_index_triplets(bool hermitianSymmetry, int dimX, int dimY, int dimZ, int numValues,
+                            const int* triplets, std::vector<int>& valueIndices,
+                            std::vector<int>& stickIndices) {
+  valueIndices.clear();
+  stickIndices.clear();
+  if (static_cast<unsigned long long>(numValues) >
+      static_cast<unsigned long long>(dimX) * static_cast<unsigned long long>(dimY) *
+          static_cast<unsigned long long>(dimZ)) {
+    throw InvalidParameterError();  // indices.hpp:124-127
+  }
+  if (numValues == 0) return;
+
+  // "centered" is a property of the whole index set, decided over all three coordinates
+  // (indices.hpp:129-135)
+  bool centered = false;
+  for (long long i = 0; i < 3LL * numValues; ++i) {
+    if (triplets[i] < 0) {
+      centered = true;
+      break;
+    }
+  }
+  const int maxX = ((hermitianSymmetry || centered) ? dimX / 2 + 1 : dimX) - 1;
+  const int maxY = (centered ? dimY / 2 + 1 : dimY) - 1;
+  const int maxZ = (centered ? dimZ / 2 + 1 : dimZ) - 1;
+  const int minX = hermitianSymmetry ? 0 : maxX - dimX + 1;
+  const int minY = maxY - dimY + 1;
+  const int minZ = maxZ - dimZ + 1;
+  for (long long i = 0; i < numValues; ++i) {
+    const int x = triplets[3 * i], y = triplets[3 * i + 1], z = triplets[3 * i + 2];
+    if (x < minX || x > maxX || y < minY || y > maxY || z < minZ || z > maxZ)
+      throw InvalidIndicesError();  // indices.hpp:145-149
+  }
+
+  const long long planeSize = static_cast<long long>(dimX) * dimY;
+  valueIndices.resize(numValues);
+  if (planeSize <= (1LL << 28)) {
+    // presence table -> rank of every occupied (x,y) key
+    std::vector<int> rankOfKey(static_cast<size_t>(planeSize), 0);
+    for (long long i = 0; i < numValues; ++i) {
+      const int x = storage_index(dimX, triplets[3 * i]);
+      const int y = storage_index(dimY, triplets[3 * i + 1]);
+      rankOfKey[static_cast<size_t>(x) * dimY + y] = 1;
+    }
+    int count = 0;
+    for (long long k = 0; k < planeSize; ++k) {
+      if (rankOfKey[k]) {
+        rankOfKey[k] = count++;
+        stickIndices.push_back(static_cast<int>(k));
+      }
+    }
+    for (long long i = 0; i < numValues; ++i) {
+      const int x = storage_index(dimX, triplets[3 * i]);
+      const int y = storage_index(dimY, triplets[3 * i + 1]);
+      const int z = storage_index(dimZ, triplets[3 * i + 2]);
+      valueIndices[i] = rankOfKey[static_cast<size_t>(x) * dimY + y] * dimZ + z;
+    }
+  } else {
+    // very large xy extent: sort the keys instead of tabulating the plane
+    std::vector<int> keys(numValues);
+    for (long long i = 0; i < numValues; ++i) {
+      keys[i] = storage_index(dimX, triplets[3 * i]) * dimY +
+                storage_index(dimY, triplets[3 * i + 1]);
+    }
+    stickIndices = keys;
+    std::sort(stickIndices.begin(), stickIndices.end());
+    stickIndices.erase(std::unique(stickIndices.begin(), stickIndices.end()), stickIndices.end());
+    for (long long i = 0; i < numValues; ++i) {
+      const int rank = static_cast<int>(
+          std::lower_bound(stickIndices.begin(), stickIndices.end(), keys[i]) -
+          stickIndices.begin());
+      valueIndices[i] = rank * dimZ + storage_index(dimZ, triplets[3 * i + 2]);
+    }
+  }
+}
+
+void check_stick_duplicates(const std::vector<std::vector<int>>& sticksPerRank) {
+  std::vector<int> all;
+  for (const auto& s : sticksPerRank) all.insert(all.end(), s.begin(), s.end());
+  std::sort(all.begin(), all.end());
+  if (std::adjacent_find(all.begin(), all.end()) != all.end()) throw DuplicateIndicesError();
+}
+
+std::shared_ptr<IndexMaps> make_local_index_maps(SpfftTransformType type, int dimX, int dimY,
+                                                 int dimZ, int numLocalElements,
+                                                 SpfftIndexFormatType indexFormat,
+                                                 const int* indices) {
+  if (indexFormat != SPFFT_INDEX_TRIPLETS) throw InternalError();  // parameters.cpp:158-160
+  auto m = std::make_shared<IndexMaps>();
+  m->type = type;
+  m->dimX = dimX;
+  m->dimY = dimY;
+  m->dimZ = dimZ;
+  m->dimXFreq = type == SPFFT_TRANS_R2C ? dimX / 2 + 1 : dimX;
+  convert_index_triplets(type == SPFFT_TRANS_R2C, dimX, dimY, dimZ, numLocalElements, indices,
+                         m->valueIndices, m->stickIndices);
+  m->sticksPerRank.assign(1, m->stickIndices);
+  check_stick_duplicates(m->sticksPerRank);
+  m->zeroZeroStickIndex = 0;
+  for (int key : m->stickIndices) {
+    if (key == 0) break;
+    ++m->zeroZeroStickIndex;
+  }
+  m->commRank = 0;
+  m->commSize = 1;
+  m->numPlanesPerRank.assign(1, dimZ);
+  m->planeOffsetPerRank.assign(1, 0);
+  m->numGlobalElements = numLocalElements;
+  return m;
+}
+
+TileMaps build_tile_maps(const IndexMaps& maps, int log2Vz, int log2Vy) {
+  TileMaps t;
+  t.log2Vz = log2Vz;
+  t.log2Vy = log2Vy;
+  const int Vz = 1 << log2Vz, Vy = 1 << log2Vy;
+  const int ns = maps.num_sticks();
+  const int ne = maps.num_values();
+  const int nz = maps.dimZ;
+  t.numStickTiles = (ns + Vz - 1) / Vz;
+  t.pitch = t.numStickTiles * Vz;
+
+  // ---- z stage: counting sort of the sparse entries by stick tile, keeping user order inside
+  t.tileStart.assign(t.numStickTiles + 1, 0);
+  for (int i = 0; i < ne; ++i) {
+    const int stick = maps.valueIndices[i] / nz;
+    ++t.tileStart[(stick >> log2Vz) + 1];
+  }
+  for (int k = 0; k < t.numStickTiles; ++k) t.tileStart[k + 1] += t.tileStart[k];
+  t.entrySrc.resize(ne);
+  t.entrySlot.resize(ne);
+  {
+    std::vector<int> cursor(t.tileStart.begin(), t.tileStart.end() - 1);
+    bool identity = true;
+    for (int i = 0; i < ne; ++i) {
+      const int vi = maps.valueIndices[i];
+      const int stick = vi / nz;
+      const int z = vi - stick * nz;
+      const int p = cursor[stick >> log2Vz]++;
+      t.entrySrc[p] = i;
+      t.entrySlot[p] = (z << log2Vz) + (stick & (Vz - 1));
+      identity = identity && (p == i);
+    }
+    t.identityOrder = identity;
+  }
+
+  // ---- duplicates (legal for the reference, Appendix B.8 of SURVEY.md): last writer wins
+  {
+    std::vector<int> stamp(static_cast<size_t>(nz) * Vz, -1);
+    std::vector<char> dropped;
+    for (int tile = 0; tile < t.numStickTiles; ++tile) {
+      for (int p = t.tileStart[tile + 1] - 1; p >= t.tileStart[tile]; --p) {
+        int& s = stamp[t.entrySlot[p]];
+        if (s == tile) {
+          if (dropped.empty()) dropped.assign(ne, 0);
+          dropped[p] = 1;
+        } else {
+          s = tile;
+        }
+      }
+    }
+    if (!dropped.empty()) {
+      t.hasDuplicates = true;
+      t.bwdTileStart.assign(t.numStickTiles + 1, 0);
+      for (int tile = 0; tile < t.numStickTiles; ++tile) {
+        t.bwdTileStart[tile] = static_cast<int>(t.bwdEntrySrc.size());
+        for (int p = t.tileStart[tile]; p < t.tileStart[tile + 1]; ++p) {
+          if (!dropped[p]) {
+            t.bwdEntrySrc.push_back(t.entrySrc[p]);
+            t.bwdEntrySlot.push_back(t.entrySlot[p]);
+          }
+        }
+      }
+      t.bwdTileStart[t.numStickTiles] = static_cast<int>(t.bwdEntrySrc.size());
+    }
+  }
+
+  if (maps.type == SPFFT_TRANS_R2C && maps.zeroZeroStickIndex < ns) {
+    t.symTile = maps.zeroZeroStickIndex >> log2Vz;
+    t.symLane = maps.zeroZeroStickIndex & (Vz - 1);
+  }
+
+  // ---- y stage
+  t.numXTiles = (maps.dimXFreq + Vy - 1) / Vy;
+  t.xtStart.assign(t.numXTiles + 1, 0);
+  t.stickSlot.resize(ns);
+  for (int s = 0; s < ns; ++s) {
+    const int key = maps.stickIndices[s];
+    const int x = key / maps.dimY;
+    const int y = key - x * maps.dimY;
+    ++t.xtStart[(x >> log2Vy) + 1];
+    t.stickSlot[s] = (y << log2Vy) + (x & (Vy - 1));
+  }
+  for (int k = 0; k < t.numXTiles; ++k) t.xtStart[k + 1] += t.xtStart[k];
+  return t;
+}
+
+sb::RadixPlan make_radix_plan(int n) {
+  sb::RadixPlan rp;
+  rp.n = n;
+  rp.numPasses = 0;
+  for (int& r : rp.radix) r = 1;
+  if (n <= 1) return rp;
+  int m = n;
+  auto push = [&](int r) {
+    if (rp.numPasses >= sb::kMaxPasses) throw InvalidParameterError();
+    rp.radix[rp.numPasses++] = r;
+  };
+  while (m % 8 == 0) {
+    push(8);
+    m /= 8;
+  }
+  if (m % 4 == 0) {
+    push(4);
+    m /= 4;
+  }
+  if (m % 2 == 0) {
+    push(2);
+    m /= 2;
+  }
+  while (m % 3 == 0) {
+    push(3);
+    m /= 3;
+  }
+  while (m % 5 == 0) {
+    push(5);
+    m /= 5;
+  }
+  for (int p = 7; static_cast<long long>(p) * p <= m; p += 2) {
+    while (m % p == 0) {
+      push(p);
+      m /= p;
+    }
+  }
+  if (m > 1) push(m);
+  return rp;
+}
+
+template <typename T>
+std::vector<sb::cx<T>> make_roots(int n) {
+  std::vector<sb::cx<T>> w(static_cast<size_t>(n > 0 ? n : 1));
+  const long double twoPi = 6.283185307179586476925286766559005768L;
+  for (int k = 0; k < n; ++k) {
+    // exact octant symmetries are not needed: long double keeps the rounding error below T's ulp
+    const long double a = twoPi * static_cast<long double>(k) / static_cast<long double>(n);
+    w[k].x = static_cast<T>(cosl(a));
+    w[k].y = static_cast<T>(-sinl(a));
+  }
+  if (n <= 0) {
+    w[0].x = T(1);
+    w[0].y = T(0);
+  }
+  return w;
+}
+template std::vector<sb::cx<float>> make_roots<float>(int);
+template std::vector<sb::cx<double>> make_roots<double>(int);
+
+int choose_log2_lanes(int n, int complexBytes, long long smemLimit) {
+  int log2V = 0;
+  while ((complexBytes << (log2V + 1)) <= 128) ++log2V;  // at most 128 bytes per tile row
+  for (; log2V >= 0; --log2V) {
+    const long long bytes = 2LL * n * (static_cast<long long>(complexBytes) << log2V);
+    if (bytes <= smemLimit) return log2V;
+  }
+  return -1;
+}
+
+}  // namespace b200
+}  // namespace spfft

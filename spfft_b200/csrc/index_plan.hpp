@@ -1,0 +1,90 @@
+// index_plan.hpp -- plan-time (host) integer work: the reference-defined index maps and the tile
+// maps the B200 kernels consume.
+//
+// Reference-defined (bit-exact contract):
+//   convert_index_triplets   src/compression/indices.hpp:120-186
+//   check_stick_duplicates   src/compression/indices.hpp:105-117
+//   Parameters (local)       src/parameters/parameters.cpp:143-180
+// Derived (ours): per-stick-tile sparse entry lists, per-x-tile stick ranges, radix plans,
+// twiddle tables.
+#pragma once
+#include <memory>
+#include <vector>
+
+#include "fft_tile.hpp"
+#include "spfft/types.h"
+
+namespace spfft {
+namespace b200 {
+
+// Immutable per-transform parameters, shared by clones (the reference's `Parameters`).
+struct IndexMaps {
+  SpfftTransformType type = SPFFT_TRANS_C2C;
+  int dimX = 0, dimY = 0, dimZ = 0, dimXFreq = 0;
+  std::vector<int> valueIndices;  // [Ne]  stick*dimZ + z      (reference freqValueIndices_)
+  std::vector<int> stickIndices;  // [Ns]  x*dimY + y, ascending (reference stickIndicesPerRank_[rank])
+  int zeroZeroStickIndex = 0;     // position of key 0 or Ns (parameters.cpp:173-179)
+  // decomposition (single rank: all planes local)
+  int commRank = 0, commSize = 1;
+  std::vector<int> numPlanesPerRank;       // [size]
+  std::vector<int> planeOffsetPerRank;     // [size]
+  std::vector<std::vector<int>> sticksPerRank;  // [size][Ns(r)]; sticksPerRank[rank] == stickIndices
+  long long numGlobalElements = 0;
+
+  int num_sticks() const { return static_cast<int>(stickIndices.size()); }
+  int num_values() const { return static_cast<int>(valueIndices.size()); }
+  int local_planes() const { return numPlanesPerRank[commRank]; }
+  int local_plane_offset() const { return planeOffsetPerRank[commRank]; }
+};
+
+// Throws InvalidParameterError / InvalidIndicesError exactly where the reference does.
+void convert_index_triplets(bool hermitianSymmetry, int dimX, int dimY, int dimZ, int numValues,
+                            const int* triplets, std::vector<int>& valueIndices,
+                            std::vector<int>& stickIndices);
+
+// Throws DuplicateIndicesError if a stick key appears twice over all ranks.
+void check_stick_duplicates(const std::vector<std::vector<int>>& sticksPerRank);
+
+// Single-rank parameters (parameters.cpp:143-180).
+std::shared_ptr<IndexMaps> make_local_index_maps(SpfftTransformType type, int dimX, int dimY,
+                                                 int dimZ, int numLocalElements,
+                                                 SpfftIndexFormatType indexFormat,
+                                                 const int* indices);
+
+// What the stage kernels read. All arrays are host vectors here; TransformEngine uploads them.
+struct TileMaps {
+  int log2Vz = 0, log2Vy = 0;
+  // z stage: stick tiles of Vz consecutive sticks
+  int numStickTiles = 0;
+  int pitch = 0;                   // numStickTiles * Vz
+  bool identityOrder = true;       // entrySrc[p] == p for all p -> kernels skip the indirection
+  std::vector<int> tileStart;      // [numStickTiles+1]
+  std::vector<int> entrySrc;       // [Ne] position in the user's value array, grouped by tile
+  std::vector<int> entrySlot;      // [Ne] z*Vz + (stick mod Vz)
+  // backward-only variant when the user passed duplicate triplets: only the LAST duplicate
+  // scatters (what the reference host loop leaves behind, compression_host.hpp:88-91)
+  bool hasDuplicates = false;
+  std::vector<int> bwdTileStart, bwdEntrySrc, bwdEntrySlot;
+  // (x=0,y=0) stick for the R2C stick symmetry
+  int symTile = -1, symLane = -1;
+  // y stage: x tiles of Vy consecutive x columns; sticks are sorted by x so each tile owns a range
+  int numXTiles = 0;
+  std::vector<int> xtStart;    // [numXTiles+1] (stick index ranges)
+  std::vector<int> stickSlot;  // [Ns] y*Vy + (x mod Vy)
+};
+
+TileMaps build_tile_maps(const IndexMaps& maps, int log2Vz, int log2Vy);
+
+// Radix schedule for the Stockham tile FFT: 8s, then 4 / 2, then 3s, 5s, then remaining primes.
+sb::RadixPlan make_radix_plan(int n);
+
+// Forward roots of unity exp(-2*pi*i*k/n), k = 0..n-1, rounded from long double.
+template <typename T>
+std::vector<sb::cx<T>> make_roots(int n);
+
+// Largest lane count (power of two, at most 128 bytes of complex<T> per tile row) such that two
+// tile buffers of n rows fit into smemLimit bytes. Returns -1 if even one lane does not fit.
+int choose_log2_lanes(int n, int complexBytes, long long smemLimit);
+
+}  // namespace b200
+}  // namespace spfft

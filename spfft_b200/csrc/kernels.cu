@@ -1,0 +1,111 @@
+// kernels.cu -- __global__ entry points of the stage kernels (sm_100a) and their launchers.
+// The bodies live in stage_kernels.hpp / fft_tile.hpp.
+#include <cuda_runtime.h>
+
+#include <atomic>
+
+#include "launch.h"
+
+namespace sb {
+
+constexpr int kThreads = 256;
+
+template <typename T, bool FWD>
+__global__ void __launch_bounds__(kThreads) k_z_stage(const __grid_constant__ ZArgs<T> a) {
+  extern __shared__ __align__(16) unsigned char smemRaw[];
+  cx<T>* smem = reinterpret_cast<cx<T>*>(smemRaw);
+  if (FWD)
+    z_forward_body<T>(a, (int)blockIdx.x, Ctx{kThreads}, smem);
+  else
+    z_backward_body<T>(a, (int)blockIdx.x, Ctx{kThreads}, smem);
+}
+
+template <typename T, bool FWD>
+__global__ void __launch_bounds__(kThreads) k_y_stage(const __grid_constant__ YArgs<T> a) {
+  extern __shared__ __align__(16) unsigned char smemRaw[];
+  cx<T>* smem = reinterpret_cast<cx<T>*>(smemRaw);
+  if (FWD)
+    y_forward_body<T>(a, (int)blockIdx.x, Ctx{kThreads}, smem);
+  else
+    y_backward_body<T>(a, (int)blockIdx.x, Ctx{kThreads}, smem);
+}
+
+template <typename T, bool FWD>
+__global__ void __launch_bounds__(kThreads) k_x_stage(const __grid_constant__ XArgs<T> a) {
+  extern __shared__ __align__(16) unsigned char smemRaw[];
+  cx<T>* smem = reinterpret_cast<cx<T>*>(smemRaw);
+  if (FWD)
+    x_forward_body<T>(a, (int)blockIdx.x, Ctx{kThreads}, smem);
+  else
+    x_backward_body<T>(a, (int)blockIdx.x, Ctx{kThreads}, smem);
+}
+
+static std::atomic<long long> g_launches{0};
+
+template <typename Kernel, typename Args>
+static int launch(Kernel kernel, const Args& args, long long blocks, size_t smemBytes,
+                  cudaStream_t stream) {
+  if (blocks <= 0) return 0;
+  if (blocks > 0x7fffffffLL) return (int)cudaErrorInvalidConfiguration;
+  if (smemBytes > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)smemBytes);
+    if (e != cudaSuccess) return (int)e;
+  }
+  kernel<<<(unsigned)blocks, kThreads, smemBytes, stream>>>(args);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return (int)cudaGetLastError();
+}
+
+template <typename T>
+static int launch_z(int forward, const ZArgs<T>& a, cudaStream_t s) {
+  const size_t smem = 2 * ((size_t)a.nz << a.log2V) * sizeof(cx<T>);
+  return forward ? launch(k_z_stage<T, true>, a, a.numTiles, smem, s)
+                 : launch(k_z_stage<T, false>, a, a.numTiles, smem, s);
+}
+template <typename T>
+static int launch_y(int forward, const YArgs<T>& a, cudaStream_t s) {
+  const size_t smem = 2 * ((size_t)a.ny << a.log2V) * sizeof(cx<T>);
+  const long long blocks = (long long)a.numXTiles * a.numPlanes;
+  return forward ? launch(k_y_stage<T, true>, a, blocks, smem, s)
+                 : launch(k_y_stage<T, false>, a, blocks, smem, s);
+}
+template <typename T>
+static int launch_x(int forward, const XArgs<T>& a, cudaStream_t s) {
+  const size_t smem = 2 * ((size_t)a.nx << a.log2V) * sizeof(cx<T>);
+  const long long blocks = (long long)a.numRowTiles * a.numPlanes;
+  return forward ? launch(k_x_stage<T, true>, a, blocks, smem, s)
+                 : launch(k_x_stage<T, false>, a, blocks, smem, s);
+}
+
+}  // namespace sb
+
+extern "C" {
+int sb_launch_z_f64(int forward, const sb::ZArgs<double>* a, void* stream) {
+  return sb::launch_z<double>(forward, *a, static_cast<cudaStream_t>(stream));
+}
+int sb_launch_z_f32(int forward, const sb::ZArgs<float>* a, void* stream) {
+  return sb::launch_z<float>(forward, *a, static_cast<cudaStream_t>(stream));
+}
+int sb_launch_y_f64(int forward, const sb::YArgs<double>* a, void* stream) {
+  return sb::launch_y<double>(forward, *a, static_cast<cudaStream_t>(stream));
+}
+int sb_launch_y_f32(int forward, const sb::YArgs<float>* a, void* stream) {
+  return sb::launch_y<float>(forward, *a, static_cast<cudaStream_t>(stream));
+}
+int sb_launch_x_f64(int forward, const sb::XArgs<double>* a, void* stream) {
+  return sb::launch_x<double>(forward, *a, static_cast<cudaStream_t>(stream));
+}
+int sb_launch_x_f32(int forward, const sb::XArgs<float>* a, void* stream) {
+  return sb::launch_x<float>(forward, *a, static_cast<cudaStream_t>(stream));
+}
+long long sb_launch_count(void) { return sb::g_launches.load(std::memory_order_relaxed); }
+int sb_max_dynamic_smem(long long* bytes) {
+  int dev = 0, v = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return (int)e;
+  e = cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+  *bytes = v;
+  return (int)e;
+}
+}

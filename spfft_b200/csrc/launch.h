@@ -1,0 +1,21 @@
+/* launch.h -- the thin internal C ABI between the host C++ (transform_engine.cpp) and the CUDA
+ * translation unit (kernels.cu). POD argument structs (stage_kernels.hpp), int error return
+ * (a cudaError_t value, 0 = success). `stream` is a cudaStream_t. */
+#pragma once
+#include "stage_kernels.hpp"
+
+extern "C" {
+/* z stage: forward == 0 -> decompress + symmetry + inverse z-FFT; else z-FFT + compress. */
+int sb_launch_z_f64(int forward, const sb::ZArgs<double>* args, void* stream);
+int sb_launch_z_f32(int forward, const sb::ZArgs<float>* args, void* stream);
+/* y stage on every (x tile, local plane). */
+int sb_launch_y_f64(int forward, const sb::YArgs<double>* args, void* stream);
+int sb_launch_y_f32(int forward, const sb::YArgs<float>* args, void* stream);
+/* x stage on every (row tile, local plane). */
+int sb_launch_x_f64(int forward, const sb::XArgs<double>* args, void* stream);
+int sb_launch_x_f32(int forward, const sb::XArgs<float>* args, void* stream);
+/* total number of kernel launches issued through this file */
+long long sb_launch_count(void);
+/* opt-in limit of dynamic shared memory per block on the current device (bytes) */
+int sb_max_dynamic_smem(long long* bytes);
+}

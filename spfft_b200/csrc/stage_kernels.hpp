@@ -1,0 +1,323 @@
+// stage_kernels.hpp -- bodies of the six generic stage kernels (any transform length).
+//
+//   backward:  z_backward  (decompress + stick symmetry + z-FFT, writes plane-major sticks)
+//              y_backward  (gather sticks of an x-tile + plane symmetry + y-FFT, writes planes)
+//              x_backward  (x-FFT rows, C2C or C2R, writes the space domain)
+//   forward :  x_forward -> y_forward -> z_forward (+ compress, + scaling)
+//
+// They replace, fused, the reference GPU stages
+//   decompress/compress   src/compression/gpu_kernels/compression_kernels.cu:40-150
+//   stick/plane symmetry  src/symmetry/gpu_kernels/symmetry_kernels.cu:39-165
+//   local transpose       src/transpose/gpu_kernels/local_transpose_kernels.cu:48-201
+//   cuFFT z / xy plans    src/fft/transform_1d_gpu.hpp:52-141, transform_2d_gpu.hpp:51-140,
+//                         transform_real_2d_gpu.hpp:54-257
+// wired in the order of src/execution/execution_gpu.cpp:254-400.
+//
+// Intermediate layouts (all complex, element counts):
+//   sticks  [z][pitch]           plane-major: row z holds the value of every local stick at z;
+//                                pitch = numSticks rounded up to the z-tile width
+//   planes  [zl][y][nxf]         x innermost (same as the reference GPU plane buffer,
+//                                src/execution/execution_gpu.cpp:88-89)
+//   space   [zl][y][nx]          complex (C2C) or real, unpadded (R2C)  -- user visible
+#pragma once
+#include <cstddef>
+#include "cx.hpp"
+#include "fft_tile.hpp"
+
+namespace sb {
+
+template <typename T>
+struct ZArgs {
+  int nz;         // dimZ = transform length
+  int log2V;      // sticks per tile = 1 << log2V
+  int numTiles;   // ceil(numSticks / V)
+  int pitch;      // row pitch of the stick buffer
+  RadixPlan rp;
+  const cx<T>* tw;        // forward roots of unity, length nz
+  const int* tileStart;   // [numTiles+1]: range of sparse entries of every stick tile
+  const int* entrySrc;    // [numEntries]: position in the user's value array; nullptr = identity
+  const int* entrySlot;   // [numEntries]: z*V + lane inside the tile
+  const cx<T>* valuesIn;  // backward input (user order)
+  cx<T>* valuesOut;       // forward output (user order)
+  cx<T>* sticks;          // [nz][pitch]
+  int symTile, symLane;   // R2C: tile / lane of the (x=0,y=0) stick, -1 if not local
+  int useScale;
+  T scale;
+};
+
+template <typename T>
+struct YArgs {
+  int ny;          // dimY = transform length
+  int log2V;       // x columns per tile
+  int nxf;         // dimXFreq
+  int numPlanes;   // local planes
+  int numXTiles;   // ceil(nxf / V)
+  int pitch;       // row pitch of the stick buffer
+  int zRowOffset;  // row of the stick buffer that holds local plane 0
+  int symmetry;    // R2C: hermitian fill of the x=0 column
+  RadixPlan rp;
+  const cx<T>* tw;
+  const int* xtStart;    // [numXTiles+1]: range of sticks per x tile (sticks are sorted by x*Ny+y)
+  const int* stickSlot;  // [numSticks]: y*V + (x mod V)
+  cx<T>* sticks;
+  cx<T>* planes;         // [numPlanes][ny][nxf]
+};
+
+template <typename T>
+struct XArgs {
+  int nx, nxf, ny;
+  int log2V;        // rows per tile
+  int numPlanes;
+  int numRowTiles;  // ceil(ny / V)
+  int r2c;
+  RadixPlan rp;
+  const cx<T>* tw;
+  cx<T>* planes;      // [numPlanes][ny][nxf]
+  const void* spaceIn;  // forward input
+  void* spaceOut;       // backward output
+};
+
+// Hermitian completion of one lane of a tile, low index first (reference semantics:
+// src/symmetry/symmetry_host.hpp:47-58,73-90; GPU twin symmetry_kernels.cu:56-78,119-141).
+template <typename T>
+SB_DEV void hermitian_fill_lane(cx<T>* A, int n, int lane, int log2V, Ctx ctx) {
+  (void)ctx;
+  const int half = n / 2;
+  SB_PHASE_BEGIN
+  for (int i = 1 + tid; i <= half; i += nthr) {
+    const cx<T> v = A[(i << log2V) + lane];
+    if (nonzero(v)) A[((n - i) << log2V) + lane] = conj(v);
+  }
+  SB_PHASE_END
+  SB_PHASE_BEGIN
+  for (int i = half + 1 + tid; i < n; i += nthr) {
+    const cx<T> v = A[(i << log2V) + lane];
+    if (nonzero(v)) A[((n - i) << log2V) + lane] = conj(v);
+  }
+  SB_PHASE_END
+}
+
+// -------------------------------------------------------------------------------------------
+// z stage
+// -------------------------------------------------------------------------------------------
+template <typename T>
+SB_DEV void z_backward_body(const ZArgs<T>& a, int tile, Ctx ctx, cx<T>* smem) {
+  const int V = 1 << a.log2V;
+  const int n = a.nz << a.log2V;
+  cx<T>* A = smem;
+  cx<T>* B = smem + n;
+  SB_PHASE_BEGIN
+  for (int i = tid; i < n; i += nthr) A[i] = mk<T>(0, 0);
+  SB_PHASE_END
+  SB_PHASE_BEGIN
+  const int e1 = a.tileStart[tile + 1];
+  for (int e = a.tileStart[tile] + tid; e < e1; e += nthr) {
+    const int src = a.entrySrc ? a.entrySrc[e] : e;
+    A[a.entrySlot[e]] = a.valuesIn[src];
+  }
+  SB_PHASE_END
+  if (tile == a.symTile) hermitian_fill_lane<T>(A, a.nz, a.symLane, a.log2V, ctx);
+  cx<T>* R = tile_fft<T, true, false>(A, B, a.rp, a.log2V, a.tw, ctx);
+  SB_PHASE_BEGIN
+  cx<T>* out = a.sticks + (size_t)tile * V;
+  for (int i = tid; i < n; i += nthr) {
+    const int z = i >> a.log2V;
+    const int lane = i & (V - 1);
+    out[(size_t)z * a.pitch + lane] = R[i];
+  }
+  SB_PHASE_END
+}
+
+template <typename T>
+SB_DEV void z_forward_body(const ZArgs<T>& a, int tile, Ctx ctx, cx<T>* smem) {
+  const int V = 1 << a.log2V;
+  const int n = a.nz << a.log2V;
+  cx<T>* A = smem;
+  cx<T>* B = smem + n;
+  SB_PHASE_BEGIN
+  const cx<T>* in = a.sticks + (size_t)tile * V;
+  for (int i = tid; i < n; i += nthr) {
+    const int z = i >> a.log2V;
+    const int lane = i & (V - 1);
+    A[i] = in[(size_t)z * a.pitch + lane];
+  }
+  SB_PHASE_END
+  cx<T>* R = tile_fft<T, false, false>(A, B, a.rp, a.log2V, a.tw, ctx);
+  SB_PHASE_BEGIN
+  const int e1 = a.tileStart[tile + 1];
+  for (int e = a.tileStart[tile] + tid; e < e1; e += nthr) {
+    const int dst = a.entrySrc ? a.entrySrc[e] : e;
+    cx<T> v = R[a.entrySlot[e]];
+    if (a.useScale) v = a.scale * v;
+    a.valuesOut[dst] = v;
+  }
+  SB_PHASE_END
+}
+
+// -------------------------------------------------------------------------------------------
+// y stage
+// -------------------------------------------------------------------------------------------
+template <typename T>
+SB_DEV void y_backward_body(const YArgs<T>& a, int block, Ctx ctx, cx<T>* smem) {
+  const int V = 1 << a.log2V;
+  const int n = a.ny << a.log2V;
+  const int xt = block % a.numXTiles;
+  const int zl = block / a.numXTiles;
+  const int e0 = a.xtStart[xt], e1 = a.xtStart[xt + 1];
+  cx<T>* planeTile = a.planes + (size_t)zl * a.ny * a.nxf + (size_t)xt * V;
+  const int lanesValid = (a.nxf - xt * V) < V ? (a.nxf - xt * V) : V;
+  if (e0 == e1) {
+    // empty x tile: the x stage still reads these columns -> store zeros, no transform
+    SB_PHASE_BEGIN
+    for (int i = tid; i < n; i += nthr) {
+      const int y = i >> a.log2V;
+      const int lane = i & (V - 1);
+      if (lane < lanesValid) planeTile[(size_t)y * a.nxf + lane] = mk<T>(0, 0);
+    }
+    SB_PHASE_END
+    return;
+  }
+  cx<T>* A = smem;
+  cx<T>* B = smem + n;
+  SB_PHASE_BEGIN
+  for (int i = tid; i < n; i += nthr) A[i] = mk<T>(0, 0);
+  SB_PHASE_END
+  SB_PHASE_BEGIN
+  const cx<T>* row = a.sticks + (size_t)(zl + a.zRowOffset) * a.pitch;
+  for (int e = e0 + tid; e < e1; e += nthr) A[a.stickSlot[e]] = row[e];
+  SB_PHASE_END
+  if (a.symmetry && xt == 0) hermitian_fill_lane<T>(A, a.ny, 0, a.log2V, ctx);
+  cx<T>* R = tile_fft<T, true, false>(A, B, a.rp, a.log2V, a.tw, ctx);
+  SB_PHASE_BEGIN
+  for (int i = tid; i < n; i += nthr) {
+    const int y = i >> a.log2V;
+    const int lane = i & (V - 1);
+    if (lane < lanesValid) planeTile[(size_t)y * a.nxf + lane] = R[i];
+  }
+  SB_PHASE_END
+}
+
+template <typename T>
+SB_DEV void y_forward_body(const YArgs<T>& a, int block, Ctx ctx, cx<T>* smem) {
+  const int V = 1 << a.log2V;
+  const int n = a.ny << a.log2V;
+  const int xt = block % a.numXTiles;
+  const int zl = block / a.numXTiles;
+  const int e0 = a.xtStart[xt], e1 = a.xtStart[xt + 1];
+  if (e0 == e1) return;  // no stick needs these columns
+  const cx<T>* planeTile = a.planes + (size_t)zl * a.ny * a.nxf + (size_t)xt * V;
+  const int lanesValid = (a.nxf - xt * V) < V ? (a.nxf - xt * V) : V;
+  cx<T>* A = smem;
+  cx<T>* B = smem + n;
+  SB_PHASE_BEGIN
+  for (int i = tid; i < n; i += nthr) {
+    const int y = i >> a.log2V;
+    const int lane = i & (V - 1);
+    A[i] = lane < lanesValid ? planeTile[(size_t)y * a.nxf + lane] : mk<T>(0, 0);
+  }
+  SB_PHASE_END
+  cx<T>* R = tile_fft<T, false, false>(A, B, a.rp, a.log2V, a.tw, ctx);
+  SB_PHASE_BEGIN
+  cx<T>* row = a.sticks + (size_t)(zl + a.zRowOffset) * a.pitch;
+  for (int e = e0 + tid; e < e1; e += nthr) row[e] = R[a.stickSlot[e]];
+  SB_PHASE_END
+}
+
+// -------------------------------------------------------------------------------------------
+// x stage (rows are contiguous in global memory; tile = V consecutive rows, swizzled lanes)
+// -------------------------------------------------------------------------------------------
+template <typename T>
+SB_DEV void x_backward_body(const XArgs<T>& a, int block, Ctx ctx, cx<T>* smem) {
+  const int V = 1 << a.log2V;
+  const int n = a.nx << a.log2V;
+  const int rt = block % a.numRowTiles;
+  const int zl = block / a.numRowTiles;
+  const int y0 = rt * V;
+  const int rows = (a.ny - y0) < V ? (a.ny - y0) : V;
+  const size_t rowBase = (size_t)zl * a.ny + y0;
+  cx<T>* A = smem;
+  cx<T>* B = smem + n;
+  if (a.r2c || rows < V) {
+    // C2R rows are completed by conjugation below; zero first so that every slot is defined
+    SB_PHASE_BEGIN
+    for (int i = tid; i < n; i += nthr) A[i] = mk<T>(0, 0);
+    SB_PHASE_END
+  }
+  SB_PHASE_BEGIN
+  const int total = rows * a.nxf;
+  const int mirrorMax = a.nx - a.nxf;  // x in [1, mirrorMax] has a distinct mirror nx - x
+  for (int i = tid; i < total; i += nthr) {
+    const int r = i / a.nxf;
+    const int x = i - r * a.nxf;
+    const cx<T> v = a.planes[(rowBase + r) * a.nxf + x];
+    A[at<true>(x, r, a.log2V)] = v;
+    if (a.r2c && x >= 1 && x <= mirrorMax) A[at<true>(a.nx - x, r, a.log2V)] = conj(v);
+  }
+  SB_PHASE_END
+  cx<T>* R = tile_fft<T, true, true>(A, B, a.rp, a.log2V, a.tw, ctx);
+  SB_PHASE_BEGIN
+  const int total = rows * a.nx;
+  if (a.r2c) {
+    T* out = static_cast<T*>(a.spaceOut);
+    for (int i = tid; i < total; i += nthr) {
+      const int r = i / a.nx;
+      const int x = i - r * a.nx;
+      out[(rowBase + r) * a.nx + x] = R[at<true>(x, r, a.log2V)].x;
+    }
+  } else {
+    cx<T>* out = static_cast<cx<T>*>(a.spaceOut);
+    for (int i = tid; i < total; i += nthr) {
+      const int r = i / a.nx;
+      const int x = i - r * a.nx;
+      out[(rowBase + r) * a.nx + x] = R[at<true>(x, r, a.log2V)];
+    }
+  }
+  SB_PHASE_END
+}
+
+template <typename T>
+SB_DEV void x_forward_body(const XArgs<T>& a, int block, Ctx ctx, cx<T>* smem) {
+  const int V = 1 << a.log2V;
+  const int n = a.nx << a.log2V;
+  const int rt = block % a.numRowTiles;
+  const int zl = block / a.numRowTiles;
+  const int y0 = rt * V;
+  const int rows = (a.ny - y0) < V ? (a.ny - y0) : V;
+  const size_t rowBase = (size_t)zl * a.ny + y0;
+  cx<T>* A = smem;
+  cx<T>* B = smem + n;
+  if (rows < V) {
+    SB_PHASE_BEGIN
+    for (int i = tid; i < n; i += nthr) A[i] = mk<T>(0, 0);
+    SB_PHASE_END
+  }
+  SB_PHASE_BEGIN
+  const int total = rows * a.nx;
+  if (a.r2c) {
+    const T* in = static_cast<const T*>(a.spaceIn);
+    for (int i = tid; i < total; i += nthr) {
+      const int r = i / a.nx;
+      const int x = i - r * a.nx;
+      A[at<true>(x, r, a.log2V)] = mk<T>(in[(rowBase + r) * a.nx + x], T(0));
+    }
+  } else {
+    const cx<T>* in = static_cast<const cx<T>*>(a.spaceIn);
+    for (int i = tid; i < total; i += nthr) {
+      const int r = i / a.nx;
+      const int x = i - r * a.nx;
+      A[at<true>(x, r, a.log2V)] = in[(rowBase + r) * a.nx + x];
+    }
+  }
+  SB_PHASE_END
+  cx<T>* R = tile_fft<T, false, true>(A, B, a.rp, a.log2V, a.tw, ctx);
+  SB_PHASE_BEGIN
+  const int total = rows * a.nxf;
+  for (int i = tid; i < total; i += nthr) {
+    const int r = i / a.nxf;
+    const int x = i - r * a.nxf;
+    a.planes[(rowBase + r) * a.nxf + x] = R[at<true>(x, r, a.log2V)];
+  }
+  SB_PHASE_END
+}
+
+}  // namespace sb

@@ -1,0 +1,145 @@
+// emu_stages.cpp -- TEST HARNESS ONLY: runs the stage kernel *bodies* (spfft_b200/csrc/
+// stage_kernels.hpp, fft_tile.hpp) block by block on the host, each phase as a loop over the
+// emulated thread ids, with the same plan builder and argument wiring as the product.
+//
+// Purpose: unit-test tile/index arithmetic and the Stockham butterflies on a machine without a
+// GPU (`pytest -m "not gpu"`). It is never linked into libspfft_b200.so, is not reachable from the
+// SpFFT API, and is not a fallback: the product fails loudly without CUDA.
+#define SB_EMULATE 1
+#include <cstring>
+#include <vector>
+
+#include "../../spfft_b200/csrc/index_plan.hpp"
+#include "../../spfft_b200/csrc/stage_args.hpp"
+#include "../../spfft_b200/csrc/stage_kernels.hpp"
+#include "spfft/exceptions.hpp"
+
+using namespace spfft::b200;
+
+namespace {
+
+template <typename T>
+int run(int type, int dimX, int dimY, int dimZ, int n, const int* triplets, int forward,
+        const void* in, void* out, int scaling, int nthreads, int maxLog2V) {
+  try {
+    auto maps = make_local_index_maps(static_cast<SpfftTransformType>(type), dimX, dimY, dimZ, n,
+                                      SPFFT_INDEX_TRIPLETS, triplets);
+    AxisPlans ax;
+    const long long smemLimit = 200 * 1024;
+    ax.log2Vx = choose_log2_lanes(dimX, sizeof(sb::cx<T>), smemLimit);
+    ax.log2Vy = choose_log2_lanes(dimY, sizeof(sb::cx<T>), smemLimit);
+    ax.log2Vz = choose_log2_lanes(dimZ, sizeof(sb::cx<T>), smemLimit);
+    if (maxLog2V >= 0) {
+      if (ax.log2Vx > maxLog2V) ax.log2Vx = maxLog2V;
+      if (ax.log2Vy > maxLog2V) ax.log2Vy = maxLog2V;
+      if (ax.log2Vz > maxLog2V) ax.log2Vz = maxLog2V;
+    }
+    ax.rpX = make_radix_plan(dimX);
+    ax.rpY = make_radix_plan(dimY);
+    ax.rpZ = make_radix_plan(dimZ);
+    TileMaps t = build_tile_maps(*maps, ax.log2Vz, ax.log2Vy);
+    auto twX = make_roots<T>(dimX), twY = make_roots<T>(dimY), twZ = make_roots<T>(dimZ);
+    PlanPointers<T> p;
+    p.twX = twX.data();
+    p.twY = twY.data();
+    p.twZ = twZ.data();
+    p.tileStart = t.tileStart.data();
+    p.entrySrc = t.identityOrder ? nullptr : t.entrySrc.data();
+    p.entrySlot = t.entrySlot.data();
+    if (t.hasDuplicates) {
+      p.bwdTileStart = t.bwdTileStart.data();
+      p.bwdEntrySrc = t.bwdEntrySrc.data();
+      p.bwdEntrySlot = t.bwdEntrySlot.data();
+    } else {
+      p.bwdTileStart = p.tileStart;
+      p.bwdEntrySrc = p.entrySrc;
+      p.bwdEntrySlot = p.entrySlot;
+    }
+    p.xtStart = t.xtStart.data();
+    p.stickSlot = t.stickSlot.data();
+
+    const size_t stickElems = static_cast<size_t>(dimZ) * t.pitch;
+    const size_t planeElems = static_cast<size_t>(dimZ) * dimY * maps->dimXFreq;
+    // poison the intermediates: every stage must fully define what the next one reads
+    std::vector<sb::cx<T>> sticks(stickElems + 1, sb::mk<T>(T(1e30), T(-1e30)));
+    std::vector<sb::cx<T>> planes(planeElems + 1, sb::mk<T>(T(1e30), T(-1e30)));
+    const int maxN = std::max(dimX, std::max(dimY, dimZ));
+    std::vector<sb::cx<T>> smem(2 * static_cast<size_t>(maxN) * 32);
+    sb::Ctx ctx{nthreads};
+
+    if (!forward) {
+      auto za = make_z_args<T>(*maps, t, ax, p, false, sticks.data(), static_cast<const T*>(in),
+                               nullptr, false);
+      for (int b = 0; b < za.numTiles; ++b) sb::z_backward_body<T>(za, b, ctx, smem.data());
+      auto ya = make_y_args<T>(*maps, t, ax, p, sticks.data(), planes.data());
+      for (int b = 0; b < ya.numXTiles * ya.numPlanes; ++b)
+        sb::y_backward_body<T>(ya, b, ctx, smem.data());
+      auto xa = make_x_args<T>(*maps, ax, p, planes.data(), nullptr, out);
+      for (int b = 0; b < xa.numRowTiles * xa.numPlanes; ++b)
+        sb::x_backward_body<T>(xa, b, ctx, smem.data());
+    } else {
+      auto xa = make_x_args<T>(*maps, ax, p, planes.data(), in, nullptr);
+      for (int b = 0; b < xa.numRowTiles * xa.numPlanes; ++b)
+        sb::x_forward_body<T>(xa, b, ctx, smem.data());
+      auto ya = make_y_args<T>(*maps, t, ax, p, sticks.data(), planes.data());
+      for (int b = 0; b < ya.numXTiles * ya.numPlanes; ++b)
+        sb::y_forward_body<T>(ya, b, ctx, smem.data());
+      auto za = make_z_args<T>(*maps, t, ax, p, true, sticks.data(), nullptr,
+                               static_cast<T*>(out), scaling != 0);
+      for (int b = 0; b < za.numTiles; ++b) sb::z_forward_body<T>(za, b, ctx, smem.data());
+    }
+    return 0;
+  } catch (const spfft::GenericError& e) {
+    return static_cast<int>(e.error_code());
+  } catch (...) {
+    return 1;
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+// Whole local transform through the emulated stage kernels. forward == 0: `in` = values
+// (2*n reals), `out` = space (z,y,x); forward != 0: `in` = space, `out` = values.
+int sb_emu_transform(int isFloat, int type, int dimX, int dimY, int dimZ, int n,
+                     const int* triplets, int forward, const void* in, void* out, int scaling,
+                     int nthreads, int maxLog2V) {
+  return isFloat ? run<float>(type, dimX, dimY, dimZ, n, triplets, forward, in, out, scaling,
+                              nthreads, maxLog2V)
+                 : run<double>(type, dimX, dimY, dimZ, n, triplets, forward, in, out, scaling,
+                               nthreads, maxLog2V);
+}
+
+// A single batched 1-D transform through sb::tile_fft (lanes = 1 << log2V sequences of length n,
+// tile layout n*V + lane), for butterfly-level tests. data is overwritten with the result.
+int sb_emu_tile_fft(int isFloat, int n, int log2V, int backward, int swizzle, void* data,
+                    int nthreads) {
+  try {
+    sb::RadixPlan rp = make_radix_plan(n);
+    sb::Ctx ctx{nthreads};
+    const size_t elems = static_cast<size_t>(n) << log2V;
+    auto go = [&](auto tag) {
+      using T = decltype(tag);
+      auto tw = make_roots<T>(n);
+      std::vector<sb::cx<T>> a(elems), b(elems);
+      std::memcpy(a.data(), data, elems * sizeof(sb::cx<T>));
+      sb::cx<T>* r;
+      if (backward)
+        r = swizzle ? sb::tile_fft<T, true, true>(a.data(), b.data(), rp, log2V, tw.data(), ctx)
+                    : sb::tile_fft<T, true, false>(a.data(), b.data(), rp, log2V, tw.data(), ctx);
+      else
+        r = swizzle ? sb::tile_fft<T, false, true>(a.data(), b.data(), rp, log2V, tw.data(), ctx)
+                    : sb::tile_fft<T, false, false>(a.data(), b.data(), rp, log2V, tw.data(), ctx);
+      std::memcpy(data, r, elems * sizeof(sb::cx<T>));
+    };
+    if (isFloat)
+      go(float{});
+    else
+      go(double{});
+    return 0;
+  } catch (...) {
+    return 1;
+  }
+}
+}
