@@ -1,4 +1,4 @@
-/* spfft/grid.h -- C API, double. See spfft/detail/*.inc for the documented declarations. */
+/* spfft/grid.h -- C API, double. See the .inc files in spfft/detail for the documented declarations. */
 #ifndef SPFFT_GRID_H
 #define SPFFT_GRID_H
 #include "spfft/config.h"

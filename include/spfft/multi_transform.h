@@ -1,4 +1,4 @@
-/* spfft/multi_transform.h -- C API, double. See spfft/detail/*.inc for the documented declarations. */
+/* spfft/multi_transform.h -- C API, double. See the .inc files in spfft/detail for the documented declarations. */
 #ifndef SPFFT_MULTI_TRANSFORM_H
 #define SPFFT_MULTI_TRANSFORM_H
 #include "spfft/config.h"

@@ -1,4 +1,4 @@
-/* spfft/multi_transform_float.h -- C API, float. See spfft/detail/*.inc for the documented declarations. */
+/* spfft/multi_transform_float.h -- C API, float. See the .inc files in spfft/detail for the documented declarations. */
 #ifndef SPFFT_MULTI_TRANSFORM_FLOAT_H
 #define SPFFT_MULTI_TRANSFORM_FLOAT_H
 #include "spfft/config.h"

@@ -1,4 +1,4 @@
-/* spfft/transform.h -- C API, double. See spfft/detail/*.inc for the documented declarations. */
+/* spfft/transform.h -- C API, double. See the .inc files in spfft/detail for the documented declarations. */
 #ifndef SPFFT_TRANSFORM_H
 #define SPFFT_TRANSFORM_H
 #include "spfft/config.h"

@@ -1,4 +1,4 @@
-/* spfft/transform_float.h -- C API, float. See spfft/detail/*.inc for the documented declarations. */
+/* spfft/transform_float.h -- C API, float. See the .inc files in spfft/detail for the documented declarations. */
 #ifndef SPFFT_TRANSFORM_FLOAT_H
 #define SPFFT_TRANSFORM_FLOAT_H
 #include "spfft/config.h"

@@ -297,3 +297,111 @@ def multi_transform_forward_ptr(transforms, inputs, outputs, scalings):
     hs = (C.c_void_p * len(transforms))(*[t.handle for t in transforms])
     t0.lib.call(f"spfft{t0._sfx}_multi_transform_forward_ptr", len(transforms), hs,
                 _ptr_array(inputs), _ptr_array(outputs), _int_array(scalings))
+
+
+# ----------------------------------------------------------------------------------------------
+# Loading the product library
+# ----------------------------------------------------------------------------------------------
+_PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG_DIR, "lib", "libspfft_b200.so")
+
+# every symbol include/spfft/*.h declares (checked at load time, tests/test_abi.py)
+_GRID_FUNCS = ["grid_create", "grid_destroy", "grid_max_dim_x", "grid_max_dim_y", "grid_max_dim_z",
+               "grid_max_num_local_z_columns", "grid_max_local_z_length", "grid_processing_unit",
+               "grid_device_id", "grid_num_threads"]
+_TRANSFORM_FUNCS = ["transform_create", "transform_create_independent", "transform_destroy",
+                    "transform_clone", "transform_forward", "transform_forward_ptr",
+                    "transform_backward", "transform_backward_ptr", "transform_get_space_domain",
+                    "transform_dim_x", "transform_dim_y", "transform_dim_z",
+                    "transform_local_z_length", "transform_local_slice_size",
+                    "transform_local_z_offset", "transform_global_size",
+                    "transform_num_local_elements", "transform_num_global_elements",
+                    "transform_device_id", "transform_num_threads", "transform_execution_mode",
+                    "transform_set_execution_mode"]
+_MULTI_FUNCS = ["multi_transform_forward", "multi_transform_forward_ptr",
+                "multi_transform_backward", "multi_transform_backward_ptr"]
+_EXT_PER_PRECISION = ["transform_index_maps", "transform_stream", "transform_set_profiling",
+                      "transform_stage_times"]
+_EXT_COMMON = ["spfft_b200_convert_index_triplets", "spfft_b200_kernel_launch_count"]
+
+
+def exported_symbols():
+    """Names of all C entry points the public headers declare."""
+    names = []
+    for prefix in ("spfft_", "spfft_float_"):
+        names += [prefix + f for f in _GRID_FUNCS + _TRANSFORM_FUNCS + _MULTI_FUNCS]
+    for prefix in ("spfft_b200_", "spfft_b200_float_"):
+        names += [prefix + f for f in _EXT_PER_PRECISION]
+    return names + _EXT_COMMON
+
+
+_LOADED = None
+
+
+def load(path: str | None = None) -> SpfftLib:
+    """dlopen the product library (no fallback: a missing library or symbol is an error)."""
+    global _LOADED
+    if path is None and _LOADED is not None:
+        return _LOADED
+    lib = SpfftLib(path or LIB_PATH)
+    missing = [s for s in exported_symbols() if not lib.has(s)]
+    if missing:
+        raise ImportError(f"{lib.path} lacks symbols: {missing}")
+    if path is None:
+        _LOADED = lib
+    return lib
+
+
+def kernel_launch_count(lib: SpfftLib) -> int:
+    v = C.c_longlong()
+    lib.call("spfft_b200_kernel_launch_count", C.byref(v))
+    return v.value
+
+
+def convert_index_triplets(lib: SpfftLib, hermitian, dim_x, dim_y, dim_z, triplets):
+    """spfft_b200_convert_index_triplets -> (valueIndices, stickIndices)."""
+    t = np.ascontiguousarray(np.asarray(triplets, dtype=np.int32).reshape(-1))
+    n = t.size // 3
+    vi = np.empty(n, dtype=np.int32)
+    si = np.empty(max(min(n, dim_x * dim_y), 1), dtype=np.int32)
+    ns = C.c_int()
+    lib.call("spfft_b200_convert_index_triplets", int(bool(hermitian)), int(dim_x), int(dim_y),
+             int(dim_z), int(n), t.ctypes.data_as(C.POINTER(C.c_int)) if n else None,
+             vi.ctypes.data_as(C.POINTER(C.c_int)), si.ctypes.data_as(C.POINTER(C.c_int)),
+             C.byref(ns))
+    return vi, si[:ns.value].copy()
+
+
+def transform_index_maps(t: Transform):
+    """(valueIndices, stickIndices) of an existing transform (copies)."""
+    pv = C.POINTER(C.c_int)()
+    ps = C.POINTER(C.c_int)()
+    nv = C.c_int()
+    ns = C.c_int()
+    name = "spfft_b200_float_transform_index_maps" if t.single else "spfft_b200_transform_index_maps"
+    t.lib.call(name, t.handle, C.byref(pv), C.byref(nv), C.byref(ps), C.byref(ns))
+    vi = np.ctypeslib.as_array(pv, shape=(nv.value,)).copy() if nv.value else np.zeros(0, np.int32)
+    si = np.ctypeslib.as_array(ps, shape=(ns.value,)).copy() if ns.value else np.zeros(0, np.int32)
+    return vi, si
+
+
+def transform_stream(t: Transform) -> int:
+    p = C.c_void_p()
+    name = "spfft_b200_float_transform_stream" if t.single else "spfft_b200_transform_stream"
+    t.lib.call(name, t.handle, C.byref(p))
+    return p.value or 0
+
+
+def set_profiling(t: Transform, enable: bool) -> None:
+    name = "spfft_b200_float_transform_set_profiling" if t.single else "spfft_b200_transform_set_profiling"
+    t.lib.call(name, t.handle, int(bool(enable)))
+
+
+def stage_times(t: Transform):
+    """[(stage name, milliseconds)] of the most recent call (profiling must be enabled)."""
+    names = (C.c_char_p * 16)()
+    ms = (C.c_float * 16)()
+    n = C.c_int()
+    name = "spfft_b200_float_transform_stage_times" if t.single else "spfft_b200_transform_stage_times"
+    t.lib.call(name, t.handle, 16, C.byref(n), names, ms)
+    return [(names[i].decode(), float(ms[i])) for i in range(n.value)]

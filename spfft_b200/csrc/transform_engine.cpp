@@ -1,0 +1,425 @@
+// transform_engine.cpp -- see transform_engine.hpp.
+#include "transform_engine.hpp"
+
+#include <algorithm>
+#include <cstring>
+
+#include "launch.h"
+
+namespace spfft {
+namespace b200 {
+
+namespace {
+
+inline size_t round_up(size_t v, size_t m) { return (v + m - 1) / m * m; }
+
+// widest stick tile any stage kernel uses; the stick pitch is rounded up to a tile
+constexpr int kMaxTileLanes = 32;
+
+template <typename T>
+struct Launch;
+template <>
+struct Launch<double> {
+  static int z(int f, const sb::ZArgs<double>& a, void* s) { return sb_launch_z_f64(f, &a, s); }
+  static int y(int f, const sb::YArgs<double>& a, void* s) { return sb_launch_y_f64(f, &a, s); }
+  static int x(int f, const sb::XArgs<double>& a, void* s) { return sb_launch_x_f64(f, &a, s); }
+};
+template <>
+struct Launch<float> {
+  static int z(int f, const sb::ZArgs<float>& a, void* s) { return sb_launch_z_f32(f, &a, s); }
+  static int y(int f, const sb::YArgs<float>& a, void* s) { return sb_launch_y_f32(f, &a, s); }
+  static int x(int f, const sb::XArgs<float>& a, void* s) { return sb_launch_x_f32(f, &a, s); }
+};
+
+inline void check_launch(int err) {
+  if (err != 0) {
+    cudaGetLastError();
+    check_gpu(static_cast<cudaError_t>(err));
+  }
+}
+
+template <typename U>
+const U* upload(std::vector<DeviceBuffer>& storage, size_t& total, const std::vector<U>& host) {
+  if (host.empty()) return nullptr;
+  storage.emplace_back(host.size() * sizeof(U));
+  total += host.size() * sizeof(U);
+  check_gpu(cudaMemcpy(storage.back().get(), host.data(), host.size() * sizeof(U),
+                       cudaMemcpyHostToDevice));
+  return storage.back().template as<const U>();
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+// GridResources
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+size_t GridResources<T>::stick_capacity(int maxDimZ, int maxSticks) {
+  return static_cast<size_t>(maxDimZ) * round_up(static_cast<size_t>(maxSticks), kMaxTileLanes);
+}
+
+template <typename T>
+GridResources<T>::GridResources(int maxDimX, int maxDimY, int maxDimZ, int maxNumLocalZSticks,
+                                SpfftProcessingUnitType processingUnit, int maxNumThreads)
+    : maxDimX_(maxDimX),
+      maxDimY_(maxDimY),
+      maxDimZ_(maxDimZ),
+      maxSticks_(maxNumLocalZSticks),
+      maxPlanes_(maxDimZ),
+      pu_(processingUnit),
+      numThreads_(maxNumThreads) {
+  // grid_internal.cpp:60-67
+  if (maxDimX <= 0 || maxDimY <= 0 || maxDimZ <= 0 || maxNumLocalZSticks < 0)
+    throw InvalidParameterError();
+  if (!(processingUnit & (SPFFT_PU_HOST | SPFFT_PU_GPU))) throw InvalidParameterError();
+  // this build executes on the GPU only: a grid without the GPU bit cannot serve any transform
+  if (!(processingUnit & SPFFT_PU_GPU)) throw InvalidParameterError();
+  if (numThreads_ < 1) numThreads_ = 1;  // host threads are not used; kept for the getter
+  check_gpu(cudaGetDevice(&deviceId_));  // grid_internal.cpp:83
+  allocate();
+}
+
+template <typename T>
+GridResources<T>::GridResources(const GridResources& o)
+    : maxDimX_(o.maxDimX_),
+      maxDimY_(o.maxDimY_),
+      maxDimZ_(o.maxDimZ_),
+      maxSticks_(o.maxSticks_),
+      maxPlanes_(o.maxPlanes_),
+      pu_(o.pu_),
+      deviceId_(o.deviceId_),
+      numThreads_(o.numThreads_) {
+  DeviceGuard guard(deviceId_);
+  allocate();
+}
+
+template <typename T>
+void GridResources<T>::allocate() {
+  const size_t volume =
+      static_cast<size_t>(maxDimX_) * static_cast<size_t>(maxDimY_) * static_cast<size_t>(maxDimZ_);
+  const size_t c = 2 * sizeof(T);
+  // A: plane-major sticks [z][pitch]; also the real space domain of R2C transforms
+  a_.allocate(std::max(c * stick_capacity(maxDimZ_, maxSticks_), sizeof(T) * volume));
+  // B: xy planes / complex space domain / staged compressed values (Ne <= volume)
+  b_.allocate(c * volume);
+}
+
+template <typename T>
+void* GridResources<T>::host_space(size_t bytes) {
+  std::lock_guard<std::mutex> lock(hostMutex_);
+  if (host_.bytes() < bytes) {
+    DeviceGuard guard(deviceId_);
+    const size_t volume = static_cast<size_t>(maxDimX_) * static_cast<size_t>(maxDimY_) *
+                          static_cast<size_t>(maxDimZ_);
+    host_.allocate(std::max(bytes, 2 * sizeof(T) * volume));
+  }
+  return host_.get();
+}
+
+// ---------------------------------------------------------------------------------------------
+// DevicePlan
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+std::shared_ptr<DevicePlan<T>> build_device_plan(const IndexMaps& m, long long smemLimit) {
+  auto plan = std::make_shared<DevicePlan<T>>();
+  if (m.dimX == 0 || m.dimY == 0 || m.dimZ == 0) return plan;
+  AxisPlans& ax = plan->axes;
+  const int cb = static_cast<int>(sizeof(sb::cx<T>));
+  ax.log2Vx = choose_log2_lanes(m.dimX, cb, smemLimit);
+  ax.log2Vy = choose_log2_lanes(m.dimY, cb, smemLimit);
+  ax.log2Vz = choose_log2_lanes(m.dimZ, cb, smemLimit);
+  // a transform length whose two tile buffers exceed shared memory is not supported
+  if (ax.log2Vx < 0 || ax.log2Vy < 0 || ax.log2Vz < 0) throw InvalidParameterError();
+  ax.rpX = make_radix_plan(m.dimX);
+  ax.rpY = make_radix_plan(m.dimY);
+  ax.rpZ = make_radix_plan(m.dimZ);
+  TileMaps t = build_tile_maps(m, ax.log2Vz, ax.log2Vy);
+  plan->numStickTiles = t.numStickTiles;
+  plan->pitch = t.pitch;
+  plan->numXTiles = t.numXTiles;
+  plan->symTile = t.symTile;
+  plan->symLane = t.symLane;
+
+  PlanPointers<T>& p = plan->ptrs;
+  auto& st = plan->storage;
+  size_t& total = plan->deviceBytes;
+  p.twX = upload(st, total, make_roots<T>(m.dimX));
+  p.twY = upload(st, total, make_roots<T>(m.dimY));
+  p.twZ = upload(st, total, make_roots<T>(m.dimZ));
+  p.tileStart = upload(st, total, t.tileStart);
+  p.entrySrc = t.identityOrder ? nullptr : upload(st, total, t.entrySrc);
+  p.entrySlot = upload(st, total, t.entrySlot);
+  if (t.hasDuplicates) {
+    p.bwdTileStart = upload(st, total, t.bwdTileStart);
+    p.bwdEntrySrc = upload(st, total, t.bwdEntrySrc);
+    p.bwdEntrySlot = upload(st, total, t.bwdEntrySlot);
+  } else {
+    p.bwdTileStart = p.tileStart;
+    p.bwdEntrySrc = p.entrySrc;
+    p.bwdEntrySlot = p.entrySlot;
+  }
+  p.xtStart = upload(st, total, t.xtStart);
+  p.stickSlot = upload(st, total, t.stickSlot);
+  return plan;
+}
+
+template std::shared_ptr<DevicePlan<double>> build_device_plan<double>(const IndexMaps&, long long);
+template std::shared_ptr<DevicePlan<float>> build_device_plan<float>(const IndexMaps&, long long);
+
+// ---------------------------------------------------------------------------------------------
+// TransformEngine
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+TransformEngine<T>::TransformEngine(SpfftProcessingUnitType executionUnit,
+                                    std::shared_ptr<GridResources<T>> grid,
+                                    std::shared_ptr<IndexMaps> maps,
+                                    std::shared_ptr<DevicePlan<T>> plan)
+    : executionUnit_(executionUnit),
+      grid_(std::move(grid)),
+      maps_(std::move(maps)),
+      plan_(std::move(plan)) {
+  // transform_internal.cpp:52-80
+  if (!grid_) throw InvalidParameterError();
+  if (maps_->local_planes() > grid_->max_num_local_xy_planes()) throw InvalidParameterError();
+  if (grid_->local() && maps_->dimZ != maps_->local_planes()) throw InvalidParameterError();
+  if (maps_->num_sticks() > grid_->max_num_local_z_columns()) throw InvalidParameterError();
+  if (maps_->dimX > grid_->max_dim_x() || maps_->dimY > grid_->max_dim_y() ||
+      maps_->dimZ > grid_->max_dim_z())
+    throw InvalidParameterError();
+  if (!(executionUnit & grid_->processing_unit())) throw InvalidParameterError();
+  if (executionUnit != SPFFT_PU_HOST && executionUnit != SPFFT_PU_GPU)
+    throw InvalidParameterError();
+  // no host execution path in this build (documented deviation, include/spfft/config.h)
+  if (executionUnit != SPFFT_PU_GPU) throw InvalidParameterError();
+
+  DeviceGuard guard(grid_->device_id());
+  if (!plan_) {
+    long long smem = 0;
+    check_gpu(static_cast<cudaError_t>(sb_max_dynamic_smem(&smem)));
+    plan_ = build_device_plan<T>(*maps_, smem);
+  }
+  // the grid limits are expressed in sticks; the padded pitch must fit as well
+  if (sizeof(sb::cx<T>) * static_cast<size_t>(maps_->dimZ) * static_cast<size_t>(plan_->pitch) >
+      grid_->bytes_a())
+    throw InvalidParameterError();
+  stream_.reset(new Stream());
+  startEvent_.reset(new Event());
+  endEvent_.reset(new Event());
+}
+
+template <typename T>
+TransformEngine<T>::~TransformEngine() {
+  // outstanding asynchronous work must not outlive the buffers
+  if (stream_) cudaStreamSynchronize(stream_->get());
+}
+
+template <typename T>
+std::shared_ptr<TransformEngine<T>> TransformEngine<T>::clone() const {
+  // transform_internal.cpp:176-179: same parameters, new grid
+  auto newGrid = std::make_shared<GridResources<T>>(*grid_);
+  auto e = std::make_shared<TransformEngine<T>>(executionUnit_, std::move(newGrid), maps_, plan_);
+  e->execMode_ = SPFFT_EXEC_SYNCHRONOUS;
+  return e;
+}
+
+template <typename T>
+size_t TransformEngine<T>::space_bytes() const {
+  const size_t n = static_cast<size_t>(maps_->dimX) * static_cast<size_t>(maps_->dimY) *
+                   static_cast<size_t>(maps_->local_planes());
+  return n * (maps_->type == SPFFT_TRANS_R2C ? sizeof(T) : 2 * sizeof(T));
+}
+
+template <typename T>
+T* TransformEngine<T>::device_space() const {
+  // C2C: the x stage works in place on the plane buffer (like the reference,
+  // execution_gpu.cpp:106-112); R2C: real rows live in array A (execution_gpu.cpp:97-103)
+  return static_cast<T*>(maps_->type == SPFFT_TRANS_R2C ? grid_->array_a() : grid_->array_b());
+}
+
+template <typename T>
+T* TransformEngine<T>::space_domain_data(SpfftProcessingUnitType location) {
+  if (location == SPFFT_PU_GPU) return device_space();
+  if (location == SPFFT_PU_HOST) return static_cast<T*>(grid_->host_space(space_bytes()));
+  throw InvalidParameterError();
+}
+
+template <typename T>
+void TransformEngine<T>::begin_call() {
+  // sticky-error probe, execution_gpu.cpp:256-258,329-331
+  if (cudaGetLastError() != cudaSuccess) throw GPUPrecedingError();
+  // order after the default stream, execution_gpu.cpp:260-261
+  check_gpu(cudaEventRecord(startEvent_->get(), nullptr));
+  check_gpu(cudaStreamWaitEvent(stream_->get(), startEvent_->get(), 0));
+  profUsed_ = 0;
+  profNames_.clear();
+  if (profiling_) record_stage("start");
+}
+
+template <typename T>
+void TransformEngine<T>::record_stage(const char* name) {
+  if (!profiling_) return;
+  if (profUsed_ == profEvents_.size()) profEvents_.emplace_back(new Event(true));
+  check_gpu(cudaEventRecord(profEvents_[profUsed_]->get(), stream_->get()));
+  profNames_.push_back(name);
+  ++profUsed_;
+}
+
+template <typename T>
+std::vector<StageTime> TransformEngine<T>::stage_times() {
+  std::vector<StageTime> out;
+  if (profUsed_ < 2) return out;
+  DeviceGuard guard(grid_->device_id());
+  check_gpu(cudaEventSynchronize(profEvents_[profUsed_ - 1]->get()));
+  for (size_t i = 1; i < profUsed_; ++i) {
+    float ms = 0.f;
+    check_gpu(cudaEventElapsedTime(&ms, profEvents_[i - 1]->get(), profEvents_[i]->get()));
+    out.push_back(StageTime{profNames_[i], ms});
+  }
+  return out;
+}
+
+template <typename T>
+void TransformEngine<T>::synchronize() {
+  DeviceGuard guard(grid_->device_id());
+  if (execMode_ == SPFFT_EXEC_SYNCHRONOUS) {
+    check_gpu(cudaStreamSynchronize(stream_->get()));
+  } else {
+    // execution_gpu.cpp:403-410: the default stream waits for the transform
+    check_gpu(cudaEventRecord(endEvent_->get(), stream_->get()));
+    check_gpu(cudaStreamWaitEvent(nullptr, endEvent_->get(), 0));
+  }
+}
+
+template <typename T>
+void TransformEngine<T>::enqueue_backward(const T* input, T* output) {
+  DeviceGuard guard(grid_->device_id());
+  begin_call();
+  const IndexMaps& m = *maps_;
+  if (space_bytes() == 0) return;
+  if (!output) throw InvalidParameterError();
+  cudaStream_t s = stream_->get();
+  const size_t ne = static_cast<size_t>(m.num_values());
+  if (ne > 0 && !input) throw InvalidParameterError();
+
+  // ---- z stage: decompress + stick symmetry + z-FFT (execution_gpu.cpp:327-369)
+  const T* values = input;
+  if (ne > 0 && !is_device_pointer(input)) {
+    check_gpu(cudaMemcpyAsync(grid_->array_b(), input, ne * 2 * sizeof(T), cudaMemcpyHostToDevice, s));
+    values = static_cast<const T*>(grid_->array_b());
+    record_stage("h2d values");
+  }
+  // tile maps are only needed by the z stage; the stage wiring below only reads scalars
+  TileMaps geo;
+  geo.numStickTiles = plan_->numStickTiles;
+  geo.pitch = plan_->pitch;
+  geo.numXTiles = plan_->numXTiles;
+  geo.symTile = plan_->symTile;
+  geo.symLane = plan_->symLane;
+  if (plan_->numStickTiles > 0) {
+    auto za = make_z_args<T>(m, geo, plan_->axes, plan_->ptrs, false, sticks(), values, nullptr,
+                             false);
+    check_launch(Launch<T>::z(0, za, s));
+    record_stage("z backward");
+  }
+  // ---- y stage: stick gather + plane symmetry + y-FFT (execution_gpu.cpp:371-390)
+  {
+    auto ya = make_y_args<T>(m, geo, plan_->axes, plan_->ptrs, sticks(), planes());
+    check_launch(Launch<T>::y(0, ya, s));
+    record_stage("y backward");
+  }
+  // ---- x stage: x-FFT (C2C / C2R) into the space domain
+  const bool outOnDevice = is_device_pointer(output);
+  T* outDev = outOnDevice ? output : device_space();
+  {
+    auto xa = make_x_args<T>(m, plan_->axes, plan_->ptrs, planes(), nullptr, outDev);
+    check_launch(Launch<T>::x(0, xa, s));
+    record_stage("x backward");
+  }
+  if (!outOnDevice) {
+    check_gpu(cudaMemcpyAsync(output, outDev, space_bytes(), cudaMemcpyDeviceToHost, s));
+    record_stage("d2h space");
+  }
+}
+
+template <typename T>
+void TransformEngine<T>::enqueue_forward(const T* input, T* output, SpfftScalingType scaling) {
+  DeviceGuard guard(grid_->device_id());
+  begin_call();
+  const IndexMaps& m = *maps_;
+  if (space_bytes() == 0) return;
+  if (!input) throw InvalidParameterError();
+  cudaStream_t s = stream_->get();
+  const size_t ne = static_cast<size_t>(m.num_values());
+  if (ne > 0 && !output) throw InvalidParameterError();
+
+  TileMaps geo;
+  geo.numStickTiles = plan_->numStickTiles;
+  geo.pitch = plan_->pitch;
+  geo.numXTiles = plan_->numXTiles;
+  geo.symTile = plan_->symTile;
+  geo.symLane = plan_->symLane;
+
+  // ---- x stage (execution_gpu.cpp:254-282)
+  const T* src = input;
+  if (!is_device_pointer(input)) {
+    check_gpu(cudaMemcpyAsync(device_space(), input, space_bytes(), cudaMemcpyHostToDevice, s));
+    src = device_space();
+    record_stage("h2d space");
+  }
+  {
+    auto xa = make_x_args<T>(m, plan_->axes, plan_->ptrs, planes(), src, nullptr);
+    check_launch(Launch<T>::x(1, xa, s));
+    record_stage("x forward");
+  }
+  if (plan_->numStickTiles == 0 || ne == 0) return;  // nothing to gather
+  // ---- y stage: y-FFT + scatter into the plane-major sticks
+  {
+    auto ya = make_y_args<T>(m, geo, plan_->axes, plan_->ptrs, sticks(), planes());
+    check_launch(Launch<T>::y(1, ya, s));
+    record_stage("y forward");
+  }
+  // ---- z stage: z-FFT + compress (+ scaling) (execution_gpu.cpp:291-324)
+  const bool outOnDevice = is_device_pointer(output);
+  T* outDev = outOnDevice ? output : static_cast<T*>(grid_->array_b());
+  {
+    auto za = make_z_args<T>(m, geo, plan_->axes, plan_->ptrs, true, sticks(), nullptr, outDev,
+                             scaling == SPFFT_FULL_SCALING);
+    check_launch(Launch<T>::z(1, za, s));
+    record_stage("z forward");
+  }
+  if (!outOnDevice) {
+    check_gpu(cudaMemcpyAsync(output, outDev, ne * 2 * sizeof(T), cudaMemcpyDeviceToHost, s));
+    record_stage("d2h values");
+  }
+}
+
+template <typename T>
+void TransformEngine<T>::backward(const T* input, T* output) {
+  enqueue_backward(input, output);
+  synchronize();
+}
+
+template <typename T>
+void TransformEngine<T>::backward(const T* input, SpfftProcessingUnitType outputLocation) {
+  backward(input, space_domain_data(outputLocation));
+}
+
+template <typename T>
+void TransformEngine<T>::forward(const T* input, T* output, SpfftScalingType scaling) {
+  enqueue_forward(input, output, scaling);
+  synchronize();
+}
+
+template <typename T>
+void TransformEngine<T>::forward(SpfftProcessingUnitType inputLocation, T* output,
+                                 SpfftScalingType scaling) {
+  forward(space_domain_data(inputLocation), output, scaling);
+}
+
+template class GridResources<double>;
+template class GridResources<float>;
+template class TransformEngine<double>;
+template class TransformEngine<float>;
+
+}  // namespace b200
+}  // namespace spfft

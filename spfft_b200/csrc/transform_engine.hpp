@@ -1,0 +1,138 @@
+// transform_engine.hpp -- host side of a transform: work buffers (GridResources), the device
+// resident plan shared by clones (DevicePlan) and the stage wiring (TransformEngine).
+//
+// Re-implements, for the GPU path only, what the reference spreads over
+//   GridInternal<T>        src/spfft/grid_internal.cpp:47-262      (buffers, limits)
+//   TransformInternal<T>   src/spfft/transform_internal.cpp:45-371 (validation, dispatch)
+//   ExecutionGPU<T>        src/execution/execution_gpu.cpp:47-410  (stream/event ordering,
+//                                                                   host/device pointer handling)
+// The kernels are reached only through the C ABI in launch.h.
+#pragma once
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "gpu_runtime.hpp"
+#include "index_plan.hpp"
+#include "spfft/types.h"
+#include "stage_args.hpp"
+
+namespace spfft {
+namespace b200 {
+
+template <typename T>
+class GridResources {
+public:
+  GridResources(int maxDimX, int maxDimY, int maxDimZ, int maxNumLocalZSticks,
+                SpfftProcessingUnitType processingUnit, int maxNumThreads);
+  // same limits, new buffers (reference: GridInternal copy ctor, grid_internal.cpp:208-262)
+  GridResources(const GridResources& other);
+  GridResources& operator=(const GridResources&) = delete;
+
+  int max_dim_x() const { return maxDimX_; }
+  int max_dim_y() const { return maxDimY_; }
+  int max_dim_z() const { return maxDimZ_; }
+  int max_num_local_z_columns() const { return maxSticks_; }
+  int max_num_local_xy_planes() const { return maxPlanes_; }
+  SpfftProcessingUnitType processing_unit() const { return pu_; }
+  int device_id() const { return deviceId_; }
+  int num_threads() const { return numThreads_; }
+  bool local() const { return true; }
+
+  // Device work arrays, capacities in bytes. A holds the plane-major stick buffer (and the real
+  // space domain of R2C transforms), B the xy planes / the complex space domain / staged values.
+  void* array_a() const { return a_.get(); }
+  void* array_b() const { return b_.get(); }
+  size_t bytes_a() const { return a_.bytes(); }
+  size_t bytes_b() const { return b_.bytes(); }
+  // Pinned host mirror of the space domain, allocated on first use.
+  void* host_space(size_t bytes);
+
+  static size_t stick_capacity(int maxDimZ, int maxSticks);
+
+private:
+  void allocate();
+  int maxDimX_, maxDimY_, maxDimZ_, maxSticks_, maxPlanes_;
+  SpfftProcessingUnitType pu_;
+  int deviceId_ = 0;
+  int numThreads_;
+  DeviceBuffer a_, b_;
+  PinnedBuffer host_;
+  std::mutex hostMutex_;
+};
+
+// Everything the kernels read that depends only on the index set: uploaded once, shared by clones.
+template <typename T>
+struct DevicePlan {
+  AxisPlans axes;
+  PlanPointers<T> ptrs;
+  // tile geometry (host copies of the scalars of TileMaps)
+  int numStickTiles = 0, pitch = 0, numXTiles = 0, symTile = -1, symLane = -1;
+  std::vector<DeviceBuffer> storage;
+  size_t deviceBytes = 0;
+};
+
+struct StageTime {
+  const char* name;
+  float ms;
+};
+
+template <typename T>
+class TransformEngine {
+public:
+  TransformEngine(SpfftProcessingUnitType executionUnit, std::shared_ptr<GridResources<T>> grid,
+                  std::shared_ptr<IndexMaps> maps, std::shared_ptr<DevicePlan<T>> plan = nullptr);
+  ~TransformEngine();
+
+  std::shared_ptr<TransformEngine<T>> clone() const;
+
+  // whole transforms (enqueue + synchronize according to the execution mode)
+  void backward(const T* input, T* output);
+  void backward(const T* input, SpfftProcessingUnitType outputLocation);
+  void forward(const T* input, T* output, SpfftScalingType scaling);
+  void forward(SpfftProcessingUnitType inputLocation, T* output, SpfftScalingType scaling);
+  // enqueue only; used by multi_transform_* (reference: multi_transform_internal.hpp:63-176)
+  void enqueue_backward(const T* input, T* output);
+  void enqueue_forward(const T* input, T* output, SpfftScalingType scaling);
+  void synchronize();
+
+  T* space_domain_data(SpfftProcessingUnitType location);
+
+  const IndexMaps& maps() const { return *maps_; }
+  const std::shared_ptr<GridResources<T>>& grid() const { return grid_; }
+  SpfftProcessingUnitType processing_unit() const { return executionUnit_; }
+  SpfftExecType execution_mode() const { return execMode_; }
+  void set_execution_mode(SpfftExecType m) { execMode_ = m; }
+  bool shared_grid(const TransformEngine<T>& other) const { return grid_ == other.grid_; }
+  void* stream() const { return stream_->get(); }
+
+  void set_profiling(bool on) { profiling_ = on; }
+  std::vector<StageTime> stage_times();
+
+private:
+  void begin_call();
+  void record_stage(const char* name);
+  size_t space_bytes() const;
+  T* device_space() const;
+  sb::cx<T>* sticks() const { return static_cast<sb::cx<T>*>(grid_->array_a()); }
+  sb::cx<T>* planes() const { return static_cast<sb::cx<T>*>(grid_->array_b()); }
+
+  SpfftProcessingUnitType executionUnit_;
+  SpfftExecType execMode_ = SPFFT_EXEC_SYNCHRONOUS;
+  std::shared_ptr<GridResources<T>> grid_;
+  std::shared_ptr<IndexMaps> maps_;
+  std::shared_ptr<DevicePlan<T>> plan_;
+  std::unique_ptr<Stream> stream_;
+  std::unique_ptr<Event> startEvent_, endEvent_;
+  bool profiling_ = false;
+  std::vector<std::unique_ptr<Event>> profEvents_;
+  std::vector<const char*> profNames_;
+  size_t profUsed_ = 0;
+};
+
+template <typename T>
+std::shared_ptr<DevicePlan<T>> build_device_plan(const IndexMaps& maps, long long smemLimit);
+
+}  // namespace b200
+}  // namespace spfft

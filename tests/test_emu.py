@@ -1,0 +1,106 @@
+"""Kernel bodies (spfft_b200/csrc/stage_kernels.hpp, fft_tile.hpp) emulated block by block on the
+CPU (tests/emu/emu_stages.cpp) against the numpy oracle. Unit-tests tile/index arithmetic and the
+butterflies where no GPU is available; the GPU parity tests proper are tests/test_gpu_parity.py."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from oracle import spfft_oracle as orc
+
+
+@pytest.fixture(scope="module")
+def emu(built):
+    lib = C.CDLL(built.EMU_LIB)
+    lib.sb_emu_transform.restype = C.c_int
+    lib.sb_emu_tile_fft.restype = C.c_int
+    return lib
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 4, 5, 7, 8, 11, 12, 13, 16, 25, 49, 60, 64, 100, 128, 192, 210])
+@pytest.mark.parametrize("backward", [0, 1])
+def test_tile_fft_double(emu, n, backward):
+    rng = np.random.default_rng(n)
+    for log2v, swz in ((0, 0), (3, 0), (3, 1)):
+        v = 1 << log2v
+        data = (rng.standard_normal((n, v)) + 1j * rng.standard_normal((n, v))).astype(np.complex128)
+        buf = data.copy()
+        if swz:  # element n of sequence `lane` lives at n*V + (lane ^ (n & (V-1)))
+            for i in range(n):
+                buf[i, np.arange(v) ^ (i & (v - 1))] = data[i]
+        assert emu.sb_emu_tile_fft(0, n, log2v, backward, swz, _ptr(buf), 64) == 0
+        out = buf.copy()
+        if swz:
+            for i in range(n):
+                out[i] = buf[i, np.arange(v) ^ (i & (v - 1))]
+        ref = np.fft.ifft(data, axis=0) * n if backward else np.fft.fft(data, axis=0)
+        assert orc.rel_l2(out, ref) < 1e-14 * max(1, np.log2(n + 1))
+
+
+def test_tile_fft_float(emu):
+    rng = np.random.default_rng(0)
+    n, log2v = 96, 4
+    data = (rng.standard_normal((n, 16)) + 1j * rng.standard_normal((n, 16))).astype(np.complex64)
+    buf = data.copy()
+    assert emu.sb_emu_tile_fft(1, n, log2v, 1, 0, _ptr(buf), 128) == 0
+    assert orc.rel_l2(buf, np.fft.ifft(data.astype(np.complex128), axis=0) * n) < 1e-6
+
+
+SHAPES = [(1, 1, 1), (2, 2, 2), (11, 12, 13), (13, 11, 2), (12, 1, 11), (1, 13, 12), (20, 18, 16)]
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+@pytest.mark.parametrize("center", [False, True])
+def test_emulated_c2c(emu, gen, shape, center):
+    nx, ny, nz = shape
+    trip, vals = gen.make(nx, ny, nz, center=center)
+    param = orc.Parameters(orc.SPFFT_TRANS_C2C, nx, ny, nz, trip)
+    out = np.full((nz, ny, nx), np.nan + 0j, dtype=np.complex128)
+    t = np.ascontiguousarray(trip.reshape(-1))
+    assert emu.sb_emu_transform(0, 0, nx, ny, nz, len(trip), _ptr(t), 0, _ptr(vals), _ptr(out), 0, 32, -1) == 0
+    ref = orc.backward(param, vals)
+    assert orc.rel_l2(out, ref) < 1e-13
+    back = np.zeros(len(trip), dtype=np.complex128)
+    assert emu.sb_emu_transform(0, 0, nx, ny, nz, len(trip), _ptr(t), 1, _ptr(out), _ptr(back), 1, 32, 1) == 0
+    assert orc.rel_l2(back, vals) < 1e-13
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+def test_emulated_r2c(emu, gen, shape):
+    from conftest import hermitian_space_values
+    nx, ny, nz = shape
+    trip, _ = gen.make(nx, ny, nz, hermitian=True)
+    vals = hermitian_space_values(orc, nx, ny, nz, trip)
+    param = orc.Parameters(orc.SPFFT_TRANS_R2C, nx, ny, nz, trip)
+    out = np.full((nz, ny, nx), np.nan, dtype=np.float64)
+    t = np.ascontiguousarray(trip.reshape(-1))
+    assert emu.sb_emu_transform(0, 1, nx, ny, nz, len(trip), _ptr(t), 0, _ptr(vals), _ptr(out), 0, 32, -1) == 0
+    ref = orc.backward(param, vals)
+    assert orc.rel_l2(out, ref) < 1e-13
+    back = np.zeros(len(trip), dtype=np.complex128)
+    assert emu.sb_emu_transform(0, 1, nx, ny, nz, len(trip), _ptr(t), 1, _ptr(out), _ptr(back), 1, 32, -1) == 0
+    # not a round trip: the random index set may hold only one of two conjugate partners on the
+    # x = Nx/2 column, which the backward transform does not complete
+    assert orc.rel_l2(back, orc.forward(param, out, orc.SPFFT_FULL_SCALING)) < 1e-13
+
+
+def test_emulated_float_and_duplicates(emu, gen):
+    nx, ny, nz = 12, 11, 13
+    trip, vals = gen.make(nx, ny, nz)
+    # duplicate triplets are legal: last one wins on backward, all receive the value on forward
+    trip = np.concatenate([trip, trip[:5]], axis=0)
+    vals = np.concatenate([vals, vals[:5] * 3.0])
+    param = orc.Parameters(orc.SPFFT_TRANS_C2C, nx, ny, nz, trip)
+    v32 = vals.astype(np.complex64)
+    out = np.zeros((nz, ny, nx), dtype=np.complex64)
+    t = np.ascontiguousarray(trip.reshape(-1))
+    assert emu.sb_emu_transform(1, 0, nx, ny, nz, len(trip), _ptr(t), 0, _ptr(v32), _ptr(out), 0, 64, -1) == 0
+    ref = orc.backward(param, vals)
+    assert orc.rel_l2(out, ref) < 2e-6
+    back = np.zeros(len(trip), dtype=np.complex64)
+    assert emu.sb_emu_transform(1, 0, nx, ny, nz, len(trip), _ptr(t), 1, _ptr(out), _ptr(back), 1, 64, -1) == 0
+    assert orc.rel_l2(back[:5], back[-5:]) < 1e-6
