@@ -1,0 +1,351 @@
+#!/usr/bin/env python
+"""bench.py -- backward+forward pairs/sec of the sparse 3D transform, with roofline and CPU baseline.
+
+One "step" = one backward (frequency -> space) + one forward (space -> frequency) transform of the
+workload, through the C ABI of libspfft_b200.so (spfft_transform_backward_ptr / forward_ptr).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--size 512] [--type c2c|r2c]
+                  [--precision double|single] [--impl b200|reference]
+
+`value`  : whole-job pairs/s with inputs and outputs resident in HBM (device pointers, external
+           space-domain buffer, SPFFT_NO_SCALING like the reference benchmark,
+           tests/programs/benchmark.cpp:61), CUDA events on the stream, max over ranks.
+`e2e`    : the same metric through the same calls with HOST (pinned) buffers: every step copies
+           the frequency values in and the space slab out (backward), the slab in and the values
+           out (forward) inside the timed region.
+`roofline`: dominant kernel, algorithmic bytes (DESIGN.md "Algorithmic bytes") / CUDA-event time
+           of that kernel measured in the timed region, against MEASURED_PEAKS.json.
+`cpu_baseline`: the reference's own host pipeline (oracle/_ref/libspfft_ref.so: ExecutionHost +
+           OpenMP over the FFTW-API shim) on the box's host cores, bounded sample, rank 0, N=1.
+`--impl reference` times that CPU implementation alone and prints the same line.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "backward+forward pairs/sec"
+UNIT = "pairs/s"
+
+
+# --------------------------------------------------------------------------------------------
+# workload
+# --------------------------------------------------------------------------------------------
+def spherical_triplets(n: int, hermitian: bool) -> np.ndarray:
+    """All centered (kx,ky,kz) with |k|^2 <= (n/2)^2 (pi/6 fill), grouped by stick in ascending
+    storage key x*Ny+y, z ascending in storage order. Vectorised twin of
+    oracle.spfft_oracle.spherical_cutoff_triplets (tests/test_bench_workload.py pins them)."""
+    r2 = (n / 2) ** 2
+    k = np.arange(-(n // 2) + (1 if n % 2 == 0 else 0), n // 2 + 1, dtype=np.int64)
+    ks = np.concatenate([k[k >= 0], k[k < 0]])  # storage order
+    out = []
+    for x in ks.tolist():
+        if hermitian and x < 0:
+            continue
+        yy, zz = np.meshgrid(ks, ks, indexing="ij")
+        keep = x * x + yy * yy + zz * zz <= r2
+        if hermitian and x == 0:
+            keep &= (yy > 0) | ((yy == 0) & (zz >= 0))
+        ysel, zsel = yy[keep], zz[keep]
+        blk = np.empty((ysel.size, 3), dtype=np.int32)
+        blk[:, 0] = x
+        blk[:, 1] = ysel
+        blk[:, 2] = zsel
+        out.append(blk)
+    return np.ascontiguousarray(np.concatenate(out, axis=0))
+
+
+def algorithmic_bytes(n, ns, ne, r2c, single):
+    """Per direction: (c+4)*Ne + 2*c*Ns*Nz + c_space*Nx*Ny*Nz, split by
+    the stage that must move them."""
+    c = 8 if single else 16
+    cs = c // 2 if r2c else c
+    z = (c + 4) * ne + c * ns * n
+    y = c * ns * n
+    x = cs * n ** 3
+    return {"z": z, "y": y, "x": x, "dir": z + y + x}
+
+
+def workload_name(args):
+    return (f"{args.size}^3 {args.type.upper()} {args.precision} spherical cutoff (pi/6 fill), "
+            f"centered indices, device pointers, external space buffer")
+
+
+# --------------------------------------------------------------------------------------------
+# clocks
+# --------------------------------------------------------------------------------------------
+class ClockSampler:
+    def __init__(self, index=0):
+        self.rows = []
+        self.index = index
+        self._stop = threading.Event()
+        self._thr = None
+
+    def _loop(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True,
+                                     text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def __enter__(self):
+        self._thr = threading.Thread(target=self._loop, daemon=True)
+        self._thr.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._thr.join(timeout=10)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [nm for i, nm in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None,
+                "sm_max_mhz": float(self.rows[0][1]) if self.rows[0][1].replace(".", "").isdigit() else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+# --------------------------------------------------------------------------------------------
+# CPU reference arm
+# --------------------------------------------------------------------------------------------
+def cpu_reference_pairs(args, trip, vals, max_seconds=30.0, max_pairs=5):
+    """Times the reference host pipeline (oracle/_ref/libspfft_ref.so) through the same C ABI with
+    SPFFT_PU_HOST, all host threads. Returns (pairs/s, cores, sample description, kind)."""
+    from spfft_b200 import capi
+    path = os.path.join(ROOT, "oracle", "_ref", "libspfft_ref.so")
+    n = args.size
+    cores = os.cpu_count() or 1
+    if not os.path.exists(path):
+        return None, cores, "oracle/_ref/libspfft_ref.so missing", "reference"
+    lib = capi.SpfftLib(path)
+    single = args.precision == "single"
+    ttype = capi.SPFFT_TRANS_R2C if args.type == "r2c" else capi.SPFFT_TRANS_C2C
+    t = capi.Transform(lib, processing_unit=capi.SPFFT_PU_HOST, transform_type=ttype, dim_x=n,
+                       dim_y=n, dim_z=n, indices=trip, max_num_threads=-1, single=single)
+    v = np.ascontiguousarray(vals.astype(np.float32 if single else np.float64))
+    out = np.zeros_like(v)
+    t.backward(v, capi.SPFFT_PU_HOST)  # warm-up pair (plans, page faults)
+    t.forward(capi.SPFFT_PU_HOST, out, capi.SPFFT_NO_SCALING)
+    times = []
+    t_start = time.perf_counter()
+    while len(times) < max_pairs and (time.perf_counter() - t_start) < max_seconds:
+        t0 = time.perf_counter()
+        t.backward(v, capi.SPFFT_PU_HOST)
+        t.forward(capi.SPFFT_PU_HOST, out, capi.SPFFT_NO_SCALING)
+        times.append(time.perf_counter() - t0)
+    t.destroy()
+    sec = float(np.mean(times))
+    sample = (f"{len(times)} full pairs of the {n}^3 workload after 1 warm-up pair, reference ExecutionHost "
+              f"+ OpenMP ({cores} threads) over the FFTW-API shim (FFTW itself is not installed), wall clock")
+    return 1.0 / sec, cores, sample, "reference"
+
+
+# --------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--size", type=int, default=512)
+    ap.add_argument("--type", choices=["c2c", "r2c"], default="c2c")
+    ap.add_argument("--precision", choices=["double", "single"], default="double")
+    ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    n = args.size
+    r2c = args.type == "r2c"
+    single = args.precision == "single"
+
+    config = {"workload": workload_name(args), "size": n, "type": args.type, "precision": args.precision,
+              "scaling_flag": "SPFFT_NO_SCALING", "l2": "inputs larger than L2" if n >= 256 else "L2-resident (fits 126 MB L2)"}
+
+    # ---------------- reference arm: CPU only, rank 0 only ----------------
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        trip = spherical_triplets(n, r2c)
+        rng = np.random.default_rng(42)
+        vals = rng.uniform(-1, 1, 2 * len(trip))
+        t0 = time.perf_counter()
+        pairs, cores, sample, kind = cpu_reference_pairs(args, trip, vals, max_seconds=25.0 * max(args.steps, 1) / 3,
+                                                         max_pairs=max(args.steps, 1))
+        line = {"impl": "reference", "metric": METRIC, "value": pairs, "unit": UNIT, "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": (1e3 / pairs) if pairs else None,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32" if single else "f64", "data": "synthetic", "config": config,
+                "cpu_baseline": {"value": pairs, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+                "e2e": {"value": pairs, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0, "wall_s": time.perf_counter() - t0}
+        print(json.dumps(line))
+        return
+
+    # ---------------- B200 arm ----------------
+    import torch
+    import torch.distributed as dist
+    from spfft_b200 import capi
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback for the product path")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    lib = capi.load()
+
+    trip = spherical_triplets(n, r2c)
+    ne = len(trip)
+    ttype = capi.SPFFT_TRANS_R2C if r2c else capi.SPFFT_TRANS_C2C
+    t = capi.Transform(lib, processing_unit=capi.SPFFT_PU_GPU, transform_type=ttype, dim_x=n, dim_y=n,
+                       dim_z=n, indices=trip, single=single)
+    _, sticks = capi.transform_index_maps(t)
+    ns = len(sticks)
+    del sticks
+    rdt = torch.float32 if single else torch.float64
+    rng = np.random.default_rng(42 + rank)
+    vals_host = rng.uniform(-1, 1, 2 * ne).astype(np.float32 if single else np.float64)
+    d_vals = torch.from_numpy(vals_host).cuda()
+    space_reals = n ** 3 * (1 if r2c else 2)
+    d_space = torch.empty(space_reals, dtype=rdt, device="cuda")
+    d_out = torch.empty(2 * ne, dtype=rdt, device="cuda")
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # asynchronous mode: the transform is ordered with the default stream only, so the timed loop
+    # has no host synchronisation inside
+    t.set_execution_mode(capi.SPFFT_EXEC_ASYNCHRONOUS)
+
+    def pair():
+        t.backward_ptr(d_vals, d_space)
+        t.forward_ptr(d_space, d_out, capi.SPFFT_NO_SCALING)
+
+    for _ in range(args.warmup):
+        pair()
+    barrier()
+    capi.set_profiling(t, True)
+    launches0 = capi.kernel_launch_count(lib)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clocks:
+        barrier()
+        ev0.record()
+        for _ in range(args.steps):
+            pair()
+        ev1.record()
+        barrier()
+    ms_total = ev0.elapsed_time(ev1)
+    launches = capi.kernel_launch_count(lib) - launches0
+    stages = capi.stage_times(t)
+    capi.set_profiling(t, False)
+    if world > 1:
+        tt = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms_total = float(tt.item())
+    ms_per_step = ms_total / args.steps
+    value = world * 1e3 / ms_per_step  # every rank runs its own transform of the named size
+
+    # ---------------- roofline of the dominant kernel ----------------
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak = float(json.load(open(peaks_path))["hbm_gbs"])
+        peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)"
+    else:
+        peak, peak_src = 6650.0, "B200_PROFILING.md fallback (of fallback)"
+    ab = algorithmic_bytes(n, ns, ne, r2c, single)
+    stage_bytes = {"z backward": ab["z"], "y backward": ab["y"], "x backward": ab["x"],
+                   "x forward": ab["x"], "y forward": ab["y"], "z forward": ab["z"],
+                   "xy backward": ab["y"] + ab["x"], "xy forward": ab["y"] + ab["x"]}
+    kernels = [(nm, ms) for nm, ms in stages if nm in stage_bytes]
+    roofline = None
+    if kernels:
+        nm, ms = max(kernels, key=lambda k: k[1])
+        achieved = stage_bytes[nm] / (ms * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "kernel": nm, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                    "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                    "algorithmic_bytes_per_launch": stage_bytes[nm], "kernel_ms": ms,
+                    "pair_algorithmic_bytes": 2 * ab["dir"],
+                    "pair_frac": 2 * ab["dir"] / (ms_per_step * 1e-3) / 1e9 / peak,
+                    "stage_ms": {k: round(v, 4) for k, v in stages}}
+
+    # ---------------- end to end through host buffers ----------------
+    e2e = None
+    if not args.no_e2e:
+        h_vals = torch.from_numpy(vals_host).pin_memory()
+        h_space = torch.empty(space_reals, dtype=rdt).pin_memory()
+        h_out = torch.empty(2 * ne, dtype=rdt).pin_memory()
+        t.set_execution_mode(capi.SPFFT_EXEC_SYNCHRONOUS)
+
+        def pair_host():
+            t.backward_ptr(h_vals.data_ptr(), h_space.data_ptr())
+            t.forward_ptr(h_space.data_ptr(), h_out.data_ptr(), capi.SPFFT_NO_SCALING)
+
+        pair_host()
+        ksteps = max(3, min(args.steps, 5))
+        barrier()
+        ev0.record()
+        for _ in range(ksteps):
+            pair_host()
+        ev1.record()
+        barrier()
+        ms_e = ev0.elapsed_time(ev1) / ksteps
+        if world > 1:
+            tt = torch.tensor([ms_e], dtype=torch.float64, device="cuda")
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            ms_e = float(tt.item())
+        bpr = 4 if single else 8
+        e2e = {"value": world * 1e3 / ms_e, "unit": UNIT,
+               "h2d_bytes_per_step": (2 * ne + space_reals) * bpr, "d2h_bytes_per_step": (space_reals + 2 * ne) * bpr,
+               "steps": ksteps, "ms_per_step": ms_e}
+        del h_vals, h_space, h_out
+
+    # ---------------- CPU baseline (rank 0, N=1) ----------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        t.destroy()
+        del d_space, d_out
+        pairs, cores, sample, kind = cpu_reference_pairs(args, trip, vals_host)
+        cpu = {"value": pairs, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32" if single else "f64",
+                "data": "synthetic", "config": config, "clocks": clocks.summary(), "e2e": e2e,
+                "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+                "num_sticks": ns, "num_elements": ne}
+        if world > 1:
+            line["config"]["parallelism"] = f"{world} independent replicas (one transform per GPU)"
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

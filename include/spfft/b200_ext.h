@@ -53,9 +53,10 @@ SPFFT_EXPORT SpfftError spfft_b200_float_transform_stream(SpfftFloatTransform tr
                                                           void** stream);
 
 /* Per-kernel device timing. With profiling enabled every stage kernel of a transform call is
- * bracketed by CUDA events on the transform's stream; after the call has completed,
- * *_stage_times returns, for the most recent backward or forward call, the number of stages,
- * their names (static strings) and milliseconds. maxStages bounds the output arrays.
+ * bracketed by CUDA events on the transform's stream. *_stage_times waits for the recorded events
+ * and returns, over all backward / forward calls since the previous query, the number of distinct
+ * stages, their names (static strings, e.g. "z backward") and the AVERAGE milliseconds per call;
+ * it then forgets the recorded events. maxStages bounds the output arrays.
  * Takes the place of the reference's host-side rt_graph timers (src/timing/timing.hpp:34-62). */
 SPFFT_EXPORT SpfftError spfft_b200_transform_set_profiling(SpfftTransform transform, int enable);
 SPFFT_EXPORT SpfftError spfft_b200_transform_stage_times(SpfftTransform transform, int maxStages,

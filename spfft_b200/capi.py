@@ -79,7 +79,8 @@ class SpfftLib:
                 f"{path} not found -- build it first (python -c 'import __graft_entry__ as g; "
                 f"g.build()'); there is no fallback implementation")
         self.path = path
-        self.lib = C.CDLL(path, mode=C.RTLD_GLOBAL if "b200" in os.path.basename(path) else 0)
+        # RTLD_LOCAL: the product and the reference host library export the same symbols
+        self.lib = C.CDLL(path, mode=getattr(os, "RTLD_LOCAL", 0) | getattr(os, "RTLD_NOW", 2))
 
     def call(self, name: str, *args):
         fn = getattr(self.lib, name)

@@ -250,9 +250,7 @@ void TransformEngine<T>::begin_call() {
   // order after the default stream, execution_gpu.cpp:260-261
   check_gpu(cudaEventRecord(startEvent_->get(), nullptr));
   check_gpu(cudaStreamWaitEvent(stream_->get(), startEvent_->get(), 0));
-  profUsed_ = 0;
-  profNames_.clear();
-  if (profiling_) record_stage("start");
+  if (profiling_) record_stage(nullptr);  // start of a call
 }
 
 template <typename T>
@@ -266,15 +264,33 @@ void TransformEngine<T>::record_stage(const char* name) {
 
 template <typename T>
 std::vector<StageTime> TransformEngine<T>::stage_times() {
+  // Accumulates over every call since the previous query: average milliseconds per stage name
+  // (in order of first appearance), then forgets the recorded events.
   std::vector<StageTime> out;
-  if (profUsed_ < 2) return out;
+  std::vector<int> counts;
+  if (profUsed_ < 2) {
+    profUsed_ = 0;
+    profNames_.clear();
+    return out;
+  }
   DeviceGuard guard(grid_->device_id());
   check_gpu(cudaEventSynchronize(profEvents_[profUsed_ - 1]->get()));
   for (size_t i = 1; i < profUsed_; ++i) {
+    if (profNames_[i] == nullptr) continue;  // boundary between two calls
     float ms = 0.f;
     check_gpu(cudaEventElapsedTime(&ms, profEvents_[i - 1]->get(), profEvents_[i]->get()));
-    out.push_back(StageTime{profNames_[i], ms});
+    size_t k = 0;
+    while (k < out.size() && out[k].name != profNames_[i]) ++k;
+    if (k == out.size()) {
+      out.push_back(StageTime{profNames_[i], 0.f});
+      counts.push_back(0);
+    }
+    out[k].ms += ms;
+    ++counts[k];
   }
+  for (size_t k = 0; k < out.size(); ++k) out[k].ms /= static_cast<float>(counts[k]);
+  profUsed_ = 0;
+  profNames_.clear();
   return out;
 }
 
