@@ -7,6 +7,9 @@
 // The second build exists only so that index arithmetic can be unit-tested without a GPU; it is
 // never linked into libspfft_b200.so and is not a fallback path.
 #pragma once
+#if !defined(__CUDACC__) || defined(SB_EMULATE)
+#include <vector>
+#endif
 
 #if defined(__CUDACC__) && !defined(SB_EMULATE)
 #define SB_HD __host__ __device__ __forceinline__
@@ -19,6 +22,11 @@
 #define SB_PHASE_END \
   }                  \
   __syncthreads();
+// like SB_PHASE_END but without the barrier (last phase of a kernel)
+#define SB_PHASE_END_NOSYNC }
+// per-thread registers that live across phases
+#define SB_REGS(type, name, n) type name[n]
+#define SB_RP(name, n) (name)
 #else
 #define SB_HD inline
 #define SB_DEV inline
@@ -27,6 +35,9 @@
   for (int tid = 0; tid < ctx.nthreads; ++tid) {      \
     const int nthr = ctx.nthreads;
 #define SB_PHASE_END }
+#define SB_PHASE_END_NOSYNC }
+#define SB_REGS(type, name, n) std::vector<type> name##_store((size_t)ctx.nthreads * (n)); type* name = name##_store.data()
+#define SB_RP(name, n) ((name) + (size_t)tid * (n))
 #endif
 
 namespace sb {

@@ -1,0 +1,135 @@
+// fast_fft.hpp -- register-resident Stockham FFT for power-of-two lengths (8 <= N <= 4096).
+//
+// Every thread keeps 8 complex values in registers; a transform of length N is done by N/8
+// threads in ceil(log8 N) radix stages (a leading radix-2 or radix-4 stage when log2 N is not a
+// multiple of 3, radix 8 otherwise) with ONE shared-memory exchange between consecutive stages.
+// The first stage takes its input from wherever the caller loaded it (global memory or a
+// shared-memory tile), the last stage leaves the result in registers for the caller to store, so
+// a tile makes 2 shared-memory round trips for N = 512 instead of the 5 of the generic
+// tile_fft (fft_tile.hpp).
+//
+// Index algebra (Stockham autosort, decimation in time). Stage s has radix R, stride
+// NS = product of the earlier radices, and N/R butterflies b:
+//     inputs   n  = b + r*N/R                (r = 0..R-1), twiddled by w_{NS*R}^{r*(b mod NS)}
+//     outputs  n' = (b - k)*R + k + q*NS     (q = 0..R-1, k = b mod NS)
+// With T = N/8 threads per transform, thread j owns the butterflies b = j + i*T (i < 8/R), i.e.
+// it always holds the elements n = j + T*m (m = 0..7) at the start of a stage, and after the last
+// stage register m holds output element j + T*m.
+//
+// Replaces the cuFFT plans of the reference (src/fft/transform_1d_gpu.hpp:52-141,
+// src/fft/transform_2d_gpu.hpp:51-140): unnormalised DFT, sign + backward / - forward.
+#pragma once
+#include "cx.hpp"
+#include "fft_tile.hpp"
+
+namespace sb {
+
+constexpr int ilog2_c(int n) { return n <= 1 ? 0 : 1 + ilog2_c(n >> 1); }
+
+template <int N>
+struct FastPlan {
+  static_assert(N >= 8 && (N & (N - 1)) == 0, "power of two >= 8");
+  static constexpr int log2N = ilog2_c(N);
+  static constexpr int R0 = (log2N % 3 == 0) ? 8 : ((log2N % 3 == 1) ? 2 : 4);
+  static constexpr int numStages = (log2N + 2) / 3;
+  static constexpr int T = N / 8;  // threads per transform
+  static constexpr int radix(int s) { return s == 0 ? R0 : 8; }
+  static constexpr int ns(int s) { return s == 0 ? 1 : R0 << (3 * (s - 1)); }
+  // stage twiddle table: for every stage s >= 1, 7*ns(s) entries laid out [r-1][k]
+  static constexpr int tw_offset(int s) { return s <= 1 ? 0 : tw_offset(s - 1) + 7 * ns(s - 1); }
+  static constexpr int tw_size() { return tw_offset(numStages); }
+};
+
+// number of entries of the stage twiddle table of a length-n plan (host side, runtime n)
+inline int fast_tw_size(int n) {
+  int log2n = 0;
+  while ((1 << log2n) < n) ++log2n;
+  const int r0 = (log2n % 3 == 0) ? 8 : ((log2n % 3 == 1) ? 2 : 4);
+  const int stages = (log2n + 2) / 3;
+  int total = 0, ns = r0;
+  for (int s = 1; s < stages; ++s) {
+    total += 7 * ns;
+    ns *= 8;
+  }
+  return total;
+}
+
+// read-only 16/8-byte load of a twiddle
+template <typename T>
+SB_DEV cx<T> ld_ro(const cx<T>* p) {
+#if SB_ON_GPU
+  if constexpr (sizeof(T) == 8) {
+    const double2 v = __ldg(reinterpret_cast<const double2*>(p));
+    return mk<T>(v.x, v.y);
+  } else {
+    const float2 v = __ldg(reinterpret_cast<const float2*>(p));
+    return mk<T>(v.x, v.y);
+  }
+#else
+  return *p;
+#endif
+}
+
+// Twiddles + butterflies of stage S on the 8 registers of thread j.
+template <typename T, int N, bool BWD, int S>
+SB_DEV void fast_stage(cx<T>* v, int j, const cx<T>* __restrict__ tw) {
+  using P = FastPlan<N>;
+  constexpr int R = P::radix(S);
+  constexpr int NS = P::ns(S);
+  constexpr int M = 8 / R;
+  if (S > 0) {  // R == 8 here
+    const int k = j & (NS - 1);
+    const cx<T>* t = tw + P::tw_offset(S) + k;
+#pragma unroll
+    for (int r = 1; r < 8; ++r) {
+      const cx<T> w = ld_ro(t + (r - 1) * NS);
+      v[r] = v[r] * (BWD ? conj(w) : w);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < M; ++i) {
+    cx<T> a[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) a[r] = v[i + M * r];
+    Butterfly<T, BWD, R>::run(a);
+#pragma unroll
+    for (int r = 0; r < R; ++r) v[i + M * r] = a[r];
+  }
+}
+
+// Where register (i + M*q) of thread j goes in the exchange after stage S.
+template <int N, int S>
+SB_HD int fast_out_index(int j, int i, int q) {
+  using P = FastPlan<N>;
+  constexpr int R = P::radix(S);
+  constexpr int NS = P::ns(S);
+  const int b = j + i * P::T;
+  const int k = b & (NS - 1);
+  return (b - k) * R + k + q * NS;
+}
+
+// XOR swizzles of the lane (16/8-byte slot inside a 128-byte tile row).
+//   SwzRow : lanes are the fastest thread index (a quarter/half warp covers a whole row), any
+//            function of n is conflict free for the exchanges; n & (V-1) additionally makes
+//            accesses that walk along n with a fixed lane (sparse scatter / gather) conflict free.
+//   SwzCol : consecutive threads walk along n with a fixed lane in every stage
+//            (n = j + T*m reads, (b-k)*R + k + q*NS writes): the varying bits of n are 3-bit
+//            groups [0,3), [3,6), [6,9) ..., so fold them down onto the slot bits.
+struct SwzRow {
+  template <int LOG2V>
+  static SB_HD int at(int n, int lane) {
+    return (n << LOG2V) + (lane ^ (n & ((1 << LOG2V) - 1)));
+  }
+};
+struct SwzCol {
+  // checked exhaustively by tools/check_swizzle.py: conflict free for N >= 64 (16-byte elements,
+  // 8 lanes) and N >= 128 (8-byte elements, 16 lanes)
+  template <int LOG2V>
+  static SB_HD int at(int n, int lane) {
+    const int f = LOG2V == 3 ? (n ^ (n >> 3) ^ (n >> 6) ^ (n >> 9))
+                             : (n ^ (n >> 3) ^ (n >> 4) ^ (n >> 6) ^ (n >> 7) ^ (n >> 8));
+    return (n << LOG2V) + (lane ^ (f & ((1 << LOG2V) - 1)));
+  }
+};
+
+}  // namespace sb

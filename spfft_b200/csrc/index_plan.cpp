@@ -273,6 +273,41 @@ std::vector<sb::cx<T>> make_roots(int n) {
 template std::vector<sb::cx<float>> make_roots<float>(int);
 template std::vector<sb::cx<double>> make_roots<double>(int);
 
+bool fast_path_length(int n, int complexBytes) {
+  if (n < 32 || (n & (n - 1)) != 0) return false;
+  const int lanes = 1 << fast_path_log2_lanes(complexBytes);
+  return lanes * (n / 8) <= 1024;  // threads per CTA
+}
+
+int fast_path_log2_lanes(int complexBytes) { return complexBytes == 16 ? 3 : 4; }
+
+template <typename T>
+std::vector<sb::cx<T>> make_fast_twiddles(int n) {
+  std::vector<sb::cx<T>> w;
+  int log2n = 0;
+  while ((1 << log2n) < n) ++log2n;
+  const int r0 = (log2n % 3 == 0) ? 8 : ((log2n % 3 == 1) ? 2 : 4);
+  const int stages = (log2n + 2) / 3;
+  const long double twoPi = 6.283185307179586476925286766559005768L;
+  int ns = r0;
+  for (int s = 1; s < stages; ++s) {
+    for (int r = 1; r < 8; ++r) {
+      for (int k = 0; k < ns; ++k) {
+        const long double a = twoPi * static_cast<long double>(r * k) / static_cast<long double>(8 * ns);
+        sb::cx<T> v;
+        v.x = static_cast<T>(cosl(a));
+        v.y = static_cast<T>(-sinl(a));
+        w.push_back(v);
+      }
+    }
+    ns *= 8;
+  }
+  if (w.empty()) w.push_back(sb::mk<T>(T(1), T(0)));
+  return w;
+}
+template std::vector<sb::cx<float>> make_fast_twiddles<float>(int);
+template std::vector<sb::cx<double>> make_fast_twiddles<double>(int);
+
 int choose_log2_lanes(int n, int complexBytes, long long smemLimit) {
   int log2V = 0;
   while ((complexBytes << (log2V + 1)) <= 128) ++log2V;  // at most 128 bytes per tile row

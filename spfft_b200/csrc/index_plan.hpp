@@ -82,6 +82,15 @@ sb::RadixPlan make_radix_plan(int n);
 template <typename T>
 std::vector<sb::cx<T>> make_roots(int n);
 
+// Register-FFT fast path (fast_fft.hpp): power-of-two lengths whose tile (8 lanes double / 16 lanes
+// float, n/8 threads per lane) fits one CTA.
+bool fast_path_length(int n, int complexBytes);
+int fast_path_log2_lanes(int complexBytes);
+// Stage twiddles of the register FFT: for every stage s >= 1 (radix 8, stride ns) the entries
+// [r-1][k] = exp(-2*pi*i*r*k/(8*ns)), r = 1..7, k < ns; rounded from long double.
+template <typename T>
+std::vector<sb::cx<T>> make_fast_twiddles(int n);
+
 // Largest lane count (power of two, at most 128 bytes of complex<T> per tile row) such that two
 // tile buffers of n rows fit into smemLimit bytes. Returns -1 if even one lane does not fit.
 int choose_log2_lanes(int n, int complexBytes, long long smemLimit);

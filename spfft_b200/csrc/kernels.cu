@@ -4,6 +4,7 @@
 
 #include <atomic>
 
+#include "fast_launch.cuh"
 #include "launch.h"
 
 namespace sb {
@@ -59,12 +60,20 @@ static int launch(Kernel kernel, const Args& args, long long blocks, size_t smem
 
 template <typename T>
 static int launch_z(int forward, const ZArgs<T>& a, cudaStream_t s) {
+  if (a.ftw) {
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return launch_z_fast<T>(forward, a, s);
+  }
   const size_t smem = 2 * ((size_t)a.nz << a.log2V) * sizeof(cx<T>);
   return forward ? launch(k_z_stage<T, true>, a, a.numTiles, smem, s)
                  : launch(k_z_stage<T, false>, a, a.numTiles, smem, s);
 }
 template <typename T>
 static int launch_y(int forward, const YArgs<T>& a, cudaStream_t s) {
+  if (a.ftw) {
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return launch_y_fast<T>(forward, a, s);
+  }
   const size_t smem = 2 * ((size_t)a.ny << a.log2V) * sizeof(cx<T>);
   const long long blocks = (long long)a.numXTiles * a.numPlanes;
   return forward ? launch(k_y_stage<T, true>, a, blocks, smem, s)
@@ -72,6 +81,10 @@ static int launch_y(int forward, const YArgs<T>& a, cudaStream_t s) {
 }
 template <typename T>
 static int launch_x(int forward, const XArgs<T>& a, cudaStream_t s) {
+  if (a.ftw) {
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return launch_x_fast<T>(forward, a, s);
+  }
   const size_t smem = 2 * ((size_t)a.nx << a.log2V) * sizeof(cx<T>);
   const long long blocks = (long long)a.numRowTiles * a.numPlanes;
   return forward ? launch(k_x_stage<T, true>, a, blocks, smem, s)

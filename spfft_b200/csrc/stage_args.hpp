@@ -14,6 +14,9 @@ struct PlanPointers {
   const sb::cx<T>* twZ = nullptr;
   const sb::cx<T>* twY = nullptr;
   const sb::cx<T>* twX = nullptr;
+  const sb::cx<T>* ftwX = nullptr;  // register-FFT stage twiddles, nullptr = generic kernels
+  const sb::cx<T>* ftwY = nullptr;
+  const sb::cx<T>* ftwZ = nullptr;
   const int* tileStart = nullptr;
   const int* entrySrc = nullptr;   // nullptr when TileMaps::identityOrder
   const int* entrySlot = nullptr;
@@ -40,6 +43,7 @@ inline sb::ZArgs<T> make_z_args(const IndexMaps& m, const TileMaps& t, const Axi
   a.pitch = t.pitch;
   a.rp = ax.rpZ;
   a.tw = p.twZ;
+  a.ftw = p.ftwZ;
   if (forward) {
     a.tileStart = p.tileStart;
     a.entrySrc = p.entrySrc;
@@ -76,6 +80,7 @@ inline sb::YArgs<T> make_y_args(const IndexMaps& m, const TileMaps& t, const Axi
   a.symmetry = m.type == SPFFT_TRANS_R2C ? 1 : 0;
   a.rp = ax.rpY;
   a.tw = p.twY;
+  a.ftw = p.ftwY;
   a.xtStart = p.xtStart;
   a.stickSlot = p.stickSlot;
   a.sticks = sticks;
@@ -97,6 +102,7 @@ inline sb::XArgs<T> make_x_args(const IndexMaps& m, const AxisPlans& ax, const P
   a.r2c = m.type == SPFFT_TRANS_R2C ? 1 : 0;
   a.rp = ax.rpX;
   a.tw = p.twX;
+  a.ftw = m.type == SPFFT_TRANS_R2C ? nullptr : p.ftwX;  // real rows: generic kernel
   a.planes = planes;
   a.spaceIn = spaceIn;
   a.spaceOut = spaceOut;

@@ -34,6 +34,7 @@ struct ZArgs {
   int pitch;      // row pitch of the stick buffer
   RadixPlan rp;
   const cx<T>* tw;        // forward roots of unity, length nz
+  const cx<T>* ftw;       // stage twiddles of the register FFT (fast_fft.hpp) or nullptr
   const int* tileStart;   // [numTiles+1]: range of sparse entries of every stick tile
   const int* entrySrc;    // [numEntries]: position in the user's value array; nullptr = identity
   const int* entrySlot;   // [numEntries]: z*V + lane inside the tile
@@ -57,6 +58,7 @@ struct YArgs {
   int symmetry;    // R2C: hermitian fill of the x=0 column
   RadixPlan rp;
   const cx<T>* tw;
+  const cx<T>* ftw;      // stage twiddles of the register FFT or nullptr (generic path)
   const int* xtStart;    // [numXTiles+1]: range of sticks per x tile (sticks are sorted by x*Ny+y)
   const int* stickSlot;  // [numSticks]: y*V + (x mod V)
   cx<T>* sticks;
@@ -72,6 +74,7 @@ struct XArgs {
   int r2c;
   RadixPlan rp;
   const cx<T>* tw;
+  const cx<T>* ftw;   // stage twiddles of the register FFT or nullptr (generic path)
   cx<T>* planes;      // [numPlanes][ny][nxf]
   const void* spaceIn;  // forward input
   void* spaceOut;       // backward output

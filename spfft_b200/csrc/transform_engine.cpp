@@ -125,9 +125,14 @@ std::shared_ptr<DevicePlan<T>> build_device_plan(const IndexMaps& m, long long s
   if (m.dimX == 0 || m.dimY == 0 || m.dimZ == 0) return plan;
   AxisPlans& ax = plan->axes;
   const int cb = static_cast<int>(sizeof(sb::cx<T>));
-  ax.log2Vx = choose_log2_lanes(m.dimX, cb, smemLimit);
-  ax.log2Vy = choose_log2_lanes(m.dimY, cb, smemLimit);
-  ax.log2Vz = choose_log2_lanes(m.dimZ, cb, smemLimit);
+  // per axis: register-FFT kernels for power-of-two lengths, generic tile kernels otherwise
+  const bool fastX = fast_path_length(m.dimX, cb) && m.type == SPFFT_TRANS_C2C;
+  const bool fastY = fast_path_length(m.dimY, cb);
+  const bool fastZ = fast_path_length(m.dimZ, cb);
+  const int fastLanes = fast_path_log2_lanes(cb);
+  ax.log2Vx = fastX ? fastLanes : choose_log2_lanes(m.dimX, cb, smemLimit);
+  ax.log2Vy = fastY ? fastLanes : choose_log2_lanes(m.dimY, cb, smemLimit);
+  ax.log2Vz = fastZ ? fastLanes : choose_log2_lanes(m.dimZ, cb, smemLimit);
   // a transform length whose two tile buffers exceed shared memory is not supported
   if (ax.log2Vx < 0 || ax.log2Vy < 0 || ax.log2Vz < 0) throw InvalidParameterError();
   ax.rpX = make_radix_plan(m.dimX);
@@ -146,6 +151,9 @@ std::shared_ptr<DevicePlan<T>> build_device_plan(const IndexMaps& m, long long s
   p.twX = upload(st, total, make_roots<T>(m.dimX));
   p.twY = upload(st, total, make_roots<T>(m.dimY));
   p.twZ = upload(st, total, make_roots<T>(m.dimZ));
+  if (fastX) p.ftwX = upload(st, total, make_fast_twiddles<T>(m.dimX));
+  if (fastY) p.ftwY = upload(st, total, make_fast_twiddles<T>(m.dimY));
+  if (fastZ) p.ftwZ = upload(st, total, make_fast_twiddles<T>(m.dimZ));
   p.tileStart = upload(st, total, t.tileStart);
   p.entrySrc = t.identityOrder ? nullptr : upload(st, total, t.entrySrc);
   p.entrySlot = upload(st, total, t.entrySlot);

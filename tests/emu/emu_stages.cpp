@@ -11,12 +11,59 @@
 
 #include "../../spfft_b200/csrc/index_plan.hpp"
 #include "../../spfft_b200/csrc/stage_args.hpp"
+#include "../../spfft_b200/csrc/fast_stage_kernels.hpp"
 #include "../../spfft_b200/csrc/stage_kernels.hpp"
 #include "spfft/exceptions.hpp"
 
 using namespace spfft::b200;
 
 namespace {
+
+// length dispatch of the register-FFT bodies (the product does the same in fast_launch.cuh)
+#define EMU_DISPATCH(n, CALL) \
+  switch (n) {                \
+    case 32: CALL(32); break; \
+    case 64: CALL(64); break; \
+    case 128: CALL(128); break; \
+    case 256: CALL(256); break; \
+    case 512: CALL(512); break; \
+    case 1024: CALL(1024); break; \
+    default: throw spfft::InternalError(); \
+  }
+
+template <typename T>
+void run_z(bool fwd, const sb::ZArgs<T>& a, int b, sb::Ctx ctx, sb::cx<T>* smem) {
+  if (!a.ftw) {
+    if (fwd) sb::z_forward_body<T>(a, b, ctx, smem); else sb::z_backward_body<T>(a, b, ctx, smem);
+    return;
+  }
+  sb::Ctx c{(1 << sb::FastLanes<T>::log2V) * (a.nz / 8)};
+#define CALL(NN) if (fwd) sb::z_forward_fast<T, NN>(a, b, c, smem); else sb::z_backward_fast<T, NN>(a, b, c, smem)
+  EMU_DISPATCH(a.nz, CALL)
+#undef CALL
+}
+template <typename T>
+void run_y(bool fwd, const sb::YArgs<T>& a, int b, sb::Ctx ctx, sb::cx<T>* smem) {
+  if (!a.ftw) {
+    if (fwd) sb::y_forward_body<T>(a, b, ctx, smem); else sb::y_backward_body<T>(a, b, ctx, smem);
+    return;
+  }
+  sb::Ctx c{(1 << sb::FastLanes<T>::log2V) * (a.ny / 8)};
+#define CALL(NN) if (fwd) sb::y_forward_fast<T, NN>(a, b, c, smem); else sb::y_backward_fast<T, NN>(a, b, c, smem)
+  EMU_DISPATCH(a.ny, CALL)
+#undef CALL
+}
+template <typename T>
+void run_x(bool fwd, const sb::XArgs<T>& a, int b, sb::Ctx ctx, sb::cx<T>* smem) {
+  if (!a.ftw) {
+    if (fwd) sb::x_forward_body<T>(a, b, ctx, smem); else sb::x_backward_body<T>(a, b, ctx, smem);
+    return;
+  }
+  sb::Ctx c{(1 << sb::FastLanes<T>::log2V) * (a.nx / 8)};
+#define CALL(NN) if (fwd) sb::x_c2c_fast<T, NN, false>(a, b, c, smem); else sb::x_c2c_fast<T, NN, true>(a, b, c, smem)
+  EMU_DISPATCH(a.nx, CALL)
+#undef CALL
+}
 
 template <typename T>
 int run(int type, int dimX, int dimY, int dimZ, int n, const int* triplets, int forward,
@@ -26,20 +73,35 @@ int run(int type, int dimX, int dimY, int dimZ, int n, const int* triplets, int 
                                       SPFFT_INDEX_TRIPLETS, triplets);
     AxisPlans ax;
     const long long smemLimit = 200 * 1024;
-    ax.log2Vx = choose_log2_lanes(dimX, sizeof(sb::cx<T>), smemLimit);
-    ax.log2Vy = choose_log2_lanes(dimY, sizeof(sb::cx<T>), smemLimit);
-    ax.log2Vz = choose_log2_lanes(dimZ, sizeof(sb::cx<T>), smemLimit);
+    const int cb = sizeof(sb::cx<T>);
+    // maxLog2V == -2 forces the generic kernels everywhere (otherwise same choice as the product)
+    const bool allowFast = maxLog2V != -2;
+    const bool fastX = allowFast && fast_path_length(dimX, cb) && type == SPFFT_TRANS_C2C;
+    const bool fastY = allowFast && fast_path_length(dimY, cb);
+    const bool fastZ = allowFast && fast_path_length(dimZ, cb);
+    const int fl = fast_path_log2_lanes(cb);
+    ax.log2Vx = choose_log2_lanes(dimX, cb, smemLimit);
+    ax.log2Vy = choose_log2_lanes(dimY, cb, smemLimit);
+    ax.log2Vz = choose_log2_lanes(dimZ, cb, smemLimit);
     if (maxLog2V >= 0) {
       if (ax.log2Vx > maxLog2V) ax.log2Vx = maxLog2V;
       if (ax.log2Vy > maxLog2V) ax.log2Vy = maxLog2V;
       if (ax.log2Vz > maxLog2V) ax.log2Vz = maxLog2V;
     }
+    if (fastX) ax.log2Vx = fl;
+    if (fastY) ax.log2Vy = fl;
+    if (fastZ) ax.log2Vz = fl;
     ax.rpX = make_radix_plan(dimX);
     ax.rpY = make_radix_plan(dimY);
     ax.rpZ = make_radix_plan(dimZ);
     TileMaps t = build_tile_maps(*maps, ax.log2Vz, ax.log2Vy);
     auto twX = make_roots<T>(dimX), twY = make_roots<T>(dimY), twZ = make_roots<T>(dimZ);
+    auto ftwX = make_fast_twiddles<T>(dimX), ftwY = make_fast_twiddles<T>(dimY),
+         ftwZ = make_fast_twiddles<T>(dimZ);
     PlanPointers<T> p;
+    if (fastX) p.ftwX = ftwX.data();
+    if (fastY) p.ftwY = ftwY.data();
+    if (fastZ) p.ftwZ = ftwZ.data();
     p.twX = twX.data();
     p.twY = twY.data();
     p.twZ = twZ.data();
@@ -70,23 +132,23 @@ int run(int type, int dimX, int dimY, int dimZ, int n, const int* triplets, int 
     if (!forward) {
       auto za = make_z_args<T>(*maps, t, ax, p, false, sticks.data(), static_cast<const T*>(in),
                                nullptr, false);
-      for (int b = 0; b < za.numTiles; ++b) sb::z_backward_body<T>(za, b, ctx, smem.data());
+      for (int b = 0; b < za.numTiles; ++b) run_z<T>(false, za, b, ctx, smem.data());
       auto ya = make_y_args<T>(*maps, t, ax, p, sticks.data(), planes.data());
       for (int b = 0; b < ya.numXTiles * ya.numPlanes; ++b)
-        sb::y_backward_body<T>(ya, b, ctx, smem.data());
+        run_y<T>(false, ya, b, ctx, smem.data());
       auto xa = make_x_args<T>(*maps, ax, p, planes.data(), nullptr, out);
       for (int b = 0; b < xa.numRowTiles * xa.numPlanes; ++b)
-        sb::x_backward_body<T>(xa, b, ctx, smem.data());
+        run_x<T>(false, xa, b, ctx, smem.data());
     } else {
       auto xa = make_x_args<T>(*maps, ax, p, planes.data(), in, nullptr);
       for (int b = 0; b < xa.numRowTiles * xa.numPlanes; ++b)
-        sb::x_forward_body<T>(xa, b, ctx, smem.data());
+        run_x<T>(true, xa, b, ctx, smem.data());
       auto ya = make_y_args<T>(*maps, t, ax, p, sticks.data(), planes.data());
       for (int b = 0; b < ya.numXTiles * ya.numPlanes; ++b)
-        sb::y_forward_body<T>(ya, b, ctx, smem.data());
+        run_y<T>(true, ya, b, ctx, smem.data());
       auto za = make_z_args<T>(*maps, t, ax, p, true, sticks.data(), nullptr,
                                static_cast<T*>(out), scaling != 0);
-      for (int b = 0; b < za.numTiles; ++b) sb::z_forward_body<T>(za, b, ctx, smem.data());
+      for (int b = 0; b < za.numTiles; ++b) run_z<T>(true, za, b, ctx, smem.data());
     }
     return 0;
   } catch (const spfft::GenericError& e) {

@@ -104,3 +104,46 @@ def test_emulated_float_and_duplicates(emu, gen):
     back = np.zeros(len(trip), dtype=np.complex64)
     assert emu.sb_emu_transform(1, 0, nx, ny, nz, len(trip), _ptr(t), 1, _ptr(out), _ptr(back), 1, 64, -1) == 0
     assert orc.rel_l2(back[:5], back[-5:]) < 1e-6
+
+
+# ---- register-FFT ("fast") bodies: power-of-two lengths, mixed with generic axes ---------------
+FAST_SHAPES = [(32, 32, 32), (64, 32, 128), (32, 12, 64), (11, 64, 32), (128, 32, 13), (256, 32, 32),
+               (32, 512, 32), (32, 32, 1024)]
+
+
+@pytest.mark.parametrize("shape", FAST_SHAPES, ids=lambda s: "x".join(map(str, s)))
+@pytest.mark.parametrize("single", [False, True])
+def test_emulated_fast_c2c(emu, gen, shape, single):
+    nx, ny, nz = shape
+    if single and max(shape) > 512:
+        pytest.skip("float fast path stops at 512")
+    trip, vals = gen.make(nx, ny, nz, center=True, stick_fraction=0.5, fill_fraction=0.6)
+    param = orc.Parameters(orc.SPFFT_TRANS_C2C, nx, ny, nz, trip)
+    cdt = np.complex64 if single else np.complex128
+    tol = 2e-6 if single else 1e-13
+    v = vals.astype(cdt)
+    out = np.full((nz, ny, nx), np.nan, dtype=cdt)
+    t = np.ascontiguousarray(trip.reshape(-1))
+    assert emu.sb_emu_transform(int(single), 0, nx, ny, nz, len(trip), _ptr(t), 0, _ptr(v), _ptr(out), 0, 64, -1) == 0
+    ref = orc.backward(param, vals)
+    assert orc.rel_l2(out, ref) < tol
+    back = np.zeros(len(trip), dtype=cdt)
+    assert emu.sb_emu_transform(int(single), 0, nx, ny, nz, len(trip), _ptr(t), 1, _ptr(out), _ptr(back), 1, 64, -1) == 0
+    assert orc.rel_l2(back, vals) < tol
+
+
+@pytest.mark.parametrize("shape", [(32, 32, 32), (64, 128, 32), (12, 32, 64), (33, 64, 32)], ids=lambda s: "x".join(map(str, s)))
+def test_emulated_fast_r2c(emu, gen, shape):
+    from conftest import hermitian_space_values
+    nx, ny, nz = shape
+    trip, _ = gen.make(nx, ny, nz, hermitian=True)
+    vals = hermitian_space_values(orc, nx, ny, nz, trip)
+    param = orc.Parameters(orc.SPFFT_TRANS_R2C, nx, ny, nz, trip)
+    out = np.full((nz, ny, nx), np.nan, dtype=np.float64)
+    t = np.ascontiguousarray(trip.reshape(-1))
+    assert emu.sb_emu_transform(0, 1, nx, ny, nz, len(trip), _ptr(t), 0, _ptr(vals), _ptr(out), 0, 32, -1) == 0
+    ref = orc.backward(param, vals)
+    assert orc.rel_l2(out, ref) < 1e-13
+    back = np.zeros(len(trip), dtype=np.complex128)
+    assert emu.sb_emu_transform(0, 1, nx, ny, nz, len(trip), _ptr(t), 1, _ptr(out), _ptr(back), 1, 32, -1) == 0
+    assert orc.rel_l2(back, orc.forward(param, out, orc.SPFFT_FULL_SCALING)) < 1e-13

@@ -408,3 +408,23 @@ def test_full_size_properties_512(torch_cuda, lib):
     t.backward_ptr(a + 2 * b, sa)
     assert float((sa[::97] - lin).norm() / lin.norm()) <= TOL[False]
     t.destroy()
+
+
+@pytest.mark.parametrize("shape", [(32, 32, 32), (64, 32, 128), (32, 12, 64), (11, 64, 32), (128, 32, 13),
+                                   (256, 32, 32), (32, 512, 32), (32, 32, 1024), (1024, 32, 32)],
+                         ids=lambda s: "x".join(map(str, s)))
+@pytest.mark.parametrize("single", [False, True])
+@pytest.mark.parametrize("ttype", [0, 1])
+def test_power_of_two_fast_path(torch_cuda, lib, gen, shape, single, ttype):
+    """Register-FFT kernels (power-of-two axes) mixed with generic axes, both precisions."""
+    from conftest import hermitian_space_values
+    nx, ny, nz = shape
+    trip, vals = gen.make(nx, ny, nz, hermitian=bool(ttype), center=not ttype, stick_fraction=0.5, fill_fraction=0.6)
+    if ttype:
+        vals = hermitian_space_values(orc, nx, ny, nz, trip)
+    param = orc.Parameters(ttype, nx, ny, nz, trip)
+    space, back = _run_pair(torch_cuda, lib, ttype, nx, ny, nz, trip, vals, single=single)
+    v = vals.astype(np.complex64).astype(np.complex128) if single else vals
+    ref = orc.backward(param, v)
+    assert orc.rel_l2(space, ref) <= TOL[single]
+    assert orc.rel_l2(back, orc.forward(param, ref, orc.SPFFT_FULL_SCALING)) <= TOL[single]
