@@ -70,6 +70,53 @@ SB_DEV cx<T> ld_ro(const cx<T>* p) {
 #endif
 }
 
+// Global loads / stores with a cache policy:
+//   Plain  : default (L1 + L2)
+//   Stream : read-once / write-once data (ld.global.cs / st.global.cs, evict first)
+//   L2Only : data handed from one CTA to another through L2 (ld.global.cg / st.global.cg): never
+//            served from a (non-coherent) L1
+enum class Mem { Plain, Stream, L2Only };
+
+template <Mem M, typename T>
+SB_DEV cx<T> ld_g(const cx<T>* p) {
+#if SB_ON_GPU
+  if constexpr (M == Mem::Plain) {
+    return *p;
+  } else if constexpr (sizeof(T) == 8) {
+    const double2 v = M == Mem::Stream ? __ldcs(reinterpret_cast<const double2*>(p))
+                                       : __ldcg(reinterpret_cast<const double2*>(p));
+    return mk<T>(v.x, v.y);
+  } else {
+    const float2 v = M == Mem::Stream ? __ldcs(reinterpret_cast<const float2*>(p))
+                                      : __ldcg(reinterpret_cast<const float2*>(p));
+    return mk<T>(v.x, v.y);
+  }
+#else
+  return *p;
+#endif
+}
+
+template <Mem M, typename T>
+SB_DEV void st_g(cx<T>* p, cx<T> v) {
+#if SB_ON_GPU
+  if constexpr (M == Mem::Plain) {
+    *p = v;
+  } else if constexpr (sizeof(T) == 8) {
+    if constexpr (M == Mem::Stream)
+      __stcs(reinterpret_cast<double2*>(p), make_double2(v.x, v.y));
+    else
+      __stcg(reinterpret_cast<double2*>(p), make_double2(v.x, v.y));
+  } else {
+    if constexpr (M == Mem::Stream)
+      __stcs(reinterpret_cast<float2*>(p), make_float2(v.x, v.y));
+    else
+      __stcg(reinterpret_cast<float2*>(p), make_float2(v.x, v.y));
+  }
+#else
+  *p = v;
+#endif
+}
+
 // Twiddles + butterflies of stage S on the 8 registers of thread j.
 template <typename T, int N, bool BWD, int S>
 SB_DEV void fast_stage(cx<T>* v, int j, const cx<T>* __restrict__ tw) {

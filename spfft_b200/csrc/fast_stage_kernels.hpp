@@ -186,24 +186,26 @@ SB_DEV void z_forward_fast(const ZArgs<T>& a, int tile, Ctx ctx, cx<T>* S) {
 }
 
 // -------------------------------------------------------------------------------------------
-// y stage
+// y stage: one tile = V consecutive x columns of one plane.
+//   stickRow : row of the plane-major stick buffer that holds this plane (all local sticks)
+//   plane    : the plane's [ny][nxf] array (the plane buffer, or a slot of the L2 scratch ring)
 // -------------------------------------------------------------------------------------------
-template <typename T, int N>
-SB_DEV void y_backward_fast(const YArgs<T>& a, int block, Ctx ctx, cx<T>* S) {
+template <typename T, int N, Mem LDS, Mem STP>
+SB_DEV void y_backward_tile(const YArgs<T>& a, int xt, const cx<T>* stickRow, cx<T>* plane, Ctx ctx,
+                            cx<T>* S) {
   constexpr int LOG2V = FastLanes<T>::log2V;
   constexpr int V = 1 << LOG2V;
   constexpr int TT = FastPlan<N>::T;
-  const int xt = block % a.numXTiles;
-  const int zl = block / a.numXTiles;
   const int e0 = a.xtStart[xt], e1 = a.xtStart[xt + 1];
-  cx<T>* planeTile = a.planes + (size_t)zl * N * a.nxf + (size_t)xt * V;
+  cx<T>* planeTile = plane + (size_t)xt * V;
   const int lanesValid = (a.nxf - xt * V) < V ? (a.nxf - xt * V) : V;
   if (e0 == e1) {
+    // empty x tile: the x stage still reads these columns -> store zeros, no transform
     SB_PHASE_BEGIN
     for (int i = tid; i < N * V; i += nthr) {
       const int y = i >> LOG2V;
       const int lane = i & (V - 1);
-      if (lane < lanesValid) planeTile[(size_t)y * a.nxf + lane] = mk<T>(0, 0);
+      if (lane < lanesValid) st_g<STP>(planeTile + (size_t)y * a.nxf + lane, mk<T>(0, 0));
     }
     SB_PHASE_END_NOSYNC
     return;
@@ -213,10 +215,9 @@ SB_DEV void y_backward_fast(const YArgs<T>& a, int block, Ctx ctx, cx<T>* S) {
   for (int i = tid; i < N * V; i += nthr) S[i] = mk<T>(0, 0);
   SB_PHASE_END
   SB_PHASE_BEGIN
-  const cx<T>* row = a.sticks + (size_t)(zl + a.zRowOffset) * a.pitch;
   for (int e = e0 + tid; e < e1; e += nthr) {
     const int slot = a.stickSlot[e];
-    S[SwzRow::at<LOG2V>(slot >> LOG2V, slot & (V - 1))] = row[e];
+    S[SwzRow::at<LOG2V>(slot >> LOG2V, slot & (V - 1))] = ld_g<LDS>(stickRow + e);
   }
   SB_PHASE_END
   if (a.symmetry && xt == 0) hermitian_fill_lane_swz<T, LOG2V, SwzRow>(S, N, 0, ctx);
@@ -231,28 +232,27 @@ SB_DEV void y_backward_fast(const YArgs<T>& a, int block, Ctx ctx, cx<T>* S) {
   fast_fft_tail<T, N, LOG2V, true, SwzRow>(v, S, a.ftw, j, lane);
   if (lane < lanesValid) {
 #pragma unroll
-    for (int m = 0; m < 8; ++m) planeTile[(size_t)(j + TT * m) * a.nxf + lane] = v[m];
+    for (int m = 0; m < 8; ++m) st_g<STP>(planeTile + (size_t)(j + TT * m) * a.nxf + lane, v[m]);
   }
   SB_PHASE_END_NOSYNC
 }
 
-template <typename T, int N>
-SB_DEV void y_forward_fast(const YArgs<T>& a, int block, Ctx ctx, cx<T>* S) {
+template <typename T, int N, Mem LDP, Mem STS>
+SB_DEV void y_forward_tile(const YArgs<T>& a, int xt, const cx<T>* plane, cx<T>* stickRow, Ctx ctx,
+                           cx<T>* S) {
   constexpr int LOG2V = FastLanes<T>::log2V;
   constexpr int V = 1 << LOG2V;
   constexpr int TT = FastPlan<N>::T;
-  const int xt = block % a.numXTiles;
-  const int zl = block / a.numXTiles;
   const int e0 = a.xtStart[xt], e1 = a.xtStart[xt + 1];
-  if (e0 == e1) return;
-  const cx<T>* planeTile = a.planes + (size_t)zl * N * a.nxf + (size_t)xt * V;
+  if (e0 == e1) return;  // no stick needs these columns
+  const cx<T>* planeTile = plane + (size_t)xt * V;
   const int lanesValid = (a.nxf - xt * V) < V ? (a.nxf - xt * V) : V;
   SB_REGS(cx<T>, vAll, 8);
   SB_PHASE_BEGIN
   SB_ROW_IDS
 #pragma unroll
   for (int m = 0; m < 8; ++m)
-    v[m] = lane < lanesValid ? planeTile[(size_t)(j + TT * m) * a.nxf + lane] : mk<T>(0, 0);
+    v[m] = lane < lanesValid ? ld_g<LDP>(planeTile + (size_t)(j + TT * m) * a.nxf + lane) : mk<T>(0, 0);
   SB_PHASE_END
   fast_fft_head<T, N, LOG2V, false, SwzRow, false>(vAll, S, a.ftw, ctx);
   SB_PHASE_BEGIN
@@ -265,52 +265,151 @@ SB_DEV void y_forward_fast(const YArgs<T>& a, int block, Ctx ctx, cx<T>* S) {
   for (int m = 0; m < 8; ++m) S[SwzRow::at<LOG2V>(j + TT * m, lane)] = v[m];
   SB_PHASE_END
   SB_PHASE_BEGIN
-  cx<T>* row = a.sticks + (size_t)(zl + a.zRowOffset) * a.pitch;
   for (int e = e0 + tid; e < e1; e += nthr) {
     const int slot = a.stickSlot[e];
-    row[e] = S[SwzRow::at<LOG2V>(slot >> LOG2V, slot & (V - 1))];
+    st_g<STS>(stickRow + e, S[SwzRow::at<LOG2V>(slot >> LOG2V, slot & (V - 1))]);
   }
   SB_PHASE_END_NOSYNC
 }
 
+template <typename T, int N>
+SB_DEV void y_backward_fast(const YArgs<T>& a, int block, Ctx ctx, cx<T>* S) {
+  const int xt = block % a.numXTiles;
+  const int zl = block / a.numXTiles;
+  y_backward_tile<T, N, Mem::Stream, Mem::Plain>(a, xt, a.sticks + (size_t)(zl + a.zRowOffset) * a.pitch,
+                                                a.planes + (size_t)zl * N * a.nxf, ctx, S);
+}
+
+template <typename T, int N>
+SB_DEV void y_forward_fast(const YArgs<T>& a, int block, Ctx ctx, cx<T>* S) {
+  const int xt = block % a.numXTiles;
+  const int zl = block / a.numXTiles;
+  y_forward_tile<T, N, Mem::Stream, Mem::Plain>(a, xt, a.planes + (size_t)zl * N * a.nxf,
+                                               a.sticks + (size_t)(zl + a.zRowOffset) * a.pitch, ctx, S);
+}
+
 // -------------------------------------------------------------------------------------------
-// x stage, complex rows (C2C). Tile = V consecutive rows; thread = (row lane, j).
+// x stage, complex rows (C2C). Tile = V consecutive rows y0 .. y0+V-1 of one plane;
+// thread = (row lane, j). in / out: the plane's [ny][N] arrays (may be the same memory).
 // -------------------------------------------------------------------------------------------
-template <typename T, int N, bool BWD>
-SB_DEV void x_c2c_fast(const XArgs<T>& a, int block, Ctx ctx, cx<T>* S) {
+template <typename T, int N, bool BWD, Mem LD, Mem ST>
+SB_DEV void x_c2c_tile(const cx<T>* in, cx<T>* out, int y0, int ny, const cx<T>* __restrict__ ftw,
+                       Ctx ctx, cx<T>* S) {
   constexpr int LOG2V = FastLanes<T>::log2V;
-  constexpr int V = 1 << LOG2V;
   constexpr int TT = FastPlan<N>::T;
-  const int rt = block % a.numRowTiles;
-  const int zl = block / a.numRowTiles;
-  const int y0 = rt * V;
-  const size_t rowBase = (size_t)zl * a.ny + y0;
-  const cx<T>* src = BWD ? a.planes : static_cast<const cx<T>*>(a.spaceIn);
-  cx<T>* dst = BWD ? static_cast<cx<T>*>(a.spaceOut) : a.planes;
   SB_REGS(cx<T>, vAll, 8);
-#define SB_COL_IDS                      \
-  cx<T>* v = SB_RP(vAll, 8);            \
-  const int lane = tid / TT;            \
-  const int j = tid & (TT - 1);         \
-  const bool valid = y0 + lane < a.ny;  \
+#define SB_COL_IDS                    \
+  cx<T>* v = SB_RP(vAll, 8);          \
+  const int lane = tid / TT;          \
+  const int j = tid & (TT - 1);       \
+  const bool valid = y0 + lane < ny;  \
   (void)nthr;
   SB_PHASE_BEGIN
   SB_COL_IDS
-  const cx<T>* in = src + (rowBase + lane) * N + j;
+  const cx<T>* src = in + (size_t)(y0 + lane) * N + j;
 #pragma unroll
-  for (int m = 0; m < 8; ++m) v[m] = valid ? in[TT * m] : mk<T>(0, 0);
+  for (int m = 0; m < 8; ++m) v[m] = valid ? ld_g<LD>(src + TT * m) : mk<T>(0, 0);
   SB_PHASE_END
-  fast_fft_head<T, N, LOG2V, BWD, SwzCol, true>(vAll, S, a.ftw, ctx);
+  fast_fft_head<T, N, LOG2V, BWD, SwzCol, true>(vAll, S, ftw, ctx);
   SB_PHASE_BEGIN
   SB_COL_IDS
-  fast_fft_tail<T, N, LOG2V, BWD, SwzCol>(v, S, a.ftw, j, lane);
+  fast_fft_tail<T, N, LOG2V, BWD, SwzCol>(v, S, ftw, j, lane);
   if (valid) {
-    cx<T>* out = dst + (rowBase + lane) * N + j;
+    cx<T>* dst = out + (size_t)(y0 + lane) * N + j;
 #pragma unroll
-    for (int m = 0; m < 8; ++m) out[TT * m] = v[m];
+    for (int m = 0; m < 8; ++m) st_g<ST>(dst + TT * m, v[m]);
   }
   SB_PHASE_END_NOSYNC
 #undef SB_COL_IDS
+}
+
+template <typename T, int N, bool BWD>
+SB_DEV void x_c2c_fast(const XArgs<T>& a, int block, Ctx ctx, cx<T>* S) {
+  constexpr int V = 1 << FastLanes<T>::log2V;
+  const int rt = block % a.numRowTiles;
+  const int zl = block / a.numRowTiles;
+  const size_t planeOff = (size_t)zl * a.ny * N;
+  const cx<T>* src = (BWD ? a.planes : static_cast<const cx<T>*>(a.spaceIn)) + planeOff;
+  cx<T>* dst = (BWD ? static_cast<cx<T>*>(a.spaceOut) : a.planes) + planeOff;
+  x_c2c_tile<T, N, BWD, Mem::Stream, Mem::Plain>(src, dst, rt * V, a.ny, a.ftw, ctx, S);
+}
+
+// -------------------------------------------------------------------------------------------
+// Fused xy stage: y tiles and x tiles of every plane as items of ONE persistent kernel, the y<->x
+// hand-off going through a small ring of scratch planes that stays resident in the 126 MB L2
+// instead of a full-size plane buffer in HBM (replaces the two passes of the reference's
+// cufftMakePlanMany 2-D plans, src/fft/transform_2d_gpu.hpp:51-140).
+//
+// Item order (handed out by an atomic counter): for step u = 0 .. P+lag-1:
+//     the A tiles of plane u (if u < P), then the B tiles of plane u-lag (if u >= lag)
+//   backward: A = y tile (sticks -> scratch),  B = x tile (scratch -> space domain)
+//   forward : A = x tile (space -> scratch),   B = y tile (scratch -> sticks)
+// B tiles of plane p wait until all A tiles of p are done; A tiles of plane p wait until all B
+// tiles of plane p-ring are done (slot reuse). Dependencies only point to earlier items, and items
+// are started in order, so waiting never deadlocks.
+// -------------------------------------------------------------------------------------------
+template <typename T>
+struct XYArgs {
+  YArgs<T> y;      // stick side: sticks, pitch, zRowOffset, xtStart, stickSlot, symmetry, ftw (y)
+  XArgs<T> x;      // space side: spaceIn / spaceOut, ny, numRowTiles, ftw (x)
+  cx<T>* scratch;  // [ring][ny][nx]
+  int ring;
+  int lag;
+  int* counters;   // [0] work counter, [1+p] A tiles done of plane p, [1+P+p] B tiles done
+};
+
+struct XYItem {
+  int plane, tile;
+  bool roleA, valid;
+};
+
+template <typename T, bool BWD>
+SB_HD int xy_tiles_a(const XYArgs<T>& a) {
+  return BWD ? a.y.numXTiles : a.x.numRowTiles;
+}
+template <typename T, bool BWD>
+SB_HD int xy_tiles_b(const XYArgs<T>& a) {
+  return BWD ? a.x.numRowTiles : a.y.numXTiles;
+}
+template <typename T, bool BWD>
+SB_HD long long xy_total_items(const XYArgs<T>& a) {
+  return (long long)(a.y.numPlanes + a.lag) * (xy_tiles_a<T, BWD>(a) + xy_tiles_b<T, BWD>(a));
+}
+template <typename T, bool BWD>
+SB_HD XYItem xy_decode(const XYArgs<T>& a, int item) {
+  const int nA = xy_tiles_a<T, BWD>(a), nB = xy_tiles_b<T, BWD>(a);
+  const int u = item / (nA + nB);
+  const int r = item - u * (nA + nB);
+  XYItem it;
+  it.roleA = r < nA;
+  it.plane = it.roleA ? u : u - a.lag;
+  it.tile = it.roleA ? r : r - nA;
+  it.valid = it.roleA ? (u < a.y.numPlanes) : (it.plane >= 0);
+  return it;
+}
+
+// The tile work of one item (no waiting / signalling: the caller does that).
+template <typename T, int N, bool BWD>
+SB_DEV void xy_run_item(const XYArgs<T>& a, const XYItem& it, Ctx ctx, cx<T>* S) {
+  constexpr int V = 1 << FastLanes<T>::log2V;
+  const size_t planeElems = (size_t)N * N;
+  cx<T>* slot = a.scratch + (size_t)(it.plane % a.ring) * planeElems;
+  cx<T>* stickRow = a.y.sticks + (size_t)(it.plane + a.y.zRowOffset) * a.y.pitch;
+  if (BWD) {
+    if (it.roleA)
+      y_backward_tile<T, N, Mem::Stream, Mem::L2Only>(a.y, it.tile, stickRow, slot, ctx, S);
+    else
+      x_c2c_tile<T, N, true, Mem::L2Only, Mem::Stream>(
+          slot, static_cast<cx<T>*>(a.x.spaceOut) + (size_t)it.plane * planeElems, it.tile * V, N,
+          a.x.ftw, ctx, S);
+  } else {
+    if (it.roleA)
+      x_c2c_tile<T, N, false, Mem::Stream, Mem::L2Only>(
+          static_cast<const cx<T>*>(a.x.spaceIn) + (size_t)it.plane * planeElems, slot, it.tile * V,
+          N, a.x.ftw, ctx, S);
+    else
+      y_forward_tile<T, N, Mem::L2Only, Mem::Plain>(a.y, it.tile, slot, stickRow, ctx, S);
+  }
 }
 
 #undef SB_ROW_IDS

@@ -1,0 +1,165 @@
+// fast_xy.cu -- fused xy stage: persistent kernel over y tiles and x tiles with the hand-off held
+// in an L2-resident scratch ring (see fast_stage_kernels.hpp), sm_100a.
+#include "fast_launch.cuh"
+#include "launch.h"
+
+namespace sb {
+
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// thread 0 spins until *p >= target, then the whole CTA proceeds
+__device__ __forceinline__ void cta_wait(const int* p, int target) {
+  if (threadIdx.x == 0) {
+    while (ld_acquire_gpu(p) < target) __nanosleep(64);
+  }
+  __syncthreads();
+}
+
+// every thread's global writes of this tile become visible before the counter moves
+__device__ __forceinline__ void cta_signal(int* p) {
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) atomicAdd(p, 1);
+}
+
+template <typename T, int N, bool FWD>
+__global__ void __launch_bounds__(FastCfg<T, N>::threads, FastCfg<T, N>::minBlocks)
+    k_xy_fused(const __grid_constant__ XYArgs<T> a) {
+  extern __shared__ __align__(16) unsigned char smemRaw[];
+  cx<T>* S = reinterpret_cast<cx<T>*>(smemRaw);
+  __shared__ int sItem;
+  constexpr bool BWD = !FWD;
+  const int P = a.y.numPlanes;
+  const int nA = xy_tiles_a<T, BWD>(a), nB = xy_tiles_b<T, BWD>(a);
+  const long long total = xy_total_items<T, BWD>(a);
+  int* aDone = a.counters + 1;
+  int* bDone = a.counters + 1 + P;
+  for (;;) {
+    if (threadIdx.x == 0) sItem = atomicAdd(&a.counters[0], 1);
+    __syncthreads();
+    const int item = sItem;
+    __syncthreads();
+    if (item >= total) break;
+    const XYItem it = xy_decode<T, BWD>(a, item);
+    if (!it.valid) continue;
+    if (it.roleA) {
+      if (it.plane >= a.ring) cta_wait(&bDone[it.plane - a.ring], nB);
+      xy_run_item<T, N, BWD>(a, it, Ctx{FastCfg<T, N>::threads}, S);
+      cta_signal(&aDone[it.plane]);
+    } else {
+      cta_wait(&aDone[it.plane], nA);
+      xy_run_item<T, N, BWD>(a, it, Ctx{FastCfg<T, N>::threads}, S);
+      cta_signal(&bDone[it.plane]);
+    }
+  }
+}
+
+template <typename T, int N>
+static int xy_blocks_per_sm(int* out) {
+  using C = FastCfg<T, N>;
+  if constexpr (C::threads > 1024) {
+    return (int)cudaErrorInvalidValue;
+  } else {
+    cudaError_t e = cudaFuncSetAttribute(k_xy_fused<T, N, false>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::smem);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaFuncSetAttribute(k_xy_fused<T, N, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)C::smem);
+    if (e != cudaSuccess) return (int)e;
+    int b0 = 0, b1 = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b0, k_xy_fused<T, N, false>, C::threads, C::smem);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b1, k_xy_fused<T, N, true>, C::threads, C::smem);
+    if (e != cudaSuccess) return (int)e;
+    *out = b0 < b1 ? b0 : b1;
+    return *out > 0 ? 0 : (int)cudaErrorInvalidConfiguration;
+  }
+}
+
+template <typename T>
+static int xy_blocks_per_sm_n(int n, int* out) {
+#define CALL(NN) return xy_blocks_per_sm<T, NN>(out)
+  SB_FAST_DISPATCH(n, CALL)
+#undef CALL
+  return (int)cudaErrorInvalidValue;
+}
+
+static int num_sms(int* out) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return (int)e;
+  return (int)cudaDeviceGetAttribute(out, cudaDevAttrMultiProcessorCount, dev);
+}
+
+template <typename T, int N>
+static int launch_xy_n(int forward, const XYArgs<T>& a, cudaStream_t s) {
+  using C = FastCfg<T, N>;
+  if constexpr (C::threads > 1024) {
+    return (int)cudaErrorInvalidValue;
+  } else {
+    int perSm = 0, sms = 0;
+    int err = xy_blocks_per_sm<T, N>(&perSm);
+    if (err) return err;
+    err = num_sms(&sms);
+    if (err) return err;
+    const long long total = forward ? xy_total_items<T, false>(a) : xy_total_items<T, true>(a);
+    if (total <= 0) return 0;
+    if (total > 0x7fffffffLL) return (int)cudaErrorInvalidConfiguration;
+    long long grid = (long long)perSm * sms;
+    if (grid > total) grid = total;
+    cudaError_t e = cudaMemsetAsync(a.counters, 0, sizeof(int) * (1 + 2 * (size_t)a.y.numPlanes), s);
+    if (e != cudaSuccess) return (int)e;
+    if (forward)
+      k_xy_fused<T, N, true><<<(unsigned)grid, C::threads, C::smem, s>>>(a);
+    else
+      k_xy_fused<T, N, false><<<(unsigned)grid, C::threads, C::smem, s>>>(a);
+    return (int)cudaGetLastError();
+  }
+}
+
+template <typename T>
+static int launch_xy(int forward, const XYArgs<T>& a, cudaStream_t s) {
+#define CALL(NN) return launch_xy_n<T, NN>(forward, a, s)
+  SB_FAST_DISPATCH(a.x.nx, CALL)
+#undef CALL
+  return (int)cudaErrorInvalidValue;
+}
+
+}  // namespace sb
+
+extern "C" {
+
+int sb_xy_fused_config(int isFloat, int n, int numPlanes, int* ring, int* lag, int* numCounters) {
+  int perSm = 0, sms = 0;
+  int err = isFloat ? sb::xy_blocks_per_sm_n<float>(n, &perSm) : sb::xy_blocks_per_sm_n<double>(n, &perSm);
+  if (err) return err;
+  err = sb::num_sms(&sms);
+  if (err) return err;
+  const int lanes = isFloat ? 16 : 8;
+  const int perStep = 2 * ((n + lanes - 1) / lanes);
+  const int resident = perSm * sms;
+  int l = (resident + perStep - 1) / perStep + 1;
+  int r = 2 * l + 2;
+  if (r < 6) r = 6;
+  if (numPlanes <= r) {
+    r = numPlanes > 0 ? numPlanes : 1;  // every plane has its own slot: no reuse waits
+  }
+  *ring = r;
+  *lag = l;
+  *numCounters = 1 + 2 * (numPlanes > 0 ? numPlanes : 0);
+  return 0;
+}
+
+int sb_launch_xy_f64(int forward, const sb::XYArgs<double>* a, void* stream) {
+  sb_note_launches(1);
+  return sb::launch_xy<double>(forward, *a, static_cast<cudaStream_t>(stream));
+}
+int sb_launch_xy_f32(int forward, const sb::XYArgs<float>* a, void* stream) {
+  sb_note_launches(1);
+  return sb::launch_xy<float>(forward, *a, static_cast<cudaStream_t>(stream));
+}
+}

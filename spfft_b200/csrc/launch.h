@@ -2,6 +2,7 @@
  * translation unit (kernels.cu). POD argument structs (stage_kernels.hpp), int error return
  * (a cudaError_t value, 0 = success). `stream` is a cudaStream_t. */
 #pragma once
+#include "fast_stage_kernels.hpp"
 #include "stage_kernels.hpp"
 
 extern "C" {
@@ -14,8 +15,16 @@ int sb_launch_y_f32(int forward, const sb::YArgs<float>* args, void* stream);
 /* x stage on every (row tile, local plane). */
 int sb_launch_x_f64(int forward, const sb::XArgs<double>* args, void* stream);
 int sb_launch_x_f32(int forward, const sb::XArgs<float>* args, void* stream);
+/* Fused xy stage (C2C, dimX == dimY, power of two): plan-time query of the scratch ring
+ * (planes), the item lag and the number of int counters the kernel needs, for `numPlanes` local
+ * planes of n x n. Returns cudaErrorInvalidValue if no fused kernel exists for n. */
+int sb_xy_fused_config(int isFloat, int n, int numPlanes, int* ring, int* lag, int* numCounters);
+/* One direction of the fused xy stage. `counters` must be zero (the launcher enqueues the memset). */
+int sb_launch_xy_f64(int forward, const sb::XYArgs<double>* args, void* stream);
+int sb_launch_xy_f32(int forward, const sb::XYArgs<float>* args, void* stream);
 /* total number of kernel launches issued through this file */
 long long sb_launch_count(void);
+void sb_note_launches(int n);
 /* opt-in limit of dynamic shared memory per block on the current device (bytes) */
 int sb_max_dynamic_smem(long long* bytes);
 }

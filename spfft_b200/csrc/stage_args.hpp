@@ -3,6 +3,7 @@
 // used in unit tests (tests/emu, host pointers), so both exercise the same wiring.
 #pragma once
 #include "index_plan.hpp"
+#include "fast_stage_kernels.hpp"
 #include "stage_kernels.hpp"
 
 namespace spfft {

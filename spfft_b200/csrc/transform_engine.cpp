@@ -23,12 +23,14 @@ struct Launch<double> {
   static int z(int f, const sb::ZArgs<double>& a, void* s) { return sb_launch_z_f64(f, &a, s); }
   static int y(int f, const sb::YArgs<double>& a, void* s) { return sb_launch_y_f64(f, &a, s); }
   static int x(int f, const sb::XArgs<double>& a, void* s) { return sb_launch_x_f64(f, &a, s); }
+  static int xy(int f, const sb::XYArgs<double>& a, void* s) { return sb_launch_xy_f64(f, &a, s); }
 };
 template <>
 struct Launch<float> {
   static int z(int f, const sb::ZArgs<float>& a, void* s) { return sb_launch_z_f32(f, &a, s); }
   static int y(int f, const sb::YArgs<float>& a, void* s) { return sb_launch_y_f32(f, &a, s); }
   static int x(int f, const sb::XArgs<float>& a, void* s) { return sb_launch_x_f32(f, &a, s); }
+  static int xy(int f, const sb::XYArgs<float>& a, void* s) { return sb_launch_xy_f32(f, &a, s); }
 };
 
 inline void check_launch(int err) {
@@ -116,6 +118,28 @@ void* GridResources<T>::host_space(size_t bytes) {
   return host_.get();
 }
 
+template <typename T>
+void* GridResources<T>::scratch(size_t bytes) {
+  std::lock_guard<std::mutex> lock(hostMutex_);
+  if (scratch_.bytes() < bytes) {
+    DeviceGuard guard(deviceId_);
+    check_gpu(cudaDeviceSynchronize());  // nothing may still be using the old allocation
+    scratch_.allocate(bytes);
+  }
+  return scratch_.get();
+}
+
+template <typename T>
+int* GridResources<T>::counters(size_t count) {
+  std::lock_guard<std::mutex> lock(hostMutex_);
+  if (counters_.bytes() < count * sizeof(int)) {
+    DeviceGuard guard(deviceId_);
+    check_gpu(cudaDeviceSynchronize());
+    counters_.allocate(count * sizeof(int));
+  }
+  return counters_.template as<int>();
+}
+
 // ---------------------------------------------------------------------------------------------
 // DevicePlan
 // ---------------------------------------------------------------------------------------------
@@ -138,6 +162,12 @@ std::shared_ptr<DevicePlan<T>> build_device_plan(const IndexMaps& m, long long s
   ax.rpX = make_radix_plan(m.dimX);
   ax.rpY = make_radix_plan(m.dimY);
   ax.rpZ = make_radix_plan(m.dimZ);
+  if (fastX && fastY && m.dimX == m.dimY && m.type == SPFFT_TRANS_C2C) {
+    // y and x stages as one persistent kernel with the hand-off in L2 (fast_xy.cu)
+    const int err = sb_xy_fused_config(sizeof(T) == 4, m.dimX, m.local_planes(), &plan->xyRing,
+                                       &plan->xyLag, &plan->xyCounters);
+    plan->fusedXY = err == 0;
+  }
   TileMaps t = build_tile_maps(m, ax.log2Vz, ax.log2Vy);
   plan->numStickTiles = t.numStickTiles;
   plan->pitch = t.pitch;
@@ -315,6 +345,20 @@ void TransformEngine<T>::synchronize() {
 }
 
 template <typename T>
+sb::XYArgs<T> TransformEngine<T>::make_xy_args(const TileMaps& geo, const T* spaceIn, T* spaceOut) {
+  const IndexMaps& m = *maps_;
+  sb::XYArgs<T> a{};
+  a.y = make_y_args<T>(m, geo, plan_->axes, plan_->ptrs, sticks(), nullptr);
+  a.x = make_x_args<T>(m, plan_->axes, plan_->ptrs, nullptr, spaceIn, spaceOut);
+  a.ring = plan_->xyRing;
+  a.lag = plan_->xyLag;
+  const size_t planeBytes = sizeof(sb::cx<T>) * static_cast<size_t>(m.dimX) * static_cast<size_t>(m.dimY);
+  a.scratch = static_cast<sb::cx<T>*>(grid_->scratch(planeBytes * static_cast<size_t>(a.ring)));
+  a.counters = grid_->counters(static_cast<size_t>(plan_->xyCounters));
+  return a;
+}
+
+template <typename T>
 void TransformEngine<T>::enqueue_backward(const T* input, T* output) {
   DeviceGuard guard(grid_->device_id());
   begin_call();
@@ -345,16 +389,18 @@ void TransformEngine<T>::enqueue_backward(const T* input, T* output) {
     check_launch(Launch<T>::z(0, za, s));
     record_stage("z backward");
   }
-  // ---- y stage: stick gather + plane symmetry + y-FFT (execution_gpu.cpp:371-390)
-  {
+  const bool outOnDevice = is_device_pointer(output);
+  T* outDev = outOnDevice ? output : device_space();
+  if (plan_->fusedXY) {
+    // ---- fused xy stage: y tiles and x tiles in one persistent kernel, hand-off through L2
+    check_launch(Launch<T>::xy(0, make_xy_args(geo, nullptr, outDev), s));
+    record_stage("xy backward");
+  } else {
+    // ---- y stage: stick gather + plane symmetry + y-FFT (execution_gpu.cpp:371-390)
     auto ya = make_y_args<T>(m, geo, plan_->axes, plan_->ptrs, sticks(), planes());
     check_launch(Launch<T>::y(0, ya, s));
     record_stage("y backward");
-  }
-  // ---- x stage: x-FFT (C2C / C2R) into the space domain
-  const bool outOnDevice = is_device_pointer(output);
-  T* outDev = outOnDevice ? output : device_space();
-  {
+    // ---- x stage: x-FFT (C2C / C2R) into the space domain
     auto xa = make_x_args<T>(m, plan_->axes, plan_->ptrs, planes(), nullptr, outDev);
     check_launch(Launch<T>::x(0, xa, s));
     record_stage("x backward");
@@ -390,14 +436,17 @@ void TransformEngine<T>::enqueue_forward(const T* input, T* output, SpfftScaling
     src = device_space();
     record_stage("h2d space");
   }
-  {
+  const bool haveSticks = plan_->numStickTiles > 0 && ne > 0;
+  if (plan_->fusedXY) {
+    if (!haveSticks) return;  // nothing would consume the planes
+    check_launch(Launch<T>::xy(1, make_xy_args(geo, src, nullptr), s));
+    record_stage("xy forward");
+  } else {
     auto xa = make_x_args<T>(m, plan_->axes, plan_->ptrs, planes(), src, nullptr);
     check_launch(Launch<T>::x(1, xa, s));
     record_stage("x forward");
-  }
-  if (plan_->numStickTiles == 0 || ne == 0) return;  // nothing to gather
-  // ---- y stage: y-FFT + scatter into the plane-major sticks
-  {
+    if (!haveSticks) return;  // nothing to gather
+    // ---- y stage: y-FFT + scatter into the plane-major sticks
     auto ya = make_y_args<T>(m, geo, plan_->axes, plan_->ptrs, sticks(), planes());
     check_launch(Launch<T>::y(1, ya, s));
     record_stage("y forward");

@@ -48,6 +48,10 @@ public:
   size_t bytes_b() const { return b_.bytes(); }
   // Pinned host mirror of the space domain, allocated on first use.
   void* host_space(size_t bytes);
+  // Scratch ring of the fused xy stage and its counters (grown on demand, shared by the
+  // transforms of this grid like the other work buffers).
+  void* scratch(size_t bytes);
+  int* counters(size_t count);
 
   static size_t stick_capacity(int maxDimZ, int maxSticks);
 
@@ -57,7 +61,7 @@ private:
   SpfftProcessingUnitType pu_;
   int deviceId_ = 0;
   int numThreads_;
-  DeviceBuffer a_, b_;
+  DeviceBuffer a_, b_, scratch_, counters_;
   PinnedBuffer host_;
   std::mutex hostMutex_;
 };
@@ -69,6 +73,9 @@ struct DevicePlan {
   PlanPointers<T> ptrs;
   // tile geometry (host copies of the scalars of TileMaps)
   int numStickTiles = 0, pitch = 0, numXTiles = 0, symTile = -1, symLane = -1;
+  // fused xy stage (fast_xy.cu): scratch ring geometry, 0 planes = separate y and x kernels
+  bool fusedXY = false;
+  int xyRing = 0, xyLag = 0, xyCounters = 0;
   std::vector<DeviceBuffer> storage;
   size_t deviceBytes = 0;
 };
@@ -112,6 +119,7 @@ public:
 
 private:
   void begin_call();
+  sb::XYArgs<T> make_xy_args(const TileMaps& geo, const T* spaceIn, T* spaceOut);
   void record_stage(const char* name);
   size_t space_bytes() const;
   T* device_space() const;
