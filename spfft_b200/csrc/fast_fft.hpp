@@ -117,6 +117,29 @@ SB_DEV void st_g(cx<T>* p, cx<T> v) {
 #endif
 }
 
+// Ask L2 to fetch [base, base+bytes) (no registers or shared memory held, no wait): issued for the
+// inputs of the tile that will run on this SM next, so that its demand loads find the data in L2
+// instead of paying the DRAM latency with only 2 CTAs per SM to hide it.
+SB_DEV void prefetch_l2(const void* base, size_t bytes, int tid, int nthr) {
+#if SB_ON_GPU
+  const char* p = static_cast<const char*>(base);
+  const size_t mis = reinterpret_cast<size_t>(p) & 127;
+  p -= mis;
+  bytes += mis;
+  for (size_t off = (size_t)tid * 128; off < bytes; off += (size_t)nthr * 128)
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p + off));
+#else
+  (void)base; (void)bytes; (void)tid; (void)nthr;
+#endif
+}
+SB_DEV void prefetch_l2_line(const void* p) {
+#if SB_ON_GPU
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+#else
+  (void)p;
+#endif
+}
+
 // Twiddles + butterflies of stage S on the 8 registers of thread j.
 template <typename T, int N, bool BWD, int S>
 SB_DEV void fast_stage(cx<T>* v, int j, const cx<T>* __restrict__ tw) {

@@ -4,6 +4,8 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <cstdlib>
+
 #include "fast_stage_kernels.hpp"
 
 namespace sb {
@@ -29,6 +31,28 @@ int launch_fast(Kernel kernel, const Args& args, long long blocks, int threads, 
   }
   kernel<<<(unsigned)blocks, threads, smemBytes, stream>>>(args);
   return (int)cudaGetLastError();
+}
+
+// Debug / tuning knob: environment variable SPFFT_B200_TUNE (integer bit mask, default 1).
+//   bit 0: L2 prefetch of the next tile's inputs
+inline int tune_flags() {
+  static const int flags = [] {
+    const char* e = getenv("SPFFT_B200_TUNE");
+    return e ? atoi(e) : 1;
+  }();
+  return flags;
+}
+
+// CTAs resident on the device for a kernel that fits `perSm` per SM = how far ahead (in tiles) the
+// tile that will run next on "this" slot is.
+inline int resident_ctas(int perSm) {
+  static const int sms = [] {
+    int dev = 0, v = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 148;
+    return v;
+  }();
+  return sms * perSm;
 }
 
 // lengths with instantiated kernels

@@ -124,15 +124,34 @@ SB_DEV void z_backward_fast(const ZArgs<T>& a, int tile, Ctx ctx, cx<T>* S) {
   constexpr int V = 1 << LOG2V;
   constexpr int TT = FastPlan<N>::T;
   SB_REGS(cx<T>, vAll, 8);
+  const int e0 = a.tileStart[tile], e1 = a.tileStart[tile + 1];  // in flight during the zero fill
   SB_PHASE_BEGIN
+  if (a.pfDist > 0 && tile + a.pfDist < a.numTiles) {
+    const int p0 = a.tileStart[tile + a.pfDist], p1 = a.tileStart[tile + a.pfDist + 1];
+    prefetch_l2(a.entrySlot + p0, (size_t)(p1 - p0) * sizeof(int), tid, nthr);
+    if (!a.entrySrc) prefetch_l2(a.valuesIn + p0, (size_t)(p1 - p0) * sizeof(cx<T>), tid, nthr);
+  }
   for (int i = tid; i < N * V; i += nthr) S[i] = mk<T>(0, 0);
   SB_PHASE_END
   SB_PHASE_BEGIN
-  const int e1 = a.tileStart[tile + 1];
-  for (int e = a.tileStart[tile] + tid; e < e1; e += nthr) {
-    const int src = a.entrySrc ? a.entrySrc[e] : e;
-    const int slot = a.entrySlot[e];
-    S[SwzRow::at<LOG2V>(slot >> LOG2V, slot & (V - 1))] = a.valuesIn[src];
+  // all loads of a batch are issued before the first shared-memory store (one DRAM round trip
+  // per batch instead of one per entry)
+  constexpr int U = 6;
+  for (int base = e0 + tid; base < e1; base += U * nthr) {
+    int slot[U];
+    cx<T> val[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int e = base + u * nthr;
+      if (e < e1) {
+        slot[u] = a.entrySlot[e];
+        val[u] = a.valuesIn[a.entrySrc ? a.entrySrc[e] : e];
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (base + u * nthr < e1) S[SwzRow::at<LOG2V>(slot[u] >> LOG2V, slot[u] & (V - 1))] = val[u];
+    }
   }
   SB_PHASE_END
   if (tile == a.symTile) hermitian_fill_lane_swz<T, LOG2V, SwzRow>(S, N, a.symLane, ctx);
@@ -157,11 +176,18 @@ SB_DEV void z_forward_fast(const ZArgs<T>& a, int tile, Ctx ctx, cx<T>* S) {
   constexpr int V = 1 << LOG2V;
   constexpr int TT = FastPlan<N>::T;
   SB_REGS(cx<T>, vAll, 8);
+  const int e0 = a.tileStart[tile], e1 = a.tileStart[tile + 1];
   SB_PHASE_BEGIN
   SB_ROW_IDS
   const cx<T>* in = a.sticks + (size_t)tile * V + lane;
 #pragma unroll
   for (int m = 0; m < 8; ++m) v[m] = in[(size_t)(j + TT * m) * a.pitch];
+  if (a.pfDist > 0 && tile + a.pfDist < a.numTiles) {
+    for (int r = tid; r < N; r += nthr)
+      prefetch_l2_line(a.sticks + (size_t)(tile + a.pfDist) * V + (size_t)r * a.pitch);
+    const int p0 = a.tileStart[tile + a.pfDist], p1 = a.tileStart[tile + a.pfDist + 1];
+    prefetch_l2(a.entrySlot + p0, (size_t)(p1 - p0) * sizeof(int), tid, nthr);
+  }
   SB_PHASE_END
   fast_fft_head<T, N, LOG2V, false, SwzRow, false>(vAll, S, a.ftw, ctx);
   SB_PHASE_BEGIN
@@ -174,13 +200,25 @@ SB_DEV void z_forward_fast(const ZArgs<T>& a, int tile, Ctx ctx, cx<T>* S) {
   for (int m = 0; m < 8; ++m) S[SwzRow::at<LOG2V>(j + TT * m, lane)] = v[m];
   SB_PHASE_END
   SB_PHASE_BEGIN
-  const int e1 = a.tileStart[tile + 1];
-  for (int e = a.tileStart[tile] + tid; e < e1; e += nthr) {
-    const int dst = a.entrySrc ? a.entrySrc[e] : e;
-    const int slot = a.entrySlot[e];
-    cx<T> val = S[SwzRow::at<LOG2V>(slot >> LOG2V, slot & (V - 1))];
-    if (a.useScale) val = a.scale * val;
-    a.valuesOut[dst] = val;
+  constexpr int U = 6;
+  for (int base = e0 + tid; base < e1; base += U * nthr) {
+    int slot[U], dst[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int e = base + u * nthr;
+      if (e < e1) {
+        slot[u] = a.entrySlot[e];
+        dst[u] = a.entrySrc ? a.entrySrc[e] : e;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (base + u * nthr < e1) {
+        cx<T> val = S[SwzRow::at<LOG2V>(slot[u] >> LOG2V, slot[u] & (V - 1))];
+        if (a.useScale) val = a.scale * val;
+        a.valuesOut[dst[u]] = val;
+      }
+    }
   }
   SB_PHASE_END_NOSYNC
 }
@@ -191,8 +229,8 @@ SB_DEV void z_forward_fast(const ZArgs<T>& a, int tile, Ctx ctx, cx<T>* S) {
 //   plane    : the plane's [ny][nxf] array (the plane buffer, or a slot of the L2 scratch ring)
 // -------------------------------------------------------------------------------------------
 template <typename T, int N, Mem LDS, Mem STP>
-SB_DEV void y_backward_tile(const YArgs<T>& a, int xt, const cx<T>* stickRow, cx<T>* plane, Ctx ctx,
-                            cx<T>* S) {
+SB_DEV void y_backward_tile(const YArgs<T>& a, int xt, const cx<T>* stickRow, cx<T>* plane,
+                            int nextXt, const cx<T>* nextStickRow, Ctx ctx, cx<T>* S) {
   constexpr int LOG2V = FastLanes<T>::log2V;
   constexpr int V = 1 << LOG2V;
   constexpr int TT = FastPlan<N>::T;
@@ -212,12 +250,29 @@ SB_DEV void y_backward_tile(const YArgs<T>& a, int xt, const cx<T>* stickRow, cx
   }
   SB_REGS(cx<T>, vAll, 8);
   SB_PHASE_BEGIN
+  if (nextXt >= 0) {
+    const int p0 = a.xtStart[nextXt], p1 = a.xtStart[nextXt + 1];
+    prefetch_l2(nextStickRow + p0, (size_t)(p1 - p0) * sizeof(cx<T>), tid, nthr);
+  }
   for (int i = tid; i < N * V; i += nthr) S[i] = mk<T>(0, 0);
   SB_PHASE_END
   SB_PHASE_BEGIN
-  for (int e = e0 + tid; e < e1; e += nthr) {
-    const int slot = a.stickSlot[e];
-    S[SwzRow::at<LOG2V>(slot >> LOG2V, slot & (V - 1))] = ld_g<LDS>(stickRow + e);
+  constexpr int U = 6;
+  for (int base = e0 + tid; base < e1; base += U * nthr) {
+    int slot[U];
+    cx<T> val[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int e = base + u * nthr;
+      if (e < e1) {
+        slot[u] = a.stickSlot[e];
+        val[u] = ld_g<LDS>(stickRow + e);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (base + u * nthr < e1) S[SwzRow::at<LOG2V>(slot[u] >> LOG2V, slot[u] & (V - 1))] = val[u];
+    }
   }
   SB_PHASE_END
   if (a.symmetry && xt == 0) hermitian_fill_lane_swz<T, LOG2V, SwzRow>(S, N, 0, ctx);
@@ -238,8 +293,8 @@ SB_DEV void y_backward_tile(const YArgs<T>& a, int xt, const cx<T>* stickRow, cx
 }
 
 template <typename T, int N, Mem LDP, Mem STS>
-SB_DEV void y_forward_tile(const YArgs<T>& a, int xt, const cx<T>* plane, cx<T>* stickRow, Ctx ctx,
-                           cx<T>* S) {
+SB_DEV void y_forward_tile(const YArgs<T>& a, int xt, const cx<T>* plane, cx<T>* stickRow,
+                           int nextXt, const cx<T>* nextPlane, Ctx ctx, cx<T>* S) {
   constexpr int LOG2V = FastLanes<T>::log2V;
   constexpr int V = 1 << LOG2V;
   constexpr int TT = FastPlan<N>::T;
@@ -253,6 +308,9 @@ SB_DEV void y_forward_tile(const YArgs<T>& a, int xt, const cx<T>* plane, cx<T>*
 #pragma unroll
   for (int m = 0; m < 8; ++m)
     v[m] = lane < lanesValid ? ld_g<LDP>(planeTile + (size_t)(j + TT * m) * a.nxf + lane) : mk<T>(0, 0);
+  if (nextXt >= 0) {
+    for (int r = tid; r < N; r += nthr) prefetch_l2_line(nextPlane + (size_t)nextXt * V + (size_t)r * a.nxf);
+  }
   SB_PHASE_END
   fast_fft_head<T, N, LOG2V, false, SwzRow, false>(vAll, S, a.ftw, ctx);
   SB_PHASE_BEGIN
@@ -265,9 +323,18 @@ SB_DEV void y_forward_tile(const YArgs<T>& a, int xt, const cx<T>* plane, cx<T>*
   for (int m = 0; m < 8; ++m) S[SwzRow::at<LOG2V>(j + TT * m, lane)] = v[m];
   SB_PHASE_END
   SB_PHASE_BEGIN
-  for (int e = e0 + tid; e < e1; e += nthr) {
-    const int slot = a.stickSlot[e];
-    st_g<STS>(stickRow + e, S[SwzRow::at<LOG2V>(slot >> LOG2V, slot & (V - 1))]);
+  constexpr int U = 6;
+  for (int base = e0 + tid; base < e1; base += U * nthr) {
+    int slot[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (base + u * nthr < e1) slot[u] = a.stickSlot[base + u * nthr];
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (base + u * nthr < e1)
+        st_g<STS>(stickRow + base + u * nthr, S[SwzRow::at<LOG2V>(slot[u] >> LOG2V, slot[u] & (V - 1))]);
+    }
   }
   SB_PHASE_END_NOSYNC
 }
@@ -276,16 +343,29 @@ template <typename T, int N>
 SB_DEV void y_backward_fast(const YArgs<T>& a, int block, Ctx ctx, cx<T>* S) {
   const int xt = block % a.numXTiles;
   const int zl = block / a.numXTiles;
-  y_backward_tile<T, N, Mem::Stream, Mem::Plain>(a, xt, a.sticks + (size_t)(zl + a.zRowOffset) * a.pitch,
-                                                a.planes + (size_t)zl * N * a.nxf, ctx, S);
+  int nextXt = -1;
+  const cx<T>* nextRow = nullptr;
+  if (a.pfDist > 0 && block + a.pfDist < a.numXTiles * a.numPlanes) {
+    nextXt = (block + a.pfDist) % a.numXTiles;
+    nextRow = a.sticks + (size_t)((block + a.pfDist) / a.numXTiles + a.zRowOffset) * a.pitch;
+  }
+  y_backward_tile<T, N, Mem::Plain, Mem::Plain>(a, xt, a.sticks + (size_t)(zl + a.zRowOffset) * a.pitch,
+                                                a.planes + (size_t)zl * N * a.nxf, nextXt, nextRow, ctx, S);
 }
 
 template <typename T, int N>
 SB_DEV void y_forward_fast(const YArgs<T>& a, int block, Ctx ctx, cx<T>* S) {
   const int xt = block % a.numXTiles;
   const int zl = block / a.numXTiles;
-  y_forward_tile<T, N, Mem::Stream, Mem::Plain>(a, xt, a.planes + (size_t)zl * N * a.nxf,
-                                               a.sticks + (size_t)(zl + a.zRowOffset) * a.pitch, ctx, S);
+  int nextXt = -1;
+  const cx<T>* nextPlane = nullptr;
+  if (a.pfDist > 0 && block + a.pfDist < a.numXTiles * a.numPlanes) {
+    nextXt = (block + a.pfDist) % a.numXTiles;
+    nextPlane = a.planes + (size_t)((block + a.pfDist) / a.numXTiles) * N * a.nxf;
+  }
+  y_forward_tile<T, N, Mem::Plain, Mem::Plain>(a, xt, a.planes + (size_t)zl * N * a.nxf,
+                                               a.sticks + (size_t)(zl + a.zRowOffset) * a.pitch, nextXt,
+                                               nextPlane, ctx, S);
 }
 
 // -------------------------------------------------------------------------------------------
@@ -294,7 +374,7 @@ SB_DEV void y_forward_fast(const YArgs<T>& a, int block, Ctx ctx, cx<T>* S) {
 // -------------------------------------------------------------------------------------------
 template <typename T, int N, bool BWD, Mem LD, Mem ST>
 SB_DEV void x_c2c_tile(const cx<T>* in, cx<T>* out, int y0, int ny, const cx<T>* __restrict__ ftw,
-                       Ctx ctx, cx<T>* S) {
+                       const cx<T>* nextRows, Ctx ctx, cx<T>* S) {
   constexpr int LOG2V = FastLanes<T>::log2V;
   constexpr int TT = FastPlan<N>::T;
   SB_REGS(cx<T>, vAll, 8);
@@ -309,6 +389,7 @@ SB_DEV void x_c2c_tile(const cx<T>* in, cx<T>* out, int y0, int ny, const cx<T>*
   const cx<T>* src = in + (size_t)(y0 + lane) * N + j;
 #pragma unroll
   for (int m = 0; m < 8; ++m) v[m] = valid ? ld_g<LD>(src + TT * m) : mk<T>(0, 0);
+  if (nextRows) prefetch_l2(nextRows, sizeof(cx<T>) * N * (1 << LOG2V), tid, nthr);
   SB_PHASE_END
   fast_fft_head<T, N, LOG2V, BWD, SwzCol, true>(vAll, S, ftw, ctx);
   SB_PHASE_BEGIN
@@ -331,7 +412,7 @@ SB_DEV void x_c2c_fast(const XArgs<T>& a, int block, Ctx ctx, cx<T>* S) {
   const size_t planeOff = (size_t)zl * a.ny * N;
   const cx<T>* src = (BWD ? a.planes : static_cast<const cx<T>*>(a.spaceIn)) + planeOff;
   cx<T>* dst = (BWD ? static_cast<cx<T>*>(a.spaceOut) : a.planes) + planeOff;
-  x_c2c_tile<T, N, BWD, Mem::Stream, Mem::Plain>(src, dst, rt * V, a.ny, a.ftw, ctx, S);
+  x_c2c_tile<T, N, BWD, Mem::Plain, Mem::Plain>(src, dst, rt * V, a.ny, a.ftw, nullptr, ctx, S);
 }
 
 // -------------------------------------------------------------------------------------------
@@ -388,27 +469,47 @@ SB_HD XYItem xy_decode(const XYArgs<T>& a, int item) {
   return it;
 }
 
-// The tile work of one item (no waiting / signalling: the caller does that).
+// The tile work of one item (no waiting / signalling: the caller does that). `nx` is the item
+// this CTA runs next (or an invalid one): its HBM-resident input is prefetched into L2.
 template <typename T, int N, bool BWD>
-SB_DEV void xy_run_item(const XYArgs<T>& a, const XYItem& it, Ctx ctx, cx<T>* S) {
+SB_DEV void xy_run_item(const XYArgs<T>& a, const XYItem& it, const XYItem& nx, Ctx ctx, cx<T>* S) {
   constexpr int V = 1 << FastLanes<T>::log2V;
   const size_t planeElems = (size_t)N * N;
   cx<T>* slot = a.scratch + (size_t)(it.plane % a.ring) * planeElems;
   cx<T>* stickRow = a.y.sticks + (size_t)(it.plane + a.y.zRowOffset) * a.y.pitch;
+  const bool pfA = nx.valid && nx.roleA;  // only A tiles read from HBM
   if (BWD) {
-    if (it.roleA)
-      y_backward_tile<T, N, Mem::Stream, Mem::L2Only>(a.y, it.tile, stickRow, slot, ctx, S);
-    else
-      x_c2c_tile<T, N, true, Mem::L2Only, Mem::Stream>(
+    const cx<T>* nextRow = a.y.sticks + (size_t)(nx.plane + a.y.zRowOffset) * a.y.pitch;
+    if (it.roleA) {
+      y_backward_tile<T, N, Mem::Plain, Mem::L2Only>(a.y, it.tile, stickRow, slot, pfA ? nx.tile : -1,
+                                                     nextRow, ctx, S);
+    } else {
+      if (pfA) {
+        SB_PHASE_BEGIN
+        const int p0 = a.y.xtStart[nx.tile], p1 = a.y.xtStart[nx.tile + 1];
+        prefetch_l2(nextRow + p0, (size_t)(p1 - p0) * sizeof(cx<T>), tid, nthr);
+        SB_PHASE_END_NOSYNC
+      }
+      x_c2c_tile<T, N, true, Mem::L2Only, Mem::Plain>(
           slot, static_cast<cx<T>*>(a.x.spaceOut) + (size_t)it.plane * planeElems, it.tile * V, N,
-          a.x.ftw, ctx, S);
+          a.x.ftw, nullptr, ctx, S);
+    }
   } else {
-    if (it.roleA)
-      x_c2c_tile<T, N, false, Mem::Stream, Mem::L2Only>(
+    const cx<T>* nextRows =
+        pfA ? static_cast<const cx<T>*>(a.x.spaceIn) + (size_t)nx.plane * planeElems + (size_t)nx.tile * V * N
+            : nullptr;
+    if (it.roleA) {
+      x_c2c_tile<T, N, false, Mem::Plain, Mem::L2Only>(
           static_cast<const cx<T>*>(a.x.spaceIn) + (size_t)it.plane * planeElems, slot, it.tile * V,
-          N, a.x.ftw, ctx, S);
-    else
-      y_forward_tile<T, N, Mem::L2Only, Mem::Plain>(a.y, it.tile, slot, stickRow, ctx, S);
+          N, a.x.ftw, nextRows, ctx, S);
+    } else {
+      if (nextRows) {
+        SB_PHASE_BEGIN
+        prefetch_l2(nextRows, sizeof(cx<T>) * N * V, tid, nthr);
+        SB_PHASE_END_NOSYNC
+      }
+      y_forward_tile<T, N, Mem::L2Only, Mem::Plain>(a.y, it.tile, slot, stickRow, -1, nullptr, ctx, S);
+    }
   }
 }
 

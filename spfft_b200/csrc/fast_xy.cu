@@ -19,11 +19,15 @@ __device__ __forceinline__ void cta_wait(const int* p, int target) {
   __syncthreads();
 }
 
-// every thread's global writes of this tile become visible before the counter moves
+// All global writes of this tile (every thread's) become visible before the counter moves:
+// barrier (CTA-scope ordering), then one cumulative gpu-scope fence + atomic by thread 0 -- the
+// pattern of a cooperative-groups grid barrier.
 __device__ __forceinline__ void cta_signal(int* p) {
-  __threadfence();
   __syncthreads();
-  if (threadIdx.x == 0) atomicAdd(p, 1);
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(p, 1);
+  }
 }
 
 template <typename T, int N, bool FWD>
@@ -31,30 +35,42 @@ __global__ void __launch_bounds__(FastCfg<T, N>::threads, FastCfg<T, N>::minBloc
     k_xy_fused(const __grid_constant__ XYArgs<T> a) {
   extern __shared__ __align__(16) unsigned char smemRaw[];
   cx<T>* S = reinterpret_cast<cx<T>*>(smemRaw);
-  __shared__ int sItem;
+  __shared__ int sQ[2];
   constexpr bool BWD = !FWD;
   const int P = a.y.numPlanes;
   const int nA = xy_tiles_a<T, BWD>(a), nB = xy_tiles_b<T, BWD>(a);
   const long long total = xy_total_items<T, BWD>(a);
   int* aDone = a.counters + 1;
   int* bDone = a.counters + 1 + P;
-  for (;;) {
-    if (threadIdx.x == 0) sItem = atomicAdd(&a.counters[0], 1);
-    __syncthreads();
-    const int item = sItem;
-    __syncthreads();
-    if (item >= total) break;
-    const XYItem it = xy_decode<T, BWD>(a, item);
-    if (!it.valid) continue;
-    if (it.roleA) {
-      if (it.plane >= a.ring) cta_wait(&bDone[it.plane - a.ring], nB);
-      xy_run_item<T, N, BWD>(a, it, Ctx{FastCfg<T, N>::threads}, S);
-      cta_signal(&aDone[it.plane]);
-    } else {
-      cta_wait(&aDone[it.plane], nA);
-      xy_run_item<T, N, BWD>(a, it, Ctx{FastCfg<T, N>::threads}, S);
-      cta_signal(&bDone[it.plane]);
+  // work items are claimed two ahead: the next item is known while the current one runs, so its
+  // input can be prefetched into L2, and the claim's round trip is off the critical path
+  if (threadIdx.x == 0) {
+    sQ[0] = atomicAdd(&a.counters[0], 1);
+    sQ[1] = atomicAdd(&a.counters[0], 1);
+  }
+  __syncthreads();
+  int cur = sQ[0], nxt = sQ[1];
+  __syncthreads();
+  for (int k = 0; cur < total; ++k) {
+    if (threadIdx.x == 0) sQ[k & 1] = atomicAdd(&a.counters[0], 1);
+    const XYItem it = xy_decode<T, BWD>(a, cur);
+    XYItem nx;
+    nx.valid = false;
+    if (nxt < total) nx = xy_decode<T, BWD>(a, nxt);
+    if (it.valid) {
+      if (it.roleA) {
+        if (it.plane >= a.ring) cta_wait(&bDone[it.plane - a.ring], nB);
+        xy_run_item<T, N, BWD>(a, it, nx, Ctx{FastCfg<T, N>::threads}, S);
+        cta_signal(&aDone[it.plane]);
+      } else {
+        cta_wait(&aDone[it.plane], nA);
+        xy_run_item<T, N, BWD>(a, it, nx, Ctx{FastCfg<T, N>::threads}, S);
+        cta_signal(&bDone[it.plane]);
+      }
     }
+    __syncthreads();
+    cur = nxt;
+    nxt = sQ[k & 1];
   }
 }
 

@@ -15,8 +15,10 @@ __global__ void __launch_bounds__(FastCfg<T, N>::threads, FastCfg<T, N>::minBloc
 }
 
 template <typename T, int N>
-static int launch_y_n(int forward, const YArgs<T>& a, cudaStream_t s) {
+static int launch_y_n(int forward, const YArgs<T>& a0, cudaStream_t s) {
   using C = FastCfg<T, N>;
+  YArgs<T> a = a0;
+  a.pfDist = (tune_flags() & 1) ? resident_ctas(C::minBlocks) : 0;
   if constexpr (C::threads > 1024) {
     return (int)cudaErrorInvalidValue;
   } else {

@@ -44,6 +44,7 @@ struct ZArgs {
   int symTile, symLane;   // R2C: tile / lane of the (x=0,y=0) stick, -1 if not local
   int useScale;
   T scale;
+  int pfDist;             // L2 prefetch distance in tiles (resident CTAs), 0 = off; set by the launcher
 };
 
 template <typename T>
@@ -63,6 +64,7 @@ struct YArgs {
   const int* stickSlot;  // [numSticks]: y*V + (x mod V)
   cx<T>* sticks;
   cx<T>* planes;         // [numPlanes][ny][nxf]
+  int pfDist;            // L2 prefetch distance in blocks, 0 = off; set by the launcher
 };
 
 template <typename T>
@@ -78,6 +80,7 @@ struct XArgs {
   cx<T>* planes;      // [numPlanes][ny][nxf]
   const void* spaceIn;  // forward input
   void* spaceOut;       // backward output
+  int pfDist;           // L2 prefetch distance in blocks, 0 = off; set by the launcher
 };
 
 // Hermitian completion of one lane of a tile, low index first (reference semantics:

@@ -2,6 +2,7 @@
 #include "transform_engine.hpp"
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 #include "launch.h"
@@ -162,7 +163,10 @@ std::shared_ptr<DevicePlan<T>> build_device_plan(const IndexMaps& m, long long s
   ax.rpX = make_radix_plan(m.dimX);
   ax.rpY = make_radix_plan(m.dimY);
   ax.rpZ = make_radix_plan(m.dimZ);
-  if (fastX && fastY && m.dimX == m.dimY && m.type == SPFFT_TRANS_C2C) {
+  // SPFFT_B200_TUNE bit 1 (debug knob): keep the y and x stages as separate kernels
+  const char* tuneEnv = std::getenv("SPFFT_B200_TUNE");
+  const bool allowFused = !(tuneEnv && (std::atoi(tuneEnv) & 2));
+  if (allowFused && fastX && fastY && m.dimX == m.dimY && m.type == SPFFT_TRANS_C2C) {
     // y and x stages as one persistent kernel with the hand-off in L2 (fast_xy.cu)
     const int err = sb_xy_fused_config(sizeof(T) == 4, m.dimX, m.local_planes(), &plan->xyRing,
                                        &plan->xyLag, &plan->xyCounters);

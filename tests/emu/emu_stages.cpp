@@ -82,7 +82,10 @@ void run_xy(bool fwd, const sb::XYArgs<T>& a, sb::cx<T>* smem) {
     } else if (aDone[it.plane] != nA) {
       throw spfft::InternalError();
     }
-#define CALL(NN) if (fwd) sb::xy_run_item<T, NN, false>(a, it, c, smem); else sb::xy_run_item<T, NN, true>(a, it, c, smem)
+    sb::XYItem nx;
+    nx.valid = false;
+    if (item + 1 < total) nx = fwd ? sb::xy_decode<T, false>(a, (int)item + 1) : sb::xy_decode<T, true>(a, (int)item + 1);
+#define CALL(NN) if (fwd) sb::xy_run_item<T, NN, false>(a, it, nx, c, smem); else sb::xy_run_item<T, NN, true>(a, it, nx, c, smem)
     EMU_DISPATCH(a.x.nx, CALL)
 #undef CALL
     ++(it.roleA ? aDone : bDone)[it.plane];
