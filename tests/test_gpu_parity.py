@@ -428,3 +428,25 @@ def test_power_of_two_fast_path(torch_cuda, lib, gen, shape, single, ttype):
     ref = orc.backward(param, v)
     assert orc.rel_l2(space, ref) <= TOL[single]
     assert orc.rel_l2(back, orc.forward(param, ref, orc.SPFFT_FULL_SCALING)) <= TOL[single]
+
+
+import glob as _glob
+
+_GOLDEN = sorted(_glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+
+
+@pytest.mark.parametrize("path", _GOLDEN, ids=lambda p: os.path.basename(p)[:-4])
+def test_golden_fixtures(torch_cuda, lib, path):
+    """Committed outputs of the reference's own host pipeline (tests/golden/make_golden.py):
+    index maps bit exact, values within the north-star tolerance."""
+    g = np.load(path)
+    ttype = int(g["type"])
+    nx, ny, nz = (int(v) for v in g["dims"])
+    single = g["values"].dtype == np.complex64
+    t = capi.Transform(lib, transform_type=ttype, dim_x=nx, dim_y=ny, dim_z=nz, indices=g["triplets"], single=single)
+    vi, si = capi.transform_index_maps(t)
+    assert np.array_equal(vi, g["value_indices"]) and np.array_equal(si, g["stick_indices"])
+    t.destroy()
+    space, back = _run_pair(torch_cuda, lib, ttype, nx, ny, nz, g["triplets"], g["values"], single=single)
+    assert orc.rel_l2(space, g["space"]) <= TOL[single]
+    assert orc.rel_l2(back, g["forward"]) <= TOL[single]
