@@ -141,7 +141,9 @@ SB_DEV void prefetch_l2_line(const void* p) {
 }
 
 // Twiddles + butterflies of stage S on the 8 registers of thread j.
-template <typename T, int N, bool BWD, int S>
+// TWS: the twiddle table lives in shared memory (persistent kernels whose L1 is invalidated by
+// their acquire / release operations) instead of global memory read through L1.
+template <typename T, int N, bool BWD, int S, bool TWS = false>
 SB_DEV void fast_stage(cx<T>* v, int j, const cx<T>* __restrict__ tw) {
   using P = FastPlan<N>;
   constexpr int R = P::radix(S);
@@ -152,7 +154,7 @@ SB_DEV void fast_stage(cx<T>* v, int j, const cx<T>* __restrict__ tw) {
     const cx<T>* t = tw + P::tw_offset(S) + k;
 #pragma unroll
     for (int r = 1; r < 8; ++r) {
-      const cx<T> w = ld_ro(t + (r - 1) * NS);
+      const cx<T> w = TWS ? t[(r - 1) * NS] : ld_ro(t + (r - 1) * NS);
       v[r] = v[r] * (BWD ? conj(w) : w);
     }
   }

@@ -21,19 +21,34 @@ struct FastLanes {
   static constexpr int log2V = sizeof(T) == 8 ? 3 : 4;
 };
 
+
+// gather-form tiles (defined below)
+template <typename T, int N, Mem STP, bool TWS = false>
+SB_DEV void y_backward_gather(const YArgs<T>& a, int xt, const cx<T>* stickRow, cx<T>* plane,
+                              int nextXt, const cx<T>* nextStickRow, Ctx ctx, cx<T>* S,
+                              const cx<T>* tw = nullptr);
+template <typename T, int N, Mem LDP, bool TWS = false>
+SB_DEV void y_forward_gather(const YArgs<T>& a, int xt, const cx<T>* plane, cx<T>* stickRow,
+                             int nextXt, const cx<T>* nextPlane, Ctx ctx, cx<T>* S,
+                             const cx<T>* tw = nullptr);
+
 // Stages 0 .. last-1 with their exchanges; on return the tile holds the input of the last stage.
-// `vAll`: the caller's SB_REGS array. COL selects the thread mapping.
-template <typename T, int N, int LOG2V, bool BWD, typename Swz, bool COL>
+// `vAll`: the caller's SB_REGS array. COL0 / COL select the thread mapping (column: consecutive
+// threads along n; row: lanes fastest) of stage 0 with its exchange write / of all later phases:
+// a change of mapping across an exchange is free, which is how the sparse-side kernels turn
+// "contiguous along n" (sparse values) into "contiguous along lanes" (plane-major rows).
+template <typename T, int N, int LOG2V, bool BWD, typename Swz, bool COL0, bool COL = COL0, bool TWS = false>
 SB_DEV void fast_fft_head(cx<T>* vAll, cx<T>* S, const cx<T>* __restrict__ tw, Ctx ctx) {
   (void)ctx;
   using P = FastPlan<N>;
   constexpr int V = 1 << LOG2V;
   constexpr int TT = P::T;
-#define SB_FAST_IDS                                   \
+#define SB_FAST_IDS_(C)                               \
   cx<T>* v = SB_RP(vAll, 8);                          \
-  const int lane = COL ? tid / TT : (tid & (V - 1));  \
-  const int j = COL ? (tid & (TT - 1)) : (tid >> LOG2V); \
+  const int lane = C ? tid / TT : (tid & (V - 1));    \
+  const int j = C ? (tid & (TT - 1)) : (tid >> LOG2V); \
   (void)nthr;
+#define SB_FAST_IDS SB_FAST_IDS_(COL)
 #define SB_FAST_WRITE(STAGE)                                                          \
   {                                                                                   \
     constexpr int R = P::radix(STAGE);                                                \
@@ -48,8 +63,8 @@ SB_DEV void fast_fft_head(cx<T>* vAll, cx<T>* S, const cx<T>* __restrict__ tw, C
 
   if constexpr (P::numStages > 1) {
     SB_PHASE_BEGIN
-    SB_FAST_IDS
-    fast_stage<T, N, BWD, 0>(v, j, tw);
+    SB_FAST_IDS_(COL0)
+    fast_stage<T, N, BWD, 0, TWS>(v, j, tw);
     SB_FAST_WRITE(0)
     SB_PHASE_END
   }
@@ -57,7 +72,7 @@ SB_DEV void fast_fft_head(cx<T>* vAll, cx<T>* S, const cx<T>* __restrict__ tw, C
     SB_PHASE_BEGIN
     SB_FAST_IDS
     SB_FAST_READ
-    fast_stage<T, N, BWD, 1>(v, j, tw);
+    fast_stage<T, N, BWD, 1, TWS>(v, j, tw);
     SB_PHASE_END
     SB_PHASE_BEGIN
     SB_FAST_IDS
@@ -68,7 +83,7 @@ SB_DEV void fast_fft_head(cx<T>* vAll, cx<T>* S, const cx<T>* __restrict__ tw, C
     SB_PHASE_BEGIN
     SB_FAST_IDS
     SB_FAST_READ
-    fast_stage<T, N, BWD, 2>(v, j, tw);
+    fast_stage<T, N, BWD, 2, TWS>(v, j, tw);
     SB_PHASE_END
     SB_PHASE_BEGIN
     SB_FAST_IDS
@@ -79,14 +94,14 @@ SB_DEV void fast_fft_head(cx<T>* vAll, cx<T>* S, const cx<T>* __restrict__ tw, C
 }
 
 // Last stage, to be called inside the caller's final phase: afterwards v[m] = X[j + T*m].
-template <typename T, int N, int LOG2V, bool BWD, typename Swz>
+template <typename T, int N, int LOG2V, bool BWD, typename Swz, bool TWS = false>
 SB_DEV void fast_fft_tail(cx<T>* v, const cx<T>* S, const cx<T>* __restrict__ tw, int j, int lane) {
   using P = FastPlan<N>;
   constexpr int TT = P::T;
   if constexpr (P::numStages > 1) {
     SB_FAST_READ
   }
-  fast_stage<T, N, BWD, P::numStages - 1>(v, j, tw);
+  fast_stage<T, N, BWD, P::numStages - 1, TWS>(v, j, tw);
 }
 
 // Hermitian completion of one lane of a swizzled tile, low index first (same semantics as
@@ -349,8 +364,12 @@ SB_DEV void y_backward_fast(const YArgs<T>& a, int block, Ctx ctx, cx<T>* S) {
     nextXt = (block + a.pfDist) % a.numXTiles;
     nextRow = a.sticks + (size_t)((block + a.pfDist) / a.numXTiles + a.zRowOffset) * a.pitch;
   }
-  y_backward_tile<T, N, Mem::Plain, Mem::Plain>(a, xt, a.sticks + (size_t)(zl + a.zRowOffset) * a.pitch,
-                                                a.planes + (size_t)zl * N * a.nxf, nextXt, nextRow, ctx, S);
+  if (a.inv)
+    y_backward_gather<T, N, Mem::Plain>(a, xt, a.sticks + (size_t)(zl + a.zRowOffset) * a.pitch,
+                                        a.planes + (size_t)zl * N * a.nxf, nextXt, nextRow, ctx, S);
+  else
+    y_backward_tile<T, N, Mem::Plain, Mem::Plain>(a, xt, a.sticks + (size_t)(zl + a.zRowOffset) * a.pitch,
+                                                  a.planes + (size_t)zl * N * a.nxf, nextXt, nextRow, ctx, S);
 }
 
 template <typename T, int N>
@@ -363,16 +382,234 @@ SB_DEV void y_forward_fast(const YArgs<T>& a, int block, Ctx ctx, cx<T>* S) {
     nextXt = (block + a.pfDist) % a.numXTiles;
     nextPlane = a.planes + (size_t)((block + a.pfDist) / a.numXTiles) * N * a.nxf;
   }
-  y_forward_tile<T, N, Mem::Plain, Mem::Plain>(a, xt, a.planes + (size_t)zl * N * a.nxf,
-                                               a.sticks + (size_t)(zl + a.zRowOffset) * a.pitch, nextXt,
-                                               nextPlane, ctx, S);
+  if (a.inv)
+    y_forward_gather<T, N, Mem::Plain>(a, xt, a.planes + (size_t)zl * N * a.nxf,
+                                       a.sticks + (size_t)(zl + a.zRowOffset) * a.pitch, nextXt, nextPlane,
+                                       ctx, S);
+  else
+    y_forward_tile<T, N, Mem::Plain, Mem::Plain>(a, xt, a.planes + (size_t)zl * N * a.nxf,
+                                                 a.sticks + (size_t)(zl + a.zRowOffset) * a.pitch, nextXt,
+                                                 nextPlane, ctx, S);
 }
+
+
+// -------------------------------------------------------------------------------------------
+// Sparse side through an inverse map ("gather" form). Instead of zero-filling a shared tile,
+// scattering the sparse entries into it and reading it back, every thread looks up where (if
+// anywhere) each of its 8 elements lives in the sparse array and loads it straight into registers.
+// The thread mapping of this first (backward) or last (forward) stage is "column" (consecutive
+// threads walk along n, i.e. along consecutive sparse entries of one stick / one x column ->
+// coalesced), all other stages and the dense side use the "row" mapping; the change of mapping
+// rides on an exchange that is needed anyway. Shared-memory traffic per tile: the two exchanges
+// only (as in the x stage) -- no zero fill, no scatter, no read-back.
+//
+// inv[((tile * threads) + tid) * 8 + m], tid = lane * T + j: offset of element n = j + T*m of the
+// tile's lane-th sequence, relative to the tile's first sparse entry; 0xFFFF = not present (zero).
+// -------------------------------------------------------------------------------------------
+constexpr unsigned short kNoEntry = 0xFFFF;
+
+struct Inv8 {
+  unsigned short i[8];
+};
+
+SB_DEV Inv8 load_inv8(const unsigned short* p) {
+  Inv8 r;
+#if SB_ON_GPU
+  const uint4 q = __ldg(reinterpret_cast<const uint4*>(p));
+  r.i[0] = q.x & 0xFFFF; r.i[1] = q.x >> 16;
+  r.i[2] = q.y & 0xFFFF; r.i[3] = q.y >> 16;
+  r.i[4] = q.z & 0xFFFF; r.i[5] = q.z >> 16;
+  r.i[6] = q.w & 0xFFFF; r.i[7] = q.w >> 16;
+#else
+  for (int m = 0; m < 8; ++m) r.i[m] = p[m];
+#endif
+  return r;
+}
+
+// Hermitian completion in gather form (same result as the in-place low-index-first fill of the
+// reference, src/symmetry/symmetry_host.hpp:47-58,73-90): element n of a sequence of length N,
+// p = given value at n, q = given value at N-n (zero if absent).
+template <typename T>
+SB_DEV cx<T> hermitian_combine(int n, int N, cx<T> p, cx<T> q) {
+  if (n == 0) return p;
+  if (2 * n == N) return conj(p);
+  if (2 * n < N) return nonzero(p) ? p : conj(q);
+  return nonzero(q) ? conj(q) : p;
+}
+
+// Loads the 8 elements of thread (lane, j) (column mapping) from `sparse` through the inverse map
+// of this tile (`invTile` = first entry of the tile's map). hermitianLane: complete that lane.
+template <typename T, int N>
+SB_DEV void gather_load(cx<T>* v, const cx<T>* sparse, const unsigned short* invTile, int tid, int j,
+                        int lane, int hermitianLane) {
+  constexpr int TT = FastPlan<N>::T;
+  const Inv8 iv = load_inv8(invTile + (size_t)tid * 8);
+#pragma unroll
+  for (int m = 0; m < 8; ++m) v[m] = iv.i[m] != kNoEntry ? sparse[iv.i[m]] : mk<T>(0, 0);
+  if (lane == hermitianLane) {
+#pragma unroll
+    for (int m = 0; m < 8; ++m) {
+      const int n = j + TT * m;
+      const int n2 = (N - n) & (N - 1);
+      const unsigned short i2 = invTile[((size_t)lane * TT + (n2 & (TT - 1))) * 8 + n2 / TT];
+      const cx<T> q = i2 != kNoEntry ? sparse[i2] : mk<T>(0, 0);
+      v[m] = hermitian_combine<T>(n, N, v[m], q);
+    }
+  }
+}
+
+#define SB_COLMAP_IDS                 \
+  cx<T>* v = SB_RP(vAll, 8);          \
+  const int lane = tid / TT;          \
+  const int j = tid & (TT - 1);       \
+  (void)nthr;
+
+template <typename T, int N>
+SB_DEV void z_backward_gather(const ZArgs<T>& a, int tile, Ctx ctx, cx<T>* S) {
+  constexpr int LOG2V = FastLanes<T>::log2V;
+  constexpr int V = 1 << LOG2V;
+  constexpr int TT = FastPlan<N>::T;
+  constexpr int THREADS = V * TT;
+  SB_REGS(cx<T>, vAll, 8);
+  const int e0 = a.tileStart[tile];
+  SB_PHASE_BEGIN
+  SB_COLMAP_IDS
+  gather_load<T, N>(v, a.valuesIn + e0, a.inv + (size_t)tile * THREADS * 8, tid, j, lane,
+                    tile == a.symTile ? a.symLane : -1);
+  if (a.pfDist > 0 && tile + a.pfDist < a.numTiles) {
+    const int p0 = a.tileStart[tile + a.pfDist], p1 = a.tileStart[tile + a.pfDist + 1];
+    prefetch_l2(a.valuesIn + p0, (size_t)(p1 - p0) * sizeof(cx<T>), tid, nthr);
+    prefetch_l2(a.inv + (size_t)(tile + a.pfDist) * THREADS * 8, (size_t)THREADS * 16, tid, nthr);
+  }
+  SB_PHASE_END_NOSYNC
+  fast_fft_head<T, N, LOG2V, true, SwzCol, true, false>(vAll, S, a.ftw, ctx);
+  SB_PHASE_BEGIN
+  SB_ROW_IDS
+  fast_fft_tail<T, N, LOG2V, true, SwzCol>(v, S, a.ftw, j, lane);
+  cx<T>* out = a.sticks + (size_t)tile * V + lane;
+#pragma unroll
+  for (int m = 0; m < 8; ++m) out[(size_t)(j + TT * m) * a.pitch] = v[m];
+  SB_PHASE_END_NOSYNC
+}
+
+template <typename T, int N>
+SB_DEV void z_forward_gather(const ZArgs<T>& a, int tile, Ctx ctx, cx<T>* S) {
+  constexpr int LOG2V = FastLanes<T>::log2V;
+  constexpr int V = 1 << LOG2V;
+  constexpr int TT = FastPlan<N>::T;
+  constexpr int THREADS = V * TT;
+  SB_REGS(cx<T>, vAll, 8);
+  const int e0 = a.tileStart[tile];
+  SB_PHASE_BEGIN
+  SB_ROW_IDS
+  const cx<T>* in = a.sticks + (size_t)tile * V + lane;
+#pragma unroll
+  for (int m = 0; m < 8; ++m) v[m] = in[(size_t)(j + TT * m) * a.pitch];
+  if (a.pfDist > 0 && tile + a.pfDist < a.numTiles) {
+    for (int r = tid; r < N; r += nthr)
+      prefetch_l2_line(a.sticks + (size_t)(tile + a.pfDist) * V + (size_t)r * a.pitch);
+    prefetch_l2(a.inv + (size_t)(tile + a.pfDist) * THREADS * 8, (size_t)THREADS * 16, tid, nthr);
+  }
+  SB_PHASE_END_NOSYNC
+  fast_fft_head<T, N, LOG2V, false, SwzCol, false, false>(vAll, S, a.ftw, ctx);
+  SB_PHASE_BEGIN
+  SB_COLMAP_IDS
+  fast_fft_tail<T, N, LOG2V, false, SwzCol>(v, S, a.ftw, j, lane);
+  const Inv8 iv = load_inv8(a.inv + ((size_t)tile * THREADS + tid) * 8);
+  cx<T>* out = a.valuesOut + e0;
+#pragma unroll
+  for (int m = 0; m < 8; ++m) {
+    if (iv.i[m] != kNoEntry) out[iv.i[m]] = a.useScale ? a.scale * v[m] : v[m];
+  }
+  SB_PHASE_END_NOSYNC
+}
+
+template <typename T, int N, Mem STP, bool TWS>
+SB_DEV void y_backward_gather(const YArgs<T>& a, int xt, const cx<T>* stickRow, cx<T>* plane,
+                              int nextXt, const cx<T>* nextStickRow, Ctx ctx, cx<T>* S,
+                              const cx<T>* tw) {
+  if (!TWS) tw = a.ftw;
+  constexpr int LOG2V = FastLanes<T>::log2V;
+  constexpr int V = 1 << LOG2V;
+  constexpr int TT = FastPlan<N>::T;
+  constexpr int THREADS = V * TT;
+  const int e0 = a.xtStart[xt], e1 = a.xtStart[xt + 1];
+  cx<T>* planeTile = plane + (size_t)xt * V;
+  const int lanesValid = (a.nxf - xt * V) < V ? (a.nxf - xt * V) : V;
+  SB_REGS(cx<T>, vAll, 8);
+  if (e0 == e1) {
+    // empty x tile: the x stage still reads these columns -> store zeros, no transform
+    SB_PHASE_BEGIN
+    for (int i = tid; i < N * V; i += nthr) {
+      const int y = i >> LOG2V;
+      const int lane = i & (V - 1);
+      if (lane < lanesValid) st_g<STP>(planeTile + (size_t)y * a.nxf + lane, mk<T>(0, 0));
+    }
+    SB_PHASE_END_NOSYNC
+    return;
+  }
+  SB_PHASE_BEGIN
+  SB_COLMAP_IDS
+  gather_load<T, N>(v, stickRow + e0, a.inv + (size_t)xt * THREADS * 8, tid, j, lane,
+                    (a.symmetry && xt == 0) ? 0 : -1);
+  if (nextXt >= 0) {
+    const int p0 = a.xtStart[nextXt], p1 = a.xtStart[nextXt + 1];
+    prefetch_l2(nextStickRow + p0, (size_t)(p1 - p0) * sizeof(cx<T>), tid, nthr);
+  }
+  SB_PHASE_END_NOSYNC
+  fast_fft_head<T, N, LOG2V, true, SwzCol, true, false, TWS>(vAll, S, tw, ctx);
+  SB_PHASE_BEGIN
+  SB_ROW_IDS
+  fast_fft_tail<T, N, LOG2V, true, SwzCol, TWS>(v, S, tw, j, lane);
+  if (lane < lanesValid) {
+#pragma unroll
+    for (int m = 0; m < 8; ++m) st_g<STP>(planeTile + (size_t)(j + TT * m) * a.nxf + lane, v[m]);
+  }
+  SB_PHASE_END_NOSYNC
+}
+
+template <typename T, int N, Mem LDP, bool TWS>
+SB_DEV void y_forward_gather(const YArgs<T>& a, int xt, const cx<T>* plane, cx<T>* stickRow,
+                             int nextXt, const cx<T>* nextPlane, Ctx ctx, cx<T>* S,
+                             const cx<T>* tw) {
+  if (!TWS) tw = a.ftw;
+  constexpr int LOG2V = FastLanes<T>::log2V;
+  constexpr int V = 1 << LOG2V;
+  constexpr int TT = FastPlan<N>::T;
+  constexpr int THREADS = V * TT;
+  const int e0 = a.xtStart[xt], e1 = a.xtStart[xt + 1];
+  if (e0 == e1) return;  // no stick needs these columns
+  const cx<T>* planeTile = plane + (size_t)xt * V;
+  const int lanesValid = (a.nxf - xt * V) < V ? (a.nxf - xt * V) : V;
+  SB_REGS(cx<T>, vAll, 8);
+  SB_PHASE_BEGIN
+  SB_ROW_IDS
+#pragma unroll
+  for (int m = 0; m < 8; ++m)
+    v[m] = lane < lanesValid ? ld_g<LDP>(planeTile + (size_t)(j + TT * m) * a.nxf + lane) : mk<T>(0, 0);
+  if (nextXt >= 0) {
+    for (int r = tid; r < N; r += nthr) prefetch_l2_line(nextPlane + (size_t)nextXt * V + (size_t)r * a.nxf);
+  }
+  SB_PHASE_END_NOSYNC
+  fast_fft_head<T, N, LOG2V, false, SwzCol, false, false, TWS>(vAll, S, tw, ctx);
+  SB_PHASE_BEGIN
+  SB_COLMAP_IDS
+  fast_fft_tail<T, N, LOG2V, false, SwzCol, TWS>(v, S, tw, j, lane);
+  const Inv8 iv = load_inv8(a.inv + ((size_t)xt * THREADS + tid) * 8);
+  cx<T>* out = stickRow + e0;
+#pragma unroll
+  for (int m = 0; m < 8; ++m) {
+    if (iv.i[m] != kNoEntry) out[iv.i[m]] = v[m];
+  }
+  SB_PHASE_END_NOSYNC
+}
+#undef SB_COLMAP_IDS
 
 // -------------------------------------------------------------------------------------------
 // x stage, complex rows (C2C). Tile = V consecutive rows y0 .. y0+V-1 of one plane;
 // thread = (row lane, j). in / out: the plane's [ny][N] arrays (may be the same memory).
 // -------------------------------------------------------------------------------------------
-template <typename T, int N, bool BWD, Mem LD, Mem ST>
+template <typename T, int N, bool BWD, Mem LD, Mem ST, bool TWS = false>
 SB_DEV void x_c2c_tile(const cx<T>* in, cx<T>* out, int y0, int ny, const cx<T>* __restrict__ ftw,
                        const cx<T>* nextRows, Ctx ctx, cx<T>* S) {
   constexpr int LOG2V = FastLanes<T>::log2V;
@@ -391,10 +628,10 @@ SB_DEV void x_c2c_tile(const cx<T>* in, cx<T>* out, int y0, int ny, const cx<T>*
   for (int m = 0; m < 8; ++m) v[m] = valid ? ld_g<LD>(src + TT * m) : mk<T>(0, 0);
   if (nextRows) prefetch_l2(nextRows, sizeof(cx<T>) * N * (1 << LOG2V), tid, nthr);
   SB_PHASE_END
-  fast_fft_head<T, N, LOG2V, BWD, SwzCol, true>(vAll, S, ftw, ctx);
+  fast_fft_head<T, N, LOG2V, BWD, SwzCol, true, true, TWS>(vAll, S, ftw, ctx);
   SB_PHASE_BEGIN
   SB_COL_IDS
-  fast_fft_tail<T, N, LOG2V, BWD, SwzCol>(v, S, ftw, j, lane);
+  fast_fft_tail<T, N, LOG2V, BWD, SwzCol, TWS>(v, S, ftw, j, lane);
   if (valid) {
     cx<T>* dst = out + (size_t)(y0 + lane) * N + j;
 #pragma unroll
@@ -471,8 +708,10 @@ SB_HD XYItem xy_decode(const XYArgs<T>& a, int item) {
 
 // The tile work of one item (no waiting / signalling: the caller does that). `nx` is the item
 // this CTA runs next (or an invalid one): its HBM-resident input is prefetched into L2.
+// `tws`: the stage twiddle table (same for x and y: both have length N) in shared memory.
 template <typename T, int N, bool BWD>
-SB_DEV void xy_run_item(const XYArgs<T>& a, const XYItem& it, const XYItem& nx, Ctx ctx, cx<T>* S) {
+SB_DEV void xy_run_item(const XYArgs<T>& a, const XYItem& it, const XYItem& nx, const cx<T>* tws,
+                        Ctx ctx, cx<T>* S) {
   constexpr int V = 1 << FastLanes<T>::log2V;
   const size_t planeElems = (size_t)N * N;
   cx<T>* slot = a.scratch + (size_t)(it.plane % a.ring) * planeElems;
@@ -481,8 +720,8 @@ SB_DEV void xy_run_item(const XYArgs<T>& a, const XYItem& it, const XYItem& nx, 
   if (BWD) {
     const cx<T>* nextRow = a.y.sticks + (size_t)(nx.plane + a.y.zRowOffset) * a.y.pitch;
     if (it.roleA) {
-      y_backward_tile<T, N, Mem::Plain, Mem::L2Only>(a.y, it.tile, stickRow, slot, pfA ? nx.tile : -1,
-                                                     nextRow, ctx, S);
+      y_backward_gather<T, N, Mem::L2Only, true>(a.y, it.tile, stickRow, slot, pfA ? nx.tile : -1,
+                                                 nextRow, ctx, S, tws);
     } else {
       if (pfA) {
         SB_PHASE_BEGIN
@@ -490,31 +729,32 @@ SB_DEV void xy_run_item(const XYArgs<T>& a, const XYItem& it, const XYItem& nx, 
         prefetch_l2(nextRow + p0, (size_t)(p1 - p0) * sizeof(cx<T>), tid, nthr);
         SB_PHASE_END_NOSYNC
       }
-      x_c2c_tile<T, N, true, Mem::L2Only, Mem::Plain>(
+      x_c2c_tile<T, N, true, Mem::L2Only, Mem::Plain, true>(
           slot, static_cast<cx<T>*>(a.x.spaceOut) + (size_t)it.plane * planeElems, it.tile * V, N,
-          a.x.ftw, nullptr, ctx, S);
+          tws, nullptr, ctx, S);
     }
   } else {
     const cx<T>* nextRows =
         pfA ? static_cast<const cx<T>*>(a.x.spaceIn) + (size_t)nx.plane * planeElems + (size_t)nx.tile * V * N
             : nullptr;
     if (it.roleA) {
-      x_c2c_tile<T, N, false, Mem::Plain, Mem::L2Only>(
+      x_c2c_tile<T, N, false, Mem::Plain, Mem::L2Only, true>(
           static_cast<const cx<T>*>(a.x.spaceIn) + (size_t)it.plane * planeElems, slot, it.tile * V,
-          N, a.x.ftw, nextRows, ctx, S);
+          N, tws, nextRows, ctx, S);
     } else {
       if (nextRows) {
         SB_PHASE_BEGIN
         prefetch_l2(nextRows, sizeof(cx<T>) * N * V, tid, nthr);
         SB_PHASE_END_NOSYNC
       }
-      y_forward_tile<T, N, Mem::L2Only, Mem::Plain>(a.y, it.tile, slot, stickRow, -1, nullptr, ctx, S);
+      y_forward_gather<T, N, Mem::L2Only, true>(a.y, it.tile, slot, stickRow, -1, nullptr, ctx, S, tws);
     }
   }
 }
 
 #undef SB_ROW_IDS
 #undef SB_FAST_IDS
+#undef SB_FAST_IDS_
 #undef SB_FAST_WRITE
 #undef SB_FAST_READ
 

@@ -5,6 +5,11 @@
 
 namespace sb {
 
+template <typename T, int N>
+constexpr size_t xy_smem() {
+  return FastCfg<T, N>::smem + sizeof(cx<T>) * (FastPlan<N>::tw_size() > 0 ? FastPlan<N>::tw_size() : 1);
+}
+
 __device__ __forceinline__ int ld_acquire_gpu(const int* p) {
   int v;
   asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -35,6 +40,10 @@ __global__ void __launch_bounds__(FastCfg<T, N>::threads, FastCfg<T, N>::minBloc
     k_xy_fused(const __grid_constant__ XYArgs<T> a) {
   extern __shared__ __align__(16) unsigned char smemRaw[];
   cx<T>* S = reinterpret_cast<cx<T>*>(smemRaw);
+  // stage twiddles in shared memory: the acquire loads / release fences below invalidate L1
+  // (CCTL.IVALL) on every item, which would send all twiddle reads to L2
+  cx<T>* tws = S + (size_t)N * FastCfg<T, N>::V;
+  for (int i = threadIdx.x; i < FastPlan<N>::tw_size(); i += blockDim.x) tws[i] = a.x.ftw[i];
   __shared__ int sQ[2];
   constexpr bool BWD = !FWD;
   const int P = a.y.numPlanes;
@@ -60,11 +69,11 @@ __global__ void __launch_bounds__(FastCfg<T, N>::threads, FastCfg<T, N>::minBloc
     if (it.valid) {
       if (it.roleA) {
         if (it.plane >= a.ring) cta_wait(&bDone[it.plane - a.ring], nB);
-        xy_run_item<T, N, BWD>(a, it, nx, Ctx{FastCfg<T, N>::threads}, S);
+        xy_run_item<T, N, BWD>(a, it, nx, tws, Ctx{FastCfg<T, N>::threads}, S);
         cta_signal(&aDone[it.plane]);
       } else {
         cta_wait(&aDone[it.plane], nA);
-        xy_run_item<T, N, BWD>(a, it, nx, Ctx{FastCfg<T, N>::threads}, S);
+        xy_run_item<T, N, BWD>(a, it, nx, tws, Ctx{FastCfg<T, N>::threads}, S);
         cta_signal(&bDone[it.plane]);
       }
     }
@@ -81,15 +90,15 @@ static int xy_blocks_per_sm(int* out) {
     return (int)cudaErrorInvalidValue;
   } else {
     cudaError_t e = cudaFuncSetAttribute(k_xy_fused<T, N, false>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::smem);
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xy_smem<T, N>());
     if (e != cudaSuccess) return (int)e;
     e = cudaFuncSetAttribute(k_xy_fused<T, N, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)C::smem);
+                             (int)xy_smem<T, N>());
     if (e != cudaSuccess) return (int)e;
     int b0 = 0, b1 = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b0, k_xy_fused<T, N, false>, C::threads, C::smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b0, k_xy_fused<T, N, false>, C::threads, xy_smem<T, N>());
     if (e != cudaSuccess) return (int)e;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b1, k_xy_fused<T, N, true>, C::threads, C::smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b1, k_xy_fused<T, N, true>, C::threads, xy_smem<T, N>());
     if (e != cudaSuccess) return (int)e;
     *out = b0 < b1 ? b0 : b1;
     return *out > 0 ? 0 : (int)cudaErrorInvalidConfiguration;
@@ -130,9 +139,9 @@ static int launch_xy_n(int forward, const XYArgs<T>& a, cudaStream_t s) {
     cudaError_t e = cudaMemsetAsync(a.counters, 0, sizeof(int) * (1 + 2 * (size_t)a.y.numPlanes), s);
     if (e != cudaSuccess) return (int)e;
     if (forward)
-      k_xy_fused<T, N, true><<<(unsigned)grid, C::threads, C::smem, s>>>(a);
+      k_xy_fused<T, N, true><<<(unsigned)grid, C::threads, xy_smem<T, N>(), s>>>(a);
     else
-      k_xy_fused<T, N, false><<<(unsigned)grid, C::threads, C::smem, s>>>(a);
+      k_xy_fused<T, N, false><<<(unsigned)grid, C::threads, xy_smem<T, N>(), s>>>(a);
     return (int)cudaGetLastError();
   }
 }

@@ -8,10 +8,18 @@ __global__ void __launch_bounds__(FastCfg<T, N>::threads, FastCfg<T, N>::minBloc
     k_z_fast(const __grid_constant__ ZArgs<T> a) {
   extern __shared__ __align__(16) unsigned char smemRaw[];
   cx<T>* S = reinterpret_cast<cx<T>*>(smemRaw);
-  if (FWD)
-    z_forward_fast<T, N>(a, (int)blockIdx.x, Ctx{FastCfg<T, N>::threads}, S);
-  else
-    z_backward_fast<T, N>(a, (int)blockIdx.x, Ctx{FastCfg<T, N>::threads}, S);
+  const Ctx ctx{FastCfg<T, N>::threads};
+  if (a.inv) {  // values in stick order: inverse-map (gather) form
+    if (FWD)
+      z_forward_gather<T, N>(a, (int)blockIdx.x, ctx, S);
+    else
+      z_backward_gather<T, N>(a, (int)blockIdx.x, ctx, S);
+  } else {
+    if (FWD)
+      z_forward_fast<T, N>(a, (int)blockIdx.x, ctx, S);
+    else
+      z_backward_fast<T, N>(a, (int)blockIdx.x, ctx, S);
+  }
 }
 
 template <typename T, int N>

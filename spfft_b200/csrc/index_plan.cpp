@@ -127,7 +127,7 @@ std::shared_ptr<IndexMaps> make_local_index_maps(SpfftTransformType type, int di
   return m;
 }
 
-TileMaps build_tile_maps(const IndexMaps& maps, int log2Vz, int log2Vy) {
+TileMaps build_tile_maps(const IndexMaps& maps, int log2Vz, int log2Vy, bool fastZ, bool fastY) {
   TileMaps t;
   t.log2Vz = log2Vz;
   t.log2Vy = log2Vy;
@@ -210,6 +210,37 @@ TileMaps build_tile_maps(const IndexMaps& maps, int log2Vz, int log2Vy) {
     t.stickSlot[s] = (y << log2Vy) + (x & (Vy - 1));
   }
   for (int k = 0; k < t.numXTiles; ++k) t.xtStart[k + 1] += t.xtStart[k];
+
+  // ---- inverse maps of the register-FFT kernels
+  if (fastZ && t.identityOrder && !t.hasDuplicates && ne > 0) {
+    const int T = nz / 8;
+    const size_t perTile = static_cast<size_t>(Vz) * T * 8;
+    t.zInv.assign(perTile * t.numStickTiles, 0xFFFF);
+    for (int p = 0; p < ne; ++p) {
+      const int vi = maps.valueIndices[p];  // identity order: entry p == value p
+      const int stick = vi / nz;
+      const int z = vi - stick * nz;
+      const int tile = stick >> log2Vz;
+      const int lane = stick & (Vz - 1);
+      const size_t tid = static_cast<size_t>(lane) * T + (z % T);
+      t.zInv[perTile * tile + tid * 8 + z / T] = static_cast<unsigned short>(p - t.tileStart[tile]);
+    }
+  }
+  if (fastY && ns > 0) {
+    const int ny = maps.dimY;
+    const int T = ny / 8;
+    const size_t perTile = static_cast<size_t>(Vy) * T * 8;
+    t.yInv.assign(perTile * t.numXTiles, 0xFFFF);
+    for (int s = 0; s < ns; ++s) {
+      const int key = maps.stickIndices[s];
+      const int x = key / ny;
+      const int y = key - x * ny;
+      const int tile = x >> log2Vy;
+      const int lane = x & (Vy - 1);
+      const size_t tid = static_cast<size_t>(lane) * T + (y % T);
+      t.yInv[perTile * tile + tid * 8 + y / T] = static_cast<unsigned short>(s - t.xtStart[tile]);
+    }
+  }
   return t;
 }
 

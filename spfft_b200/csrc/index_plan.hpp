@@ -71,9 +71,15 @@ struct TileMaps {
   int numXTiles = 0;
   std::vector<int> xtStart;    // [numXTiles+1] (stick index ranges)
   std::vector<int> stickSlot;  // [Ns] y*Vy + (x mod Vy)
+  // inverse maps of the register-FFT kernels (fast_stage_kernels.hpp, "gather form"), built only
+  // for axes on the fast path: [tile][thread = lane*T + j][m] -> offset of element j + T*m of
+  // the lane-th sequence from the tile's first entry / stick, 0xFFFF = absent.
+  // zInv needs the values in stick order (identityOrder) and no duplicates.
+  std::vector<unsigned short> zInv, yInv;
 };
 
-TileMaps build_tile_maps(const IndexMaps& maps, int log2Vz, int log2Vy);
+TileMaps build_tile_maps(const IndexMaps& maps, int log2Vz, int log2Vy, bool fastZ = false,
+                         bool fastY = false);
 
 // Radix schedule for the Stockham tile FFT: 8s, then 4 / 2, then 3s, 5s, then remaining primes.
 sb::RadixPlan make_radix_plan(int n);

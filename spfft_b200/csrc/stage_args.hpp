@@ -26,6 +26,8 @@ struct PlanPointers {
   const int* bwdEntrySlot = nullptr;
   const int* xtStart = nullptr;
   const int* stickSlot = nullptr;
+  const unsigned short* zInv = nullptr;  // gather-form inverse maps (nullptr: scatter form)
+  const unsigned short* yInv = nullptr;
 };
 
 struct AxisPlans {
@@ -45,6 +47,7 @@ inline sb::ZArgs<T> make_z_args(const IndexMaps& m, const TileMaps& t, const Axi
   a.rp = ax.rpZ;
   a.tw = p.twZ;
   a.ftw = p.ftwZ;
+  a.inv = p.zInv;
   if (forward) {
     a.tileStart = p.tileStart;
     a.entrySrc = p.entrySrc;
@@ -82,6 +85,7 @@ inline sb::YArgs<T> make_y_args(const IndexMaps& m, const TileMaps& t, const Axi
   a.rp = ax.rpY;
   a.tw = p.twY;
   a.ftw = p.ftwY;
+  a.inv = p.yInv;
   a.xtStart = p.xtStart;
   a.stickSlot = p.stickSlot;
   a.sticks = sticks;

@@ -45,6 +45,9 @@ struct ZArgs {
   int useScale;
   T scale;
   int pfDist;             // L2 prefetch distance in tiles (resident CTAs), 0 = off; set by the launcher
+  // register-FFT kernels, values in stick order without duplicates: inverse map
+  // [tile][thread][8] -> offset of the element's value from the tile's first entry, 0xFFFF = none
+  const unsigned short* inv;
 };
 
 template <typename T>
@@ -65,6 +68,9 @@ struct YArgs {
   cx<T>* sticks;
   cx<T>* planes;         // [numPlanes][ny][nxf]
   int pfDist;            // L2 prefetch distance in blocks, 0 = off; set by the launcher
+  // register-FFT kernels: inverse map [x tile][thread][8] -> offset of the element's stick from
+  // the tile's first stick, 0xFFFF = none
+  const unsigned short* inv;
 };
 
 template <typename T>

@@ -172,7 +172,7 @@ std::shared_ptr<DevicePlan<T>> build_device_plan(const IndexMaps& m, long long s
                                        &plan->xyLag, &plan->xyCounters);
     plan->fusedXY = err == 0;
   }
-  TileMaps t = build_tile_maps(m, ax.log2Vz, ax.log2Vy);
+  TileMaps t = build_tile_maps(m, ax.log2Vz, ax.log2Vy, fastZ, fastY);
   plan->numStickTiles = t.numStickTiles;
   plan->pitch = t.pitch;
   plan->numXTiles = t.numXTiles;
@@ -190,7 +190,10 @@ std::shared_ptr<DevicePlan<T>> build_device_plan(const IndexMaps& m, long long s
   if (fastZ) p.ftwZ = upload(st, total, make_fast_twiddles<T>(m.dimZ));
   p.tileStart = upload(st, total, t.tileStart);
   p.entrySrc = t.identityOrder ? nullptr : upload(st, total, t.entrySrc);
-  p.entrySlot = upload(st, total, t.entrySlot);
+  p.zInv = upload(st, total, t.zInv);
+  p.yInv = upload(st, total, t.yInv);
+  // the gather-form z kernels do not read entrySlot
+  if (!p.zInv) p.entrySlot = upload(st, total, t.entrySlot);
   if (t.hasDuplicates) {
     p.bwdTileStart = upload(st, total, t.bwdTileStart);
     p.bwdEntrySrc = upload(st, total, t.bwdEntrySrc);

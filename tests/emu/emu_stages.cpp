@@ -38,7 +38,12 @@ void run_z(bool fwd, const sb::ZArgs<T>& a, int b, sb::Ctx ctx, sb::cx<T>* smem)
     return;
   }
   sb::Ctx c{(1 << sb::FastLanes<T>::log2V) * (a.nz / 8)};
-#define CALL(NN) if (fwd) sb::z_forward_fast<T, NN>(a, b, c, smem); else sb::z_backward_fast<T, NN>(a, b, c, smem)
+#define CALL(NN)                                                                         \
+  if (a.inv) {                                                                           \
+    if (fwd) sb::z_forward_gather<T, NN>(a, b, c, smem); else sb::z_backward_gather<T, NN>(a, b, c, smem); \
+  } else {                                                                               \
+    if (fwd) sb::z_forward_fast<T, NN>(a, b, c, smem); else sb::z_backward_fast<T, NN>(a, b, c, smem);     \
+  }
   EMU_DISPATCH(a.nz, CALL)
 #undef CALL
 }
@@ -85,7 +90,7 @@ void run_xy(bool fwd, const sb::XYArgs<T>& a, sb::cx<T>* smem) {
     sb::XYItem nx;
     nx.valid = false;
     if (item + 1 < total) nx = fwd ? sb::xy_decode<T, false>(a, (int)item + 1) : sb::xy_decode<T, true>(a, (int)item + 1);
-#define CALL(NN) if (fwd) sb::xy_run_item<T, NN, false>(a, it, nx, c, smem); else sb::xy_run_item<T, NN, true>(a, it, nx, c, smem)
+#define CALL(NN) if (fwd) sb::xy_run_item<T, NN, false>(a, it, nx, a.x.ftw, c, smem); else sb::xy_run_item<T, NN, true>(a, it, nx, a.x.ftw, c, smem)
     EMU_DISPATCH(a.x.nx, CALL)
 #undef CALL
     ++(it.roleA ? aDone : bDone)[it.plane];
@@ -121,7 +126,7 @@ int run(int type, int dimX, int dimY, int dimZ, int n, const int* triplets, int 
     ax.rpX = make_radix_plan(dimX);
     ax.rpY = make_radix_plan(dimY);
     ax.rpZ = make_radix_plan(dimZ);
-    TileMaps t = build_tile_maps(*maps, ax.log2Vz, ax.log2Vy);
+    TileMaps t = build_tile_maps(*maps, ax.log2Vz, ax.log2Vy, fastZ, fastY);
     auto twX = make_roots<T>(dimX), twY = make_roots<T>(dimY), twZ = make_roots<T>(dimZ);
     auto ftwX = make_fast_twiddles<T>(dimX), ftwY = make_fast_twiddles<T>(dimY),
          ftwZ = make_fast_twiddles<T>(dimZ);
@@ -144,6 +149,8 @@ int run(int type, int dimX, int dimY, int dimZ, int n, const int* triplets, int 
       p.bwdEntrySrc = p.entrySrc;
       p.bwdEntrySlot = p.entrySlot;
     }
+    if (!t.zInv.empty()) p.zInv = t.zInv.data();
+    if (!t.yInv.empty()) p.yInv = t.yInv.data();
     p.xtStart = t.xtStart.data();
     p.stickSlot = t.stickSlot.data();
 

@@ -113,11 +113,15 @@ FAST_SHAPES = [(32, 32, 32), (64, 32, 128), (32, 12, 64), (11, 64, 32), (128, 32
 
 @pytest.mark.parametrize("shape", FAST_SHAPES, ids=lambda s: "x".join(map(str, s)))
 @pytest.mark.parametrize("single", [False, True])
-def test_emulated_fast_c2c(emu, gen, shape, single):
+@pytest.mark.parametrize("shuffle", [False, True])
+def test_emulated_fast_c2c(emu, gen, shape, single, shuffle):
     nx, ny, nz = shape
     if single and max(shape) > 512:
         pytest.skip("float fast path stops at 512")
     trip, vals = gen.make(nx, ny, nz, center=True, stick_fraction=0.5, fill_fraction=0.6)
+    if shuffle:  # arbitrary user order -> scatter-form z kernels instead of the inverse-map form
+        perm = np.random.default_rng(5).permutation(len(trip))
+        trip, vals = np.ascontiguousarray(trip[perm]), vals[perm]
     param = orc.Parameters(orc.SPFFT_TRANS_C2C, nx, ny, nz, trip)
     cdt = np.complex64 if single else np.complex128
     tol = 2e-6 if single else 1e-13
