@@ -19,6 +19,57 @@
 extern "C" {
 #endif
 
+/* ---- distributed transforms over the GPUs of one NVSwitch box (NCCL instead of MPI) ----------
+ *
+ * One process per GPU. Rank 0 obtains an id, the application broadcasts its 128 bytes by any means
+ * (torch.distributed, MPI, a file), every rank creates its communicator on its current device, then
+ * a distributed grid; transforms created from that grid are distributed: frequency domain = the
+ * z-sticks this rank passed, space domain = `localZLength` consecutive xy planes, in rank order.
+ * These entry points mirror spfft_grid_create_distributed (include/spfft/grid.h:84-96) and
+ * spfft_transform_create_independent_distributed (transform.h:115-128) with SpfftB200Comm in place
+ * of MPI_Comm; everything else (spfft_transform_create / backward / forward / getters) is the
+ * unchanged SpFFT API. The exchange is one grouped ncclSend/ncclRecv per direction on the
+ * transform's stream. */
+SPFFT_EXPORT SpfftError spfft_b200_nccl_unique_id(char* id128);
+SPFFT_EXPORT SpfftError spfft_b200_comm_create(SpfftB200Comm* comm, int numRanks, int rank,
+                                               const char* id128);
+SPFFT_EXPORT SpfftError spfft_b200_comm_destroy(SpfftB200Comm comm);
+SPFFT_EXPORT SpfftError spfft_b200_comm_size(SpfftB200Comm comm, int* size);
+SPFFT_EXPORT SpfftError spfft_b200_comm_rank(SpfftB200Comm comm, int* rank);
+
+SPFFT_EXPORT SpfftError spfft_grid_create_distributed_nccl(
+    SpfftGrid* grid, int maxDimX, int maxDimY, int maxDimZ, int maxNumLocalZColumns,
+    int maxLocalZLength, SpfftProcessingUnitType processingUnit, int maxNumThreads,
+    SpfftB200Comm comm, SpfftExchangeType exchangeType);
+SPFFT_EXPORT SpfftError spfft_float_grid_create_distributed_nccl(
+    SpfftFloatGrid* grid, int maxDimX, int maxDimY, int maxDimZ, int maxNumLocalZColumns,
+    int maxLocalZLength, SpfftProcessingUnitType processingUnit, int maxNumThreads,
+    SpfftB200Comm comm, SpfftExchangeType exchangeType);
+SPFFT_EXPORT SpfftError spfft_transform_create_independent_distributed_nccl(
+    SpfftTransform* transform, int maxNumThreads, SpfftB200Comm comm,
+    SpfftExchangeType exchangeType, SpfftProcessingUnitType processingUnit,
+    SpfftTransformType transformType, int dimX, int dimY, int dimZ, int localZLength,
+    int numLocalElements, SpfftIndexFormatType indexFormat, const int* indices);
+SPFFT_EXPORT SpfftError spfft_float_transform_create_independent_distributed_nccl(
+    SpfftFloatTransform* transform, int maxNumThreads, SpfftB200Comm comm,
+    SpfftExchangeType exchangeType, SpfftProcessingUnitType processingUnit,
+    SpfftTransformType transformType, int dimX, int dimY, int dimZ, int localZLength,
+    int numLocalElements, SpfftIndexFormatType indexFormat, const int* indices);
+
+/* Host-only view of the exchange a rank would perform (no GPU, no NCCL): block offsets / counts
+ * (in complex elements) inside the stick-side buffer [dimZ][pitch(rank)] and the plane-side buffer
+ * (one block [localPlanes][pitch(r)] per source rank), and the y-stage tables over all ranks'
+ * sticks sorted by x*dimY+y (slot = y*Vy + x mod Vy, srcBase + plane*srcPitch = position in the
+ * plane-side buffer). sticksAllRanks: the ranks' stick lists back to back. Per-rank outputs have
+ * commSize entries, per-stick outputs sum(numSticksPerRank) entries, xtStart numXTiles+1
+ * (at most dimX+1). Used by the CPU multi-process tests. */
+SPFFT_EXPORT SpfftError spfft_b200_exchange_plan(
+    int transformType, int isFloat, int dimX, int dimY, int dimZ, int commSize, int commRank,
+    const int* numSticksPerRank, const int* sticksAllRanks, const int* planesPerRank,
+    int* pitchPerRank, long long* stickOffset, long long* stickCount, long long* planeOffset,
+    long long* planeCount, int* numXTiles, int* log2Vy, int* xtStart, int* stickSlot, int* srcBase,
+    int* srcPitch);
+
 /* ---- plan inspection (host only, no GPU needed) -------------------------------------------- */
 
 /* The index conversion every transform performs at creation, exposed so that tests can compare it

@@ -31,6 +31,10 @@ enum SpfftScalingType { SPFFT_NO_SCALING, SPFFT_FULL_SCALING };
  * with respect to the default stream. */
 enum SpfftExecType { SPFFT_EXEC_SYNCHRONOUS, SPFFT_EXEC_ASYNCHRONOUS };
 
+/* Handle of an NCCL based communicator (spfft/b200_ext.h): stands where the reference's API takes
+ * an MPI_Comm. */
+typedef void* SpfftB200Comm;
+
 #ifndef __cplusplus
 typedef enum SpfftExchangeType SpfftExchangeType;
 typedef enum SpfftProcessingUnitType SpfftProcessingUnitType;

@@ -323,7 +323,12 @@ _MULTI_FUNCS = ["multi_transform_forward", "multi_transform_forward_ptr",
                 "multi_transform_backward", "multi_transform_backward_ptr"]
 _EXT_PER_PRECISION = ["transform_index_maps", "transform_stream", "transform_set_profiling",
                       "transform_stage_times"]
-_EXT_COMMON = ["spfft_b200_convert_index_triplets", "spfft_b200_kernel_launch_count"]
+_EXT_COMMON = ["spfft_b200_convert_index_triplets", "spfft_b200_kernel_launch_count",
+               "spfft_b200_nccl_unique_id", "spfft_b200_comm_create", "spfft_b200_comm_destroy",
+               "spfft_b200_comm_size", "spfft_b200_comm_rank", "spfft_b200_exchange_plan",
+               "spfft_grid_create_distributed_nccl", "spfft_float_grid_create_distributed_nccl",
+               "spfft_transform_create_independent_distributed_nccl",
+               "spfft_float_transform_create_independent_distributed_nccl"]
 
 
 def exported_symbols():
@@ -406,3 +411,100 @@ def stage_times(t: Transform):
     name = "spfft_b200_float_transform_stage_times" if t.single else "spfft_b200_transform_stage_times"
     t.lib.call(name, t.handle, 16, C.byref(n), names, ms)
     return [(names[i].decode(), float(ms[i])) for i in range(n.value)]
+
+
+# ----------------------------------------------------------------------------------------------
+# Distributed transforms (include/spfft/b200_ext.h): NCCL communicator in place of MPI_Comm
+# ----------------------------------------------------------------------------------------------
+def nccl_unique_id(lib: SpfftLib) -> bytes:
+    """128-byte id created on rank 0; broadcast it to every rank (e.g. torch.distributed)."""
+    buf = C.create_string_buffer(128)
+    lib.call("spfft_b200_nccl_unique_id", buf)
+    return buf.raw
+
+
+class Comm:
+    """SpfftB200Comm: this rank's NCCL communicator on the current CUDA device."""
+
+    def __init__(self, lib: SpfftLib, num_ranks: int, rank: int, unique_id: bytes):
+        self.lib = lib
+        self.handle = C.c_void_p()
+        lib.call("spfft_b200_comm_create", C.byref(self.handle), int(num_ranks), int(rank),
+                 C.c_char_p(unique_id))
+        self.size, self.rank = int(num_ranks), int(rank)
+
+    def destroy(self):
+        if self.handle:
+            self.lib.call("spfft_b200_comm_destroy", self.handle)
+            self.handle = C.c_void_p()
+
+
+def comm_from_torch(lib: SpfftLib) -> Comm:
+    """Communicator over the ranks of the default torch.distributed process group (the id travels
+    through a broadcast of that group; the current CUDA device must already be set)."""
+    import torch
+    import torch.distributed as dist
+    rank, world = dist.get_rank(), dist.get_world_size()
+    payload = [nccl_unique_id(lib) if rank == 0 else None]
+    dist.broadcast_object_list(payload, src=0)
+    return Comm(lib, world, rank, payload[0])
+
+
+class DistributedGrid(Grid):
+    """spfft_grid_create_distributed_nccl (mirror of spfft_grid_create_distributed, grid.h:84-96)."""
+
+    def __init__(self, lib: SpfftLib, comm: Comm, max_dim_x, max_dim_y, max_dim_z,
+                 max_num_local_z_columns, max_local_z_length, processing_unit=SPFFT_PU_GPU,
+                 max_num_threads=-1, exchange_type=SPFFT_EXCH_DEFAULT, single=False):
+        self.lib = lib
+        self.single = single
+        self._sfx = "_float" if single else ""
+        self.handle = C.c_void_p()
+        self.comm = comm
+        lib.call("spfft" + self._sfx + "_grid_create_distributed_nccl", C.byref(self.handle),
+                 int(max_dim_x), int(max_dim_y), int(max_dim_z), int(max_num_local_z_columns),
+                 int(max_local_z_length), int(processing_unit), int(max_num_threads), comm.handle,
+                 int(exchange_type))
+
+
+def distributed_transform(lib: SpfftLib, comm: Comm, transform_type, dim_x, dim_y, dim_z,
+                          local_z_length, indices, processing_unit=SPFFT_PU_GPU, max_num_threads=-1,
+                          exchange_type=SPFFT_EXCH_DEFAULT, single=False) -> Transform:
+    """spfft_transform_create_independent_distributed_nccl (mirror of transform.h:115-128)."""
+    idx = np.ascontiguousarray(np.asarray(indices, dtype=np.int32).reshape(-1))
+    n = idx.size // 3
+    h = C.c_void_p()
+    sfx = "_float" if single else ""
+    lib.call(f"spfft{sfx}_transform_create_independent_distributed_nccl", C.byref(h),
+             int(max_num_threads), comm.handle, int(exchange_type), int(processing_unit),
+             int(transform_type), int(dim_x), int(dim_y), int(dim_z), int(local_z_length), int(n),
+             SPFFT_INDEX_TRIPLETS, idx.ctypes.data_as(C.POINTER(C.c_int)) if n else None)
+    return Transform(lib, single=single, _handle=h)
+
+
+def exchange_plan(lib: SpfftLib, transform_type, single, dim_x, dim_y, dim_z, comm_rank,
+                  sticks_per_rank, planes_per_rank):
+    """spfft_b200_exchange_plan: host-only view of one rank's stick<->slab exchange (dict)."""
+    size = len(sticks_per_rank)
+    ns = np.array([len(s) for s in sticks_per_rank], dtype=np.int32)
+    allsticks = np.ascontiguousarray(np.concatenate([np.asarray(s, np.int32) for s in sticks_per_rank])
+                                     if ns.sum() else np.zeros(1, np.int32))
+    planes = np.ascontiguousarray(planes_per_rank, dtype=np.int32)
+    total = int(ns.sum())
+    out = {"pitch": np.zeros(size, np.int32), "stick_offset": np.zeros(size, np.int64),
+           "stick_count": np.zeros(size, np.int64), "plane_offset": np.zeros(size, np.int64),
+           "plane_count": np.zeros(size, np.int64), "xt_start": np.zeros(dim_x + 2, np.int32),
+           "stick_slot": np.zeros(max(total, 1), np.int32), "src_base": np.zeros(max(total, 1), np.int32),
+           "src_pitch": np.zeros(max(total, 1), np.int32)}
+    nxt, l2vy = C.c_int(), C.c_int()
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    lib.call("spfft_b200_exchange_plan", int(transform_type), int(bool(single)), int(dim_x), int(dim_y),
+             int(dim_z), size, int(comm_rank), p(ns), p(allsticks), p(planes), p(out["pitch"]),
+             p(out["stick_offset"]), p(out["stick_count"]), p(out["plane_offset"]),
+             p(out["plane_count"]), C.byref(nxt), C.byref(l2vy), p(out["xt_start"]),
+             p(out["stick_slot"]), p(out["src_base"]), p(out["src_pitch"]))
+    out["num_x_tiles"], out["log2_vy"] = nxt.value, l2vy.value
+    out["xt_start"] = out["xt_start"][:nxt.value + 1]
+    for k in ("stick_slot", "src_base", "src_pitch"):
+        out[k] = out[k][:total]
+    return out

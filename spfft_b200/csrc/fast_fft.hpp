@@ -132,6 +132,17 @@ SB_DEV void prefetch_l2(const void* base, size_t bytes, int tid, int nthr) {
   (void)base; (void)bytes; (void)tid; (void)nthr;
 #endif
 }
+// Tell L2 that [base, base+bytes) (128-byte aligned lines) will not be read again before it is
+// overwritten: dirty lines of the y<->x hand-off are dropped instead of written back to HBM.
+SB_DEV void discard_l2(const void* base, size_t bytes, int tid, int nthr) {
+#if SB_ON_GPU
+  const char* p = static_cast<const char*>(base);
+  for (size_t off = (size_t)tid * 128; off < bytes; off += (size_t)nthr * 128)
+    asm volatile("discard.global.L2 [%0], 128;" ::"l"(p + off) : "memory");
+#else
+  (void)base; (void)bytes; (void)tid; (void)nthr;
+#endif
+}
 SB_DEV void prefetch_l2_line(const void* p) {
 #if SB_ON_GPU
   asm volatile("prefetch.global.L2 [%0];" ::"l"(p));

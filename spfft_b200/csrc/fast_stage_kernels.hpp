@@ -245,7 +245,7 @@ SB_DEV void z_forward_fast(const ZArgs<T>& a, int tile, Ctx ctx, cx<T>* S) {
 // -------------------------------------------------------------------------------------------
 template <typename T, int N, Mem LDS, Mem STP>
 SB_DEV void y_backward_tile(const YArgs<T>& a, int xt, const cx<T>* stickRow, cx<T>* plane,
-                            int nextXt, const cx<T>* nextStickRow, Ctx ctx, cx<T>* S) {
+                            int nextXt, const cx<T>* nextStickRow, Ctx ctx, cx<T>* S, int zl = 0) {
   constexpr int LOG2V = FastLanes<T>::log2V;
   constexpr int V = 1 << LOG2V;
   constexpr int TT = FastPlan<N>::T;
@@ -281,7 +281,8 @@ SB_DEV void y_backward_tile(const YArgs<T>& a, int xt, const cx<T>* stickRow, cx
       const int e = base + u * nthr;
       if (e < e1) {
         slot[u] = a.stickSlot[e];
-        val[u] = ld_g<LDS>(stickRow + e);
+        val[u] = a.srcBase ? a.sticks[(size_t)a.srcBase[e] + (size_t)zl * a.srcPitch[e]]
+                           : ld_g<LDS>(stickRow + e);
       }
     }
 #pragma unroll
@@ -309,7 +310,7 @@ SB_DEV void y_backward_tile(const YArgs<T>& a, int xt, const cx<T>* stickRow, cx
 
 template <typename T, int N, Mem LDP, Mem STS>
 SB_DEV void y_forward_tile(const YArgs<T>& a, int xt, const cx<T>* plane, cx<T>* stickRow,
-                           int nextXt, const cx<T>* nextPlane, Ctx ctx, cx<T>* S) {
+                           int nextXt, const cx<T>* nextPlane, Ctx ctx, cx<T>* S, int zl = 0) {
   constexpr int LOG2V = FastLanes<T>::log2V;
   constexpr int V = 1 << LOG2V;
   constexpr int TT = FastPlan<N>::T;
@@ -347,8 +348,11 @@ SB_DEV void y_forward_tile(const YArgs<T>& a, int xt, const cx<T>* plane, cx<T>*
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      if (base + u * nthr < e1)
-        st_g<STS>(stickRow + base + u * nthr, S[SwzRow::at<LOG2V>(slot[u] >> LOG2V, slot[u] & (V - 1))]);
+      if (base + u * nthr < e1) {
+        const int e = base + u * nthr;
+        cx<T>* dst = a.srcBase ? a.sticks + (size_t)a.srcBase[e] + (size_t)zl * a.srcPitch[e] : stickRow + e;
+        st_g<STS>(dst, S[SwzRow::at<LOG2V>(slot[u] >> LOG2V, slot[u] & (V - 1))]);
+      }
     }
   }
   SB_PHASE_END_NOSYNC
@@ -360,7 +364,7 @@ SB_DEV void y_backward_fast(const YArgs<T>& a, int block, Ctx ctx, cx<T>* S) {
   const int zl = block / a.numXTiles;
   int nextXt = -1;
   const cx<T>* nextRow = nullptr;
-  if (a.pfDist > 0 && block + a.pfDist < a.numXTiles * a.numPlanes) {
+  if (a.pfDist > 0 && !a.srcBase && block + a.pfDist < a.numXTiles * a.numPlanes) {
     nextXt = (block + a.pfDist) % a.numXTiles;
     nextRow = a.sticks + (size_t)((block + a.pfDist) / a.numXTiles + a.zRowOffset) * a.pitch;
   }
@@ -369,7 +373,7 @@ SB_DEV void y_backward_fast(const YArgs<T>& a, int block, Ctx ctx, cx<T>* S) {
                                         a.planes + (size_t)zl * N * a.nxf, nextXt, nextRow, ctx, S);
   else
     y_backward_tile<T, N, Mem::Plain, Mem::Plain>(a, xt, a.sticks + (size_t)(zl + a.zRowOffset) * a.pitch,
-                                                  a.planes + (size_t)zl * N * a.nxf, nextXt, nextRow, ctx, S);
+                                                  a.planes + (size_t)zl * N * a.nxf, nextXt, nextRow, ctx, S, zl);
 }
 
 template <typename T, int N>
@@ -389,7 +393,7 @@ SB_DEV void y_forward_fast(const YArgs<T>& a, int block, Ctx ctx, cx<T>* S) {
   else
     y_forward_tile<T, N, Mem::Plain, Mem::Plain>(a, xt, a.planes + (size_t)zl * N * a.nxf,
                                                  a.sticks + (size_t)(zl + a.zRowOffset) * a.pitch, nextXt,
-                                                 nextPlane, ctx, S);
+                                                 nextPlane, ctx, S, zl);
 }
 
 
@@ -539,6 +543,9 @@ SB_DEV void y_backward_gather(const YArgs<T>& a, int xt, const cx<T>* stickRow, 
   SB_REGS(cx<T>, vAll, 8);
   if (e0 == e1) {
     // empty x tile: the x stage still reads these columns -> store zeros, no transform
+    // (barrier: in the fused kernel thread 0 may have waited for the slot to become free)
+    SB_PHASE_BEGIN
+    SB_PHASE_END
     SB_PHASE_BEGIN
     for (int i = tid; i < N * V; i += nthr) {
       const int y = i >> LOG2V;

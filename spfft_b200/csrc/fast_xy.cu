@@ -16,14 +16,6 @@ __device__ __forceinline__ int ld_acquire_gpu(const int* p) {
   return v;
 }
 
-// thread 0 spins until *p >= target, then the whole CTA proceeds
-__device__ __forceinline__ void cta_wait(const int* p, int target) {
-  if (threadIdx.x == 0) {
-    while (ld_acquire_gpu(p) < target) __nanosleep(64);
-  }
-  __syncthreads();
-}
-
 // All global writes of this tile (every thread's) become visible before the counter moves:
 // barrier (CTA-scope ordering), then one cumulative gpu-scope fence + atomic by thread 0 -- the
 // pattern of a cooperative-groups grid barrier.
@@ -46,6 +38,7 @@ __global__ void __launch_bounds__(FastCfg<T, N>::threads, FastCfg<T, N>::minBloc
   for (int i = threadIdx.x; i < FastPlan<N>::tw_size(); i += blockDim.x) tws[i] = a.x.ftw[i];
   __shared__ int sQ[2];
   constexpr bool BWD = !FWD;
+  constexpr int V = FastCfg<T, N>::V;
   const int P = a.y.numPlanes;
   const int nA = xy_tiles_a<T, BWD>(a), nB = xy_tiles_b<T, BWD>(a);
   const long long total = xy_total_items<T, BWD>(a);
@@ -68,16 +61,39 @@ __global__ void __launch_bounds__(FastCfg<T, N>::threads, FastCfg<T, N>::minBloc
     if (nxt < total) nx = xy_decode<T, BWD>(a, nxt);
     if (it.valid) {
       if (it.roleA) {
-        if (it.plane >= a.ring) cta_wait(&bDone[it.plane - a.ring], nB);
+        // slot reuse: the B tiles of plane - ring must have read the slot before this tile's final
+        // store phase. Thread 0 waits here; the barriers inside the tile order every thread's
+        // stores after it (no extra barrier).
+        if (it.plane >= a.ring && threadIdx.x == 0) {
+          while (ld_acquire_gpu(&bDone[it.plane - a.ring]) < nB) __nanosleep(64);
+        }
         xy_run_item<T, N, BWD>(a, it, nx, tws, Ctx{FastCfg<T, N>::threads}, S);
         cta_signal(&aDone[it.plane]);
       } else {
-        cta_wait(&aDone[it.plane], nA);
+        // the first thing a B tile does is read the hand-off plane: every warp waits on its own
+        // (one polling lane per warp) instead of a CTA-wide barrier
+        if ((threadIdx.x & 31) == 0) {
+          while (ld_acquire_gpu(&aDone[it.plane]) < nA) __nanosleep(64);
+        }
+        __syncwarp();
         xy_run_item<T, N, BWD>(a, it, nx, tws, Ctx{FastCfg<T, N>::threads}, S);
+        // all loads of the tile are complete (their values were consumed before the tile's first
+        // barrier): drop the dirty hand-off lines from L2 instead of writing them back to HBM
+        {
+          const cx<T>* slot = a.scratch + (size_t)(it.plane % a.ring) * N * N;
+          if (BWD) {  // x tile: V whole rows, contiguous
+            discard_l2(slot + (size_t)it.tile * V * N, sizeof(cx<T>) * V * N, threadIdx.x, blockDim.x);
+          } else {    // y tile: one 128-byte column segment per row
+            for (int y = threadIdx.x; y < N; y += blockDim.x)
+              discard_l2(slot + (size_t)y * N + (size_t)it.tile * V, sizeof(cx<T>) * V, 0, 1);
+          }
+        }
         cta_signal(&bDone[it.plane]);
       }
+    } else {
+      __syncthreads();
     }
-    __syncthreads();
+    // (cta_signal's barrier doubles as the end-of-item barrier: sQ[k & 1] is visible, S is free)
     cur = nxt;
     nxt = sQ[k & 1];
   }
@@ -170,6 +186,9 @@ int sb_xy_fused_config(int isFloat, int n, int numPlanes, int* ring, int* lag, i
   int l = (resident + perStep - 1) / perStep + 1;
   int r = 2 * l + 2;
   if (r < 6) r = 6;
+  // debug knobs: SPFFT_B200_XY_LAG / SPFFT_B200_XY_RING override the defaults (ring > lag)
+  if (const char* e = getenv("SPFFT_B200_XY_LAG")) l = atoi(e) > 0 ? atoi(e) : l;
+  if (const char* e = getenv("SPFFT_B200_XY_RING")) r = atoi(e) > l ? atoi(e) : l + 1;
   if (numPlanes <= r) {
     r = numPlanes > 0 ? numPlanes : 1;  // every plane has its own slot: no reuse waits
   }

@@ -127,6 +127,90 @@ std::shared_ptr<IndexMaps> make_local_index_maps(SpfftTransformType type, int di
   return m;
 }
 
+void finish_distributed_index_maps(IndexMaps& m, int commRank,
+                                   const std::vector<std::vector<long long>>& countsPerRank,
+                                   std::vector<std::vector<int>> sticksPerRank) {
+  const int size = static_cast<int>(countsPerRank.size());
+  m.commRank = commRank;
+  m.commSize = size;
+  m.sticksPerRank = std::move(sticksPerRank);
+  check_stick_duplicates(m.sticksPerRank);  // parameters.cpp:76
+  long long sticksTotal = 0, planesTotal = 0;
+  m.numGlobalElements = 0;
+  m.numPlanesPerRank.clear();
+  m.planeOffsetPerRank.clear();
+  for (const auto& c : countsPerRank) {
+    // dimensions must match on all ranks (parameters.cpp:95-99)
+    if (c[0] != m.dimX || c[1] != m.dimY || c[2] != m.dimZ) throw MPIParameterMismatchError();
+    planesTotal += c[3];
+    sticksTotal += c[4];
+  }
+  if (sticksTotal > static_cast<long long>(m.dimX) * m.dimY) throw MPIParameterMismatchError();
+  if (planesTotal != m.dimZ) throw MPIParameterMismatchError();
+  int offset = 0;
+  for (const auto& c : countsPerRank) {
+    m.numPlanesPerRank.push_back(static_cast<int>(c[3]));
+    m.planeOffsetPerRank.push_back(offset);
+    offset += static_cast<int>(c[3]);
+    m.numGlobalElements += c[5];
+  }
+}
+
+ExchangePlan build_exchange_plan(const IndexMaps& m, int log2Vz, int log2Vy) {
+  ExchangePlan x;
+  const int P = m.commSize, me = m.commRank;
+  const int Vz = 1 << log2Vz, Vy = 1 << log2Vy;
+  x.commSize = P;
+  x.commRank = me;
+  x.pitchPerRank.resize(P);
+  for (int r = 0; r < P; ++r) {
+    const int ns = static_cast<int>(m.sticksPerRank[r].size());
+    x.pitchPerRank[r] = (ns + Vz - 1) / Vz * Vz;
+  }
+  const long long myPitch = x.pitchPerRank[me];
+  const long long myPlanes = m.numPlanesPerRank[me];
+  x.stickOffset.resize(P);
+  x.stickCount.resize(P);
+  x.planeOffset.resize(P);
+  x.planeCount.resize(P);
+  long long q = 0;
+  for (int r = 0; r < P; ++r) {
+    x.stickOffset[r] = static_cast<long long>(m.planeOffsetPerRank[r]) * myPitch;
+    x.stickCount[r] = static_cast<long long>(m.numPlanesPerRank[r]) * myPitch;
+    x.planeOffset[r] = q;
+    x.planeCount[r] = myPlanes * x.pitchPerRank[r];
+    q += x.planeCount[r];
+  }
+  x.planeSideElements = q;
+  if (q > 0x7fffffffLL) throw OverflowError();
+
+  // all sticks of all ranks, ordered by key: (key, rank, local index)
+  struct Entry {
+    int key, rank, idx;
+  };
+  std::vector<Entry> all;
+  for (int r = 0; r < P; ++r) {
+    const auto& v = m.sticksPerRank[r];
+    for (int i = 0; i < static_cast<int>(v.size()); ++i) all.push_back(Entry{v[i], r, i});
+  }
+  std::sort(all.begin(), all.end(), [](const Entry& a, const Entry& b) { return a.key < b.key; });
+  x.numXTiles = (m.dimXFreq + Vy - 1) / Vy;
+  x.xtStart.assign(x.numXTiles + 1, 0);
+  x.stickSlot.resize(all.size());
+  x.srcBase.resize(all.size());
+  x.srcPitch.resize(all.size());
+  for (size_t e = 0; e < all.size(); ++e) {
+    const int xx = all[e].key / m.dimY;
+    const int yy = all[e].key - xx * m.dimY;
+    ++x.xtStart[(xx >> log2Vy) + 1];
+    x.stickSlot[e] = (yy << log2Vy) + (xx & (Vy - 1));
+    x.srcBase[e] = static_cast<int>(x.planeOffset[all[e].rank] + all[e].idx);
+    x.srcPitch[e] = x.pitchPerRank[all[e].rank];
+  }
+  for (int k = 0; k < x.numXTiles; ++k) x.xtStart[k + 1] += x.xtStart[k];
+  return x;
+}
+
 TileMaps build_tile_maps(const IndexMaps& maps, int log2Vz, int log2Vy, bool fastZ, bool fastY) {
   TileMaps t;
   t.log2Vz = log2Vz;

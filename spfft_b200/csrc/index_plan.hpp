@@ -51,6 +51,36 @@ std::shared_ptr<IndexMaps> make_local_index_maps(SpfftTransformType type, int di
                                                  SpfftIndexFormatType indexFormat,
                                                  const int* indices);
 
+// Distributed parameters (parameters.cpp:43-140). `countsPerRank` holds, for every rank, the six
+// values the reference all-gathers (dimX, dimY, dimZ, numLocalXYPlanes, numLocalZSticks,
+// numLocalElements); `sticksPerRank` the all-gathered stick lists. Throws
+// MPIParameterMismatchError / DuplicateIndicesError exactly where the reference does.
+// `local` must already hold this rank's valueIndices / stickIndices.
+void finish_distributed_index_maps(IndexMaps& local, int commRank,
+                                   const std::vector<std::vector<long long>>& countsPerRank,
+                                   std::vector<std::vector<int>> sticksPerRank);
+
+// The stick <-> slab exchange of one rank (the compact wire format of
+// transpose_mpi_compact_buffered_host.cpp:83-175, re-blocked for the plane-major stick buffer):
+//   stick side  A : [dimZ][pitch(rank)]            rows of destination r are one contiguous block
+//   plane side  Q : for every source r a block [localPlanes][pitch(r)], blocks back to back
+// backward: send A blocks -> receive into Q; forward: send Q blocks -> receive into A.
+struct ExchangePlan {
+  int commSize = 1, commRank = 0;
+  std::vector<int> pitchPerRank;                 // stick row pitch of every rank (tile padded)
+  std::vector<long long> stickOffset, stickCount;  // per peer: block inside A (elements)
+  std::vector<long long> planeOffset, planeCount;  // per peer: block inside Q (elements)
+  long long planeSideElements = 0;               // size of Q
+  // y stage tables over ALL sticks of all ranks, sorted by x*dimY + y
+  std::vector<int> xtStart;    // [numXTiles+1]
+  std::vector<int> stickSlot;  // [NsTotal] y*Vy + (x mod Vy)
+  std::vector<int> srcBase;    // [NsTotal] offset of the stick's value at local plane 0 inside Q
+  std::vector<int> srcPitch;   // [NsTotal] distance between consecutive local planes
+  int numXTiles = 0;
+};
+
+ExchangePlan build_exchange_plan(const IndexMaps& maps, int log2Vz, int log2Vy);
+
 // What the stage kernels read. All arrays are host vectors here; TransformEngine uploads them.
 struct TileMaps {
   int log2Vz = 0, log2Vy = 0;

@@ -71,6 +71,11 @@ struct YArgs {
   // register-FFT kernels: inverse map [x tile][thread][8] -> offset of the element's stick from
   // the tile's first stick, 0xFFFF = none
   const unsigned short* inv;
+  // distributed transforms: `sticks` is the plane-side exchange buffer and stick e of local plane
+  // zl lives at sticks[srcBase[e] + zl*srcPitch[e]] (ExchangePlan, index_plan.hpp); nullptr: the
+  // local plane-major layout sticks[(zl + zRowOffset)*pitch + e]
+  const int* srcBase;
+  const int* srcPitch;
 };
 
 template <typename T>
@@ -196,7 +201,8 @@ SB_DEV void y_backward_body(const YArgs<T>& a, int block, Ctx ctx, cx<T>* smem) 
   SB_PHASE_END
   SB_PHASE_BEGIN
   const cx<T>* row = a.sticks + (size_t)(zl + a.zRowOffset) * a.pitch;
-  for (int e = e0 + tid; e < e1; e += nthr) A[a.stickSlot[e]] = row[e];
+  for (int e = e0 + tid; e < e1; e += nthr)
+    A[a.stickSlot[e]] = a.srcBase ? a.sticks[(size_t)a.srcBase[e] + (size_t)zl * a.srcPitch[e]] : row[e];
   SB_PHASE_END
   if (a.symmetry && xt == 0) hermitian_fill_lane<T>(A, a.ny, 0, a.log2V, ctx);
   cx<T>* R = tile_fft<T, true, false>(A, B, a.rp, a.log2V, a.tw, ctx);
@@ -231,7 +237,12 @@ SB_DEV void y_forward_body(const YArgs<T>& a, int block, Ctx ctx, cx<T>* smem) {
   cx<T>* R = tile_fft<T, false, false>(A, B, a.rp, a.log2V, a.tw, ctx);
   SB_PHASE_BEGIN
   cx<T>* row = a.sticks + (size_t)(zl + a.zRowOffset) * a.pitch;
-  for (int e = e0 + tid; e < e1; e += nthr) row[e] = R[a.stickSlot[e]];
+  for (int e = e0 + tid; e < e1; e += nthr) {
+    if (a.srcBase)
+      a.sticks[(size_t)a.srcBase[e] + (size_t)zl * a.srcPitch[e]] = R[a.stickSlot[e]];
+    else
+      row[e] = R[a.stickSlot[e]];
+  }
   SB_PHASE_END
 }
 

@@ -83,6 +83,43 @@ GridResources<T>::GridResources(int maxDimX, int maxDimY, int maxDimZ, int maxNu
 }
 
 template <typename T>
+GridResources<T>::GridResources(int maxDimX, int maxDimY, int maxDimZ, int maxNumLocalZSticks,
+                                int maxLocalZLength, SpfftProcessingUnitType processingUnit,
+                                int maxNumThreads, std::shared_ptr<Communicator> comm,
+                                SpfftExchangeType exchangeType)
+    : maxDimX_(maxDimX),
+      maxDimY_(maxDimY),
+      maxDimZ_(maxDimZ),
+      maxSticks_(maxNumLocalZSticks),
+      maxPlanes_(maxLocalZLength),
+      pu_(processingUnit),
+      numThreads_(maxNumThreads),
+      comm_(std::move(comm)),
+      exchangeType_(exchangeType) {
+  // grid_internal.cpp:121-148
+  if (!comm_) throw InvalidParameterError();
+  if (static_cast<long long>(maxDimX) * maxDimY * maxLocalZLength > 0x7fffffffLL) throw OverflowError();
+  if (static_cast<long long>(maxNumLocalZSticks) * maxDimZ > 0x7fffffffLL) throw OverflowError();
+  if (maxDimX <= 0 || maxDimY <= 0 || maxDimZ <= 0 || maxNumLocalZSticks < 0 || maxLocalZLength < 0)
+    throw InvalidParameterError();
+  if (!(processingUnit & SPFFT_PU_GPU)) throw InvalidParameterError();
+  if (exchangeType < SPFFT_EXCH_DEFAULT || exchangeType > SPFFT_EXCH_UNBUFFERED)
+    throw InvalidParameterError();
+  if (numThreads_ < 1) numThreads_ = 1;
+  deviceId_ = comm_->device_id();
+  // parameters must agree on all ranks (grid_internal.cpp:150-168)
+  {
+    const int mine[2] = {static_cast<int>(exchangeType), static_cast<int>(processingUnit)};
+    const std::vector<int> all = comm_->all_gather_ints(mine, 2);
+    for (int r = 0; r < comm_->size(); ++r)
+      if (all[2 * r] != mine[0] || all[2 * r + 1] != mine[1]) throw MPIParameterMismatchError();
+  }
+  if (exchangeType_ == SPFFT_EXCH_DEFAULT) exchangeType_ = SPFFT_EXCH_COMPACT_BUFFERED;
+  DeviceGuard guard(deviceId_);
+  allocate();
+}
+
+template <typename T>
 GridResources<T>::GridResources(const GridResources& o)
     : maxDimX_(o.maxDimX_),
       maxDimY_(o.maxDimY_),
@@ -91,20 +128,30 @@ GridResources<T>::GridResources(const GridResources& o)
       maxPlanes_(o.maxPlanes_),
       pu_(o.pu_),
       deviceId_(o.deviceId_),
-      numThreads_(o.numThreads_) {
+      numThreads_(o.numThreads_),
+      comm_(o.comm_),
+      exchangeType_(o.exchangeType_) {
   DeviceGuard guard(deviceId_);
   allocate();
 }
 
 template <typename T>
 void GridResources<T>::allocate() {
+  // local slab volume (all planes for a local grid)
   const size_t volume =
-      static_cast<size_t>(maxDimX_) * static_cast<size_t>(maxDimY_) * static_cast<size_t>(maxDimZ_);
+      static_cast<size_t>(maxDimX_) * static_cast<size_t>(maxDimY_) * static_cast<size_t>(maxPlanes_);
   const size_t c = 2 * sizeof(T);
+  const size_t stickElems = stick_capacity(maxDimZ_, maxSticks_);
   // A: plane-major sticks [z][pitch]; also the real space domain of R2C transforms
-  a_.allocate(std::max(c * stick_capacity(maxDimZ_, maxSticks_), sizeof(T) * volume));
-  // B: xy planes / complex space domain / staged compressed values (Ne <= volume)
-  b_.allocate(c * volume);
+  a_.allocate(std::max(c * stickElems, sizeof(T) * volume));
+  // B: xy planes / complex space domain / staged compressed values (Ne <= Ns*Nz, <= volume locally)
+  b_.allocate(c * std::max(volume, local() ? size_t(0) : stickElems));
+  if (!local()) {
+    // Q: plane-side exchange buffer, one block [maxPlanes][pitch(r)] per source rank
+    const size_t sticksAllRanks = static_cast<size_t>(maxDimX_) * static_cast<size_t>(maxDimY_) +
+                                  static_cast<size_t>(kMaxTileLanes) * comm_->size();
+    q_.allocate(c * static_cast<size_t>(maxPlanes_) * sticksAllRanks);
+  }
 }
 
 template <typename T>
@@ -113,7 +160,7 @@ void* GridResources<T>::host_space(size_t bytes) {
   if (host_.bytes() < bytes) {
     DeviceGuard guard(deviceId_);
     const size_t volume = static_cast<size_t>(maxDimX_) * static_cast<size_t>(maxDimY_) *
-                          static_cast<size_t>(maxDimZ_);
+                          static_cast<size_t>(maxPlanes_);
     host_.allocate(std::max(bytes, 2 * sizeof(T) * volume));
   }
   return host_.get();
@@ -144,28 +191,67 @@ int* GridResources<T>::counters(size_t count) {
 // ---------------------------------------------------------------------------------------------
 // DevicePlan
 // ---------------------------------------------------------------------------------------------
-template <typename T>
-std::shared_ptr<DevicePlan<T>> build_device_plan(const IndexMaps& m, long long smemLimit) {
-  auto plan = std::make_shared<DevicePlan<T>>();
-  if (m.dimX == 0 || m.dimY == 0 || m.dimZ == 0) return plan;
-  AxisPlans& ax = plan->axes;
-  const int cb = static_cast<int>(sizeof(sb::cx<T>));
+void choose_tile_lanes(const IndexMaps& m, int cb, long long smemLimit, AxisPlans& ax, bool& fastX,
+                       bool& fastY, bool& fastZ) {
   // per axis: register-FFT kernels for power-of-two lengths, generic tile kernels otherwise
-  const bool fastX = fast_path_length(m.dimX, cb) && m.type == SPFFT_TRANS_C2C;
-  const bool fastY = fast_path_length(m.dimY, cb);
-  const bool fastZ = fast_path_length(m.dimZ, cb);
+  fastX = fast_path_length(m.dimX, cb) && m.type == SPFFT_TRANS_C2C;
+  fastY = fast_path_length(m.dimY, cb);
+  fastZ = fast_path_length(m.dimZ, cb);
   const int fastLanes = fast_path_log2_lanes(cb);
   ax.log2Vx = fastX ? fastLanes : choose_log2_lanes(m.dimX, cb, smemLimit);
   ax.log2Vy = fastY ? fastLanes : choose_log2_lanes(m.dimY, cb, smemLimit);
   ax.log2Vz = fastZ ? fastLanes : choose_log2_lanes(m.dimZ, cb, smemLimit);
   // a transform length whose two tile buffers exceed shared memory is not supported
   if (ax.log2Vx < 0 || ax.log2Vy < 0 || ax.log2Vz < 0) throw InvalidParameterError();
+}
+
+std::shared_ptr<IndexMaps> make_distributed_index_maps(Communicator& comm, SpfftTransformType type,
+                                                       int dimX, int dimY, int dimZ, int localZLength,
+                                                       int numLocalElements,
+                                                       SpfftIndexFormatType indexFormat,
+                                                       const int* indices) {
+  // local part exactly as for a single rank (index conversion, zeroZeroStickIndex)
+  auto m = make_local_index_maps(type, dimX, dimY, dimZ, numLocalElements, indexFormat, indices);
+  const int P = comm.size();
+  const int mine[6] = {dimX, dimY, dimZ, localZLength, m->num_sticks(), numLocalElements};
+  const std::vector<int> all = comm.all_gather_ints(mine, 6);  // parameters.cpp:89
+  std::vector<std::vector<long long>> counts(P, std::vector<long long>(6));
+  int maxSticks = 0;
+  for (int r = 0; r < P; ++r) {
+    for (int k = 0; k < 6; ++k) counts[r][k] = all[6 * r + k];
+    maxSticks = std::max(maxSticks, all[6 * r + 4]);
+  }
+  // stick lists of all ranks (the reference sends them point to point, indices.hpp:58-102)
+  std::vector<std::vector<int>> sticks(P);
+  if (maxSticks > 0) {
+    std::vector<int> padded(static_cast<size_t>(maxSticks), -1);
+    std::copy(m->stickIndices.begin(), m->stickIndices.end(), padded.begin());
+    const std::vector<int> gathered = comm.all_gather_ints(padded.data(), maxSticks);
+    for (int r = 0; r < P; ++r)
+      sticks[r].assign(gathered.begin() + static_cast<size_t>(r) * maxSticks,
+                       gathered.begin() + static_cast<size_t>(r) * maxSticks + all[6 * r + 4]);
+  }
+  finish_distributed_index_maps(*m, comm.rank(), counts, std::move(sticks));
+  return m;
+}
+
+template <typename T>
+std::shared_ptr<DevicePlan<T>> build_device_plan(const IndexMaps& m, long long smemLimit) {
+  auto plan = std::make_shared<DevicePlan<T>>();
+  if (m.dimX == 0 || m.dimY == 0 || m.dimZ == 0) return plan;
+  AxisPlans& ax = plan->axes;
+  const int cb = static_cast<int>(sizeof(sb::cx<T>));
+  bool fastX = false, fastY = false, fastZ = false;
+  choose_tile_lanes(m, cb, smemLimit, ax, fastX, fastY, fastZ);
   ax.rpX = make_radix_plan(m.dimX);
   ax.rpY = make_radix_plan(m.dimY);
   ax.rpZ = make_radix_plan(m.dimZ);
-  // SPFFT_B200_TUNE bit 1 (debug knob): keep the y and x stages as separate kernels
+  // SPFFT_B200_TUNE bit 2 (value 4) selects the fused xy kernel. It moves only the algorithmic
+  // bytes (hand-off kept in L2, dirty lines discarded) but its per-item acquire/release overhead
+  // currently makes it slower than the separate y and x kernels (profiles/r01_summary.md), so the
+  // separate kernels are the default.
   const char* tuneEnv = std::getenv("SPFFT_B200_TUNE");
-  const bool allowFused = !(tuneEnv && (std::atoi(tuneEnv) & 2));
+  const bool allowFused = tuneEnv && (std::atoi(tuneEnv) & 4);
   if (allowFused && fastX && fastY && m.dimX == m.dimY && m.type == SPFFT_TRANS_C2C) {
     // y and x stages as one persistent kernel with the hand-off in L2 (fast_xy.cu)
     const int err = sb_xy_fused_config(sizeof(T) == 4, m.dimX, m.local_planes(), &plan->xyRing,
@@ -191,7 +277,7 @@ std::shared_ptr<DevicePlan<T>> build_device_plan(const IndexMaps& m, long long s
   p.tileStart = upload(st, total, t.tileStart);
   p.entrySrc = t.identityOrder ? nullptr : upload(st, total, t.entrySrc);
   p.zInv = upload(st, total, t.zInv);
-  p.yInv = upload(st, total, t.yInv);
+  if (m.commSize == 1) p.yInv = upload(st, total, t.yInv);
   // the gather-form z kernels do not read entrySlot
   if (!p.zInv) p.entrySlot = upload(st, total, t.entrySlot);
   if (t.hasDuplicates) {
@@ -203,8 +289,21 @@ std::shared_ptr<DevicePlan<T>> build_device_plan(const IndexMaps& m, long long s
     p.bwdEntrySrc = p.entrySrc;
     p.bwdEntrySlot = p.entrySlot;
   }
-  p.xtStart = upload(st, total, t.xtStart);
-  p.stickSlot = upload(st, total, t.stickSlot);
+  if (m.commSize > 1) {
+    // y stage over ALL ranks' sticks, read from / written to the plane-side exchange buffer
+    plan->distributed = true;
+    plan->exchange = build_exchange_plan(m, ax.log2Vz, ax.log2Vy);
+    plan->numXTiles = plan->exchange.numXTiles;
+    p.xtStart = upload(st, total, plan->exchange.xtStart);
+    p.stickSlot = upload(st, total, plan->exchange.stickSlot);
+    plan->srcBase = upload(st, total, plan->exchange.srcBase);
+    plan->srcPitch = upload(st, total, plan->exchange.srcPitch);
+    p.yInv = nullptr;  // the inverse-map form needs contiguous stick rows
+    plan->fusedXY = false;
+  } else {
+    p.xtStart = upload(st, total, t.xtStart);
+    p.stickSlot = upload(st, total, t.stickSlot);
+  }
   return plan;
 }
 
@@ -227,6 +326,10 @@ TransformEngine<T>::TransformEngine(SpfftProcessingUnitType executionUnit,
   if (!grid_) throw InvalidParameterError();
   if (maps_->local_planes() > grid_->max_num_local_xy_planes()) throw InvalidParameterError();
   if (grid_->local() && maps_->dimZ != maps_->local_planes()) throw InvalidParameterError();
+  if (!grid_->local() && (grid_->communicator()->size() != maps_->commSize ||
+                          grid_->communicator()->rank() != maps_->commRank))
+    throw InternalError();  // transform_internal.cpp:81-84
+  if (grid_->local() && maps_->commSize != 1) throw InternalError();
   if (maps_->num_sticks() > grid_->max_num_local_z_columns()) throw InvalidParameterError();
   if (maps_->dimX > grid_->max_dim_x() || maps_->dimY > grid_->max_dim_y() ||
       maps_->dimZ > grid_->max_dim_z())
@@ -246,6 +349,9 @@ TransformEngine<T>::TransformEngine(SpfftProcessingUnitType executionUnit,
   // the grid limits are expressed in sticks; the padded pitch must fit as well
   if (sizeof(sb::cx<T>) * static_cast<size_t>(maps_->dimZ) * static_cast<size_t>(plan_->pitch) >
       grid_->bytes_a())
+    throw InvalidParameterError();
+  if (plan_->distributed &&
+      sizeof(sb::cx<T>) * static_cast<size_t>(plan_->exchange.planeSideElements) > grid_->bytes_q())
     throw InvalidParameterError();
   stream_.reset(new Stream());
   startEvent_.reset(new Event());
@@ -355,7 +461,8 @@ template <typename T>
 sb::XYArgs<T> TransformEngine<T>::make_xy_args(const TileMaps& geo, const T* spaceIn, T* spaceOut) {
   const IndexMaps& m = *maps_;
   sb::XYArgs<T> a{};
-  a.y = make_y_args<T>(m, geo, plan_->axes, plan_->ptrs, sticks(), nullptr);
+  a.y = make_y_stage_args(geo);
+  a.y.planes = nullptr;
   a.x = make_x_args<T>(m, plan_->axes, plan_->ptrs, nullptr, spaceIn, spaceOut);
   a.ring = plan_->xyRing;
   a.lag = plan_->xyLag;
@@ -366,12 +473,28 @@ sb::XYArgs<T> TransformEngine<T>::make_xy_args(const TileMaps& geo, const T* spa
 }
 
 template <typename T>
+sb::YArgs<T> TransformEngine<T>::make_y_stage_args(const TileMaps& geo) {
+  auto ya = make_y_args<T>(*maps_, geo, plan_->axes, plan_->ptrs, sticks(), planes());
+  if (plan_->distributed) {
+    // sticks of all ranks, read from / written to the plane-side exchange buffer
+    ya.sticks = static_cast<sb::cx<T>*>(grid_->array_q());
+    ya.srcBase = plan_->srcBase;
+    ya.srcPitch = plan_->srcPitch;
+    ya.zRowOffset = 0;
+  }
+  return ya;
+}
+
+template <typename T>
 void TransformEngine<T>::enqueue_backward(const T* input, T* output) {
   DeviceGuard guard(grid_->device_id());
   begin_call();
   const IndexMaps& m = *maps_;
-  if (space_bytes() == 0) return;
-  if (!output) throw InvalidParameterError();
+  const bool dist = plan_->distributed;
+  if (static_cast<size_t>(m.dimX) * m.dimY * m.dimZ == 0) return;
+  const bool haveSpace = space_bytes() > 0;
+  if (!haveSpace && !dist) return;
+  if (haveSpace && !output) throw InvalidParameterError();
   cudaStream_t s = stream_->get();
   const size_t ne = static_cast<size_t>(m.num_values());
   if (ne > 0 && !input) throw InvalidParameterError();
@@ -383,7 +506,7 @@ void TransformEngine<T>::enqueue_backward(const T* input, T* output) {
     values = static_cast<const T*>(grid_->array_b());
     record_stage("h2d values");
   }
-  // tile maps are only needed by the z stage; the stage wiring below only reads scalars
+  // the stage wiring only reads the scalars of the tile maps
   TileMaps geo;
   geo.numStickTiles = plan_->numStickTiles;
   geo.pitch = plan_->pitch;
@@ -396,6 +519,17 @@ void TransformEngine<T>::enqueue_backward(const T* input, T* output) {
     check_launch(Launch<T>::z(0, za, s));
     record_stage("z backward");
   }
+  // ---- exchange: every rank sends, for every peer, the rows of that peer's slab (one contiguous
+  // block of the plane-major stick buffer) -- replaces pack + MPI_Alltoallv + unpack
+  // (transpose_mpi_compact_buffered_gpu.cpp:163-224)
+  if (dist) {
+    const ExchangePlan& x = plan_->exchange;
+    grid_->communicator()->all_to_all_v(sticks(), x.stickOffset.data(), x.stickCount.data(),
+                                        grid_->array_q(), x.planeOffset.data(), x.planeCount.data(),
+                                        static_cast<int>(sizeof(sb::cx<T>)), s);
+    record_stage("exchange backward");
+  }
+  if (!haveSpace) return;
   const bool outOnDevice = is_device_pointer(output);
   T* outDev = outOnDevice ? output : device_space();
   if (plan_->fusedXY) {
@@ -404,8 +538,7 @@ void TransformEngine<T>::enqueue_backward(const T* input, T* output) {
     record_stage("xy backward");
   } else {
     // ---- y stage: stick gather + plane symmetry + y-FFT (execution_gpu.cpp:371-390)
-    auto ya = make_y_args<T>(m, geo, plan_->axes, plan_->ptrs, sticks(), planes());
-    check_launch(Launch<T>::y(0, ya, s));
+    check_launch(Launch<T>::y(0, make_y_stage_args(geo), s));
     record_stage("y backward");
     // ---- x stage: x-FFT (C2C / C2R) into the space domain
     auto xa = make_x_args<T>(m, plan_->axes, plan_->ptrs, planes(), nullptr, outDev);
@@ -423,8 +556,11 @@ void TransformEngine<T>::enqueue_forward(const T* input, T* output, SpfftScaling
   DeviceGuard guard(grid_->device_id());
   begin_call();
   const IndexMaps& m = *maps_;
-  if (space_bytes() == 0) return;
-  if (!input) throw InvalidParameterError();
+  const bool dist = plan_->distributed;
+  if (static_cast<size_t>(m.dimX) * m.dimY * m.dimZ == 0) return;
+  const bool haveSpace = space_bytes() > 0;
+  if (!haveSpace && !dist) return;
+  if (haveSpace && !input) throw InvalidParameterError();
   cudaStream_t s = stream_->get();
   const size_t ne = static_cast<size_t>(m.num_values());
   if (ne > 0 && !output) throw InvalidParameterError();
@@ -435,29 +571,41 @@ void TransformEngine<T>::enqueue_forward(const T* input, T* output, SpfftScaling
   geo.numXTiles = plan_->numXTiles;
   geo.symTile = plan_->symTile;
   geo.symLane = plan_->symLane;
+  // sticks anywhere (all ranks)? otherwise nothing consumes the planes
+  const bool anySticks = dist ? !plan_->exchange.stickSlot.empty() : (plan_->numStickTiles > 0 && ne > 0);
 
   // ---- x stage (execution_gpu.cpp:254-282)
-  const T* src = input;
-  if (!is_device_pointer(input)) {
-    check_gpu(cudaMemcpyAsync(device_space(), input, space_bytes(), cudaMemcpyHostToDevice, s));
-    src = device_space();
-    record_stage("h2d space");
+  if (haveSpace) {
+    const T* src = input;
+    if (!is_device_pointer(input)) {
+      check_gpu(cudaMemcpyAsync(device_space(), input, space_bytes(), cudaMemcpyHostToDevice, s));
+      src = device_space();
+      record_stage("h2d space");
+    }
+    if (plan_->fusedXY) {
+      if (anySticks) {
+        check_launch(Launch<T>::xy(1, make_xy_args(geo, src, nullptr), s));
+        record_stage("xy forward");
+      }
+    } else {
+      auto xa = make_x_args<T>(m, plan_->axes, plan_->ptrs, planes(), src, nullptr);
+      check_launch(Launch<T>::x(1, xa, s));
+      record_stage("x forward");
+      if (anySticks) {
+        // ---- y stage: y-FFT + scatter into the plane-major sticks / the exchange buffer
+        check_launch(Launch<T>::y(1, make_y_stage_args(geo), s));
+        record_stage("y forward");
+      }
+    }
   }
-  const bool haveSticks = plan_->numStickTiles > 0 && ne > 0;
-  if (plan_->fusedXY) {
-    if (!haveSticks) return;  // nothing would consume the planes
-    check_launch(Launch<T>::xy(1, make_xy_args(geo, src, nullptr), s));
-    record_stage("xy forward");
-  } else {
-    auto xa = make_x_args<T>(m, plan_->axes, plan_->ptrs, planes(), src, nullptr);
-    check_launch(Launch<T>::x(1, xa, s));
-    record_stage("x forward");
-    if (!haveSticks) return;  // nothing to gather
-    // ---- y stage: y-FFT + scatter into the plane-major sticks
-    auto ya = make_y_args<T>(m, geo, plan_->axes, plan_->ptrs, sticks(), planes());
-    check_launch(Launch<T>::y(1, ya, s));
-    record_stage("y forward");
+  if (dist) {
+    const ExchangePlan& x = plan_->exchange;
+    grid_->communicator()->all_to_all_v(grid_->array_q(), x.planeOffset.data(), x.planeCount.data(),
+                                        sticks(), x.stickOffset.data(), x.stickCount.data(),
+                                        static_cast<int>(sizeof(sb::cx<T>)), s);
+    record_stage("exchange forward");
   }
+  if (plan_->numStickTiles == 0 || ne == 0) return;  // no local values to produce
   // ---- z stage: z-FFT + compress (+ scaling) (execution_gpu.cpp:291-324)
   const bool outOnDevice = is_device_pointer(output);
   T* outDev = outOnDevice ? output : static_cast<T*>(grid_->array_b());

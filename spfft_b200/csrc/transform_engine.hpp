@@ -15,6 +15,7 @@
 
 #include "gpu_runtime.hpp"
 #include "index_plan.hpp"
+#include "nccl_dyn.hpp"
 #include "spfft/types.h"
 #include "stage_args.hpp"
 
@@ -26,6 +27,11 @@ class GridResources {
 public:
   GridResources(int maxDimX, int maxDimY, int maxDimZ, int maxNumLocalZSticks,
                 SpfftProcessingUnitType processingUnit, int maxNumThreads);
+  // Distributed grid over the GPUs of an NCCL communicator (reference: the MPI constructor,
+  // grid_internal.cpp:104-206)
+  GridResources(int maxDimX, int maxDimY, int maxDimZ, int maxNumLocalZSticks, int maxLocalZLength,
+                SpfftProcessingUnitType processingUnit, int maxNumThreads,
+                std::shared_ptr<Communicator> comm, SpfftExchangeType exchangeType);
   // same limits, new buffers (reference: GridInternal copy ctor, grid_internal.cpp:208-262)
   GridResources(const GridResources& other);
   GridResources& operator=(const GridResources&) = delete;
@@ -38,7 +44,12 @@ public:
   SpfftProcessingUnitType processing_unit() const { return pu_; }
   int device_id() const { return deviceId_; }
   int num_threads() const { return numThreads_; }
-  bool local() const { return true; }
+  bool local() const { return !comm_ || comm_->size() == 1; }
+  const std::shared_ptr<Communicator>& communicator() const { return comm_; }
+  SpfftExchangeType exchange_type() const { return exchangeType_; }
+  // plane-side exchange buffer of distributed transforms
+  void* array_q() const { return q_.get(); }
+  size_t bytes_q() const { return q_.bytes(); }
 
   // Device work arrays, capacities in bytes. A holds the plane-major stick buffer (and the real
   // space domain of R2C transforms), B the xy planes / the complex space domain / staged values.
@@ -61,7 +72,9 @@ private:
   SpfftProcessingUnitType pu_;
   int deviceId_ = 0;
   int numThreads_;
-  DeviceBuffer a_, b_, scratch_, counters_;
+  DeviceBuffer a_, b_, q_, scratch_, counters_;
+  std::shared_ptr<Communicator> comm_;
+  SpfftExchangeType exchangeType_ = SPFFT_EXCH_DEFAULT;
   PinnedBuffer host_;
   std::mutex hostMutex_;
 };
@@ -76,6 +89,12 @@ struct DevicePlan {
   // fused xy stage (fast_xy.cu): scratch ring geometry, 0 planes = separate y and x kernels
   bool fusedXY = false;
   int xyRing = 0, xyLag = 0, xyCounters = 0;
+  // distributed transforms: the stick <-> slab exchange (host offsets/counts) and the y-stage
+  // tables over all ranks' sticks
+  bool distributed = false;
+  ExchangePlan exchange;
+  const int* srcBase = nullptr;
+  const int* srcPitch = nullptr;
   std::vector<DeviceBuffer> storage;
   size_t deviceBytes = 0;
 };
@@ -120,6 +139,7 @@ public:
 private:
   void begin_call();
   sb::XYArgs<T> make_xy_args(const TileMaps& geo, const T* spaceIn, T* spaceOut);
+  sb::YArgs<T> make_y_stage_args(const TileMaps& geo);
   void record_stage(const char* name);
   size_t space_bytes() const;
   T* device_space() const;
@@ -141,6 +161,19 @@ private:
 
 template <typename T>
 std::shared_ptr<DevicePlan<T>> build_device_plan(const IndexMaps& maps, long long smemLimit);
+
+// Parameters of a distributed transform (parameters.cpp:43-140): local index conversion, then the
+// stick lists and plane counts of all ranks gathered over the communicator (collective call).
+std::shared_ptr<IndexMaps> make_distributed_index_maps(Communicator& comm, SpfftTransformType type,
+                                                       int dimX, int dimY, int dimZ, int localZLength,
+                                                       int numLocalElements,
+                                                       SpfftIndexFormatType indexFormat,
+                                                       const int* indices);
+
+// tile widths (log2 lanes) the stage kernels of a transform use; isFast* tell which axes run the
+// register-FFT kernels
+void choose_tile_lanes(const IndexMaps& m, int complexBytes, long long smemLimit, AxisPlans& ax,
+                       bool& fastX, bool& fastY, bool& fastZ);
 
 }  // namespace b200
 }  // namespace spfft

@@ -1,0 +1,118 @@
+"""Multi-GPU parity check of the distributed transform, one process per GPU (torchrun).
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \
+        --master-port 29511 tests/dist_gpu_check.py
+
+Every rank builds its part of the reference tests' fixtures (tests/mpi_tests/test_transform.cpp:
+uniform, all sticks on rank 0, sticks on rank 0 / planes on the last rank, R2C), runs backward and
+forward through the C ABI (spfft_grid_create_distributed_nccl + spfft_transform_create) and
+compares its slab / its values with the numpy oracle of the whole problem.
+Exit code 0 = all cases within tolerance on all ranks.
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def main():
+    import torch
+    import torch.distributed as dist
+    from conftest import FixtureGen, hermitian_space_values
+    from oracle import spfft_oracle as orc
+    from spfft_b200 import capi
+
+    rank = int(os.environ["RANK"])
+    world = int(os.environ["WORLD_SIZE"])
+    torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", rank)))
+    dist.init_process_group("nccl", device_id=torch.device("cuda", torch.cuda.current_device()))
+    lib = capi.load()
+    comm = capi.comm_from_torch(lib)
+    gen = FixtureGen(os.path.join(ROOT, "oracle", "_ref", "liboracle_gen.so"))
+
+    uniform = [1.0] * world
+    first = [1.0] + [0.0] * (world - 1)
+    last = [0.0] * (world - 1) + [1.0]
+    cases = [
+        (0, (11, 12, 13), uniform, uniform, False, False),
+        (0, (12, 13, 11), first, uniform, False, False),
+        (0, (13, 11, 12), first, last, False, False),
+        (1, (12, 11, 13), uniform, uniform, False, False),
+        (1, (13, 12, 11), first, uniform, False, False),
+        (0, (32, 32, 32), uniform, uniform, True, False),
+        (0, (64, 32, 128), uniform, [1.0 + r for r in range(world)], True, False),
+        (1, (64, 64, 32), uniform, uniform, False, False),
+        (0, (32, 64, 32), uniform, uniform, True, True),
+        (0, (100, 100, 100), uniform, uniform, False, False),
+    ]
+    worst = 0.0
+    ok = True
+    for ttype, (nx, ny, nz), sdist, pdist, center, single in cases:
+        tol = 1e-5 if single else 1e-12
+        trips, vals = [], []
+        for r in range(world):
+            t, v = gen.make(nx, ny, nz, hermitian=bool(ttype), center=center, num_ranks=world, rank=r,
+                            stick_distribution=sdist)
+            trips.append(t)
+            vals.append(v)
+        if ttype:
+            full = hermitian_space_values(orc, nx, ny, nz, np.concatenate(trips))
+            off = 0
+            for r in range(world):
+                vals[r] = full[off:off + len(trips[r])]
+                off += len(trips[r])
+        planes = gen.plane_split(nz, pdist)
+        params = orc.distributed_parameters(ttype, nx, ny, nz, trips, planes)
+        ref_slabs = orc.backward_distributed(params, vals)
+        ref_back = orc.forward_distributed(params, ref_slabs, orc.SPFFT_FULL_SCALING)
+
+        max_sticks = max(p.num_sticks for p in params)
+        grid = capi.DistributedGrid(lib, comm, nx, ny, nz, max_sticks, max(planes), single=single)
+        t = grid.create_transform(capi.SPFFT_PU_GPU, ttype, nx, ny, nz, planes[rank], trips[rank])
+        assert t.local_z_length() == planes[rank] and t.local_z_offset() == sum(planes[:rank])
+        assert t.num_global_elements() == sum(len(x) for x in trips)
+        cdt = np.complex64 if single else np.complex128
+        rdt = torch.float32 if single else torch.float64
+        n = len(trips[rank])
+        d_v = torch.from_numpy(np.ascontiguousarray(vals[rank].astype(cdt)).view(np.float32 if single else np.float64).copy()).cuda() if n else None
+        nreal = planes[rank] * ny * nx * (1 if ttype else 2)
+        d_s = torch.full((max(nreal, 1),), float("nan"), dtype=rdt, device="cuda")
+        for _ in range(2):
+            t.backward_ptr(d_v, d_s)
+        sdt = (np.float32 if single else np.float64) if ttype else cdt
+        space = d_s.cpu().numpy()[:nreal].view(sdt).reshape(planes[rank], ny, nx)
+        d_o = torch.zeros(max(2 * n, 1), dtype=rdt, device="cuda")
+        t.forward_ptr(d_s, d_o, capi.SPFFT_FULL_SCALING)
+        back = d_o.cpu().numpy()[:2 * n].view(cdt)
+        eb = orc.rel_l2(space, ref_slabs[rank]) if nreal else 0.0
+        ef = orc.rel_l2(back, ref_back[rank]) if n else 0.0
+        # independent-distributed constructor + host pointers on one case
+        if (nx, ny, nz) == (11, 12, 13):
+            t2 = capi.distributed_transform(lib, comm, ttype, nx, ny, nz, planes[rank], trips[rank])
+            t2.backward(np.ascontiguousarray(vals[rank]), capi.SPFFT_PU_HOST)
+            sp2 = t2.space_domain_host_view(ttype).copy() if nreal else np.zeros(0)
+            eb = max(eb, orc.rel_l2(sp2, ref_slabs[rank]) if nreal else 0.0)
+            t2.destroy()
+        good = eb <= tol and ef <= tol
+        ok = ok and good
+        worst = max(worst, eb / tol, ef / tol)
+        print(f"[rank {rank}] type={ttype} {nx}x{ny}x{nz} sticks={params[rank].num_sticks} planes={planes[rank]} "
+              f"bwd={eb:.2e} fwd={ef:.2e} {'ok' if good else 'FAIL'}", flush=True)
+        t.destroy()
+        grid.destroy()
+    flag = torch.tensor([0 if ok else 1], device="cuda")
+    dist.all_reduce(flag)
+    dist.barrier()
+    if rank == 0:
+        print("DIST_GPU_CHECK", "PASS" if int(flag.item()) == 0 else "FAIL", f"worst err/tol {worst:.3f}", flush=True)
+    comm.destroy()
+    dist.destroy_process_group()
+    sys.exit(0 if int(flag.item()) == 0 else 1)
+
+
+if __name__ == "__main__":
+    main()

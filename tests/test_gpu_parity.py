@@ -450,3 +450,36 @@ def test_golden_fixtures(torch_cuda, lib, path):
     space, back = _run_pair(torch_cuda, lib, ttype, nx, ny, nz, g["triplets"], g["values"], single=single)
     assert orc.rel_l2(space, g["space"]) <= TOL[single]
     assert orc.rel_l2(back, g["forward"]) <= TOL[single]
+
+
+def test_fused_xy_kernel(torch_cuda, lib, gen):
+    """The persistent fused y+x kernel (SPFFT_B200_TUNE bit 2): same results as the default path."""
+    old = os.environ.get("SPFFT_B200_TUNE")
+    os.environ["SPFFT_B200_TUNE"] = "5"
+    try:
+        for shape, single in [((64, 64, 32), False), ((128, 128, 64), False), ((32, 32, 130), True)]:
+            nx, ny, nz = shape
+            trip, vals = gen.make(nx, ny, nz, center=True, stick_fraction=0.6)
+            param = orc.Parameters(0, nx, ny, nz, trip)
+            space, back = _run_pair(torch_cuda, lib, 0, nx, ny, nz, trip, vals, single=single)
+            v = vals.astype(np.complex64).astype(np.complex128) if single else vals
+            assert orc.rel_l2(space, orc.backward(param, v)) <= TOL[single]
+            assert orc.rel_l2(back, v) <= TOL[single]
+    finally:
+        if old is None:
+            del os.environ["SPFFT_B200_TUNE"]
+        else:
+            os.environ["SPFFT_B200_TUNE"] = old
+
+
+def test_distributed_two_gpus(torch_cuda):
+    """One process per GPU over NCCL (tests/dist_gpu_check.py); skipped on a single-GPU box."""
+    import subprocess
+    import sys
+    if torch_cuda.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29533",
+                          os.path.join(root, "tests", "dist_gpu_check.py")], capture_output=True, text=True, timeout=900)
+    assert res.returncode == 0 and "DIST_GPU_CHECK PASS" in res.stdout, res.stdout[-3000:] + res.stderr[-3000:]
