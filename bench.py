@@ -44,7 +44,7 @@ UNIT = "pairs/s"
 def spherical_triplets(n: int, hermitian: bool) -> np.ndarray:
     """All centered (kx,ky,kz) with |k|^2 <= (n/2)^2 (pi/6 fill), grouped by stick in ascending
     storage key x*Ny+y, z ascending in storage order. Vectorised twin of
-    oracle.spfft_oracle.spherical_cutoff_triplets (tests/test_bench_workload.py pins them)."""
+    oracle.spfft_oracle.spherical_cutoff_triplets (tests/test_oracle.py pins them)."""
     r2 = (n / 2) ** 2
     k = np.arange(-(n // 2) + (1 if n % 2 == 0 else 0), n // 2 + 1, dtype=np.int64)
     ks = np.concatenate([k[k >= 0], k[k < 0]])  # storage order
@@ -219,10 +219,32 @@ def main():
     lib = capi.load()
 
     trip = spherical_triplets(n, r2c)
-    ne = len(trip)
+    ne_total = len(trip)
     ttype = capi.SPFFT_TRANS_R2C if r2c else capi.SPFFT_TRANS_C2C
-    t = capi.Transform(lib, processing_unit=capi.SPFFT_PU_GPU, transform_type=ttype, dim_x=n, dim_y=n,
-                       dim_z=n, indices=trip, single=single)
+    comm = None
+    nz_local = n
+    if world > 1:
+        # ONE transform of the named size sharded over the GPUs (strong scaling): frequency domain =
+        # contiguous x ranges of whole z-sticks balanced by element count (docs/source/details.rst:
+        # 58-59), space domain = slabs of n/world planes (benchmark.cpp:171-172)
+        keys = (trip[:, 0].astype(np.int64) % n) * n + (trip[:, 1].astype(np.int64) % n)
+        stick_start = np.flatnonzero(np.concatenate([[True], keys[1:] != keys[:-1]]))
+        cuts = [0]
+        for r in range(1, world):
+            target = ne_total * r // world
+            cuts.append(int(stick_start[min(int(np.searchsorted(stick_start, target)), len(stick_start) - 1)]))
+        cuts.append(ne_total)
+        trip = np.ascontiguousarray(trip[cuts[rank]:cuts[rank + 1]])
+        nz_local = n // world + (1 if rank < n % world else 0)
+        comm = capi.comm_from_torch(lib)
+        ns_all = int(len(stick_start))
+        max_sticks = ns_all  # generous upper bound for the grid
+        grid = capi.DistributedGrid(lib, comm, n, n, n, max_sticks, (n + world - 1) // world, single=single)
+        t = grid.create_transform(capi.SPFFT_PU_GPU, ttype, n, n, n, nz_local, trip)
+    else:
+        t = capi.Transform(lib, processing_unit=capi.SPFFT_PU_GPU, transform_type=ttype, dim_x=n, dim_y=n,
+                           dim_z=n, indices=trip, single=single)
+    ne = len(trip)
     _, sticks = capi.transform_index_maps(t)
     ns = len(sticks)
     del sticks
@@ -230,7 +252,7 @@ def main():
     rng = np.random.default_rng(42 + rank)
     vals_host = rng.uniform(-1, 1, 2 * ne).astype(np.float32 if single else np.float64)
     d_vals = torch.from_numpy(vals_host).cuda()
-    space_reals = n ** 3 * (1 if r2c else 2)
+    space_reals = n * n * nz_local * (1 if r2c else 2)
     d_space = torch.empty(space_reals, dtype=rdt, device="cuda")
     d_out = torch.empty(2 * ne, dtype=rdt, device="cuda")
 
@@ -269,7 +291,7 @@ def main():
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         ms_total = float(tt.item())
     ms_per_step = ms_total / args.steps
-    value = world * 1e3 / ms_per_step  # every rank runs its own transform of the named size
+    value = 1e3 / ms_per_step  # N > 1: ONE transform of the named size sharded over the GPUs
 
     # ---------------- roofline of the dominant kernel ----------------
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -279,6 +301,11 @@ def main():
     else:
         peak, peak_src = 6650.0, "B200_PROFILING.md fallback (of fallback)"
     ab = algorithmic_bytes(n, ns, ne, r2c, single)
+    if world > 1:  # this rank's share: its sticks over all z, all sticks over its planes, its slab
+        c = 8 if single else 16
+        ab = {"z": (c + 4) * ne + c * ns * n, "y": c * ns_all * nz_local,
+              "x": (c // 2 if r2c else c) * n * n * nz_local}
+        ab["dir"] = ab["z"] + ab["y"] + ab["x"]
     stage_bytes = {"z backward": ab["z"], "y backward": ab["y"], "x backward": ab["x"],
                    "x forward": ab["x"], "y forward": ab["y"], "z forward": ab["z"],
                    "xy backward": ab["y"] + ab["x"], "xy forward": ab["y"] + ab["x"]}
@@ -292,7 +319,23 @@ def main():
                     "algorithmic_bytes_per_launch": stage_bytes[nm], "kernel_ms": ms,
                     "pair_algorithmic_bytes": 2 * ab["dir"],
                     "pair_frac": 2 * ab["dir"] / (ms_per_step * 1e-3) / 1e9 / peak,
+                    "scope": "rank 0's share of the sharded transform" if world > 1 else "whole transform",
                     "stage_ms": {k: round(v, 4) for k, v in stages}}
+
+    # ---------------- NVLink share of the exchange (N > 1) ----------------
+    nvlink = None
+    if world > 1:
+        c = 8 if single else 16
+        sent = c * ns * n * (world - 1) / world  # bytes this rank sends (= receives) per exchange
+        ex = [ms for nm, ms in stages if nm.startswith("exchange")]
+        ex_ms = float(np.mean(ex)) if ex else float("nan")
+        tt = torch.tensor([ex_ms, sent], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ex_ms, sent = float(tt[0].item()), float(tt[1].item())
+        nvlink = {"exchange_ms": ex_ms, "bytes_sent_per_gpu": sent, "achieved": sent / (ex_ms * 1e-3) / 1e9,
+                  "peak": 770.0, "unit": "GB/s", "frac": sent / (ex_ms * 1e-3) / 1e9 / 770.0,
+                  "peak_source": "B200_PROFILING.md measured peer copy per direction per GPU",
+                  "collective": "ncclGroupStart / ncclSend+ncclRecv per peer / ncclGroupEnd on the transform's stream"}
 
     # ---------------- end to end through host buffers ----------------
     e2e = None
@@ -320,7 +363,7 @@ def main():
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             ms_e = float(tt.item())
         bpr = 4 if single else 8
-        e2e = {"value": world * 1e3 / ms_e, "unit": UNIT,
+        e2e = {"value": 1e3 / ms_e, "unit": UNIT,
                "h2d_bytes_per_step": (2 * ne + space_reals) * bpr, "d2h_bytes_per_step": (space_reals + 2 * ne) * bpr,
                "steps": ksteps, "ms_per_step": ms_e}
         del h_vals, h_space, h_out
@@ -336,12 +379,15 @@ def main():
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f32" if single else "f64",
+                "scaling": "strong" if world > 1 else "weak", "vs_baseline": None, "dtype": "f32" if single else "f64",
                 "data": "synthetic", "config": config, "clocks": clocks.summary(), "e2e": e2e,
                 "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
                 "num_sticks": ns, "num_elements": ne}
+        line["config"]["l2"] = config["l2"]
         if world > 1:
-            line["config"]["parallelism"] = f"{world} independent replicas (one transform per GPU)"
+            line["config"]["parallelism"] = (f"one {n}^3 transform sharded over {world} GPUs: z-stick pencils (contiguous "
+                                             f"x ranges) <-> z slabs, one NCCL all-to-all per direction")
+            line["nvlink"] = nvlink
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

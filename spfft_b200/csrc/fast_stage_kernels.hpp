@@ -368,7 +368,12 @@ SB_DEV void y_backward_fast(const YArgs<T>& a, int block, Ctx ctx, cx<T>* S) {
     nextXt = (block + a.pfDist) % a.numXTiles;
     nextRow = a.sticks + (size_t)((block + a.pfDist) / a.numXTiles + a.zRowOffset) * a.pitch;
   }
-  if (a.inv)
+  if (a.srcBase && a.inv && a.tilePitch[xt] != 0) {
+    // distributed, all sticks of this tile from one rank: contiguous inside that rank's block.
+    // The gather form indexes relative to the tile's first stick, so pass row - xtStart[xt].
+    const cx<T>* row = a.sticks + (size_t)a.tileBase[xt] + (size_t)zl * a.tilePitch[xt] - a.xtStart[xt];
+    y_backward_gather<T, N, Mem::Plain>(a, xt, row, a.planes + (size_t)zl * N * a.nxf, -1, nullptr, ctx, S);
+  } else if (a.inv && !a.srcBase)
     y_backward_gather<T, N, Mem::Plain>(a, xt, a.sticks + (size_t)(zl + a.zRowOffset) * a.pitch,
                                         a.planes + (size_t)zl * N * a.nxf, nextXt, nextRow, ctx, S);
   else
@@ -386,7 +391,10 @@ SB_DEV void y_forward_fast(const YArgs<T>& a, int block, Ctx ctx, cx<T>* S) {
     nextXt = (block + a.pfDist) % a.numXTiles;
     nextPlane = a.planes + (size_t)((block + a.pfDist) / a.numXTiles) * N * a.nxf;
   }
-  if (a.inv)
+  if (a.srcBase && a.inv && a.tilePitch[xt] != 0) {
+    cx<T>* row = a.sticks + (size_t)a.tileBase[xt] + (size_t)zl * a.tilePitch[xt] - a.xtStart[xt];
+    y_forward_gather<T, N, Mem::Plain>(a, xt, a.planes + (size_t)zl * N * a.nxf, row, nextXt, nextPlane, ctx, S);
+  } else if (a.inv && !a.srcBase)
     y_forward_gather<T, N, Mem::Plain>(a, xt, a.planes + (size_t)zl * N * a.nxf,
                                        a.sticks + (size_t)(zl + a.zRowOffset) * a.pitch, nextXt, nextPlane,
                                        ctx, S);

@@ -156,7 +156,7 @@ void finish_distributed_index_maps(IndexMaps& m, int commRank,
   }
 }
 
-ExchangePlan build_exchange_plan(const IndexMaps& m, int log2Vz, int log2Vy) {
+ExchangePlan build_exchange_plan(const IndexMaps& m, int log2Vz, int log2Vy, bool fastY) {
   ExchangePlan x;
   const int P = m.commSize, me = m.commRank;
   const int Vz = 1 << log2Vz, Vy = 1 << log2Vy;
@@ -208,6 +208,35 @@ ExchangePlan build_exchange_plan(const IndexMaps& m, int log2Vz, int log2Vy) {
     x.srcPitch[e] = x.pitchPerRank[all[e].rank];
   }
   for (int k = 0; k < x.numXTiles; ++k) x.xtStart[k + 1] += x.xtStart[k];
+
+  // single-source tiles + inverse map for the gather-form y kernels
+  x.tileBase.assign(x.numXTiles, 0);
+  x.tilePitch.assign(x.numXTiles, 0);
+  for (int t = 0; t < x.numXTiles; ++t) {
+    const int e0 = x.xtStart[t], e1 = x.xtStart[t + 1];
+    if (e0 == e1) continue;
+    bool single = true;
+    for (int e = e0 + 1; e < e1 && single; ++e)
+      single = all[e].rank == all[e0].rank && all[e].idx == all[e0].idx + (e - e0);
+    if (single) {
+      x.tileBase[t] = x.srcBase[e0];
+      x.tilePitch[t] = x.srcPitch[e0];
+    }
+  }
+  if (fastY && !all.empty()) {
+    const int ny = m.dimY;
+    const int T = ny / 8;
+    const size_t perTile = static_cast<size_t>(Vy) * T * 8;
+    x.yInv.assign(perTile * x.numXTiles, 0xFFFF);
+    for (size_t e = 0; e < all.size(); ++e) {
+      const int xx = all[e].key / ny;
+      const int yy = all[e].key - xx * ny;
+      const int tile = xx >> log2Vy;
+      const int lane = xx & (Vy - 1);
+      const size_t tid = static_cast<size_t>(lane) * T + (yy % T);
+      x.yInv[perTile * tile + tid * 8 + yy / T] = static_cast<unsigned short>(e - x.xtStart[tile]);
+    }
+  }
   return x;
 }
 

@@ -76,10 +76,15 @@ struct ExchangePlan {
   std::vector<int> stickSlot;  // [NsTotal] y*Vy + (x mod Vy)
   std::vector<int> srcBase;    // [NsTotal] offset of the stick's value at local plane 0 inside Q
   std::vector<int> srcPitch;   // [NsTotal] distance between consecutive local planes
+  // x tiles whose sticks all come from ONE rank (the usual case: ranks own contiguous x ranges)
+  // are contiguous inside that rank's block: first stick at tileBase + plane*tilePitch, so the
+  // inverse-map (gather) form of the y kernels applies; tilePitch == 0 marks a mixed tile
+  std::vector<int> tileBase, tilePitch;  // [numXTiles]
+  std::vector<unsigned short> yInv;      // inverse map over the global sorted stick list (fast y only)
   int numXTiles = 0;
 };
 
-ExchangePlan build_exchange_plan(const IndexMaps& maps, int log2Vz, int log2Vy);
+ExchangePlan build_exchange_plan(const IndexMaps& maps, int log2Vz, int log2Vy, bool fastY = false);
 
 // What the stage kernels read. All arrays are host vectors here; TransformEngine uploads them.
 struct TileMaps {

@@ -76,6 +76,9 @@ struct YArgs {
   // local plane-major layout sticks[(zl + zRowOffset)*pitch + e]
   const int* srcBase;
   const int* srcPitch;
+  // per x tile: sticks contiguous at sticks[tileBase[xt] + zl*tilePitch[xt] + i] (tilePitch != 0)
+  const int* tileBase;
+  const int* tilePitch;
 };
 
 template <typename T>

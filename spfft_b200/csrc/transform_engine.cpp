@@ -292,13 +292,16 @@ std::shared_ptr<DevicePlan<T>> build_device_plan(const IndexMaps& m, long long s
   if (m.commSize > 1) {
     // y stage over ALL ranks' sticks, read from / written to the plane-side exchange buffer
     plan->distributed = true;
-    plan->exchange = build_exchange_plan(m, ax.log2Vz, ax.log2Vy);
+    plan->exchange = build_exchange_plan(m, ax.log2Vz, ax.log2Vy, fastY);
     plan->numXTiles = plan->exchange.numXTiles;
     p.xtStart = upload(st, total, plan->exchange.xtStart);
     p.stickSlot = upload(st, total, plan->exchange.stickSlot);
     plan->srcBase = upload(st, total, plan->exchange.srcBase);
     plan->srcPitch = upload(st, total, plan->exchange.srcPitch);
-    p.yInv = nullptr;  // the inverse-map form needs contiguous stick rows
+    plan->tileBase = upload(st, total, plan->exchange.tileBase);
+    plan->tilePitch = upload(st, total, plan->exchange.tilePitch);
+    // inverse-map form for the tiles whose sticks are contiguous in one source block
+    p.yInv = upload(st, total, plan->exchange.yInv);
     plan->fusedXY = false;
   } else {
     p.xtStart = upload(st, total, t.xtStart);
@@ -480,6 +483,8 @@ sb::YArgs<T> TransformEngine<T>::make_y_stage_args(const TileMaps& geo) {
     ya.sticks = static_cast<sb::cx<T>*>(grid_->array_q());
     ya.srcBase = plan_->srcBase;
     ya.srcPitch = plan_->srcPitch;
+    ya.tileBase = plan_->tileBase;
+    ya.tilePitch = plan_->tilePitch;
     ya.zRowOffset = 0;
   }
   return ya;

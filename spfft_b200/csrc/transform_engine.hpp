@@ -95,6 +95,9 @@ struct DevicePlan {
   ExchangePlan exchange;
   const int* srcBase = nullptr;
   const int* srcPitch = nullptr;
+  const int* tileBase = nullptr;
+  const int* tilePitch = nullptr;
+  const unsigned short* distYInv = nullptr;
   std::vector<DeviceBuffer> storage;
   size_t deviceBytes = 0;
 };

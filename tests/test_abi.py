@@ -23,7 +23,7 @@ def _declared_symbols():
         for m in re.finditer(r"SPFFT_FN\((\w+)\)\(", open(os.path.join(detail, inc)).read()):
             names.add("spfft_" + m.group(1))
             names.add("spfft_float_" + m.group(1))
-    for m in re.finditer(r"\b(spfft_b200_\w+)\s*\(", open(os.path.join(INC, "spfft", "b200_ext.h")).read()):
+    for m in re.finditer(r"SPFFT_EXPORT\s+SpfftError\s+(spfft_\w+)\s*\(", open(os.path.join(INC, "spfft", "b200_ext.h")).read()):
         names.add(m.group(1))
     return sorted(names)
 
