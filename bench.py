@@ -308,7 +308,8 @@ def main():
         ab["dir"] = ab["z"] + ab["y"] + ab["x"]
     stage_bytes = {"z backward": ab["z"], "y backward": ab["y"], "x backward": ab["x"],
                    "x forward": ab["x"], "y forward": ab["y"], "z forward": ab["z"],
-                   "xy backward": ab["y"] + ab["x"], "xy forward": ab["y"] + ab["x"]}
+                   "xy backward": ab["y"] + ab["x"], "xy forward": ab["y"] + ab["x"],
+                   "z backward + exchange": ab["z"], "y forward + exchange": ab["y"]}
     kernels = [(nm, ms) for nm, ms in stages if nm in stage_bytes]
     roofline = None
     if kernels:
@@ -327,15 +328,30 @@ def main():
     if world > 1:
         c = 8 if single else 16
         sent = c * ns * n * (world - 1) / world  # bytes this rank sends (= receives) per exchange
-        ex = [ms for nm, ms in stages if nm.startswith("exchange")]
+        peer = capi.peer_exchange(t)
+        if peer:
+            # the exchange is fused into the z (backward) / y (forward) kernels: their duration is
+            # the time the NVLink bytes had to move in
+            ex = [ms for nm, ms in stages if nm.endswith("+ exchange")]
+            bar = [ms for nm, ms in stages if nm.startswith("barrier")]
+            how = ("fused: z-stage (backward) and y-stage (forward) kernels store straight into the owner's buffer over "
+                   "NVLink peer memory (CUDA IPC), flag barrier through the same mapped memory; no NCCL on the data path")
+        else:
+            ex = [ms for nm, ms in stages if nm.startswith("exchange")]
+            bar = []
+            how = "ncclGroupStart / ncclSend+ncclRecv per peer / ncclGroupEnd on the transform's stream"
         ex_ms = float(np.mean(ex)) if ex else float("nan")
-        tt = torch.tensor([ex_ms, sent], dtype=torch.float64, device="cuda")
+        bar_ms = float(np.mean(bar)) if bar else 0.0
+        tt = torch.tensor([ex_ms, sent, bar_ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        ex_ms, sent = float(tt[0].item()), float(tt[1].item())
-        nvlink = {"exchange_ms": ex_ms, "bytes_sent_per_gpu": sent, "achieved": sent / (ex_ms * 1e-3) / 1e9,
+        ex_ms, sent, bar_ms = float(tt[0].item()), float(tt[1].item()), float(tt[2].item())
+        nvlink = {"exchange_ms": ex_ms, "barrier_ms": bar_ms, "bytes_sent_per_gpu": sent,
+                  "achieved": sent / (ex_ms * 1e-3) / 1e9,
                   "peak": 770.0, "unit": "GB/s", "frac": sent / (ex_ms * 1e-3) / 1e9 / 770.0,
                   "peak_source": "B200_PROFILING.md measured peer copy per direction per GPU",
-                  "collective": "ncclGroupStart / ncclSend+ncclRecv per peer / ncclGroupEnd on the transform's stream"}
+                  "exchange_ms_is": ("duration of the fused compute+exchange kernel (mean of the two directions, max over "
+                                     "ranks)" if peer else "duration of the NCCL group (mean of the two directions, max over ranks)"),
+                  "collective": how}
 
     # ---------------- end to end through host buffers ----------------
     e2e = None
@@ -386,7 +402,8 @@ def main():
         line["config"]["l2"] = config["l2"]
         if world > 1:
             line["config"]["parallelism"] = (f"one {n}^3 transform sharded over {world} GPUs: z-stick pencils (contiguous "
-                                             f"x ranges) <-> z slabs, one NCCL all-to-all per direction")
+                                             f"x ranges) <-> z slabs, one all-to-all per direction "
+                                             f"({'fused into the stage kernels over NVLink peer memory' if nvlink and 'fused' in nvlink['collective'] else 'NCCL grouped send/recv'})")
             line["nvlink"] = nvlink
         print(json.dumps(line))
     if world > 1:

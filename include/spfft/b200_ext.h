@@ -56,6 +56,15 @@ SPFFT_EXPORT SpfftError spfft_float_transform_create_independent_distributed_ncc
     SpfftTransformType transformType, int dimX, int dimY, int dimZ, int localZLength,
     int numLocalElements, SpfftIndexFormatType indexFormat, const int* indices);
 
+/* Whether a distributed transform exchanges through peer-mapped memory (CUDA IPC over NVLink /
+ * NVSwitch): the z stage (backward) and the y stage (forward) then store their results straight
+ * into the destination rank's buffer and a flag barrier through the same mapped memory orders the
+ * stages -- compute and exchange are one kernel. 0: grouped ncclSend/ncclRecv (peer mapping
+ * unavailable, more than 8 ranks, or SPFFT_B200_P2P=0 in the environment). */
+SPFFT_EXPORT SpfftError spfft_b200_transform_peer_exchange(SpfftTransform transform, int* enabled);
+SPFFT_EXPORT SpfftError spfft_b200_float_transform_peer_exchange(SpfftFloatTransform transform,
+                                                                 int* enabled);
+
 /* Host-only view of the exchange a rank would perform (no GPU, no NCCL): block offsets / counts
  * (in complex elements) inside the stick-side buffer [dimZ][pitch(rank)] and the plane-side buffer
  * (one block [localPlanes][pitch(r)] per source rank), and the y-stage tables over all ranks'

@@ -321,7 +321,8 @@ _TRANSFORM_FUNCS = ["transform_create", "transform_create_independent", "transfo
                     "transform_set_execution_mode"]
 _MULTI_FUNCS = ["multi_transform_forward", "multi_transform_forward_ptr",
                 "multi_transform_backward", "multi_transform_backward_ptr"]
-_EXT_PER_PRECISION = ["transform_index_maps", "transform_stream", "transform_set_profiling",
+_EXT_PER_PRECISION = ["transform_index_maps", "transform_stream", "transform_peer_exchange",
+                      "transform_set_profiling",
                       "transform_stage_times"]
 _EXT_COMMON = ["spfft_b200_convert_index_triplets", "spfft_b200_kernel_launch_count",
                "spfft_b200_nccl_unique_id", "spfft_b200_comm_create", "spfft_b200_comm_destroy",
@@ -396,6 +397,14 @@ def transform_stream(t: Transform) -> int:
     name = "spfft_b200_float_transform_stream" if t.single else "spfft_b200_transform_stream"
     t.lib.call(name, t.handle, C.byref(p))
     return p.value or 0
+
+
+def peer_exchange(t: Transform) -> bool:
+    """spfft_b200_transform_peer_exchange: exchange fused into the stage kernels over peer memory?"""
+    v = C.c_int()
+    name = "spfft_b200_float_transform_peer_exchange" if t.single else "spfft_b200_transform_peer_exchange"
+    t.lib.call(name, t.handle, C.byref(v))
+    return bool(v.value)
 
 
 def set_profiling(t: Transform, enable: bool) -> None:

@@ -179,9 +179,9 @@ SB_DEV void z_backward_fast(const ZArgs<T>& a, int tile, Ctx ctx, cx<T>* S) {
   SB_PHASE_BEGIN
   SB_ROW_IDS
   fast_fft_tail<T, N, LOG2V, true, SwzRow>(v, S, a.ftw, j, lane);
-  cx<T>* out = a.sticks + (size_t)tile * V + lane;
+  const size_t col = (size_t)tile * V + lane;
 #pragma unroll
-  for (int m = 0; m < 8; ++m) out[(size_t)(j + TT * m) * a.pitch] = v[m];
+  for (int m = 0; m < 8; ++m) z_row<T>(a, j + TT * m)[col] = v[m];
   SB_PHASE_END_NOSYNC
 }
 
@@ -350,7 +350,7 @@ SB_DEV void y_forward_tile(const YArgs<T>& a, int xt, const cx<T>* plane, cx<T>*
     for (int u = 0; u < U; ++u) {
       if (base + u * nthr < e1) {
         const int e = base + u * nthr;
-        cx<T>* dst = a.srcBase ? a.sticks + (size_t)a.srcBase[e] + (size_t)zl * a.srcPitch[e] : stickRow + e;
+        cx<T>* dst = a.srcBase ? y_dist_stick<T, true>(a, e, zl) : stickRow + e;
         st_g<STS>(dst, S[SwzRow::at<LOG2V>(slot[u] >> LOG2V, slot[u] & (V - 1))]);
       }
     }
@@ -392,7 +392,7 @@ SB_DEV void y_forward_fast(const YArgs<T>& a, int block, Ctx ctx, cx<T>* S) {
     nextPlane = a.planes + (size_t)((block + a.pfDist) / a.numXTiles) * N * a.nxf;
   }
   if (a.srcBase && a.inv && a.tilePitch[xt] != 0) {
-    cx<T>* row = a.sticks + (size_t)a.tileBase[xt] + (size_t)zl * a.tilePitch[xt] - a.xtStart[xt];
+    cx<T>* row = y_dist_tile<T, true>(a, xt, zl) - a.xtStart[xt];
     y_forward_gather<T, N, Mem::Plain>(a, xt, a.planes + (size_t)zl * N * a.nxf, row, nextXt, nextPlane, ctx, S);
   } else if (a.inv && !a.srcBase)
     y_forward_gather<T, N, Mem::Plain>(a, xt, a.planes + (size_t)zl * N * a.nxf,
@@ -498,9 +498,9 @@ SB_DEV void z_backward_gather(const ZArgs<T>& a, int tile, Ctx ctx, cx<T>* S) {
   SB_PHASE_BEGIN
   SB_ROW_IDS
   fast_fft_tail<T, N, LOG2V, true, SwzCol>(v, S, a.ftw, j, lane);
-  cx<T>* out = a.sticks + (size_t)tile * V + lane;
+  const size_t col = (size_t)tile * V + lane;
 #pragma unroll
-  for (int m = 0; m < 8; ++m) out[(size_t)(j + TT * m) * a.pitch] = v[m];
+  for (int m = 0; m < 8; ++m) z_row<T>(a, j + TT * m)[col] = v[m];
   SB_PHASE_END_NOSYNC
 }
 

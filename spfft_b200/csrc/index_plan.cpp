@@ -183,6 +183,23 @@ ExchangePlan build_exchange_plan(const IndexMaps& m, int log2Vz, int log2Vy, boo
   }
   x.planeSideElements = q;
   if (q > 0x7fffffffLL) throw OverflowError();
+  // peer-memory form, backward: where row z of MY sticks lives inside the plane-side buffer of the
+  // rank d that owns plane z (block of source `me` inside d's buffer, row z - planeOffset(d))
+  if (P <= 255) {
+    x.rowRank.assign(m.dimZ, 0);
+    x.rowOff.assign(m.dimZ, 0);
+    for (int d = 0; d < P; ++d) {
+      long long blockOfMe = 0;  // offset of my block inside d's buffer
+      for (int r = 0; r < me; ++r)
+        blockOfMe += static_cast<long long>(m.numPlanesPerRank[d]) * x.pitchPerRank[r];
+      for (int zl = 0; zl < m.numPlanesPerRank[d]; ++zl) {
+        const int z = m.planeOffsetPerRank[d] + zl;
+        if (z < 0 || z >= m.dimZ) throw InternalError();
+        x.rowRank[z] = static_cast<unsigned char>(d);
+        x.rowOff[z] = blockOfMe + static_cast<long long>(zl) * myPitch;
+      }
+    }
+  }
 
   // all sticks of all ranks, ordered by key: (key, rank, local index)
   struct Entry {
@@ -207,11 +224,24 @@ ExchangePlan build_exchange_plan(const IndexMaps& m, int log2Vz, int log2Vy, boo
     x.srcBase[e] = static_cast<int>(x.planeOffset[all[e].rank] + all[e].idx);
     x.srcPitch[e] = x.pitchPerRank[all[e].rank];
   }
+  // peer-memory form, forward: row planeOffset(me) + zl of the owner's plane-major stick buffer
+  if (P <= 255) {
+    x.stickRank.resize(all.size());
+    x.fwdBase.resize(all.size());
+    for (size_t e = 0; e < all.size(); ++e) {
+      const long long base = static_cast<long long>(m.planeOffsetPerRank[me]) *
+                                 x.pitchPerRank[all[e].rank] + all[e].idx;
+      if (base + myPlanes * x.pitchPerRank[all[e].rank] > 0x7fffffffLL) throw OverflowError();
+      x.stickRank[e] = static_cast<unsigned char>(all[e].rank);
+      x.fwdBase[e] = static_cast<int>(base);
+    }
+  }
   for (int k = 0; k < x.numXTiles; ++k) x.xtStart[k + 1] += x.xtStart[k];
 
   // single-source tiles + inverse map for the gather-form y kernels
   x.tileBase.assign(x.numXTiles, 0);
   x.tilePitch.assign(x.numXTiles, 0);
+  x.tileFwdBase.assign(x.numXTiles, 0);
   for (int t = 0; t < x.numXTiles; ++t) {
     const int e0 = x.xtStart[t], e1 = x.xtStart[t + 1];
     if (e0 == e1) continue;
@@ -221,6 +251,7 @@ ExchangePlan build_exchange_plan(const IndexMaps& m, int log2Vz, int log2Vy, boo
     if (single) {
       x.tileBase[t] = x.srcBase[e0];
       x.tilePitch[t] = x.srcPitch[e0];
+      if (!x.fwdBase.empty()) x.tileFwdBase[t] = x.fwdBase[e0];
     }
   }
   if (fastY && !all.empty()) {

@@ -82,6 +82,16 @@ struct ExchangePlan {
   std::vector<int> tileBase, tilePitch;  // [numXTiles]
   std::vector<unsigned short> yInv;      // inverse map over the global sorted stick list (fast y only)
   int numXTiles = 0;
+  // Peer-memory form of the exchange (the kernels store straight into the destination rank's
+  // buffer over NVLink, no send/recv):
+  //   backward: row z of this rank's sticks -> buffer Q of rank rowRank[z] at element rowOff[z]
+  //   forward : stick e of local plane zl   -> buffer A of rank stickRank[e] at element
+  //             fwdBase[e] + zl*srcPitch[e]; single-source tiles at tileFwdBase[t] + zl*tilePitch[t]
+  std::vector<unsigned char> rowRank;   // [dimZ]
+  std::vector<long long> rowOff;        // [dimZ]
+  std::vector<unsigned char> stickRank; // [NsTotal]
+  std::vector<int> fwdBase;             // [NsTotal]
+  std::vector<int> tileFwdBase;         // [numXTiles]
 };
 
 ExchangePlan build_exchange_plan(const IndexMaps& maps, int log2Vz, int log2Vy, bool fastY = false);

@@ -41,6 +41,35 @@ __global__ void __launch_bounds__(kThreads) k_x_stage(const __grid_constant__ XA
     x_backward_body<T>(a, (int)blockIdx.x, Ctx{kThreads}, smem);
 }
 
+// Barrier over the ranks of a distributed transform through peer-mapped flags (one int per
+// source rank on every rank). Thread r publishes `epoch` in rank r's slot for this rank, then waits
+// for rank r's epoch in the local slot. Launched after the kernel whose peer stores it publishes
+// (stream order = kernel boundary, so those stores are complete), it replaces the
+// cudaStreamSynchronize + MPI_Alltoallv pair of transpose_mpi_compact_buffered_gpu.cpp:186-217.
+struct PeerBarrierArgs {
+  int* flags[kMaxPeers];  // flags[r] = rank r's flag array (mapped), flags[me] local
+  int numRanks, me, epoch;
+};
+
+__global__ void k_peer_barrier(const __grid_constant__ PeerBarrierArgs a) {
+  const int r = (int)threadIdx.x;
+  if (r >= a.numRanks) return;
+  __threadfence_system();
+  asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(a.flags[r] + a.me), "r"(a.epoch) : "memory");
+  const int* mine = a.flags[a.me] + r;
+  unsigned long long t0 = 0;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  for (;;) {
+    int v;
+    asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(mine) : "memory");
+    if (v - a.epoch >= 0) break;  // wrap-safe comparison
+    unsigned long long t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+    if (t1 - t0 > 30ull * 1000000000ull) __trap();  // a peer never arrived: fail instead of hanging
+    __nanosleep(200);
+  }
+}
+
 static std::atomic<long long> g_launches{0};
 
 template <typename Kernel, typename Args>
@@ -111,6 +140,17 @@ int sb_launch_x_f64(int forward, const sb::XArgs<double>* a, void* stream) {
 }
 int sb_launch_x_f32(int forward, const sb::XArgs<float>* a, void* stream) {
   return sb::launch_x<float>(forward, *a, static_cast<cudaStream_t>(stream));
+}
+int sb_launch_peer_barrier(int* const* flags, int numRanks, int me, int epoch, void* stream) {
+  if (numRanks < 1 || numRanks > sb::kMaxPeers) return (int)cudaErrorInvalidValue;
+  sb::PeerBarrierArgs a{};
+  for (int r = 0; r < numRanks; ++r) a.flags[r] = flags[r];
+  a.numRanks = numRanks;
+  a.me = me;
+  a.epoch = epoch;
+  sb::k_peer_barrier<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(a);
+  sb::g_launches.fetch_add(1, std::memory_order_relaxed);
+  return (int)cudaGetLastError();
 }
 void sb_note_launches(int n) { sb::g_launches.fetch_add(n, std::memory_order_relaxed); }
 long long sb_launch_count(void) { return sb::g_launches.load(std::memory_order_relaxed); }

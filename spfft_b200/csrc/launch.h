@@ -22,6 +22,9 @@ int sb_xy_fused_config(int isFloat, int n, int numPlanes, int* ring, int* lag, i
 /* One direction of the fused xy stage. `counters` must be zero (the launcher enqueues the memset). */
 int sb_launch_xy_f64(int forward, const sb::XYArgs<double>* args, void* stream);
 int sb_launch_xy_f32(int forward, const sb::XYArgs<float>* args, void* stream);
+/* Barrier over the ranks of a distributed transform through peer-mapped flag arrays
+ * (flags[r] = rank r's array of numRanks ints, zero-initialised; epoch increases by one per call). */
+int sb_launch_peer_barrier(int* const* flags, int numRanks, int me, int epoch, void* stream);
 /* total number of kernel launches issued through this file */
 long long sb_launch_count(void);
 void sb_note_launches(int n);

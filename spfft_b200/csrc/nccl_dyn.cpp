@@ -94,6 +94,18 @@ std::vector<int> Communicator::all_gather_ints(const int* local, int count) {
   return out;
 }
 
+std::vector<char> Communicator::all_gather_bytes(const void* local, size_t bytes) {
+  std::vector<char> out(bytes * size_);
+  if (bytes == 0) return out;
+  DeviceGuard guard(device_);
+  DeviceBuffer send(bytes), recv(bytes * size_);
+  check_gpu(cudaMemcpy(send.get(), local, bytes, cudaMemcpyHostToDevice));
+  check_nccl(api().AllGather(send.get(), recv.get(), bytes, kNcclInt8, comm_, nullptr));
+  check_gpu(cudaStreamSynchronize(nullptr));
+  check_gpu(cudaMemcpy(out.data(), recv.get(), bytes * size_, cudaMemcpyDeviceToHost));
+  return out;
+}
+
 void Communicator::all_to_all_v(const void* sendBuf, const long long* sendOffset,
                                 const long long* sendCount, void* recvBuf,
                                 const long long* recvOffset, const long long* recvCount,

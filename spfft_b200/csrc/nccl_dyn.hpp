@@ -34,6 +34,8 @@ public:
 
   // plan-time helpers (blocking): gather `count` ints from every rank
   std::vector<int> all_gather_ints(const int* local, int count);
+  // same for `bytes` raw bytes per rank (IPC handles of the peer-memory exchange)
+  std::vector<char> all_gather_bytes(const void* local, size_t bytes);
 
   // The stick<->slab exchange: for every peer r send `sendCount[r]` elements of `elemBytes` from
   // sendBuf + sendOffset[r] and receive recvCount[r] into recvBuf + recvOffset[r] (offsets and

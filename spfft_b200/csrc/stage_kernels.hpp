@@ -26,6 +26,9 @@
 
 namespace sb {
 
+// Distributed transforms over NVLink peer memory: at most this many GPUs (one NVSwitch box)
+constexpr int kMaxPeers = 8;
+
 template <typename T>
 struct ZArgs {
   int nz;         // dimZ = transform length
@@ -48,7 +51,21 @@ struct ZArgs {
   // register-FFT kernels, values in stick order without duplicates: inverse map
   // [tile][thread][8] -> offset of the element's value from the tile's first entry, 0xFFFF = none
   const unsigned short* inv;
+  // Distributed backward over peer memory (replaces pack + MPI_Alltoallv + unpack,
+  // transpose_mpi_compact_buffered_gpu.cpp:163-224): the kernel stores row z of its sticks straight
+  // into the plane-side buffer of the rank that owns plane z, at peer[rowRank[z]] + rowOff[z]
+  // (peer[me] = the local buffer). rowRank == nullptr: local rows sticks + z*pitch.
+  cx<T>* peer[kMaxPeers];
+  const unsigned char* rowRank;  // [nz]
+  const long long* rowOff;       // [nz] element offset of this rank's row inside the owner's buffer
 };
+
+// Row z of the stick buffer a z kernel writes (backward) / reads (forward).
+template <typename T>
+SB_DEV cx<T>* z_row(const ZArgs<T>& a, int z) {
+  if (a.rowRank) return a.peer[a.rowRank[z]] + a.rowOff[z];
+  return a.sticks + (size_t)z * a.pitch;
+}
 
 template <typename T>
 struct YArgs {
@@ -79,7 +96,32 @@ struct YArgs {
   // per x tile: sticks contiguous at sticks[tileBase[xt] + zl*tilePitch[xt] + i] (tilePitch != 0)
   const int* tileBase;
   const int* tilePitch;
+  // Distributed forward over peer memory: stick e of local plane zl is stored straight into the
+  // stick buffer of its owner, at peer[stickRank[e]] + fwdBase[e] + zl*srcPitch[e] (row
+  // planeOffset(me) + zl of the owner's plane-major buffer); single-source tiles at
+  // peer[stickRank[first stick]] + tileFwdBase[xt] + zl*tilePitch[xt] + i. stickRank == nullptr:
+  // `sticks` + srcBase / tileBase (local exchange buffer).
+  cx<T>* peer[kMaxPeers];
+  const unsigned char* stickRank;  // [numSticks over all ranks]
+  const int* fwdBase;              // [numSticks over all ranks]
+  const int* tileFwdBase;          // [numXTiles]
 };
+
+// Where stick e (global sorted list) of local plane zl lives for a distributed y kernel:
+// backward reads the local plane-side buffer, forward writes the owner's stick buffer.
+template <typename T, bool FWD>
+SB_DEV cx<T>* y_dist_stick(const YArgs<T>& a, int e, int zl) {
+  if (FWD && a.stickRank)
+    return a.peer[a.stickRank[e]] + (size_t)a.fwdBase[e] + (size_t)zl * a.srcPitch[e];
+  return a.sticks + (size_t)a.srcBase[e] + (size_t)zl * a.srcPitch[e];
+}
+// First stick of single-source tile xt (tilePitch[xt] != 0) at local plane zl.
+template <typename T, bool FWD>
+SB_DEV cx<T>* y_dist_tile(const YArgs<T>& a, int xt, int zl) {
+  if (FWD && a.stickRank)
+    return a.peer[a.stickRank[a.xtStart[xt]]] + (size_t)a.tileFwdBase[xt] + (size_t)zl * a.tilePitch[xt];
+  return a.sticks + (size_t)a.tileBase[xt] + (size_t)zl * a.tilePitch[xt];
+}
 
 template <typename T>
 struct XArgs {
@@ -139,11 +181,10 @@ SB_DEV void z_backward_body(const ZArgs<T>& a, int tile, Ctx ctx, cx<T>* smem) {
   if (tile == a.symTile) hermitian_fill_lane<T>(A, a.nz, a.symLane, a.log2V, ctx);
   cx<T>* R = tile_fft<T, true, false>(A, B, a.rp, a.log2V, a.tw, ctx);
   SB_PHASE_BEGIN
-  cx<T>* out = a.sticks + (size_t)tile * V;
   for (int i = tid; i < n; i += nthr) {
     const int z = i >> a.log2V;
     const int lane = i & (V - 1);
-    out[(size_t)z * a.pitch + lane] = R[i];
+    z_row<T>(a, z)[(size_t)tile * V + lane] = R[i];
   }
   SB_PHASE_END
 }
@@ -242,7 +283,7 @@ SB_DEV void y_forward_body(const YArgs<T>& a, int block, Ctx ctx, cx<T>* smem) {
   cx<T>* row = a.sticks + (size_t)(zl + a.zRowOffset) * a.pitch;
   for (int e = e0 + tid; e < e1; e += nthr) {
     if (a.srcBase)
-      a.sticks[(size_t)a.srcBase[e] + (size_t)zl * a.srcPitch[e]] = R[a.stickSlot[e]];
+      *y_dist_stick<T, true>(a, e, zl) = R[a.stickSlot[e]];
     else
       row[e] = R[a.stickSlot[e]];
   }

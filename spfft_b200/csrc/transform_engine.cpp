@@ -117,6 +117,7 @@ GridResources<T>::GridResources(int maxDimX, int maxDimY, int maxDimZ, int maxNu
   if (exchangeType_ == SPFFT_EXCH_DEFAULT) exchangeType_ = SPFFT_EXCH_COMPACT_BUFFERED;
   DeviceGuard guard(deviceId_);
   allocate();
+  map_peers();
 }
 
 template <typename T>
@@ -133,6 +134,7 @@ GridResources<T>::GridResources(const GridResources& o)
       exchangeType_(o.exchangeType_) {
   DeviceGuard guard(deviceId_);
   allocate();
+  map_peers();  // collective for distributed grids, like every grid / transform creation
 }
 
 template <typename T>
@@ -152,6 +154,39 @@ void GridResources<T>::allocate() {
                                   static_cast<size_t>(kMaxTileLanes) * comm_->size();
     q_.allocate(c * static_cast<size_t>(maxPlanes_) * sticksAllRanks);
   }
+}
+
+template <typename T>
+void GridResources<T>::map_peers() {
+  // Peer-memory exchange: map arrays A and Q and the barrier flags of every rank (CUDA IPC).
+  // SPFFT_B200_P2P=0 keeps the NCCL send/recv exchange. Collective; every rank takes the same
+  // decision (PeerWindow votes).
+  peerOk_ = false;
+  if (local()) return;
+  const char* env = std::getenv("SPFFT_B200_P2P");
+  int want = !(env && std::atoi(env) == 0) && comm_->size() <= sb::kMaxPeers ? 1 : 0;
+  {
+    const std::vector<int> votes = comm_->all_gather_ints(&want, 1);
+    for (int v : votes) want = want && v;
+  }
+  if (!want) return;
+  flags_.allocate(sizeof(int) * sb::kMaxPeers);
+  check_gpu(cudaMemset(flags_.get(), 0, flags_.bytes()));
+  check_gpu(cudaDeviceSynchronize());
+  peerA_.open(*comm_, a_.get());
+  peerQ_.open(*comm_, q_.get());
+  peerFlags_.open(*comm_, flags_.get());
+  peerOk_ = peerA_.mapped() && peerQ_.mapped() && peerFlags_.mapped();
+  barrierEpoch_ = 0;
+}
+
+template <typename T>
+void GridResources<T>::enqueue_peer_barrier(cudaStream_t stream) {
+  if (!peerOk_) throw InternalError();
+  int* flags[sb::kMaxPeers] = {};
+  for (int r = 0; r < comm_->size(); ++r) flags[r] = static_cast<int*>(peerFlags_.ptr(r));
+  ++barrierEpoch_;
+  check_launch(sb_launch_peer_barrier(flags, comm_->size(), comm_->rank(), barrierEpoch_, stream));
 }
 
 template <typename T>
@@ -302,6 +337,11 @@ std::shared_ptr<DevicePlan<T>> build_device_plan(const IndexMaps& m, long long s
     plan->tilePitch = upload(st, total, plan->exchange.tilePitch);
     // inverse-map form for the tiles whose sticks are contiguous in one source block
     p.yInv = upload(st, total, plan->exchange.yInv);
+    plan->rowRank = upload(st, total, plan->exchange.rowRank);
+    plan->rowOff = upload(st, total, plan->exchange.rowOff);
+    plan->stickRank = upload(st, total, plan->exchange.stickRank);
+    plan->fwdBase = upload(st, total, plan->exchange.fwdBase);
+    plan->tileFwdBase = upload(st, total, plan->exchange.tileFwdBase);
     plan->fusedXY = false;
   } else {
     p.xtStart = upload(st, total, t.xtStart);
@@ -464,7 +504,7 @@ template <typename T>
 sb::XYArgs<T> TransformEngine<T>::make_xy_args(const TileMaps& geo, const T* spaceIn, T* spaceOut) {
   const IndexMaps& m = *maps_;
   sb::XYArgs<T> a{};
-  a.y = make_y_stage_args(geo);
+  a.y = make_y_stage_args(geo, false);
   a.y.planes = nullptr;
   a.x = make_x_args<T>(m, plan_->axes, plan_->ptrs, nullptr, spaceIn, spaceOut);
   a.ring = plan_->xyRing;
@@ -476,8 +516,15 @@ sb::XYArgs<T> TransformEngine<T>::make_xy_args(const TileMaps& geo, const T* spa
 }
 
 template <typename T>
-sb::YArgs<T> TransformEngine<T>::make_y_stage_args(const TileMaps& geo) {
+sb::YArgs<T> TransformEngine<T>::make_y_stage_args(const TileMaps& geo, bool forward) {
   auto ya = make_y_args<T>(*maps_, geo, plan_->axes, plan_->ptrs, sticks(), planes());
+  if (plan_->distributed && forward && peer_exchange()) {
+    // forward over peer memory: every stick goes straight into its owner's stick buffer
+    for (int r = 0; r < maps_->commSize; ++r) ya.peer[r] = static_cast<sb::cx<T>*>(grid_->peer_a(r));
+    ya.stickRank = plan_->stickRank;
+    ya.fwdBase = plan_->fwdBase;
+    ya.tileFwdBase = plan_->tileFwdBase;
+  }
   if (plan_->distributed) {
     // sticks of all ranks, read from / written to the plane-side exchange buffer
     ya.sticks = static_cast<sb::cx<T>*>(grid_->array_q());
@@ -518,16 +565,29 @@ void TransformEngine<T>::enqueue_backward(const T* input, T* output) {
   geo.numXTiles = plan_->numXTiles;
   geo.symTile = plan_->symTile;
   geo.symLane = plan_->symLane;
+  const bool peer = dist && peer_exchange();
+  // peers may still read the plane-side buffer this call's z stage stores into
+  if (peer) grid_->enqueue_peer_barrier(s);
   if (plan_->numStickTiles > 0) {
     auto za = make_z_args<T>(m, geo, plan_->axes, plan_->ptrs, false, sticks(), values, nullptr,
                              false);
+    if (peer) {
+      // the z stage stores every row straight into the plane-side buffer of the rank that owns
+      // the plane: compute and exchange are one kernel
+      for (int r = 0; r < m.commSize; ++r) za.peer[r] = static_cast<sb::cx<T>*>(grid_->peer_q(r));
+      za.rowRank = plan_->rowRank;
+      za.rowOff = plan_->rowOff;
+    }
     check_launch(Launch<T>::z(0, za, s));
-    record_stage("z backward");
+    record_stage(peer ? "z backward + exchange" : "z backward");
   }
   // ---- exchange: every rank sends, for every peer, the rows of that peer's slab (one contiguous
   // block of the plane-major stick buffer) -- replaces pack + MPI_Alltoallv + unpack
   // (transpose_mpi_compact_buffered_gpu.cpp:163-224)
-  if (dist) {
+  if (peer) {
+    grid_->enqueue_peer_barrier(s);
+    record_stage("barrier backward");
+  } else if (dist) {
     const ExchangePlan& x = plan_->exchange;
     grid_->communicator()->all_to_all_v(sticks(), x.stickOffset.data(), x.stickCount.data(),
                                         grid_->array_q(), x.planeOffset.data(), x.planeCount.data(),
@@ -543,7 +603,7 @@ void TransformEngine<T>::enqueue_backward(const T* input, T* output) {
     record_stage("xy backward");
   } else {
     // ---- y stage: stick gather + plane symmetry + y-FFT (execution_gpu.cpp:371-390)
-    check_launch(Launch<T>::y(0, make_y_stage_args(geo), s));
+    check_launch(Launch<T>::y(0, make_y_stage_args(geo, false), s));
     record_stage("y backward");
     // ---- x stage: x-FFT (C2C / C2R) into the space domain
     auto xa = make_x_args<T>(m, plan_->axes, plan_->ptrs, planes(), nullptr, outDev);
@@ -579,6 +639,9 @@ void TransformEngine<T>::enqueue_forward(const T* input, T* output, SpfftScaling
   // sticks anywhere (all ranks)? otherwise nothing consumes the planes
   const bool anySticks = dist ? !plan_->exchange.stickSlot.empty() : (plan_->numStickTiles > 0 && ne > 0);
 
+  const bool peer = dist && peer_exchange();
+  // peers may still read the stick buffer this call's y stage stores into
+  if (peer) grid_->enqueue_peer_barrier(s);
   // ---- x stage (execution_gpu.cpp:254-282)
   if (haveSpace) {
     const T* src = input;
@@ -598,12 +661,15 @@ void TransformEngine<T>::enqueue_forward(const T* input, T* output, SpfftScaling
       record_stage("x forward");
       if (anySticks) {
         // ---- y stage: y-FFT + scatter into the plane-major sticks / the exchange buffer
-        check_launch(Launch<T>::y(1, make_y_stage_args(geo), s));
-        record_stage("y forward");
+        check_launch(Launch<T>::y(1, make_y_stage_args(geo, true), s));
+        record_stage(peer ? "y forward + exchange" : "y forward");
       }
     }
   }
-  if (dist) {
+  if (peer) {
+    grid_->enqueue_peer_barrier(s);
+    record_stage("barrier forward");
+  } else if (dist) {
     const ExchangePlan& x = plan_->exchange;
     grid_->communicator()->all_to_all_v(grid_->array_q(), x.planeOffset.data(), x.planeCount.data(),
                                         sticks(), x.stickOffset.data(), x.stickCount.data(),

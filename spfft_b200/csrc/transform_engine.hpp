@@ -16,6 +16,7 @@
 #include "gpu_runtime.hpp"
 #include "index_plan.hpp"
 #include "nccl_dyn.hpp"
+#include "peer_memory.hpp"
 #include "spfft/types.h"
 #include "stage_args.hpp"
 
@@ -66,8 +67,19 @@ public:
 
   static size_t stick_capacity(int maxDimZ, int maxSticks);
 
+  // Peer-memory exchange (peer_memory.hpp): true when arrays A and Q and the barrier flags of every
+  // rank are mapped into this process. peer_a / peer_q: the mapped buffers in rank order.
+  bool peer_exchange() const { return peerOk_; }
+  void* peer_a(int rank) const { return peerA_.ptr(rank); }
+  void* peer_q(int rank) const { return peerQ_.ptr(rank); }
+  // Enqueue a barrier over all ranks on `stream`: every rank's earlier work on its stream
+  // (stores into peer memory included) is complete and visible before anything enqueued after the
+  // barrier on any rank starts. All ranks must call it in the same sequence.
+  void enqueue_peer_barrier(cudaStream_t stream);
+
 private:
   void allocate();
+  void map_peers();
   int maxDimX_, maxDimY_, maxDimZ_, maxSticks_, maxPlanes_;
   SpfftProcessingUnitType pu_;
   int deviceId_ = 0;
@@ -77,6 +89,10 @@ private:
   SpfftExchangeType exchangeType_ = SPFFT_EXCH_DEFAULT;
   PinnedBuffer host_;
   std::mutex hostMutex_;
+  DeviceBuffer flags_;
+  PeerWindow peerA_, peerQ_, peerFlags_;
+  bool peerOk_ = false;
+  int barrierEpoch_ = 0;
 };
 
 // Everything the kernels read that depends only on the index set: uploaded once, shared by clones.
@@ -98,6 +114,12 @@ struct DevicePlan {
   const int* tileBase = nullptr;
   const int* tilePitch = nullptr;
   const unsigned short* distYInv = nullptr;
+  // peer-memory form of the exchange (ExchangePlan::rowRank ...)
+  const unsigned char* rowRank = nullptr;
+  const long long* rowOff = nullptr;
+  const unsigned char* stickRank = nullptr;
+  const int* fwdBase = nullptr;
+  const int* tileFwdBase = nullptr;
   std::vector<DeviceBuffer> storage;
   size_t deviceBytes = 0;
 };
@@ -136,18 +158,21 @@ public:
   bool shared_grid(const TransformEngine<T>& other) const { return grid_ == other.grid_; }
   void* stream() const { return stream_->get(); }
 
+  // distributed transform whose exchange is fused into the stage kernels (peer memory)
+  bool uses_peer_exchange() const { return plan_ && plan_->distributed && peer_exchange(); }
   void set_profiling(bool on) { profiling_ = on; }
   std::vector<StageTime> stage_times();
 
 private:
   void begin_call();
   sb::XYArgs<T> make_xy_args(const TileMaps& geo, const T* spaceIn, T* spaceOut);
-  sb::YArgs<T> make_y_stage_args(const TileMaps& geo);
+  sb::YArgs<T> make_y_stage_args(const TileMaps& geo, bool forward);
   void record_stage(const char* name);
   size_t space_bytes() const;
   T* device_space() const;
   sb::cx<T>* sticks() const { return static_cast<sb::cx<T>*>(grid_->array_a()); }
   sb::cx<T>* planes() const { return static_cast<sb::cx<T>*>(grid_->array_b()); }
+  bool peer_exchange() const { return grid_->peer_exchange() && plan_->rowRank && plan_->stickRank; }
 
   SpfftProcessingUnitType executionUnit_;
   SpfftExecType execMode_ = SPFFT_EXEC_SYNCHRONOUS;

@@ -51,7 +51,11 @@ def main():
     ]
     worst = 0.0
     ok = True
-    for ttype, (nx, ny, nz), sdist, pdist, center, single in cases:
+    # every case through both exchanges: fused peer-memory stores (default) and NCCL send/recv
+    modes = [m for m in os.environ.get("DIST_CHECK_MODES", "1,0").split(",") if m]
+    cases = [c + (mode,) for mode in modes for c in cases]
+    for ttype, (nx, ny, nz), sdist, pdist, center, single, mode in cases:
+        os.environ["SPFFT_B200_P2P"] = mode
         tol = 1e-5 if single else 1e-12
         trips, vals = [], []
         for r in range(world):
@@ -74,6 +78,9 @@ def main():
         grid = capi.DistributedGrid(lib, comm, nx, ny, nz, max_sticks, max(planes), single=single)
         t = grid.create_transform(capi.SPFFT_PU_GPU, ttype, nx, ny, nz, planes[rank], trips[rank])
         assert t.local_z_length() == planes[rank] and t.local_z_offset() == sum(planes[:rank])
+        peer = capi.peer_exchange(t)
+        if mode == "0":
+            assert not peer
         assert t.num_global_elements() == sum(len(x) for x in trips)
         cdt = np.complex64 if single else np.complex128
         rdt = torch.float32 if single else torch.float64
@@ -100,7 +107,7 @@ def main():
         good = eb <= tol and ef <= tol
         ok = ok and good
         worst = max(worst, eb / tol, ef / tol)
-        print(f"[rank {rank}] type={ttype} {nx}x{ny}x{nz} sticks={params[rank].num_sticks} planes={planes[rank]} "
+        print(f"[rank {rank}] {'peer' if peer else 'nccl'} type={ttype} {nx}x{ny}x{nz} sticks={params[rank].num_sticks} planes={planes[rank]} "
               f"bwd={eb:.2e} fwd={ef:.2e} {'ok' if good else 'FAIL'}", flush=True)
         t.destroy()
         grid.destroy()
