@@ -350,7 +350,8 @@ def load(path: str | None = None) -> SpfftLib:
     global _LOADED
     if path is None and _LOADED is not None:
         return _LOADED
-    lib = SpfftLib(path or LIB_PATH)
+    # SPFFT_B200_LIB: experiment builds of the same library (tools/build_variant.py)
+    lib = SpfftLib(path or os.environ.get("SPFFT_B200_LIB") or LIB_PATH)
     missing = [s for s in exported_symbols() if not lib.has(s)]
     if missing:
         raise ImportError(f"{lib.path} lacks symbols: {missing}")

@@ -24,6 +24,10 @@
   __syncthreads();
 // like SB_PHASE_END but without the barrier (last phase of a kernel)
 #define SB_PHASE_END_NOSYNC }
+// barrier only if the (compile-time) condition holds
+#define SB_PHASE_END_IF(c) \
+  }                        \
+  if (c) __syncthreads();
 // per-thread registers that live across phases
 #define SB_REGS(type, name, n) type name[n]
 #define SB_RP(name, n) (name)
@@ -36,6 +40,7 @@
     const int nthr = ctx.nthreads;
 #define SB_PHASE_END }
 #define SB_PHASE_END_NOSYNC }
+#define SB_PHASE_END_IF(c) }
 #define SB_REGS(type, name, n) std::vector<type> name##_store((size_t)ctx.nthreads * (n)); type* name = name##_store.data()
 #define SB_RP(name, n) ((name) + (size_t)tid * (n))
 #endif
@@ -85,8 +90,20 @@ SB_HD bool nonzero(cx<T> a) {
 }
 
 // Execution context: empty on the GPU, carries the emulated block size on the CPU.
+// Bookkeeping one thread of a persistent kernel does while the loads of its tile are in flight
+// (fast_xy.cu): claim a later work item and look at the next item's dependency counter.
+struct ItemChores {
+  int* claimCounter;      // *claimOut = atomicAdd(claimCounter, 1)
+  int* claimOut;
+  const int* depCounter;  // *readyOut = depCounter ? (acquire-load(*depCounter) >= depNeed) : 1
+  int depNeed;
+  int* readyOut;
+};
+
 struct Ctx {
   int nthreads;
+  int traceItem = -1;                    // experiments only (SB_XY_TRACE)
+  const ItemChores* chores = nullptr;    // persistent kernels only
 };
 
 }  // namespace sb

@@ -22,6 +22,22 @@
 #include "cx.hpp"
 #include "fft_tile.hpp"
 
+// Phase timeline of the persistent fused xy kernel (experiments only, -DSB_XY_TRACE): thread 0 of
+// the first CTAs stores clock64() at numbered points of its first items (tools/xy_trace.py).
+#if SB_ON_GPU && defined(SB_XY_TRACE)
+namespace sb {
+constexpr int kTraceCtas = 8, kTraceItems = 96, kTraceMarks = 16;
+static __device__ long long g_xy_trace[kTraceCtas * kTraceItems * kTraceMarks];  // one per TU; fast_xy.cu reads its own
+__device__ __forceinline__ void trace_mark(int item, int id) {
+  if (threadIdx.x == 0 && blockIdx.x < kTraceCtas && item >= 0 && item < kTraceItems)
+    g_xy_trace[((size_t)blockIdx.x * kTraceItems + item) * kTraceMarks + id] = clock64();
+}
+}  // namespace sb
+#define SB_MARK(ctx, id) ::sb::trace_mark((ctx).traceItem, id)
+#else
+#define SB_MARK(ctx, id)
+#endif
+
 namespace sb {
 
 constexpr int ilog2_c(int n) { return n <= 1 ? 0 : 1 + ilog2_c(n >> 1); }
@@ -148,6 +164,27 @@ SB_DEV void prefetch_l2_line(const void* p) {
   asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
 #else
   (void)p;
+#endif
+}
+
+// Thread 0's bookkeeping of a persistent kernel (ItemChores, cx.hpp): called right after the loads
+// of the tile were issued, so its two L2 round trips overlap the load latency.
+SB_DEV void run_item_chores(const Ctx& ctx) {
+#if SB_ON_GPU
+  if (ctx.chores && threadIdx.x == 0) {
+    const ItemChores c = *ctx.chores;
+    const int claimed = atomicAdd(c.claimCounter, 1);
+    int ready = 1;
+    if (c.depCounter) {
+      int v;
+      asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(c.depCounter) : "memory");
+      ready = v >= c.depNeed;
+    }
+    *c.claimOut = claimed;
+    *c.readyOut = ready;
+  }
+#else
+  (void)ctx;
 #endif
 }
 

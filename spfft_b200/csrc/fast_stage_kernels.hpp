@@ -16,9 +16,17 @@
 
 namespace sb {
 
+// lanes per tile row: 128 bytes (8 double / 16 float complex). SB_LOG2V_F64 / SB_LOG2V_F32 are
+// build-time tuning overrides (experiments only).
+#ifndef SB_LOG2V_F64
+#define SB_LOG2V_F64 3
+#endif
+#ifndef SB_LOG2V_F32
+#define SB_LOG2V_F32 4
+#endif
 template <typename T>
 struct FastLanes {
-  static constexpr int log2V = sizeof(T) == 8 ? 3 : 4;
+  static constexpr int log2V = sizeof(T) == 8 ? SB_LOG2V_F64 : SB_LOG2V_F32;
 };
 
 
@@ -61,6 +69,8 @@ SB_DEV void fast_fft_head(cx<T>* vAll, cx<T>* S, const cx<T>* __restrict__ tw, C
 #define SB_FAST_READ \
   _Pragma("unroll") for (int m = 0; m < 8; ++m) v[m] = S[Swz::template at<LOG2V>(j + TT * m, lane)];
 
+  SB_MARK(ctx, 2);
+  run_item_chores(ctx);
   if constexpr (P::numStages > 1) {
     SB_PHASE_BEGIN
     SB_FAST_IDS_(COL0)
@@ -68,16 +78,19 @@ SB_DEV void fast_fft_head(cx<T>* vAll, cx<T>* S, const cx<T>* __restrict__ tw, C
     SB_FAST_WRITE(0)
     SB_PHASE_END
   }
+  SB_MARK(ctx, 3);
   if constexpr (P::numStages > 2) {
     SB_PHASE_BEGIN
     SB_FAST_IDS
     SB_FAST_READ
     fast_stage<T, N, BWD, 1, TWS>(v, j, tw);
     SB_PHASE_END
+    SB_MARK(ctx, 4);
     SB_PHASE_BEGIN
     SB_FAST_IDS
     SB_FAST_WRITE(1)
     SB_PHASE_END
+    SB_MARK(ctx, 5);
   }
   if constexpr (P::numStages > 3) {
     SB_PHASE_BEGIN
@@ -94,13 +107,21 @@ SB_DEV void fast_fft_head(cx<T>* vAll, cx<T>* S, const cx<T>* __restrict__ tw, C
 }
 
 // Last stage, to be called inside the caller's final phase: afterwards v[m] = X[j + T*m].
-template <typename T, int N, int LOG2V, bool BWD, typename Swz, bool TWS = false>
-SB_DEV void fast_fft_tail(cx<T>* v, const cx<T>* S, const cx<T>* __restrict__ tw, int j, int lane) {
+// The two halves exist separately for the persistent kernels, which put a barrier between the last
+// read of the tile buffer and the rest (warps then run ahead into the next item without another
+// CTA-wide barrier).
+template <typename T, int N, int LOG2V, typename Swz>
+SB_DEV void fast_fft_tail_read(cx<T>* v, const cx<T>* S, int j, int lane) {
   using P = FastPlan<N>;
   constexpr int TT = P::T;
   if constexpr (P::numStages > 1) {
     SB_FAST_READ
   }
+}
+template <typename T, int N, int LOG2V, bool BWD, typename Swz, bool TWS = false>
+SB_DEV void fast_fft_tail(cx<T>* v, const cx<T>* S, const cx<T>* __restrict__ tw, int j, int lane) {
+  using P = FastPlan<N>;
+  fast_fft_tail_read<T, N, LOG2V, Swz>(v, S, j, lane);
   fast_stage<T, N, BWD, P::numStages - 1, TWS>(v, j, tw);
 }
 
@@ -551,7 +572,8 @@ SB_DEV void y_backward_gather(const YArgs<T>& a, int xt, const cx<T>* stickRow, 
   SB_REGS(cx<T>, vAll, 8);
   if (e0 == e1) {
     // empty x tile: the x stage still reads these columns -> store zeros, no transform
-    // (barrier: in the fused kernel thread 0 may have waited for the slot to become free)
+    // (barrier: persistent kernels publish thread 0's bookkeeping through it)
+    run_item_chores(ctx);
     SB_PHASE_BEGIN
     SB_PHASE_END
     SB_PHASE_BEGIN
@@ -575,7 +597,12 @@ SB_DEV void y_backward_gather(const YArgs<T>& a, int xt, const cx<T>* stickRow, 
   fast_fft_head<T, N, LOG2V, true, SwzCol, true, false, TWS>(vAll, S, tw, ctx);
   SB_PHASE_BEGIN
   SB_ROW_IDS
-  fast_fft_tail<T, N, LOG2V, true, SwzCol, TWS>(v, S, tw, j, lane);
+  fast_fft_tail_read<T, N, LOG2V, SwzCol>(v, S, j, lane);
+  SB_PHASE_END_IF(TWS)
+  SB_MARK(ctx, 8);
+  SB_PHASE_BEGIN
+  SB_ROW_IDS
+  fast_stage<T, N, true, FastPlan<N>::numStages - 1, TWS>(v, j, tw);
   if (lane < lanesValid) {
 #pragma unroll
     for (int m = 0; m < 8; ++m) st_g<STP>(planeTile + (size_t)(j + TT * m) * a.nxf + lane, v[m]);
@@ -593,7 +620,15 @@ SB_DEV void y_forward_gather(const YArgs<T>& a, int xt, const cx<T>* plane, cx<T
   constexpr int TT = FastPlan<N>::T;
   constexpr int THREADS = V * TT;
   const int e0 = a.xtStart[xt], e1 = a.xtStart[xt + 1];
-  if (e0 == e1) return;  // no stick needs these columns
+  if (e0 == e1) {  // no stick needs these columns
+    // (persistent kernel: every item passes at least one barrier)
+    run_item_chores(ctx);
+    SB_PHASE_BEGIN
+    (void)tid;
+    (void)nthr;
+    SB_PHASE_END_IF(TWS)
+    return;
+  }
   const cx<T>* planeTile = plane + (size_t)xt * V;
   const int lanesValid = (a.nxf - xt * V) < V ? (a.nxf - xt * V) : V;
   SB_REGS(cx<T>, vAll, 8);
@@ -609,7 +644,12 @@ SB_DEV void y_forward_gather(const YArgs<T>& a, int xt, const cx<T>* plane, cx<T
   fast_fft_head<T, N, LOG2V, false, SwzCol, false, false, TWS>(vAll, S, tw, ctx);
   SB_PHASE_BEGIN
   SB_COLMAP_IDS
-  fast_fft_tail<T, N, LOG2V, false, SwzCol, TWS>(v, S, tw, j, lane);
+  fast_fft_tail_read<T, N, LOG2V, SwzCol>(v, S, j, lane);
+  SB_PHASE_END_IF(TWS)
+  SB_MARK(ctx, 8);
+  SB_PHASE_BEGIN
+  SB_COLMAP_IDS
+  fast_stage<T, N, false, FastPlan<N>::numStages - 1, TWS>(v, j, tw);
   const Inv8 iv = load_inv8(a.inv + ((size_t)xt * THREADS + tid) * 8);
   cx<T>* out = stickRow + e0;
 #pragma unroll
@@ -642,11 +682,16 @@ SB_DEV void x_c2c_tile(const cx<T>* in, cx<T>* out, int y0, int ny, const cx<T>*
 #pragma unroll
   for (int m = 0; m < 8; ++m) v[m] = valid ? ld_g<LD>(src + TT * m) : mk<T>(0, 0);
   if (nextRows) prefetch_l2(nextRows, sizeof(cx<T>) * N * (1 << LOG2V), tid, nthr);
-  SB_PHASE_END
+  SB_PHASE_END_NOSYNC  // first use of the tile buffer is the exchange after stage 0
   fast_fft_head<T, N, LOG2V, BWD, SwzCol, true, true, TWS>(vAll, S, ftw, ctx);
   SB_PHASE_BEGIN
   SB_COL_IDS
-  fast_fft_tail<T, N, LOG2V, BWD, SwzCol, TWS>(v, S, ftw, j, lane);
+  fast_fft_tail_read<T, N, LOG2V, SwzCol>(v, S, j, lane);
+  SB_PHASE_END_IF(TWS)
+  SB_MARK(ctx, 8);
+  SB_PHASE_BEGIN
+  SB_COL_IDS
+  fast_stage<T, N, BWD, FastPlan<N>::numStages - 1, TWS>(v, j, ftw);
   if (valid) {
     cx<T>* dst = out + (size_t)(y0 + lane) * N + j;
 #pragma unroll

@@ -16,15 +16,42 @@ __device__ __forceinline__ int ld_acquire_gpu(const int* p) {
   return v;
 }
 
-// All global writes of this tile (every thread's) become visible before the counter moves:
-// barrier (CTA-scope ordering), then one cumulative gpu-scope fence + atomic by thread 0 -- the
-// pattern of a cooperative-groups grid barrier.
-__device__ __forceinline__ void cta_signal(int* p) {
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    __threadfence();
-    atomicAdd(p, 1);
+// Item completion without a CTA-wide barrier. Every warp, after its last global store of the item,
+// arrives on a shared-memory counter; the warp that arrives last (all stores of the CTA are then
+// ordered before it at CTA scope) optionally drops the consumed hand-off lines from L2, and
+// publishes the item with one gpu-scope fence + atomic -- the cumulative release of a
+// cooperative-groups grid barrier, but paid by one warp while the others already run the next item.
+template <typename DiscardFn>
+__device__ __forceinline__ void warp_arrive_and_signal(int* sArrive, int numWarps, int* doneCounter,
+                                                       DiscardFn discard) {
+  const int lane = threadIdx.x & 31;
+  __syncwarp();
+  int last = 0;
+  if (lane == 0) {
+    __threadfence_block();
+    last = atomicAdd(sArrive, 1) == numWarps - 1;
+    __threadfence_block();
   }
+  last = __shfl_sync(0xffffffffu, last, 0);
+  if (last) {
+    if (lane == 0) *sArrive = 0;  // next use: two items later, after barriers every warp passes
+    discard(lane);
+    __syncwarp();
+    if (lane == 0) {
+      __threadfence();
+      atomicAdd(doneCounter, 1);
+    }
+  }
+}
+
+// Is the dependency of `it` satisfied? A tile: its scratch slot was consumed (B tiles of
+// plane - ring done); B tile: the hand-off plane is complete (A tiles of its plane done).
+template <typename T>
+__device__ __forceinline__ bool xy_item_ready(const XYArgs<T>& a, const XYItem& it, const int* aDone,
+                                              const int* bDone, int nA, int nB) {
+  if (!it.valid) return true;
+  if (it.roleA) return it.plane < a.ring || ld_acquire_gpu(&bDone[it.plane - a.ring]) >= nB;
+  return ld_acquire_gpu(&aDone[it.plane]) >= nA;
 }
 
 template <typename T, int N, bool FWD>
@@ -36,64 +63,93 @@ __global__ void __launch_bounds__(FastCfg<T, N>::threads, FastCfg<T, N>::minBloc
   // (CCTL.IVALL) on every item, which would send all twiddle reads to L2
   cx<T>* tws = S + (size_t)N * FastCfg<T, N>::V;
   for (int i = threadIdx.x; i < FastPlan<N>::tw_size(); i += blockDim.x) tws[i] = a.x.ftw[i];
-  __shared__ int sQ[2];
+  __shared__ int sQ[2];       // item claimed two iterations ahead
+  __shared__ int sReady[2];   // dependency of the NEXT item already seen satisfied (early poll)
+  __shared__ int sArrive[2];  // warps that finished the current item (by item parity)
   constexpr bool BWD = !FWD;
   constexpr int V = FastCfg<T, N>::V;
+  constexpr int WARPS = FastCfg<T, N>::threads / 32;
   const int P = a.y.numPlanes;
   const int nA = xy_tiles_a<T, BWD>(a), nB = xy_tiles_b<T, BWD>(a);
   const long long total = xy_total_items<T, BWD>(a);
   int* aDone = a.counters + 1;
   int* bDone = a.counters + 1 + P;
-  // work items are claimed two ahead: the next item is known while the current one runs, so its
-  // input can be prefetched into L2, and the claim's round trip is off the critical path
   if (threadIdx.x == 0) {
     sQ[0] = atomicAdd(&a.counters[0], 1);
     sQ[1] = atomicAdd(&a.counters[0], 1);
+    sReady[0] = sReady[1] = 0;
+    sArrive[0] = sArrive[1] = 0;
   }
   __syncthreads();
   int cur = sQ[0], nxt = sQ[1];
   __syncthreads();
   for (int k = 0; cur < total; ++k) {
-    if (threadIdx.x == 0) sQ[k & 1] = atomicAdd(&a.counters[0], 1);
     const XYItem it = xy_decode<T, BWD>(a, cur);
     XYItem nx;
     nx.valid = false;
     if (nxt < total) nx = xy_decode<T, BWD>(a, nxt);
-    if (it.valid) {
-      if (it.roleA) {
-        // slot reuse: the B tiles of plane - ring must have read the slot before this tile's final
-        // store phase. Thread 0 waits here; the barriers inside the tile order every thread's
-        // stores after it (no extra barrier).
-        if (it.plane >= a.ring && threadIdx.x == 0) {
-          while (ld_acquire_gpu(&bDone[it.plane - a.ring]) < nB) __nanosleep(64);
-        }
-        xy_run_item<T, N, BWD>(a, it, nx, tws, Ctx{FastCfg<T, N>::threads}, S);
-        cta_signal(&aDone[it.plane]);
-      } else {
-        // the first thing a B tile does is read the hand-off plane: every warp waits on its own
-        // (one polling lane per warp) instead of a CTA-wide barrier
-        if ((threadIdx.x & 31) == 0) {
-          while (ld_acquire_gpu(&aDone[it.plane]) < nA) __nanosleep(64);
-        }
-        __syncwarp();
-        xy_run_item<T, N, BWD>(a, it, nx, tws, Ctx{FastCfg<T, N>::threads}, S);
-        // all loads of the tile are complete (their values were consumed before the tile's first
-        // barrier): drop the dirty hand-off lines from L2 instead of writing them back to HBM
-        {
-          const cx<T>* slot = a.scratch + (size_t)(it.plane % a.ring) * N * N;
-          if (BWD) {  // x tile: V whole rows, contiguous
-            discard_l2(slot + (size_t)it.tile * V * N, sizeof(cx<T>) * V * N, threadIdx.x, blockDim.x);
-          } else {    // y tile: one 128-byte column segment per row
-            for (int y = threadIdx.x; y < N; y += blockDim.x)
-              discard_l2(slot + (size_t)y * N + (size_t)it.tile * V, sizeof(cx<T>) * V, 0, 1);
-          }
-        }
-        cta_signal(&bDone[it.plane]);
+    Ctx ctx{FastCfg<T, N>::threads};
+    ctx.traceItem = k;
+    SB_MARK(ctx, 0);
+#ifdef SB_XY_TRACE
+    if (threadIdx.x == 0 && blockIdx.x < kTraceCtas && k < kTraceItems)
+      g_xy_trace[((size_t)blockIdx.x * kTraceItems + k) * kTraceMarks + 15] =
+          it.valid ? (it.roleA ? 1 : 2) + 4 * (long long)it.plane + 4096LL * it.tile : 0;
+#endif
+    // Dependency of this item: normally seen satisfied one item ago by thread 0 (sReady, ordered
+    // by the barriers of the previous item); otherwise every warp polls on its own. For A tiles
+    // only the final stores depend on it, but they are ordered after this point anyway.
+    if (it.valid && !sReady[k & 1]) {
+      if ((threadIdx.x & 31) == 0) {
+        while (!xy_item_ready<T>(a, it, aDone, bDone, nA, nB)) __nanosleep(64);
       }
+      __syncwarp();
+    }
+    SB_MARK(ctx, 1);
+    // Thread 0 claims the item after next and looks at the next item's dependency while the
+    // loads of this item are in flight (run_item_chores, called by the tile right after its loads)
+    ItemChores chores;
+    chores.claimCounter = &a.counters[0];
+    chores.claimOut = &sQ[k & 1];
+    chores.readyOut = &sReady[(k + 1) & 1];
+    chores.depCounter = nullptr;
+    chores.depNeed = 0;
+    if (nx.valid) {
+      if (nx.roleA) {
+        if (nx.plane >= a.ring) {
+          chores.depCounter = &bDone[nx.plane - a.ring];
+          chores.depNeed = nB;
+        }
+      } else {
+        chores.depCounter = &aDone[nx.plane];
+        chores.depNeed = nA;
+      }
+    }
+    ctx.chores = &chores;
+    if (it.valid) {
+      xy_run_item<T, N, BWD>(a, it, nx, tws, ctx, S);
+      SB_MARK(ctx, 6);
+      if (it.roleA) {
+        warp_arrive_and_signal(&sArrive[k & 1], WARPS, &aDone[it.plane], [](int) {});
+      } else {
+        // the consumed hand-off lines are dropped from L2 instead of being written back to HBM
+        const cx<T>* slot = a.scratch + (size_t)(it.plane % a.ring) * N * N;
+        const int tile = it.tile;
+        warp_arrive_and_signal(&sArrive[k & 1], WARPS, &bDone[it.plane], [&](int lane) {
+          if (BWD) {  // x tile: V whole rows, contiguous
+            discard_l2(slot + (size_t)tile * V * N, sizeof(cx<T>) * V * N, lane, 32);
+          } else {    // y tile: one 128-byte column segment per row
+            for (int y = lane; y < N; y += 32)
+              discard_l2(slot + (size_t)y * N + (size_t)tile * V, sizeof(cx<T>) * V, 0, 1);
+          }
+        });
+      }
+      SB_MARK(ctx, 7);
     } else {
+      run_item_chores(ctx);
       __syncthreads();
     }
-    // (cta_signal's barrier doubles as the end-of-item barrier: sQ[k & 1] is visible, S is free)
+    // every item passes at least one barrier after thread 0 wrote sQ / sReady
     cur = nxt;
     nxt = sQ[k & 1];
   }
@@ -196,6 +252,19 @@ int sb_xy_fused_config(int isFloat, int n, int numPlanes, int* ring, int* lag, i
   *lag = l;
   *numCounters = 1 + 2 * (numPlanes > 0 ? numPlanes : 0);
   return 0;
+}
+
+__attribute__((visibility("default"))) int sb_xy_trace_read(long long* host, int maxEntries) {
+#ifdef SB_XY_TRACE
+  const int n = sb::kTraceCtas * sb::kTraceItems * sb::kTraceMarks;
+  if (maxEntries < n) return -1;
+  if (cudaMemcpyFromSymbol(host, sb::g_xy_trace, sizeof(long long) * n) != cudaSuccess) return -2;
+  return n;
+#else
+  (void)host;
+  (void)maxEntries;
+  return 0;
+#endif
 }
 
 int sb_launch_xy_f64(int forward, const sb::XYArgs<double>* a, void* stream) {

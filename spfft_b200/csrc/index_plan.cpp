@@ -6,6 +6,7 @@
 #include <cstdint>
 #include <numeric>
 
+#include "fast_stage_kernels.hpp"
 #include "spfft/exceptions.hpp"
 
 namespace spfft {
@@ -454,7 +455,9 @@ bool fast_path_length(int n, int complexBytes) {
   return lanes * (n / 8) <= 1024;  // threads per CTA
 }
 
-int fast_path_log2_lanes(int complexBytes) { return complexBytes == 16 ? 3 : 4; }
+int fast_path_log2_lanes(int complexBytes) {
+  return complexBytes == 16 ? sb::FastLanes<double>::log2V : sb::FastLanes<float>::log2V;
+}
 
 template <typename T>
 std::vector<sb::cx<T>> make_fast_twiddles(int n) {
