@@ -15,19 +15,22 @@
 #define SB_HD __host__ __device__ __forceinline__
 #define SB_DEV __device__ __forceinline__
 #define SB_ON_GPU 1
-#define SB_PHASE_BEGIN                 \
-  {                                    \
-    const int tid = (int)threadIdx.x;  \
-    const int nthr = (int)blockDim.x;
+// A "group" is the set of threads that work on one tile: the whole CTA (Ctx{blockDim.x}) or, in
+// the pipelined persistent kernels, `nthreads` consecutive threads starting at `tidBase` that
+// synchronise on their own named barrier `barId`.
+#define SB_PHASE_BEGIN                               \
+  {                                                  \
+    const int tid = (int)threadIdx.x - ctx.tidBase;  \
+    const int nthr = ctx.nthreads;
 #define SB_PHASE_END \
   }                  \
-  __syncthreads();
+  ::sb::group_sync(ctx);
 // like SB_PHASE_END but without the barrier (last phase of a kernel)
 #define SB_PHASE_END_NOSYNC }
 // barrier only if the (compile-time) condition holds
 #define SB_PHASE_END_IF(c) \
   }                        \
-  if (c) __syncthreads();
+  if (c) ::sb::group_sync(ctx);
 // per-thread registers that live across phases
 #define SB_REGS(type, name, n) type name[n]
 #define SB_RP(name, n) (name)
@@ -104,6 +107,17 @@ struct Ctx {
   int nthreads;
   int traceItem = -1;                    // experiments only (SB_XY_TRACE)
   const ItemChores* chores = nullptr;    // persistent kernels only
+  int tidBase = 0;                       // first thread of the group (pipelined kernels)
+  int barId = 0;                         // named barrier of the group, 0 = __syncthreads()
 };
+
+#if SB_ON_GPU
+__device__ __forceinline__ void group_sync(const Ctx& ctx) {
+  if (ctx.barId == 0)
+    __syncthreads();
+  else
+    asm volatile("bar.sync %0, %1;" ::"r"(ctx.barId), "r"(ctx.nthreads) : "memory");
+}
+#endif
 
 }  // namespace sb

@@ -25,6 +25,11 @@ int sb_launch_xy_f32(int forward, const sb::XYArgs<float>* args, void* stream);
 /* Barrier over the ranks of a distributed transform through peer-mapped flag arrays
  * (flags[r] = rank r's array of numRanks ints, zero-initialised; epoch increases by one per call). */
 int sb_launch_peer_barrier(int* const* flags, int numRanks, int me, int epoch, void* stream);
+/* Pipelined persistent xy stage (fast_pipe.cu: TMA-staged tiles, warp groups; double precision,
+ * C2C, dimX == dimY == n in {128, 256, 512}): plan-time query like sb_xy_fused_config (returns
+ * cudaErrorInvalidValue when unsupported) and the launch of one direction. */
+int sb_xy_pipe_config(int isFloat, int n, int numPlanes, int* ring, int* lag, int* numCounters);
+int sb_launch_xy_pipe_f64(int forward, const sb::XYArgs<double>* args, void* stream);
 /* total number of kernel launches issued through this file */
 long long sb_launch_count(void);
 void sb_note_launches(int n);

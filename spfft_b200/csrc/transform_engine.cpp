@@ -25,6 +25,7 @@ struct Launch<double> {
   static int y(int f, const sb::YArgs<double>& a, void* s) { return sb_launch_y_f64(f, &a, s); }
   static int x(int f, const sb::XArgs<double>& a, void* s) { return sb_launch_x_f64(f, &a, s); }
   static int xy(int f, const sb::XYArgs<double>& a, void* s) { return sb_launch_xy_f64(f, &a, s); }
+  static int xy_pipe(int f, const sb::XYArgs<double>& a, void* s) { return sb_launch_xy_pipe_f64(f, &a, s); }
 };
 template <>
 struct Launch<float> {
@@ -32,6 +33,7 @@ struct Launch<float> {
   static int y(int f, const sb::YArgs<float>& a, void* s) { return sb_launch_y_f32(f, &a, s); }
   static int x(int f, const sb::XArgs<float>& a, void* s) { return sb_launch_x_f32(f, &a, s); }
   static int xy(int f, const sb::XYArgs<float>& a, void* s) { return sb_launch_xy_f32(f, &a, s); }
+  static int xy_pipe(int, const sb::XYArgs<float>&, void*) { return static_cast<int>(cudaErrorInvalidValue); }
 };
 
 inline void check_launch(int err) {
@@ -287,7 +289,15 @@ std::shared_ptr<DevicePlan<T>> build_device_plan(const IndexMaps& m, long long s
   // separate kernels are the default.
   const char* tuneEnv = std::getenv("SPFFT_B200_TUNE");
   const bool allowFused = tuneEnv && (std::atoi(tuneEnv) & 4);
-  if (allowFused && fastX && fastY && m.dimX == m.dimY && m.type == SPFFT_TRANS_C2C) {
+  const bool allowPipe = tuneEnv && (std::atoi(tuneEnv) & 8);
+  if (allowPipe && fastX && fastY && m.dimX == m.dimY && m.type == SPFFT_TRANS_C2C && m.commSize == 1 &&
+      ax.log2Vx == ax.log2Vy) {
+    // y and x stages as one pipelined persistent kernel (fast_pipe.cu)
+    const int err = sb_xy_pipe_config(sizeof(T) == 4, m.dimX, m.local_planes(), &plan->xyRing,
+                                      &plan->xyLag, &plan->xyCounters);
+    plan->fusedXY = plan->pipeXY = err == 0;
+  }
+  if (!plan->fusedXY && allowFused && fastX && fastY && m.dimX == m.dimY && m.type == SPFFT_TRANS_C2C) {
     // y and x stages as one persistent kernel with the hand-off in L2 (fast_xy.cu)
     const int err = sb_xy_fused_config(sizeof(T) == 4, m.dimX, m.local_planes(), &plan->xyRing,
                                        &plan->xyLag, &plan->xyCounters);
@@ -599,7 +609,8 @@ void TransformEngine<T>::enqueue_backward(const T* input, T* output) {
   T* outDev = outOnDevice ? output : device_space();
   if (plan_->fusedXY) {
     // ---- fused xy stage: y tiles and x tiles in one persistent kernel, hand-off through L2
-    check_launch(Launch<T>::xy(0, make_xy_args(geo, nullptr, outDev), s));
+    check_launch(plan_->pipeXY ? Launch<T>::xy_pipe(0, make_xy_args(geo, nullptr, outDev), s)
+                               : Launch<T>::xy(0, make_xy_args(geo, nullptr, outDev), s));
     record_stage("xy backward");
   } else {
     // ---- y stage: stick gather + plane symmetry + y-FFT (execution_gpu.cpp:371-390)
@@ -652,7 +663,8 @@ void TransformEngine<T>::enqueue_forward(const T* input, T* output, SpfftScaling
     }
     if (plan_->fusedXY) {
       if (anySticks) {
-        check_launch(Launch<T>::xy(1, make_xy_args(geo, src, nullptr), s));
+        check_launch(plan_->pipeXY ? Launch<T>::xy_pipe(1, make_xy_args(geo, src, nullptr), s)
+                                   : Launch<T>::xy(1, make_xy_args(geo, src, nullptr), s));
         record_stage("xy forward");
       }
     } else {

@@ -104,6 +104,7 @@ struct DevicePlan {
   int numStickTiles = 0, pitch = 0, numXTiles = 0, symTile = -1, symLane = -1;
   // fused xy stage (fast_xy.cu): scratch ring geometry, 0 planes = separate y and x kernels
   bool fusedXY = false;
+  bool pipeXY = false;  // fusedXY through the pipelined kernel (fast_pipe.cu) instead of fast_xy.cu
   int xyRing = 0, xyLag = 0, xyCounters = 0;
   // distributed transforms: the stick <-> slab exchange (host offsets/counts) and the y-stage
   // tables over all ranks' sticks

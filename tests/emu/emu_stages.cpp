@@ -6,12 +6,15 @@
 // GPU (`pytest -m "not gpu"`). It is never linked into libspfft_b200.so, is not reachable from the
 // SpFFT API, and is not a fallback: the product fails loudly without CUDA.
 #define SB_EMULATE 1
+#include <cstdlib>
+#include <algorithm>
 #include <cstring>
 #include <vector>
 
 #include "../../spfft_b200/csrc/index_plan.hpp"
 #include "../../spfft_b200/csrc/stage_args.hpp"
 #include "../../spfft_b200/csrc/fast_stage_kernels.hpp"
+#include "../../spfft_b200/csrc/fast_pipe_kernels.hpp"
 #include "../../spfft_b200/csrc/stage_kernels.hpp"
 #include "spfft/exceptions.hpp"
 
@@ -72,8 +75,37 @@ void run_x(bool fwd, const sb::XArgs<T>& a, int b, sb::Ctx ctx, sb::cx<T>* smem)
 
 // fused xy stage: the items in hand-out order, one after the other (every dependency of an item
 // is an earlier item, so sequential execution satisfies all waits of the GPU kernel)
+// pipelined xy stage (fast_pipe.cu): same item order; the bulk copy that stages a tile is a memcpy
+// into a poisoned buffer, then the tile body runs on it
+template <typename T>
+void run_xy_pipe(bool fwd, const sb::XYArgs<T>& a) {
+  const int n = a.x.nx;
+  const int V = 1 << sb::FastLanes<T>::log2V;
+  sb::Ctx c{V * (n / 8)};
+  std::vector<sb::cx<T>> buf(static_cast<size_t>(n) * V);
+  const long long total = fwd ? sb::xy_total_items<T, false>(a) : sb::xy_total_items<T, true>(a);
+  for (long long item = 0; item < total; ++item) {
+    const sb::XYItem it = fwd ? sb::xy_decode<T, false>(a, (int)item) : sb::xy_decode<T, true>(a, (int)item);
+    if (!it.valid) continue;
+    std::fill(buf.begin(), buf.end(), sb::mk<T>(T(1e30), T(-1e30)));
+#define CALL(NN)                                                                                    \
+  {                                                                                                 \
+    unsigned bytes = 0;                                                                             \
+    const sb::cx<T>* src = fwd ? sb::pipe_item_source<T, NN, false>(a, it, &bytes)                  \
+                               : sb::pipe_item_source<T, NN, true>(a, it, &bytes);                  \
+    if (bytes > buf.size() * sizeof(sb::cx<T>)) throw spfft::InternalError();                       \
+    if (bytes) std::memcpy(buf.data(), src, bytes);                                                 \
+    if (fwd) sb::pipe_run_item<T, NN, false>(a, it, buf.data(), a.x.ftw, c);                        \
+    else sb::pipe_run_item<T, NN, true>(a, it, buf.data(), a.x.ftw, c);                             \
+  }
+    EMU_DISPATCH(n, CALL)
+#undef CALL
+  }
+}
+
 template <typename T>
 void run_xy(bool fwd, const sb::XYArgs<T>& a, sb::cx<T>* smem) {
+  if (getenv("SB_EMU_PIPE")) return run_xy_pipe<T>(fwd, a);
   sb::Ctx c{(1 << sb::FastLanes<T>::log2V) * (a.x.nx / 8)};
   std::vector<int> aDone(a.y.numPlanes, 0), bDone(a.y.numPlanes, 0);
   const long long total = fwd ? sb::xy_total_items<T, false>(a) : sb::xy_total_items<T, true>(a);

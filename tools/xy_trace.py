@@ -31,7 +31,8 @@ buf = (C.c_longlong * (CT * IT * MK))()
 
 
 def dump(label):
-    got = raw.sb_xy_trace_read(buf, CT * IT * MK)
+    reader = raw.sb_pipe_trace_read if (int(os.environ.get("SPFFT_B200_TUNE", "0")) & 8) else raw.sb_xy_trace_read
+    got = reader(buf, CT * IT * MK)
     if got <= 0:
         print("no trace in this build", got)
         return
