@@ -331,18 +331,15 @@ int sb_xy_pipe_config(int isFloat, int n, int numPlanes, int* ring, int* lag, in
   return 0;
 }
 
-__attribute__((visibility("default"))) int sb_pipe_trace_read(long long* host, int maxEntries) {
 #ifdef SB_XY_TRACE
+/* experiment builds only (tools/xy_trace.py) */
+__attribute__((visibility("default"))) int sb_pipe_trace_read(long long* host, int maxEntries) {
   const int n = sb::kTraceCtas * sb::kTraceItems * sb::kTraceMarks;
   if (maxEntries < n) return -1;
   if (cudaMemcpyFromSymbol(host, sb::g_xy_trace, sizeof(long long) * n) != cudaSuccess) return -2;
   return n;
-#else
-  (void)host;
-  (void)maxEntries;
-  return 0;
-#endif
 }
+#endif
 
 int sb_launch_xy_pipe_f64(int forward, const sb::XYArgs<double>* a, void* stream) {
   sb_note_launches(1);
