@@ -225,14 +225,15 @@ def main():
     nz_local = n
     if world > 1:
         # ONE transform of the named size sharded over the GPUs (strong scaling): frequency domain =
-        # contiguous x ranges of whole z-sticks balanced by element count (docs/source/details.rst:
+        # contiguous x ranges of whole z-sticks balanced by stick count (docs/source/details.rst:
         # 58-59), space domain = slabs of n/world planes (benchmark.cpp:171-172)
         keys = (trip[:, 0].astype(np.int64) % n) * n + (trip[:, 1].astype(np.int64) % n)
         stick_start = np.flatnonzero(np.concatenate([[True], keys[1:] != keys[:-1]]))
+        # balanced by STICK count: the z-FFT, the stick buffer and the exchange all scale with the
+        # number of sticks a rank owns, only the sparse-value traffic with its elements
         cuts = [0]
         for r in range(1, world):
-            target = ne_total * r // world
-            cuts.append(int(stick_start[min(int(np.searchsorted(stick_start, target)), len(stick_start) - 1)]))
+            cuts.append(int(stick_start[len(stick_start) * r // world]))
         cuts.append(ne_total)
         trip = np.ascontiguousarray(trip[cuts[rank]:cuts[rank + 1]])
         nz_local = n // world + (1 if rank < n % world else 0)

@@ -404,12 +404,12 @@ SB_DEV void y_backward_fast(const YArgs<T>& a, int block, Ctx ctx, cx<T>* S) {
 
 template <typename T, int N>
 SB_DEV void y_forward_fast(const YArgs<T>& a, int block, Ctx ctx, cx<T>* S) {
-  const int xt = block % a.numXTiles;
+  const int xt = (block % a.numXTiles + a.xtRotate) % a.numXTiles;
   const int zl = block / a.numXTiles;
   int nextXt = -1;
   const cx<T>* nextPlane = nullptr;
   if (a.pfDist > 0 && block + a.pfDist < a.numXTiles * a.numPlanes) {
-    nextXt = (block + a.pfDist) % a.numXTiles;
+    nextXt = ((block + a.pfDist) % a.numXTiles + a.xtRotate) % a.numXTiles;
     nextPlane = a.planes + (size_t)((block + a.pfDist) / a.numXTiles) * N * a.nxf;
   }
   if (a.srcBase && a.inv && a.tilePitch[xt] != 0) {
@@ -699,6 +699,74 @@ SB_DEV void x_c2c_tile(const cx<T>* in, cx<T>* out, int y0, int ny, const cx<T>*
   }
   SB_PHASE_END_NOSYNC
 #undef SB_COL_IDS
+}
+
+// -------------------------------------------------------------------------------------------
+// x stage, real rows (R2C / C2R) on the full-length complex register FFT.
+//   backward (C2R): row of nxf = N/2+1 complex -> hermitian completion while loading
+//                   (X[N-x] = conj(X[x]), reference: cuFFT Z2D of transform_real_2d_gpu.hpp:54-256
+//                   reads only the non-redundant half) -> FFT -> real parts, unpadded rows of N
+//   forward (R2C) : N reals -> FFT -> first nxf outputs
+// Memory traffic is the minimum (half spectrum + real row); the arithmetic is that of a complex
+// row, which the memory-bound stage can afford.
+// -------------------------------------------------------------------------------------------
+template <typename T, int N, bool BWD>
+SB_DEV void x_r2c_tile(const XArgs<T>& a, size_t rowBase, int y0, Ctx ctx, cx<T>* S) {
+  constexpr int LOG2V = FastLanes<T>::log2V;
+  constexpr int TT = FastPlan<N>::T;
+  constexpr int NXF = N / 2 + 1;
+  SB_REGS(cx<T>, vAll, 8);
+#define SB_COL_IDS                      \
+  cx<T>* v = SB_RP(vAll, 8);            \
+  const int lane = tid / TT;            \
+  const int j = tid & (TT - 1);         \
+  const bool valid = y0 + lane < a.ny;  \
+  (void)nthr;
+  SB_PHASE_BEGIN
+  SB_COL_IDS
+  if (BWD) {
+    const cx<T>* src = a.planes + (rowBase + lane) * NXF;
+#pragma unroll
+    for (int m = 0; m < 8; ++m) {
+      const int x = j + TT * m;
+      cx<T> val = mk<T>(0, 0);
+      if (valid) val = x < NXF ? src[x] : conj(src[N - x]);
+      v[m] = val;
+    }
+  } else {
+    const T* src = static_cast<const T*>(a.spaceIn) + (rowBase + lane) * N;
+#pragma unroll
+    for (int m = 0; m < 8; ++m) v[m] = mk<T>(valid ? src[j + TT * m] : T(0), T(0));
+  }
+  SB_PHASE_END_NOSYNC
+  fast_fft_head<T, N, LOG2V, BWD, SwzCol, true, true>(vAll, S, a.ftw, ctx);
+  SB_PHASE_BEGIN
+  SB_COL_IDS
+  fast_fft_tail<T, N, LOG2V, BWD, SwzCol>(v, S, a.ftw, j, lane);
+  if (valid) {
+    if (BWD) {
+      T* dst = static_cast<T*>(a.spaceOut) + (rowBase + lane) * N;
+#pragma unroll
+      for (int m = 0; m < 8; ++m) dst[j + TT * m] = v[m].x;
+    } else {
+      cx<T>* dst = a.planes + (rowBase + lane) * NXF;
+#pragma unroll
+      for (int m = 0; m < 8; ++m) {
+        const int x = j + TT * m;
+        if (x < NXF) dst[x] = v[m];
+      }
+    }
+  }
+  SB_PHASE_END_NOSYNC
+#undef SB_COL_IDS
+}
+
+template <typename T, int N, bool BWD>
+SB_DEV void x_r2c_fast(const XArgs<T>& a, int block, Ctx ctx, cx<T>* S) {
+  constexpr int V = 1 << FastLanes<T>::log2V;
+  const int rt = block % a.numRowTiles;
+  const int zl = block / a.numRowTiles;
+  x_r2c_tile<T, N, BWD>(a, (size_t)zl * a.ny + (size_t)rt * V, rt * V, ctx, S);
 }
 
 template <typename T, int N, bool BWD>

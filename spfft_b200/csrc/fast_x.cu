@@ -1,4 +1,4 @@
-// fast_x.cu -- x stage on complex rows (C2C) on the register FFT, sm_100a.
+// fast_x.cu -- x stage on complex rows (C2C) and real rows (R2C / C2R) on the register FFT, sm_100a.
 #include "fast_launch.cuh"
 
 namespace sb {
@@ -11,6 +11,15 @@ __global__ void __launch_bounds__(FastCfg<T, N>::threads, FastCfg<T, N>::minBloc
   x_c2c_fast<T, N, !FWD>(a, (int)blockIdx.x, Ctx{FastCfg<T, N>::threads}, S);
 }
 
+// real rows (R2C forward / C2R backward)
+template <typename T, int N, bool FWD>
+__global__ void __launch_bounds__(FastCfg<T, N>::threads, FastCfg<T, N>::minBlocks)
+    k_x_real_fast(const __grid_constant__ XArgs<T> a) {
+  extern __shared__ __align__(16) unsigned char smemRaw[];
+  cx<T>* S = reinterpret_cast<cx<T>*>(smemRaw);
+  x_r2c_fast<T, N, !FWD>(a, (int)blockIdx.x, Ctx{FastCfg<T, N>::threads}, S);
+}
+
 template <typename T, int N>
 static int launch_x_n(int forward, const XArgs<T>& a, cudaStream_t s) {
   using C = FastCfg<T, N>;
@@ -18,6 +27,9 @@ static int launch_x_n(int forward, const XArgs<T>& a, cudaStream_t s) {
     return (int)cudaErrorInvalidValue;
   } else {
     const long long blocks = (long long)a.numRowTiles * a.numPlanes;
+    if (a.r2c)
+      return forward ? launch_fast(k_x_real_fast<T, N, true>, a, blocks, C::threads, C::smem, s)
+                     : launch_fast(k_x_real_fast<T, N, false>, a, blocks, C::threads, C::smem, s);
     return forward ? launch_fast(k_x_fast<T, N, true>, a, blocks, C::threads, C::smem, s)
                    : launch_fast(k_x_fast<T, N, false>, a, blocks, C::threads, C::smem, s);
   }

@@ -255,6 +255,16 @@ ExchangePlan build_exchange_plan(const IndexMaps& m, int log2Vz, int log2Vy, boo
       if (!x.fwdBase.empty()) x.tileFwdBase[t] = x.fwdBase[e0];
     }
   }
+  // forward visiting order: start at the first x tile whose sticks belong to the next rank
+  if (!x.stickRank.empty() && P > 1) {
+    const int next = (me + 1) % P;
+    for (int t = 0; t < x.numXTiles; ++t) {
+      if (x.xtStart[t] < x.xtStart[t + 1] && x.stickRank[x.xtStart[t]] == next) {
+        x.fwdTileRotate = t;
+        break;
+      }
+    }
+  }
   if (fastY && !all.empty()) {
     const int ny = m.dimY;
     const int T = ny / 8;

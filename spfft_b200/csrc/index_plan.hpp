@@ -92,6 +92,7 @@ struct ExchangePlan {
   std::vector<unsigned char> stickRank; // [NsTotal]
   std::vector<int> fwdBase;             // [NsTotal]
   std::vector<int> tileFwdBase;         // [numXTiles]
+  int fwdTileRotate = 0;                // first x tile owned by the next rank (forward visiting order)
 };
 
 ExchangePlan build_exchange_plan(const IndexMaps& maps, int log2Vz, int log2Vy, bool fastY = false);

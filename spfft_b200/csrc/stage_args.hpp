@@ -107,7 +107,7 @@ inline sb::XArgs<T> make_x_args(const IndexMaps& m, const AxisPlans& ax, const P
   a.r2c = m.type == SPFFT_TRANS_R2C ? 1 : 0;
   a.rp = ax.rpX;
   a.tw = p.twX;
-  a.ftw = m.type == SPFFT_TRANS_R2C ? nullptr : p.ftwX;  // real rows: generic kernel
+  a.ftw = p.ftwX;
   a.planes = planes;
   a.spaceIn = spaceIn;
   a.spaceOut = spaceOut;

@@ -105,6 +105,9 @@ struct YArgs {
   const unsigned char* stickRank;  // [numSticks over all ranks]
   const int* fwdBase;              // [numSticks over all ranks]
   const int* tileFwdBase;          // [numXTiles]
+  // forward kernels visit the x tiles of a plane starting at tile xtRotate: with peer stores
+  // every rank then targets a different destination at any time (no ingress hot spot)
+  int xtRotate;
 };
 
 // Where stick e (global sorted list) of local plane zl lives for a distributed y kernel:
@@ -263,7 +266,7 @@ template <typename T>
 SB_DEV void y_forward_body(const YArgs<T>& a, int block, Ctx ctx, cx<T>* smem) {
   const int V = 1 << a.log2V;
   const int n = a.ny << a.log2V;
-  const int xt = block % a.numXTiles;
+  const int xt = (block % a.numXTiles + a.xtRotate) % a.numXTiles;
   const int zl = block / a.numXTiles;
   const int e0 = a.xtStart[xt], e1 = a.xtStart[xt + 1];
   if (e0 == e1) return;  // no stick needs these columns

@@ -231,7 +231,7 @@ int* GridResources<T>::counters(size_t count) {
 void choose_tile_lanes(const IndexMaps& m, int cb, long long smemLimit, AxisPlans& ax, bool& fastX,
                        bool& fastY, bool& fastZ) {
   // per axis: register-FFT kernels for power-of-two lengths, generic tile kernels otherwise
-  fastX = fast_path_length(m.dimX, cb) && m.type == SPFFT_TRANS_C2C;
+  fastX = fast_path_length(m.dimX, cb);  // complex rows and real rows (x_r2c_tile)
   fastY = fast_path_length(m.dimY, cb);
   fastZ = fast_path_length(m.dimZ, cb);
   const int fastLanes = fast_path_log2_lanes(cb);
@@ -534,6 +534,7 @@ sb::YArgs<T> TransformEngine<T>::make_y_stage_args(const TileMaps& geo, bool for
     ya.stickRank = plan_->stickRank;
     ya.fwdBase = plan_->fwdBase;
     ya.tileFwdBase = plan_->tileFwdBase;
+    ya.xtRotate = plan_->exchange.fwdTileRotate;
   }
   if (plan_->distributed) {
     // sticks of all ranks, read from / written to the plane-side exchange buffer

@@ -68,7 +68,12 @@ void run_x(bool fwd, const sb::XArgs<T>& a, int b, sb::Ctx ctx, sb::cx<T>* smem)
     return;
   }
   sb::Ctx c{(1 << sb::FastLanes<T>::log2V) * (a.nx / 8)};
-#define CALL(NN) if (fwd) sb::x_c2c_fast<T, NN, false>(a, b, c, smem); else sb::x_c2c_fast<T, NN, true>(a, b, c, smem)
+#define CALL(NN)                                                                                     \
+  if (a.r2c) {                                                                                       \
+    if (fwd) sb::x_r2c_fast<T, NN, false>(a, b, c, smem); else sb::x_r2c_fast<T, NN, true>(a, b, c, smem); \
+  } else {                                                                                           \
+    if (fwd) sb::x_c2c_fast<T, NN, false>(a, b, c, smem); else sb::x_c2c_fast<T, NN, true>(a, b, c, smem); \
+  }
   EMU_DISPATCH(a.nx, CALL)
 #undef CALL
 }
@@ -140,7 +145,7 @@ int run(int type, int dimX, int dimY, int dimZ, int n, const int* triplets, int 
     const int cb = sizeof(sb::cx<T>);
     // maxLog2V == -2 forces the generic kernels everywhere (otherwise same choice as the product)
     const bool allowFast = maxLog2V != -2;
-    const bool fastX = allowFast && fast_path_length(dimX, cb) && type == SPFFT_TRANS_C2C;
+    const bool fastX = allowFast && fast_path_length(dimX, cb);
     const bool fastY = allowFast && fast_path_length(dimY, cb);
     const bool fastZ = allowFast && fast_path_length(dimZ, cb);
     const int fl = fast_path_log2_lanes(cb);

@@ -452,12 +452,15 @@ def test_golden_fixtures(torch_cuda, lib, path):
     assert orc.rel_l2(back, g["forward"]) <= TOL[single]
 
 
-def test_fused_xy_kernel(torch_cuda, lib, gen):
-    """The persistent fused y+x kernel (SPFFT_B200_TUNE bit 2): same results as the default path."""
+@pytest.mark.parametrize("tune", ["5", "9"], ids=["fused", "pipelined"])
+def test_fused_xy_kernel(torch_cuda, lib, gen, tune):
+    """The persistent fused y+x kernels (SPFFT_B200_TUNE bit 2: fast_xy.cu, bit 3: the TMA-staged
+    pipelined kernel of fast_pipe.cu, double precision from 128 up): same results as the default path."""
     old = os.environ.get("SPFFT_B200_TUNE")
-    os.environ["SPFFT_B200_TUNE"] = "5"
+    os.environ["SPFFT_B200_TUNE"] = tune
     try:
-        for shape, single in [((64, 64, 32), False), ((128, 128, 64), False), ((32, 32, 130), True)]:
+        for shape, single in [((64, 64, 32), False), ((128, 128, 64), False), ((32, 32, 130), True),
+                              ((256, 256, 37), False)]:
             nx, ny, nz = shape
             trip, vals = gen.make(nx, ny, nz, center=True, stick_fraction=0.6)
             param = orc.Parameters(0, nx, ny, nz, trip)
