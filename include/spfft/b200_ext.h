@@ -79,6 +79,16 @@ SPFFT_EXPORT SpfftError spfft_b200_exchange_plan(
     long long* planeCount, int* numXTiles, int* log2Vy, int* xtStart, int* stickSlot, int* srcBase,
     int* srcPitch);
 
+/* The peer-memory form of the same exchange (host only): where the fused kernels store.
+ * backward: row z of this rank's plane-major stick buffer goes to element rowOff[z] of the
+ * plane-side buffer of rank rowRank[z] (dimZ entries each); forward: stick e (global sorted list,
+ * same order as stickSlot above) of local plane zl goes to element fwdBase[e] + zl*srcPitch[e] of
+ * the stick buffer of rank stickRank[e]; fwdTileRotate = x tile the forward kernels start at. */
+SPFFT_EXPORT SpfftError spfft_b200_exchange_plan_peer(
+    int transformType, int isFloat, int dimX, int dimY, int dimZ, int commSize, int commRank,
+    const int* numSticksPerRank, const int* sticksAllRanks, const int* planesPerRank, int* rowRank,
+    long long* rowOff, int* stickRank, int* fwdBase, int* fwdTileRotate);
+
 /* ---- plan inspection (host only, no GPU needed) -------------------------------------------- */
 
 /* The index conversion every transform performs at creation, exposed so that tests can compare it

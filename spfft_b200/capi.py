@@ -327,6 +327,7 @@ _EXT_PER_PRECISION = ["transform_index_maps", "transform_stream", "transform_pee
 _EXT_COMMON = ["spfft_b200_convert_index_triplets", "spfft_b200_kernel_launch_count",
                "spfft_b200_nccl_unique_id", "spfft_b200_comm_create", "spfft_b200_comm_destroy",
                "spfft_b200_comm_size", "spfft_b200_comm_rank", "spfft_b200_exchange_plan",
+               "spfft_b200_exchange_plan_peer",
                "spfft_grid_create_distributed_nccl", "spfft_float_grid_create_distributed_nccl",
                "spfft_transform_create_independent_distributed_nccl",
                "spfft_float_transform_create_independent_distributed_nccl"]
@@ -517,4 +518,14 @@ def exchange_plan(lib: SpfftLib, transform_type, single, dim_x, dim_y, dim_z, co
     out["xt_start"] = out["xt_start"][:nxt.value + 1]
     for k in ("stick_slot", "src_base", "src_pitch"):
         out[k] = out[k][:total]
+    # peer-memory form of the same exchange (where the fused kernels store)
+    peer = {"row_rank": np.zeros(dim_z, np.int32), "row_off": np.zeros(dim_z, np.int64),
+            "stick_rank": np.zeros(max(total, 1), np.int32), "fwd_base": np.zeros(max(total, 1), np.int32)}
+    rot = C.c_int()
+    lib.call("spfft_b200_exchange_plan_peer", int(transform_type), int(bool(single)), int(dim_x), int(dim_y),
+             int(dim_z), size, int(comm_rank), p(ns), p(allsticks), p(planes), p(peer["row_rank"]),
+             p(peer["row_off"]), p(peer["stick_rank"]), p(peer["fwd_base"]), C.byref(rot))
+    out["row_rank"], out["row_off"] = peer["row_rank"], peer["row_off"]
+    out["stick_rank"], out["fwd_base"] = peer["stick_rank"][:total], peer["fwd_base"][:total]
+    out["fwd_tile_rotate"] = rot.value
     return out

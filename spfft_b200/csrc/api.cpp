@@ -126,6 +126,42 @@ SpfftError spfft_b200_comm_rank(SpfftB200Comm comm, int* rank) {
   return SPFFT_SUCCESS;
 }
 
+// the exchange plan rank `commRank` would build (host only)
+static spfft::b200::ExchangePlan host_exchange_plan(int transformType, int isFloat, int dimX, int dimY,
+                                                    int dimZ, int commSize, int commRank,
+                                                    const int* numSticksPerRank,
+                                                    const int* sticksAllRanks, const int* planesPerRank,
+                                                    int* log2Vy) {
+  using namespace spfft::b200;
+  if (commSize < 1 || commRank < 0 || commRank >= commSize || dimX <= 0 || dimY <= 0 || dimZ <= 0)
+    throw spfft::InvalidParameterError();
+  IndexMaps m;
+  m.type = static_cast<SpfftTransformType>(transformType);
+  m.dimX = dimX;
+  m.dimY = dimY;
+  m.dimZ = dimZ;
+  m.dimXFreq = m.type == SPFFT_TRANS_R2C ? dimX / 2 + 1 : dimX;
+  std::vector<std::vector<long long>> counts(commSize, std::vector<long long>(6, 0));
+  std::vector<std::vector<int>> sticks(commSize);
+  const int* cursor = sticksAllRanks;
+  for (int r = 0; r < commSize; ++r) {
+    counts[r][0] = dimX;
+    counts[r][1] = dimY;
+    counts[r][2] = dimZ;
+    counts[r][3] = planesPerRank[r];
+    counts[r][4] = numSticksPerRank[r];
+    sticks[r].assign(cursor, cursor + numSticksPerRank[r]);
+    cursor += numSticksPerRank[r];
+  }
+  m.stickIndices = sticks[commRank];
+  finish_distributed_index_maps(m, commRank, counts, std::move(sticks));
+  AxisPlans ax;
+  bool fx, fy, fz;
+  choose_tile_lanes(m, isFloat ? 8 : 16, 232448, ax, fx, fy, fz);
+  if (log2Vy) *log2Vy = ax.log2Vy;
+  return build_exchange_plan(m, ax.log2Vz, ax.log2Vy);
+}
+
 SpfftError spfft_b200_exchange_plan(int transformType, int isFloat, int dimX, int dimY, int dimZ,
                                     int commSize, int commRank, const int* numSticksPerRank,
                                     const int* sticksAllRanks, const int* planesPerRank,
@@ -134,44 +170,42 @@ SpfftError spfft_b200_exchange_plan(int transformType, int isFloat, int dimX, in
                                     long long* planeCount, int* numXTiles, int* log2Vy, int* xtStart,
                                     int* stickSlot, int* srcBase, int* srcPitch) {
   try {
-    using namespace spfft::b200;
-    if (commSize < 1 || commRank < 0 || commRank >= commSize || dimX <= 0 || dimY <= 0 || dimZ <= 0)
-      throw spfft::InvalidParameterError();
-    IndexMaps m;
-    m.type = static_cast<SpfftTransformType>(transformType);
-    m.dimX = dimX;
-    m.dimY = dimY;
-    m.dimZ = dimZ;
-    m.dimXFreq = m.type == SPFFT_TRANS_R2C ? dimX / 2 + 1 : dimX;
-    std::vector<std::vector<long long>> counts(commSize, std::vector<long long>(6, 0));
-    std::vector<std::vector<int>> sticks(commSize);
-    const int* cursor = sticksAllRanks;
-    for (int r = 0; r < commSize; ++r) {
-      counts[r][0] = dimX;
-      counts[r][1] = dimY;
-      counts[r][2] = dimZ;
-      counts[r][3] = planesPerRank[r];
-      counts[r][4] = numSticksPerRank[r];
-      sticks[r].assign(cursor, cursor + numSticksPerRank[r]);
-      cursor += numSticksPerRank[r];
-    }
-    m.stickIndices = sticks[commRank];
-    finish_distributed_index_maps(m, commRank, counts, std::move(sticks));
-    AxisPlans ax;
-    bool fx, fy, fz;
-    choose_tile_lanes(m, isFloat ? 8 : 16, 232448, ax, fx, fy, fz);
-    const ExchangePlan x = build_exchange_plan(m, ax.log2Vz, ax.log2Vy);
+    const spfft::b200::ExchangePlan x =
+        host_exchange_plan(transformType, isFloat, dimX, dimY, dimZ, commSize, commRank,
+                           numSticksPerRank, sticksAllRanks, planesPerRank, log2Vy);
     std::copy(x.pitchPerRank.begin(), x.pitchPerRank.end(), pitchPerRank);
     std::copy(x.stickOffset.begin(), x.stickOffset.end(), stickOffset);
     std::copy(x.stickCount.begin(), x.stickCount.end(), stickCount);
     std::copy(x.planeOffset.begin(), x.planeOffset.end(), planeOffset);
     std::copy(x.planeCount.begin(), x.planeCount.end(), planeCount);
     *numXTiles = x.numXTiles;
-    *log2Vy = ax.log2Vy;
     std::copy(x.xtStart.begin(), x.xtStart.end(), xtStart);
     std::copy(x.stickSlot.begin(), x.stickSlot.end(), stickSlot);
     std::copy(x.srcBase.begin(), x.srcBase.end(), srcBase);
     std::copy(x.srcPitch.begin(), x.srcPitch.end(), srcPitch);
+  } catch (const spfft::GenericError& e) {
+    return e.error_code();
+  } catch (...) {
+    return SPFFT_UNKNOWN_ERROR;
+  }
+  return SPFFT_SUCCESS;
+}
+
+SpfftError spfft_b200_exchange_plan_peer(int transformType, int isFloat, int dimX, int dimY, int dimZ,
+                                         int commSize, int commRank, const int* numSticksPerRank,
+                                         const int* sticksAllRanks, const int* planesPerRank,
+                                         int* rowRank, long long* rowOff, int* stickRank, int* fwdBase,
+                                         int* fwdTileRotate) {
+  try {
+    const spfft::b200::ExchangePlan x =
+        host_exchange_plan(transformType, isFloat, dimX, dimY, dimZ, commSize, commRank,
+                           numSticksPerRank, sticksAllRanks, planesPerRank, nullptr);
+    if (x.rowRank.empty() && dimZ > 0) throw spfft::InvalidParameterError();  // more than 255 ranks
+    std::copy(x.rowRank.begin(), x.rowRank.end(), rowRank);
+    std::copy(x.rowOff.begin(), x.rowOff.end(), rowOff);
+    std::copy(x.stickRank.begin(), x.stickRank.end(), stickRank);
+    std::copy(x.fwdBase.begin(), x.fwdBase.end(), fwdBase);
+    *fwdTileRotate = x.fwdTileRotate;
   } catch (const spfft::GenericError& e) {
     return e.error_code();
   } catch (...) {

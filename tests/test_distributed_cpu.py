@@ -153,3 +153,70 @@ def test_exchange_plan_two_ranks_gloo(built, case):
         assert min(r[3] for r in results) == 0
     if case[3] == [0.0, 1.0]:
         assert min(r[4] for r in results) == 0
+
+
+# ---- peer-memory form of the exchange: the fused kernels' store addresses ----------------------------
+@pytest.mark.parametrize("world", [2, 3, 8])
+@pytest.mark.parametrize("ttype,shape", [(0, (11, 12, 13)), (1, (12, 11, 13)), (0, (32, 32, 16))],
+                         ids=["c2c_11x12x13", "r2c_12x11x13", "c2c_32x32x16"])
+def test_peer_store_tables_match_block_exchange(built, gen, ttype, shape, world):
+    """Single process, all ranks' plans (the plan query is host only). Storing every rank's rows /
+    sticks straight into the owners' buffers through rowRank/rowOff (backward) and
+    stickRank/fwdBase (forward) must give exactly the buffers the block send/recv exchange gives."""
+    from spfft_b200 import capi
+    lib = capi.load()
+    nx, ny, nz = shape
+    rng = np.random.default_rng(3)
+    sdist = list(rng.uniform(0.2, 1.0, world))
+    if world == 3:
+        sdist[1] = 0.0  # a rank without sticks
+    trips = [gen.make(nx, ny, nz, hermitian=bool(ttype), num_ranks=world, rank=r, stick_distribution=sdist)[0]
+             for r in range(world)]
+    planes = gen.plane_split(nz, [1.0] * (world - 1) + [0.0 if world == 3 else 2.0])
+    sticks = [capi.convert_index_triplets(lib, bool(ttype), nx, ny, nz, t)[1] for t in trips]
+    plans = [capi.exchange_plan(lib, ttype, False, nx, ny, nz, r, sticks, planes) for r in range(world)]
+    pitch = [int(plans[0]["pitch"][r]) for r in range(world)]
+    # backward: stick-side buffers A_r [nz][pitch_r] -> plane-side buffers Q_d
+    A = [rng.standard_normal(nz * pitch[r]) + 1j * rng.standard_normal(nz * pitch[r]) for r in range(world)]
+    qsize = [int(plans[d]["plane_offset"][-1] + plans[d]["plane_count"][-1]) for d in range(world)]
+    Q_blocks = [np.zeros(qsize[d], np.complex128) for d in range(world)]
+    Q_peer = [np.zeros(qsize[d], np.complex128) for d in range(world)]
+    for me in range(world):
+        pl = plans[me]
+        for d in range(world):  # block exchange: contiguous block of A_me -> block `me` of Q_d
+            so, sc = int(pl["stick_offset"][d]), int(pl["stick_count"][d])
+            po = int(plans[d]["plane_offset"][me])
+            assert sc == int(plans[d]["plane_count"][me])
+            Q_blocks[d][po:po + sc] = A[me][so:so + sc]
+        for z in range(nz):     # peer stores: row z -> owner's buffer
+            d, off = int(pl["row_rank"][z]), int(pl["row_off"][z])
+            Q_peer[d][off:off + pitch[me]] = A[me][z * pitch[me]:(z + 1) * pitch[me]]
+    for d in range(world):
+        assert np.array_equal(Q_blocks[d], Q_peer[d])
+    # forward: every rank scatters its planes' stick values; block exchange Q_me -> A_r vs peer stores
+    A_blocks = [np.zeros(nz * pitch[r], np.complex128) for r in range(world)]
+    A_peer = [np.zeros(nz * pitch[r], np.complex128) for r in range(world)]
+    for me in range(world):
+        pl = plans[me]
+        nzl = planes[me]
+        total = len(pl["stick_slot"])
+        vals = rng.standard_normal((nzl, total)) + 1j * rng.standard_normal((nzl, total))
+        q = np.zeros(qsize[me], np.complex128)
+        for e in range(total):
+            for zl in range(nzl):
+                q[int(pl["src_base"][e]) + zl * int(pl["src_pitch"][e])] = vals[zl, e]
+                r = int(pl["stick_rank"][e])
+                A_peer[r][int(pl["fwd_base"][e]) + zl * int(pl["src_pitch"][e])] = vals[zl, e]
+        for r in range(world):
+            po, pc = int(pl["plane_offset"][r]), int(pl["plane_count"][r])
+            so = int(plans[r]["stick_offset"][me])
+            A_blocks[r][so:so + pc] = q[po:po + pc]
+    for r in range(world):
+        assert np.array_equal(A_blocks[r], A_peer[r])
+    # the forward visiting order starts at a tile of the next rank (when it owns sticks)
+    for me in range(world):
+        pl = plans[me]
+        t = pl["fwd_tile_rotate"]
+        nxt = (me + 1) % world
+        if t > 0:
+            assert int(pl["stick_rank"][pl["xt_start"][t]]) == nxt
