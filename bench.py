@@ -316,8 +316,13 @@ def main():
     if kernels:
         nm, ms = max(kernels, key=lambda k: k[1])
         achieved = stage_bytes[nm] / (ms * 1e-3) / 1e9
+        # DRAM bytes per launch of that kernel from the committed ncu capture (same workload only)
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")
+        if world == 1 and os.path.exists(tpath):
+            traffic = json.load(open(tpath)).get(f"{n}^3 {args.type} {args.precision}", {}).get(nm)
         roofline = {"bound": "hbm", "kernel": nm, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                    "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                    "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": stage_bytes[nm], "kernel_ms": ms,
                     "pair_algorithmic_bytes": 2 * ab["dir"],
                     "pair_frac": 2 * ab["dir"] / (ms_per_step * 1e-3) / 1e9 / peak,

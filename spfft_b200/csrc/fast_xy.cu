@@ -138,7 +138,8 @@ __global__ void __launch_bounds__(FastCfg<T, N>::threads, FastCfg<T, N>::minBloc
         warp_arrive_and_signal(&sArrive[k & 1], WARPS, &bDone[it.plane], [&](int lane) {
           if (BWD) {  // x tile: V whole rows, contiguous
             discard_l2(slot + (size_t)tile * V * N, sizeof(cx<T>) * V * N, lane, 32);
-          } else {    // y tile: one 128-byte column segment per row
+          } else if (sizeof(cx<T>) * V >= 128) {  // y tile: one 128-byte column segment per row
+            // (64-byte float segments share their line with the neighbour tile: no discard)
             for (int y = lane; y < N; y += 32)
               discard_l2(slot + (size_t)y * N + (size_t)tile * V, sizeof(cx<T>) * V, 0, 1);
           }
