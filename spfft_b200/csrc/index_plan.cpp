@@ -267,8 +267,9 @@ ExchangePlan build_exchange_plan(const IndexMaps& m, int log2Vz, int log2Vy, boo
   }
   if (fastY && !all.empty()) {
     const int ny = m.dimY;
-    const int T = ny / 8;
-    const size_t perTile = static_cast<size_t>(Vy) * T * 8;
+    const int vpt = fast_path_values_per_thread(ny);
+    const int T = ny / vpt;
+    const size_t perTile = static_cast<size_t>(Vy) * T * vpt;
     x.yInv.assign(perTile * x.numXTiles, 0xFFFF);
     for (size_t e = 0; e < all.size(); ++e) {
       const int xx = all[e].key / ny;
@@ -276,7 +277,7 @@ ExchangePlan build_exchange_plan(const IndexMaps& m, int log2Vz, int log2Vy, boo
       const int tile = xx >> log2Vy;
       const int lane = xx & (Vy - 1);
       const size_t tid = static_cast<size_t>(lane) * T + (yy % T);
-      x.yInv[perTile * tile + tid * 8 + yy / T] = static_cast<unsigned short>(e - x.xtStart[tile]);
+      x.yInv[perTile * tile + tid * vpt + yy / T] = static_cast<unsigned short>(e - x.xtStart[tile]);
     }
   }
   return x;
@@ -368,8 +369,9 @@ TileMaps build_tile_maps(const IndexMaps& maps, int log2Vz, int log2Vy, bool fas
 
   // ---- inverse maps of the register-FFT kernels
   if (fastZ && t.identityOrder && !t.hasDuplicates && ne > 0) {
-    const int T = nz / 8;
-    const size_t perTile = static_cast<size_t>(Vz) * T * 8;
+    const int vpt = fast_path_values_per_thread(nz);
+    const int T = nz / vpt;
+    const size_t perTile = static_cast<size_t>(Vz) * T * vpt;
     t.zInv.assign(perTile * t.numStickTiles, 0xFFFF);
     for (int p = 0; p < ne; ++p) {
       const int vi = maps.valueIndices[p];  // identity order: entry p == value p
@@ -378,13 +380,14 @@ TileMaps build_tile_maps(const IndexMaps& maps, int log2Vz, int log2Vy, bool fas
       const int tile = stick >> log2Vz;
       const int lane = stick & (Vz - 1);
       const size_t tid = static_cast<size_t>(lane) * T + (z % T);
-      t.zInv[perTile * tile + tid * 8 + z / T] = static_cast<unsigned short>(p - t.tileStart[tile]);
+      t.zInv[perTile * tile + tid * vpt + z / T] = static_cast<unsigned short>(p - t.tileStart[tile]);
     }
   }
   if (fastY && ns > 0) {
     const int ny = maps.dimY;
-    const int T = ny / 8;
-    const size_t perTile = static_cast<size_t>(Vy) * T * 8;
+    const int vpt = fast_path_values_per_thread(ny);
+    const int T = ny / vpt;
+    const size_t perTile = static_cast<size_t>(Vy) * T * vpt;
     t.yInv.assign(perTile * t.numXTiles, 0xFFFF);
     for (int s = 0; s < ns; ++s) {
       const int key = maps.stickIndices[s];
@@ -393,7 +396,7 @@ TileMaps build_tile_maps(const IndexMaps& maps, int log2Vz, int log2Vy, bool fas
       const int tile = x >> log2Vy;
       const int lane = x & (Vy - 1);
       const size_t tid = static_cast<size_t>(lane) * T + (y % T);
-      t.yInv[perTile * tile + tid * 8 + y / T] = static_cast<unsigned short>(s - t.xtStart[tile]);
+      t.yInv[perTile * tile + tid * vpt + y / T] = static_cast<unsigned short>(s - t.xtStart[tile]);
     }
   }
   return t;
@@ -460,10 +463,16 @@ template std::vector<sb::cx<float>> make_roots<float>(int);
 template std::vector<sb::cx<double>> make_roots<double>(int);
 
 bool fast_path_length(int n, int complexBytes) {
+  if (n % 3 == 0) {  // 3 * 2^k, sub-transforms of 32 .. 256 (fast3_stage_kernels.hpp)
+    const int m = n / 3;
+    return m >= 32 && m <= 256 && (m & (m - 1)) == 0;
+  }
   if (n < 32 || (n & (n - 1)) != 0) return false;
   const int lanes = 1 << fast_path_log2_lanes(complexBytes);
   return lanes * (n / 8) <= 1024;  // threads per CTA
 }
+
+int fast_path_values_per_thread(int n) { return n % 3 == 0 ? 24 : 8; }
 
 int fast_path_log2_lanes(int complexBytes) {
   return complexBytes == 16 ? sb::FastLanes<double>::log2V : sb::FastLanes<float>::log2V;
@@ -472,6 +481,23 @@ int fast_path_log2_lanes(int complexBytes) {
 template <typename T>
 std::vector<sb::cx<T>> make_fast_twiddles(int n) {
   std::vector<sb::cx<T>> w;
+  const long double twoPiL = 6.283185307179586476925286766559005768L;
+  if (n > 0 && n % 3 == 0) {
+    // N = 3*M: [r-1][k] = exp(-2*pi*i*r*k/N), r = 1,2, k < M, then the stage twiddles of length M
+    const int m = n / 3;
+    for (int r = 1; r <= 2; ++r) {
+      for (int k = 0; k < m; ++k) {
+        const long double a = twoPiL * static_cast<long double>(r * k) / static_cast<long double>(n);
+        sb::cx<T> v;
+        v.x = static_cast<T>(cosl(a));
+        v.y = static_cast<T>(-sinl(a));
+        w.push_back(v);
+      }
+    }
+    const std::vector<sb::cx<T>> sub = make_fast_twiddles<T>(m);
+    w.insert(w.end(), sub.begin(), sub.end());
+    return w;
+  }
   int log2n = 0;
   while ((1 << log2n) < n) ++log2n;
   const int r0 = (log2n % 3 == 0) ? 8 : ((log2n % 3 == 1) ? 2 : 4);

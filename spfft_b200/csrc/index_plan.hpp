@@ -134,9 +134,12 @@ sb::RadixPlan make_radix_plan(int n);
 template <typename T>
 std::vector<sb::cx<T>> make_roots(int n);
 
-// Register-FFT fast path (fast_fft.hpp): power-of-two lengths whose tile (8 lanes double / 16 lanes
-// float, n/8 threads per lane) fits one CTA.
+// Register-FFT fast path: power-of-two lengths whose tile (8 lanes, n/8 threads per lane) fits one
+// CTA (fast_fft.hpp), and 3 * 2^k lengths 96 .. 768 (fast3_stage_kernels.hpp, n/24 threads per lane).
 bool fast_path_length(int n, int complexBytes);
+// complex values a thread of the fast path holds (8, or 24 for 3 * 2^k): the inverse maps are laid
+// out [tile][thread = lane*(n/vpt) + j][vpt]
+int fast_path_values_per_thread(int n);
 int fast_path_log2_lanes(int complexBytes);
 // Stage twiddles of the register FFT: for every stage s >= 1 (radix 8, stride ns) the entries
 // [r-1][k] = exp(-2*pi*i*r*k/(8*ns)), r = 1..7, k < ns; rounded from long double.

@@ -4,6 +4,7 @@
 
 #include <atomic>
 
+#include "fast3_launch.cuh"
 #include "fast_launch.cuh"
 #include "launch.h"
 
@@ -91,7 +92,7 @@ template <typename T>
 static int launch_z(int forward, const ZArgs<T>& a, cudaStream_t s) {
   if (a.ftw) {
     g_launches.fetch_add(1, std::memory_order_relaxed);
-    return launch_z_fast<T>(forward, a, s);
+    return is_fast3_length(a.nz) ? launch_z_fast3<T>(forward, a, s) : launch_z_fast<T>(forward, a, s);
   }
   const size_t smem = 2 * ((size_t)a.nz << a.log2V) * sizeof(cx<T>);
   return forward ? launch(k_z_stage<T, true>, a, a.numTiles, smem, s)
@@ -101,7 +102,7 @@ template <typename T>
 static int launch_y(int forward, const YArgs<T>& a, cudaStream_t s) {
   if (a.ftw) {
     g_launches.fetch_add(1, std::memory_order_relaxed);
-    return launch_y_fast<T>(forward, a, s);
+    return is_fast3_length(a.ny) ? launch_y_fast3<T>(forward, a, s) : launch_y_fast<T>(forward, a, s);
   }
   const size_t smem = 2 * ((size_t)a.ny << a.log2V) * sizeof(cx<T>);
   const long long blocks = (long long)a.numXTiles * a.numPlanes;
@@ -112,7 +113,7 @@ template <typename T>
 static int launch_x(int forward, const XArgs<T>& a, cudaStream_t s) {
   if (a.ftw) {
     g_launches.fetch_add(1, std::memory_order_relaxed);
-    return launch_x_fast<T>(forward, a, s);
+    return is_fast3_length(a.nx) ? launch_x_fast3<T>(forward, a, s) : launch_x_fast<T>(forward, a, s);
   }
   const size_t smem = 2 * ((size_t)a.nx << a.log2V) * sizeof(cx<T>);
   const long long blocks = (long long)a.numRowTiles * a.numPlanes;

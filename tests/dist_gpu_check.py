@@ -48,6 +48,10 @@ def main():
         (1, (64, 64, 32), uniform, uniform, False, False),
         (0, (32, 64, 32), uniform, uniform, True, True),
         (0, (100, 100, 100), uniform, uniform, False, False),
+        # N = 3 * 2^k register-FFT kernels (gather form on single-source tiles, scatter form on mixed ones)
+        (0, (96, 96, 96), uniform, uniform, True, False),
+        (1, (192, 96, 32), uniform, [1.0 + r for r in range(world)], False, False),
+        (0, (32, 192, 96), first, last, True, True),
     ]
     worst = 0.0
     ok = True

@@ -14,6 +14,7 @@
 #include "../../spfft_b200/csrc/index_plan.hpp"
 #include "../../spfft_b200/csrc/stage_args.hpp"
 #include "../../spfft_b200/csrc/fast_stage_kernels.hpp"
+#include "../../spfft_b200/csrc/fast3_stage_kernels.hpp"
 #include "../../spfft_b200/csrc/fast_pipe_kernels.hpp"
 #include "../../spfft_b200/csrc/stage_kernels.hpp"
 #include "spfft/exceptions.hpp"
@@ -34,10 +35,27 @@ namespace {
     default: throw spfft::InternalError(); \
   }
 
+// N = 3 * 2^k register-FFT bodies (the product dispatches in fast3_launch.cuh)
+#define EMU_DISPATCH3(n, CALL) \
+  switch (n) {                 \
+    case 96: CALL(96); break;  \
+    case 192: CALL(192); break; \
+    case 384: CALL(384); break; \
+    case 768: CALL(768); break; \
+    default: throw spfft::InternalError(); \
+  }
+
 template <typename T>
 void run_z(bool fwd, const sb::ZArgs<T>& a, int b, sb::Ctx ctx, sb::cx<T>* smem) {
   if (!a.ftw) {
     if (fwd) sb::z_forward_body<T>(a, b, ctx, smem); else sb::z_backward_body<T>(a, b, ctx, smem);
+    return;
+  }
+  if (sb::is_fast3_length(a.nz)) {
+    sb::Ctx c3{(1 << sb::FastLanes<T>::log2V) * (a.nz / 24)};
+#define CALL(NN) if (fwd) sb::z_forward_fast3<T, NN>(a, b, c3, smem); else sb::z_backward_fast3<T, NN>(a, b, c3, smem)
+    EMU_DISPATCH3(a.nz, CALL)
+#undef CALL
     return;
   }
   sb::Ctx c{(1 << sb::FastLanes<T>::log2V) * (a.nz / 8)};
@@ -56,6 +74,13 @@ void run_y(bool fwd, const sb::YArgs<T>& a, int b, sb::Ctx ctx, sb::cx<T>* smem)
     if (fwd) sb::y_forward_body<T>(a, b, ctx, smem); else sb::y_backward_body<T>(a, b, ctx, smem);
     return;
   }
+  if (sb::is_fast3_length(a.ny)) {
+    sb::Ctx c3{(1 << sb::FastLanes<T>::log2V) * (a.ny / 24)};
+#define CALL(NN) if (fwd) sb::y_forward_fast3<T, NN>(a, b, c3, smem); else sb::y_backward_fast3<T, NN>(a, b, c3, smem)
+    EMU_DISPATCH3(a.ny, CALL)
+#undef CALL
+    return;
+  }
   sb::Ctx c{(1 << sb::FastLanes<T>::log2V) * (a.ny / 8)};
 #define CALL(NN) if (fwd) sb::y_forward_fast<T, NN>(a, b, c, smem); else sb::y_backward_fast<T, NN>(a, b, c, smem)
   EMU_DISPATCH(a.ny, CALL)
@@ -65,6 +90,18 @@ template <typename T>
 void run_x(bool fwd, const sb::XArgs<T>& a, int b, sb::Ctx ctx, sb::cx<T>* smem) {
   if (!a.ftw) {
     if (fwd) sb::x_forward_body<T>(a, b, ctx, smem); else sb::x_backward_body<T>(a, b, ctx, smem);
+    return;
+  }
+  if (sb::is_fast3_length(a.nx)) {
+    sb::Ctx c3{(1 << sb::FastLanes<T>::log2V) * (a.nx / 24)};
+#define CALL(NN)                                                                                       \
+  if (a.r2c) {                                                                                         \
+    if (fwd) sb::x_r2c_fast3<T, NN, false>(a, b, c3, smem); else sb::x_r2c_fast3<T, NN, true>(a, b, c3, smem); \
+  } else {                                                                                             \
+    if (fwd) sb::x_c2c_fast3<T, NN, false>(a, b, c3, smem); else sb::x_c2c_fast3<T, NN, true>(a, b, c3, smem); \
+  }
+    EMU_DISPATCH3(a.nx, CALL)
+#undef CALL
     return;
   }
   sb::Ctx c{(1 << sb::FastLanes<T>::log2V) * (a.nx / 8)};
@@ -201,7 +238,7 @@ int run(int type, int dimX, int dimY, int dimZ, int n, const int* triplets, int 
     sb::Ctx ctx{nthreads};
 
     // fused xy stage exactly when the product fuses; a small ring / lag exercises slot reuse
-    const bool fused = fastX && fastY && dimX == dimY && type == SPFFT_TRANS_C2C;
+    const bool fused = fastX && fastY && dimX == dimY && type == SPFFT_TRANS_C2C && dimX % 3 != 0;
     const int ring = dimZ > 3 ? 3 : dimZ, lag = dimZ > 3 ? 2 : 1;
     std::vector<sb::cx<T>> scratch(static_cast<size_t>(ring) * dimX * dimY + 1,
                                    sb::mk<T>(T(1e30), T(-1e30)));

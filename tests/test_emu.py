@@ -108,7 +108,10 @@ def test_emulated_float_and_duplicates(emu, gen):
 
 # ---- register-FFT ("fast") bodies: power-of-two lengths, mixed with generic axes ---------------
 FAST_SHAPES = [(32, 32, 32), (64, 32, 128), (32, 12, 64), (11, 64, 32), (128, 32, 13), (256, 32, 32),
-               (32, 512, 32), (32, 32, 1024)]
+               (32, 512, 32), (32, 32, 1024),
+               # 3 * 2^k lengths (fast3_stage_kernels.hpp), alone and mixed with the other kernel families
+               (96, 96, 96), (192, 32, 12), (12, 192, 32), (32, 13, 192), (384, 96, 32), (32, 384, 96),
+               (96, 32, 384), (768, 12, 32), (12, 768, 32), (33, 32, 768)]
 
 
 @pytest.mark.parametrize("shape", FAST_SHAPES, ids=lambda s: "x".join(map(str, s)))
@@ -116,8 +119,6 @@ FAST_SHAPES = [(32, 32, 32), (64, 32, 128), (32, 12, 64), (11, 64, 32), (128, 32
 @pytest.mark.parametrize("shuffle", [False, True])
 def test_emulated_fast_c2c(emu, gen, shape, single, shuffle):
     nx, ny, nz = shape
-    if single and max(shape) > 512:
-        pytest.skip("float fast path stops at 512")
     trip, vals = gen.make(nx, ny, nz, center=True, stick_fraction=0.5, fill_fraction=0.6)
     if shuffle:  # arbitrary user order -> scatter-form z kernels instead of the inverse-map form
         perm = np.random.default_rng(5).permutation(len(trip))
@@ -136,7 +137,9 @@ def test_emulated_fast_c2c(emu, gen, shape, single, shuffle):
     assert orc.rel_l2(back, vals) < tol
 
 
-@pytest.mark.parametrize("shape", [(32, 32, 32), (64, 128, 32), (12, 32, 64), (33, 64, 32)], ids=lambda s: "x".join(map(str, s)))
+@pytest.mark.parametrize("shape", [(32, 32, 32), (64, 128, 32), (12, 32, 64), (33, 64, 32), (96, 96, 96), (192, 32, 96),
+                                   (32, 192, 12), (384, 96, 32), (33, 96, 192), (768, 12, 96)],
+                         ids=lambda s: "x".join(map(str, s)))
 def test_emulated_fast_r2c(emu, gen, shape):
     from conftest import hermitian_space_values
     nx, ny, nz = shape

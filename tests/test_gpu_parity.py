@@ -430,6 +430,31 @@ def test_power_of_two_fast_path(torch_cuda, lib, gen, shape, single, ttype):
     assert orc.rel_l2(back, orc.forward(param, ref, orc.SPFFT_FULL_SCALING)) <= TOL[single]
 
 
+@pytest.mark.parametrize("shape", [(96, 96, 96), (192, 32, 12), (12, 192, 32), (32, 13, 192), (384, 96, 32), (32, 384, 96),
+                                   (96, 32, 384), (768, 12, 32), (12, 768, 32), (33, 32, 768), (192, 192, 192)],
+                         ids=lambda s: "x".join(map(str, s)))
+@pytest.mark.parametrize("single", [False, True])
+@pytest.mark.parametrize("ttype", [0, 1])
+@pytest.mark.parametrize("shuffle", [False, True])
+def test_three_times_power_of_two_fast_path(torch_cuda, lib, gen, shape, single, ttype, shuffle):
+    """Register-FFT kernels for N = 3 * 2^k axes (fast3_stage_kernels.hpp) mixed with the other kernel
+    families, both precisions; shuffle = values in arbitrary user order (scatter-form z kernels)."""
+    from conftest import hermitian_space_values
+    nx, ny, nz = shape
+    trip, vals = gen.make(nx, ny, nz, hermitian=bool(ttype), center=not ttype, stick_fraction=0.5, fill_fraction=0.6)
+    if ttype:
+        vals = hermitian_space_values(orc, nx, ny, nz, trip)
+    if shuffle:
+        perm = np.random.default_rng(7).permutation(len(trip))
+        trip, vals = np.ascontiguousarray(trip[perm]), np.ascontiguousarray(vals[perm])
+    param = orc.Parameters(ttype, nx, ny, nz, trip)
+    space, back = _run_pair(torch_cuda, lib, ttype, nx, ny, nz, trip, vals, single=single)
+    v = vals.astype(np.complex64).astype(np.complex128) if single else vals
+    ref = orc.backward(param, v)
+    assert orc.rel_l2(space, ref) <= TOL[single]
+    assert orc.rel_l2(back, orc.forward(param, ref, orc.SPFFT_FULL_SCALING)) <= TOL[single]
+
+
 import glob as _glob
 
 _GOLDEN = sorted(_glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
