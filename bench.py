@@ -171,6 +171,9 @@ def main():
     ap.add_argument("--type", choices=["c2c", "r2c"], default="c2c")
     ap.add_argument("--precision", choices=["double", "single"], default="double")
     ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
+    ap.add_argument("--bands", type=int, default=1,
+                    help="B independent transforms of the same plan (clones, one per band) executed through "
+                         "spfft_multi_transform_*: BASELINE.json config 5 (256 bands at 192^3); N=1 only")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -183,7 +186,12 @@ def main():
     r2c = args.type == "r2c"
     single = args.precision == "single"
 
-    config = {"workload": workload_name(args), "size": n, "type": args.type, "precision": args.precision,
+    bands = max(1, args.bands)
+    if bands > 1 and world > 1:
+        raise SystemExit("--bands is a single-GPU workload (independent bands need no exchange)")
+    config = {"workload": workload_name(args) + (f", batch of {bands} bands (clones of one plan) through "
+                                                 f"spfft_multi_transform_backward_ptr / forward_ptr" if bands > 1 else ""),
+              "bands": bands, "size": n, "type": args.type, "precision": args.precision,
               "scaling_flag": "SPFFT_NO_SCALING", "l2": "inputs larger than L2" if n >= 256 else "L2-resident (fits 126 MB L2)"}
 
     # ---------------- reference arm: CPU only, rank 0 only ----------------
@@ -256,6 +264,11 @@ def main():
     space_reals = n * n * nz_local * (1 if r2c else 2)
     d_space = torch.empty(space_reals, dtype=rdt, device="cuda")
     d_out = torch.empty(2 * ne, dtype=rdt, device="cuda")
+    # bands: one clone (own work buffers and stream, shared immutable plan) and own buffers per band
+    ts = [t] + [t.clone() for _ in range(bands - 1)]
+    b_vals = [d_vals] + [d_vals * (1.0 + 0.001 * b) for b in range(1, bands)]
+    b_space = [d_space] + [torch.empty_like(d_space) for _ in range(bands - 1)]
+    b_out = [d_out] + [torch.empty_like(d_out) for _ in range(bands - 1)]
 
     def barrier():
         if world > 1:
@@ -264,11 +277,17 @@ def main():
 
     # asynchronous mode: the transform is ordered with the default stream only, so the timed loop
     # has no host synchronisation inside
-    t.set_execution_mode(capi.SPFFT_EXEC_ASYNCHRONOUS)
+    for tb in ts:
+        tb.set_execution_mode(capi.SPFFT_EXEC_ASYNCHRONOUS)
+    no_scaling = [capi.SPFFT_NO_SCALING] * bands
 
     def pair():
-        t.backward_ptr(d_vals, d_space)
-        t.forward_ptr(d_space, d_out, capi.SPFFT_NO_SCALING)
+        if bands == 1:
+            t.backward_ptr(d_vals, d_space)
+            t.forward_ptr(d_space, d_out, capi.SPFFT_NO_SCALING)
+        else:
+            capi.multi_transform_backward_ptr(ts, b_vals, b_space)
+            capi.multi_transform_forward_ptr(ts, b_space, b_out, no_scaling)
 
     for _ in range(args.warmup):
         pair()
@@ -292,7 +311,8 @@ def main():
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         ms_total = float(tt.item())
     ms_per_step = ms_total / args.steps
-    value = 1e3 / ms_per_step  # N > 1: ONE transform of the named size sharded over the GPUs
+    # N > 1: ONE transform of the named size sharded over the GPUs; bands: B pairs per step
+    value = bands * 1e3 / ms_per_step
 
     # ---------------- roofline of the dominant kernel ----------------
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -325,9 +345,13 @@ def main():
                     "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": stage_bytes[nm], "kernel_ms": ms,
                     "pair_algorithmic_bytes": 2 * ab["dir"],
-                    "pair_frac": 2 * ab["dir"] / (ms_per_step * 1e-3) / 1e9 / peak,
+                    "pair_frac": bands * 2 * ab["dir"] / (ms_per_step * 1e-3) / 1e9 / peak,
                     "scope": "rank 0's share of the sharded transform" if world > 1 else "whole transform",
                     "stage_ms": {k: round(v, 4) for k, v in stages}}
+        if bands > 1:
+            roofline["note"] = ("bands run concurrently on their own streams: the per-kernel times of band 0 include "
+                                "the overlap with other bands' kernels; pair_frac (all bands' algorithmic bytes / step "
+                                "time) is the meaningful fraction")
 
     # ---------------- NVLink share of the exchange (N > 1) ----------------
     nvlink = None
@@ -362,14 +386,21 @@ def main():
     # ---------------- end to end through host buffers ----------------
     e2e = None
     if not args.no_e2e:
-        h_vals = torch.from_numpy(vals_host).pin_memory()
-        h_space = torch.empty(space_reals, dtype=rdt).pin_memory()
-        h_out = torch.empty(2 * ne, dtype=rdt).pin_memory()
-        t.set_execution_mode(capi.SPFFT_EXEC_SYNCHRONOUS)
+        eb = min(bands, 8)  # host-buffer bands (bounded pinned memory); copies of different bands overlap
+        h_vals = [torch.from_numpy(vals_host).pin_memory() for _ in range(eb)]
+        h_space = [torch.empty(space_reals, dtype=rdt).pin_memory() for _ in range(eb)]
+        h_out = [torch.empty(2 * ne, dtype=rdt).pin_memory() for _ in range(eb)]
+        for tb in ts:
+            tb.set_execution_mode(capi.SPFFT_EXEC_SYNCHRONOUS)
 
         def pair_host():
-            t.backward_ptr(h_vals.data_ptr(), h_space.data_ptr())
-            t.forward_ptr(h_space.data_ptr(), h_out.data_ptr(), capi.SPFFT_NO_SCALING)
+            if eb == 1:
+                t.backward_ptr(h_vals[0].data_ptr(), h_space[0].data_ptr())
+                t.forward_ptr(h_space[0].data_ptr(), h_out[0].data_ptr(), capi.SPFFT_NO_SCALING)
+            else:
+                capi.multi_transform_backward_ptr(ts[:eb], [h.data_ptr() for h in h_vals], [h.data_ptr() for h in h_space])
+                capi.multi_transform_forward_ptr(ts[:eb], [h.data_ptr() for h in h_space], [h.data_ptr() for h in h_out],
+                                                 no_scaling[:eb])
 
         pair_host()
         ksteps = max(3, min(args.steps, 5))
@@ -385,16 +416,17 @@ def main():
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             ms_e = float(tt.item())
         bpr = 4 if single else 8
-        e2e = {"value": 1e3 / ms_e, "unit": UNIT,
-               "h2d_bytes_per_step": (2 * ne + space_reals) * bpr, "d2h_bytes_per_step": (space_reals + 2 * ne) * bpr,
-               "steps": ksteps, "ms_per_step": ms_e}
+        e2e = {"value": eb * 1e3 / ms_e, "unit": UNIT,
+               "h2d_bytes_per_step": eb * (2 * ne + space_reals) * bpr, "d2h_bytes_per_step": eb * (space_reals + 2 * ne) * bpr,
+               "steps": ksteps, "ms_per_step": ms_e, "bands": eb}
         del h_vals, h_space, h_out
 
     # ---------------- CPU baseline (rank 0, N=1) ----------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        t.destroy()
-        del d_space, d_out
+        for tb in ts:
+            tb.destroy()
+        del d_space, d_out, b_space, b_out, b_vals
         pairs, cores, sample, kind = cpu_reference_pairs(args, trip, vals_host)
         cpu = {"value": pairs, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample}
 

@@ -7,15 +7,22 @@
 namespace sb {
 
 // One CTA = one tile of V lanes, V * N/24 threads (64 for N = 192) with 24 complex values each.
-// Register budget: 128 per thread (512 threads per SM) for double up to N = 192, 168 (384 threads)
-// for the three-stage lengths whose live ranges span more phases (ptxas -v: spills otherwise);
-// float 80 / 128. The small CTAs keep the barriers cheap (2 warps at N = 192) and many tiles at
+// Register budget: 168 per thread (384 threads per SM) for double, float 80 (N <= 192) / 128. The small CTAs keep the barriers cheap (2 warps at N = 192) and many tiles at
 // different phases resident per SM.
+// threads per SM the register cap of the kernels for N <= 192 is derived from. Measured at 192^3
+// (profiles/r01_v4_fast3.md): double 384 (168 registers, no spills) is 35 % faster than 512 (128
+// registers, 16-80 bytes of spills).
+#ifndef SB_F3_PSM_F64
+#define SB_F3_PSM_F64 384
+#endif
+#ifndef SB_F3_PSM_F32
+#define SB_F3_PSM_F32 768
+#endif
 template <typename T, int N>
 struct Fast3Cfg {
   static constexpr int V = 1 << FastLanes<T>::log2V;
   static constexpr int threads = V * Fast3Plan<N>::T;
-  static constexpr int perSmThreads = sizeof(T) == 8 ? (N <= 192 ? 512 : 384) : (N <= 192 ? 768 : 512);
+  static constexpr int perSmThreads = sizeof(T) == 8 ? (N <= 192 ? SB_F3_PSM_F64 : 384) : (N <= 192 ? SB_F3_PSM_F32 : 512);
   static constexpr int minBlocks = perSmThreads / threads > 16 ? 16 : (perSmThreads / threads < 1 ? 1 : perSmThreads / threads);
   static constexpr size_t smem = (size_t)N * V * sizeof(cx<T>);
 };

@@ -543,14 +543,49 @@ SB_DEV void y_forward_fast3(const YArgs<T>& a, int block, Ctx ctx, cx<T>* S) {
 
 // -------------------------------------------------------------------------------------------
 // x stage. Tile = V consecutive rows of one plane, thread = (row lane, j), column mapping on both
-// sides: natural-order loads (DIT3); the stores of a thread are the 3 consecutive elements
-// 3*(j + T*m) + {0,1,2}, i.e. a group of T threads still covers a contiguous 3*T-element span.
+// sides. SB_X3_MODE selects how the side that is not in natural order reaches global memory:
+//   0: DIT3, natural loads; a thread stores the 3 consecutive elements 3*(j + T*m) + {0,1,2}
+//      (stride-3 across threads: half-filled 32-byte sectors on their way to L2)
+//   1: DIF3, natural stores; the loads are the stride-3 ones (the three loads of a thread hit the
+//      same lines, L1 serves two of them)
+//   2: DIT3 + one more pass through the tile buffer to store in natural order
 // -------------------------------------------------------------------------------------------
+// Measured (profiles/r01_v4_fast3.md): mode 1 is the fastest (x stage at 384^3 double 0.377 -> 0.299 ms,
+// at 192^3 single 0.0355 -> 0.0246 ms); mode 2 gains little over mode 0.
+#ifndef SB_X3_MODE
+#define SB_X3_MODE 1
+#endif
+
+// registers of a finished DIT3 transform -> natural order (v[m] = X[j + T*m]) through the tile
+template <typename T, int N, int LOG2V>
+SB_DEV void dit3_to_natural(cx<T>* vAll, cx<T>* S, Ctx ctx) {
+  (void)ctx;
+  constexpr int TT = Fast3Plan<N>::T;
+  SB_PHASE_BEGIN  // (the caller's last phase ended with a barrier: every thread is done reading S)
+  (void)nthr;
+  cx<T>* v = SB_RP(vAll, 24);
+  const LaneJ id = fast_ids<LOG2V, TT, true>(tid);
+#pragma unroll
+  for (int k1 = 0; k1 < 3; ++k1) {
+#pragma unroll
+    for (int m = 0; m < 8; ++m) S[SwzCol::at<LOG2V>(k1 + 3 * (id.j + TT * m), id.lane)] = v[8 * k1 + m];
+  }
+  SB_PHASE_END
+  SB_PHASE_BEGIN
+  (void)nthr;
+  cx<T>* v = SB_RP(vAll, 24);
+  const LaneJ id = fast_ids<LOG2V, TT, true>(tid);
+#pragma unroll
+  for (int m = 0; m < 24; ++m) v[m] = S[SwzCol::at<LOG2V>(id.j + TT * m, id.lane)];
+  SB_PHASE_END_NOSYNC
+}
+
 template <typename T, int N, bool BWD>
 SB_DEV void x_c2c_fast3(const XArgs<T>& a, int block, Ctx ctx, cx<T>* S) {
   constexpr int LOG2V = FastLanes<T>::log2V;
   constexpr int V = 1 << LOG2V;
   constexpr int TT = Fast3Plan<N>::T;
+  constexpr bool DIT = SB_X3_MODE != 1;
   const int rt = block % a.numRowTiles;
   const int zl = block / a.numRowTiles;
   const size_t planeOff = (size_t)zl * a.ny * N;
@@ -563,17 +598,25 @@ SB_DEV void x_c2c_fast3(const XArgs<T>& a, int block, Ctx ctx, cx<T>* S) {
   cx<T>* v = SB_RP(vAll, 24);
   const LaneJ id = fast_ids<LOG2V, TT, true>(tid);
   const bool valid = y0 + id.lane < a.ny;
-  const cx<T>* src = in + (size_t)(y0 + id.lane) * N + id.j;
+  const cx<T>* src = in + (size_t)(y0 + id.lane) * N;
+  if (DIT) {
 #pragma unroll
-  for (int m = 0; m < 24; ++m) v[m] = valid ? src[TT * m] : mk<T>(0, 0);
+    for (int m = 0; m < 24; ++m) v[m] = valid ? src[id.j + TT * m] : mk<T>(0, 0);
+  } else {
+#pragma unroll
+    for (int m = 0; m < 8; ++m) {
+#pragma unroll
+      for (int n1 = 0; n1 < 3; ++n1) v[8 * n1 + m] = valid ? src[n1 + 3 * (id.j + TT * m)] : mk<T>(0, 0);
+    }
+  }
   SB_PHASE_END_NOSYNC
-  fast3_head<T, N, LOG2V, BWD, SwzCol, true, true, true>(vAll, S, a.ftw, ctx);
+  fast3_head<T, N, LOG2V, BWD, SwzCol, true, true, DIT>(vAll, S, a.ftw, ctx);
   SB_PHASE_BEGIN
   (void)nthr;
   cx<T>* v = SB_RP(vAll, 24);
   const LaneJ id = fast_ids<LOG2V, TT, true>(tid);
-  fast3_tail<T, N, LOG2V, BWD, SwzCol, true>(v, S, a.ftw, id.j, id.lane);
-  if (y0 + id.lane < a.ny) {
+  fast3_tail<T, N, LOG2V, BWD, SwzCol, DIT>(v, S, a.ftw, id.j, id.lane);
+  if (SB_X3_MODE == 0 && y0 + id.lane < a.ny) {
     cx<T>* dst = out + (size_t)(y0 + id.lane) * N;
 #pragma unroll
     for (int m = 0; m < 8; ++m) {
@@ -581,69 +624,132 @@ SB_DEV void x_c2c_fast3(const XArgs<T>& a, int block, Ctx ctx, cx<T>* S) {
       for (int k1 = 0; k1 < 3; ++k1) dst[k1 + 3 * (id.j + TT * m)] = v[8 * k1 + m];
     }
   }
-  SB_PHASE_END_NOSYNC
+  SB_PHASE_END_IF(SB_X3_MODE == 2)
+  if (SB_X3_MODE != 0) {
+    if (SB_X3_MODE == 2) dit3_to_natural<T, N, LOG2V>(vAll, S, ctx);
+    SB_PHASE_BEGIN
+    (void)nthr;
+    cx<T>* v = SB_RP(vAll, 24);
+    const LaneJ id = fast_ids<LOG2V, TT, true>(tid);
+    if (y0 + id.lane < a.ny) {
+      cx<T>* dst = out + (size_t)(y0 + id.lane) * N + id.j;
+#pragma unroll
+      for (int m = 0; m < 24; ++m) dst[TT * m] = v[m];
+    }
+    SB_PHASE_END_NOSYNC
+  }
 }
 
-// real rows (same contract as x_r2c_tile): C2R completes the half spectrum by conjugation while
-// loading, R2C stores the first N/2+1 outputs
+// real rows, two per lane (same contract and packing as x_r2c_pair_tile in fast_stage_kernels.hpp)
 template <typename T, int N, bool BWD>
 SB_DEV void x_r2c_fast3(const XArgs<T>& a, int block, Ctx ctx, cx<T>* S) {
   constexpr int LOG2V = FastLanes<T>::log2V;
   constexpr int V = 1 << LOG2V;
   constexpr int TT = Fast3Plan<N>::T;
   constexpr int NXF = N / 2 + 1;
-  const int rt = block % a.numRowTiles;
+  constexpr bool DIT = SB_X3_MODE != 1;
+  const int rt = block % a.numRowTiles;  // numRowTiles = ceil(ny / 2V), stage_args.hpp
   const int zl = block / a.numRowTiles;
-  const int y0 = rt * V;
-  const size_t rowBase = (size_t)zl * a.ny + (size_t)y0;
+  const int y0 = rt * 2 * V;
+  const size_t planeRow0 = (size_t)zl * a.ny;
   SB_REGS(cx<T>, vAll, 24);
-  SB_PHASE_BEGIN
+#define SB_PAIR_IDS                                          \
+  cx<T>* v = SB_RP(vAll, 24);                                \
+  const LaneJ id = fast_ids<LOG2V, TT, true>(tid);           \
+  const int yA = y0 + 2 * id.lane;                           \
+  const bool validA = yA < a.ny;                             \
+  const bool validB = yA + 1 < a.ny;                         \
   (void)nthr;
-  cx<T>* v = SB_RP(vAll, 24);
-  const LaneJ id = fast_ids<LOG2V, TT, true>(tid);
-  const bool valid = y0 + id.lane < a.ny;
+  // element held in register r before the transform / after it
+#define SB_IN_INDEX(r) (DIT ? id.j + TT * (r) : (r) / 8 + 3 * (id.j + TT * ((r) % 8)))
+#define SB_OUT_INDEX(r) (DIT ? (r) / 8 + 3 * (id.j + TT * ((r) % 8)) : id.j + TT * (r))
+  SB_PHASE_BEGIN
+  SB_PAIR_IDS
   if (BWD) {
-    const cx<T>* src = a.planes + (rowBase + id.lane) * NXF;
+    const cx<T>* srcA = a.planes + (planeRow0 + yA) * NXF;
+    const cx<T>* srcB = srcA + NXF;
 #pragma unroll
-    for (int m = 0; m < 24; ++m) {
-      const int x = id.j + TT * m;
-      cx<T> val = mk<T>(0, 0);
-      if (valid) val = x < NXF ? src[x] : conj(src[N - x]);
-      v[m] = val;
+    for (int r = 0; r < 24; ++r) {
+      const int n = SB_IN_INDEX(r);
+      const bool hi = n >= NXF;
+      const int x = hi ? N - n : n;
+      const cx<T> A = validA ? srcA[x] : mk<T>(0, 0);
+      const cx<T> B = validB ? srcB[x] : mk<T>(0, 0);
+      v[r] = pack_half_spectra<T>(A, B, x == 0 || 2 * x == N, hi);
     }
   } else {
-    const T* src = static_cast<const T*>(a.spaceIn) + (rowBase + id.lane) * N;
+    const T* srcA = static_cast<const T*>(a.spaceIn) + (planeRow0 + yA) * N;
+    const T* srcB = srcA + N;
 #pragma unroll
-    for (int m = 0; m < 24; ++m) v[m] = mk<T>(valid ? src[id.j + TT * m] : T(0), T(0));
-  }
-  SB_PHASE_END_NOSYNC
-  fast3_head<T, N, LOG2V, BWD, SwzCol, true, true, true>(vAll, S, a.ftw, ctx);
-  SB_PHASE_BEGIN
-  (void)nthr;
-  cx<T>* v = SB_RP(vAll, 24);
-  const LaneJ id = fast_ids<LOG2V, TT, true>(tid);
-  fast3_tail<T, N, LOG2V, BWD, SwzCol, true>(v, S, a.ftw, id.j, id.lane);
-  if (y0 + id.lane < a.ny) {
-    if (BWD) {
-      T* dst = static_cast<T*>(a.spaceOut) + (rowBase + id.lane) * N;
-#pragma unroll
-      for (int m = 0; m < 8; ++m) {
-#pragma unroll
-        for (int k1 = 0; k1 < 3; ++k1) dst[k1 + 3 * (id.j + TT * m)] = v[8 * k1 + m].x;
-      }
-    } else {
-      cx<T>* dst = a.planes + (rowBase + id.lane) * NXF;
-#pragma unroll
-      for (int m = 0; m < 8; ++m) {
-#pragma unroll
-        for (int k1 = 0; k1 < 3; ++k1) {
-          const int x = k1 + 3 * (id.j + TT * m);
-          if (x < NXF) dst[x] = v[8 * k1 + m];
-        }
-      }
+    for (int r = 0; r < 24; ++r) {
+      const int n = SB_IN_INDEX(r);
+      v[r] = mk<T>(validA ? srcA[n] : T(0), validB ? srcB[n] : T(0));
     }
   }
   SB_PHASE_END_NOSYNC
+  fast3_head<T, N, LOG2V, BWD, SwzCol, true, true, DIT>(vAll, S, a.ftw, ctx);
+  if (BWD) {
+    SB_PHASE_BEGIN
+    SB_PAIR_IDS
+    fast3_tail<T, N, LOG2V, BWD, SwzCol, DIT>(v, S, a.ftw, id.j, id.lane);
+    if (SB_X3_MODE != 2) {
+      T* dstA = static_cast<T*>(a.spaceOut) + (planeRow0 + yA) * N;
+      T* dstB = dstA + N;
+#pragma unroll
+      for (int r = 0; r < 24; ++r) {
+        const int k = SB_OUT_INDEX(r);
+        if (validA) dstA[k] = v[r].x;
+        if (validB) dstB[k] = v[r].y;
+      }
+    }
+    SB_PHASE_END_IF(SB_X3_MODE == 2)
+    if (SB_X3_MODE == 2) {
+      dit3_to_natural<T, N, LOG2V>(vAll, S, ctx);
+      SB_PHASE_BEGIN
+      SB_PAIR_IDS
+      T* dstA = static_cast<T*>(a.spaceOut) + (planeRow0 + yA) * N;
+      T* dstB = dstA + N;
+#pragma unroll
+      for (int r = 0; r < 24; ++r) {
+        if (validA) dstA[id.j + TT * r] = v[r].x;
+        if (validB) dstB[id.j + TT * r] = v[r].y;
+      }
+      SB_PHASE_END_NOSYNC
+    }
+  } else {
+    SB_PHASE_BEGIN
+    SB_PAIR_IDS
+    (void)validA;
+    (void)validB;
+    fast3_tail<T, N, LOG2V, BWD, SwzCol, DIT>(v, S, a.ftw, id.j, id.lane);
+    SB_PHASE_END  // every thread has read its inputs of the last stage
+    SB_PHASE_BEGIN
+    SB_PAIR_IDS
+    (void)validA;
+    (void)validB;
+#pragma unroll
+    for (int r = 0; r < 24; ++r) S[SwzCol::at<LOG2V>(SB_OUT_INDEX(r), id.lane)] = v[r];
+    SB_PHASE_END
+    SB_PHASE_BEGIN
+    SB_PAIR_IDS
+    cx<T>* dstA = a.planes + (planeRow0 + yA) * NXF;
+    cx<T>* dstB = dstA + NXF;
+#pragma unroll
+    for (int r = 0; r < 24; ++r) {
+      const int k = id.j + TT * r;
+      if (k < NXF) {
+        const cx<T> zk = DIT ? S[SwzCol::at<LOG2V>(k, id.lane)] : v[r];
+        cx<T> A, B;
+        unpack_half_spectra<T>(zk, S[SwzCol::at<LOG2V>(k == 0 ? 0 : N - k, id.lane)], A, B);
+        if (validA) dstA[k] = A;
+        if (validB) dstB[k] = B;
+      }
+    }
+    SB_PHASE_END_NOSYNC
+  }
+#undef SB_PAIR_IDS
+#undef SB_IN_INDEX
+#undef SB_OUT_INDEX
 }
 
 }  // namespace sb

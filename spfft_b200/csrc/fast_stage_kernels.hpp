@@ -704,71 +704,132 @@ SB_DEV void x_c2c_tile(const cx<T>* in, cx<T>* out, int y0, int ny, const cx<T>*
 }
 
 // -------------------------------------------------------------------------------------------
-// x stage, real rows (R2C / C2R) on the full-length complex register FFT.
-//   backward (C2R): row of nxf = N/2+1 complex -> hermitian completion while loading
-//                   (X[N-x] = conj(X[x]), reference: cuFFT Z2D of transform_real_2d_gpu.hpp:54-256
-//                   reads only the non-redundant half) -> FFT -> real parts, unpadded rows of N
-//   forward (R2C) : N reals -> FFT -> first nxf outputs
-// Memory traffic is the minimum (half spectrum + real row); the arithmetic is that of a complex
-// row, which the memory-bound stage can afford.
+// x stage, real rows (R2C / C2R): TWO real rows per complex register FFT. A lane of the tile holds
+// the rows yA = y0 + 2*lane and yB = yA + 1 as z = a + i*b (the tile covers 2*V rows).
+//   backward (C2R): the half spectra A, B (nxf = N/2+1 complex each) are completed by conjugation
+//                   while loading and combined to Z = A + i*B; one backward FFT gives a = Re z,
+//                   b = Im z (unpadded real rows of N). Like cuFFT's Z2D (reference:
+//                   transform_real_2d_gpu.hpp:54-256) the imaginary parts of X[0] and X[N/2] do
+//                   not enter the result.
+//   forward (R2C) : z = a + i*b -> FFT -> A[k] = (Z[k] + conj(Z[N-k]))/2,
+//                   B[k] = (Z[k] - conj(Z[N-k]))/(2i), k <= N/2; Z[N-k] comes from the tile buffer.
+// Memory traffic is the minimum (half spectra + real rows) and a row costs half a complex FFT.
 // -------------------------------------------------------------------------------------------
+template <typename T>
+SB_HD cx<T> pack_half_spectra(cx<T> A, cx<T> B, bool edge, bool mirrored) {
+  if (edge) {  // x == 0 or x == N/2: real by symmetry
+    A.y = T(0);
+    B.y = T(0);
+  }
+  if (mirrored) {
+    A = conj(A);
+    B = conj(B);
+  }
+  return mk<T>(A.x - B.y, A.y + B.x);
+}
+// A[k], B[k] from Z[k] and Z[N-k]
+template <typename T>
+SB_HD void unpack_half_spectra(cx<T> zk, cx<T> zn, cx<T>& A, cx<T>& B) {
+  const cx<T> c = conj(zn);
+  A = T(0.5) * (zk + c);
+  const cx<T> d = zk - c;
+  B = mk<T>(T(0.5) * d.y, T(-0.5) * d.x);
+}
+
 template <typename T, int N, bool BWD>
-SB_DEV void x_r2c_tile(const XArgs<T>& a, size_t rowBase, int y0, Ctx ctx, cx<T>* S) {
+SB_DEV void x_r2c_pair_tile(const XArgs<T>& a, size_t planeRow0, int y0, Ctx ctx, cx<T>* S) {
   constexpr int LOG2V = FastLanes<T>::log2V;
   constexpr int TT = FastPlan<N>::T;
   constexpr int NXF = N / 2 + 1;
   SB_REGS(cx<T>, vAll, 8);
-#define SB_COL_IDS                      \
-  cx<T>* v = SB_RP(vAll, 8);            \
-  const int lane = tid / TT;            \
-  const int j = tid & (TT - 1);         \
-  const bool valid = y0 + lane < a.ny;  \
+#define SB_COL_IDS                         \
+  cx<T>* v = SB_RP(vAll, 8);               \
+  const int lane = tid / TT;               \
+  const int j = tid & (TT - 1);            \
+  const int yA = y0 + 2 * lane;            \
+  const bool validA = yA < a.ny;           \
+  const bool validB = yA + 1 < a.ny;       \
   (void)nthr;
   SB_PHASE_BEGIN
   SB_COL_IDS
   if (BWD) {
-    const cx<T>* src = a.planes + (rowBase + lane) * NXF;
+    const cx<T>* srcA = a.planes + (planeRow0 + yA) * NXF;
+    const cx<T>* srcB = srcA + NXF;
 #pragma unroll
     for (int m = 0; m < 8; ++m) {
-      const int x = j + TT * m;
-      cx<T> val = mk<T>(0, 0);
-      if (valid) val = x < NXF ? src[x] : conj(src[N - x]);
-      v[m] = val;
+      const int n = j + TT * m;
+      const bool hi = n >= NXF;
+      const int x = hi ? N - n : n;
+      const cx<T> A = validA ? srcA[x] : mk<T>(0, 0);
+      const cx<T> B = validB ? srcB[x] : mk<T>(0, 0);
+      v[m] = pack_half_spectra<T>(A, B, x == 0 || 2 * x == N, hi);
     }
   } else {
-    const T* src = static_cast<const T*>(a.spaceIn) + (rowBase + lane) * N;
+    const T* srcA = static_cast<const T*>(a.spaceIn) + (planeRow0 + yA) * N;
+    const T* srcB = srcA + N;
 #pragma unroll
-    for (int m = 0; m < 8; ++m) v[m] = mk<T>(valid ? src[j + TT * m] : T(0), T(0));
+    for (int m = 0; m < 8; ++m)
+      v[m] = mk<T>(validA ? srcA[j + TT * m] : T(0), validB ? srcB[j + TT * m] : T(0));
   }
   SB_PHASE_END_NOSYNC
   fast_fft_head<T, N, LOG2V, BWD, SwzCol, true, true>(vAll, S, a.ftw, ctx);
-  SB_PHASE_BEGIN
-  SB_COL_IDS
-  fast_fft_tail<T, N, LOG2V, BWD, SwzCol>(v, S, a.ftw, j, lane);
-  if (valid) {
-    if (BWD) {
-      T* dst = static_cast<T*>(a.spaceOut) + (rowBase + lane) * N;
+  if (BWD) {
+    SB_PHASE_BEGIN
+    SB_COL_IDS
+    fast_fft_tail<T, N, LOG2V, BWD, SwzCol>(v, S, a.ftw, j, lane);
+    T* dstA = static_cast<T*>(a.spaceOut) + (planeRow0 + yA) * N;
+    T* dstB = dstA + N;
 #pragma unroll
-      for (int m = 0; m < 8; ++m) dst[j + TT * m] = v[m].x;
-    } else {
-      cx<T>* dst = a.planes + (rowBase + lane) * NXF;
+    for (int m = 0; m < 8; ++m) {
+      if (validA) dstA[j + TT * m] = v[m].x;
+      if (validB) dstB[j + TT * m] = v[m].y;
+    }
+    SB_PHASE_END_NOSYNC
+  } else {
+    SB_PHASE_BEGIN
+    SB_COL_IDS
+    (void)validA;
+    (void)validB;
+    fast_fft_tail<T, N, LOG2V, BWD, SwzCol>(v, S, a.ftw, j, lane);
+    SB_PHASE_END  // every thread has read its inputs of the last stage
+    SB_PHASE_BEGIN
+    SB_COL_IDS
+    (void)validA;
+    (void)validB;
 #pragma unroll
-      for (int m = 0; m < 8; ++m) {
-        const int x = j + TT * m;
-        if (x < NXF) dst[x] = v[m];
+    for (int m = 0; m < 8; ++m) S[SwzCol::at<LOG2V>(j + TT * m, lane)] = v[m];
+    SB_PHASE_END
+    SB_PHASE_BEGIN
+    SB_COL_IDS
+    cx<T>* dstA = a.planes + (planeRow0 + yA) * NXF;
+    cx<T>* dstB = dstA + NXF;
+#pragma unroll
+    for (int m = 0; m < 8; ++m) {
+      const int k = j + TT * m;
+      if (k < NXF) {
+        cx<T> A, B;
+        unpack_half_spectra<T>(v[m], S[SwzCol::at<LOG2V>((N - k) & (N - 1), lane)], A, B);
+        if (validA) dstA[k] = A;
+        if (validB) dstB[k] = B;
       }
     }
+    SB_PHASE_END_NOSYNC
   }
-  SB_PHASE_END_NOSYNC
 #undef SB_COL_IDS
+}
+
+// row tiles per plane of the real-row kernels (2*V rows each)
+template <typename T>
+SB_HD int x_pair_row_tiles(int ny) {
+  return (ny + (2 << FastLanes<T>::log2V) - 1) / (2 << FastLanes<T>::log2V);
 }
 
 template <typename T, int N, bool BWD>
 SB_DEV void x_r2c_fast(const XArgs<T>& a, int block, Ctx ctx, cx<T>* S) {
   constexpr int V = 1 << FastLanes<T>::log2V;
-  const int rt = block % a.numRowTiles;
+  const int rt = block % a.numRowTiles;  // numRowTiles = x_pair_row_tiles(ny), stage_args.hpp
   const int zl = block / a.numRowTiles;
-  x_r2c_tile<T, N, BWD>(a, (size_t)zl * a.ny + (size_t)rt * V, rt * V, ctx, S);
+  x_r2c_pair_tile<T, N, BWD>(a, (size_t)zl * a.ny, rt * 2 * V, ctx, S);
 }
 
 template <typename T, int N, bool BWD>

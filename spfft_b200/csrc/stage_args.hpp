@@ -103,8 +103,10 @@ inline sb::XArgs<T> make_x_args(const IndexMaps& m, const AxisPlans& ax, const P
   a.log2V = ax.log2Vx;
   a.numPlanes = m.local_planes();
   const int V = 1 << ax.log2Vx;
-  a.numRowTiles = (m.dimY + V - 1) / V;
   a.r2c = m.type == SPFFT_TRANS_R2C ? 1 : 0;
+  // the register-FFT real-row kernels transform two rows per lane (x_r2c_pair_tile)
+  const int rowsPerTile = (a.r2c && p.ftwX) ? 2 * V : V;
+  a.numRowTiles = (m.dimY + rowsPerTile - 1) / rowsPerTile;
   a.rp = ax.rpX;
   a.tw = p.twX;
   a.ftw = p.ftwX;
