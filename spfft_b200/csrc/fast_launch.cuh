@@ -33,6 +33,21 @@ int launch_fast(Kernel kernel, const Args& args, long long blocks, int threads, 
   return (int)cudaGetLastError();
 }
 
+// one launch over `bands` transforms of the same plan: grid (blocks, bands)
+template <typename Kernel, typename Args, typename Table>
+int launch_bands(Kernel kernel, const Args& args, const Table& table, long long blocks, int bands,
+                 int threads, size_t smemBytes, cudaStream_t stream) {
+  if (blocks <= 0 || bands <= 0) return 0;
+  if (blocks > 0x7fffffffLL || bands > 65535) return (int)cudaErrorInvalidConfiguration;
+  if (smemBytes > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)smemBytes);
+    if (e != cudaSuccess) return (int)e;
+  }
+  kernel<<<dim3((unsigned)blocks, (unsigned)bands), threads, smemBytes, stream>>>(args, table);
+  return (int)cudaGetLastError();
+}
+
 // Debug / tuning knob: environment variable SPFFT_B200_TUNE (integer bit mask, default 1).
 //   bit 0: L2 prefetch of the next tile's inputs
 inline int tune_flags() {

@@ -559,6 +559,22 @@ SB_DEV void z_forward_gather(const ZArgs<T>& a, int tile, Ctx ctx, cx<T>* S) {
   SB_PHASE_END_NOSYNC
 }
 
+// z stage entry: inverse-map (gather) form when the values are in stick order, scatter form otherwise
+template <typename T, int N, bool FWD>
+SB_DEV void z_fast_any(const ZArgs<T>& a, int tile, Ctx ctx, cx<T>* S) {
+  if (a.inv) {
+    if (FWD)
+      z_forward_gather<T, N>(a, tile, ctx, S);
+    else
+      z_backward_gather<T, N>(a, tile, ctx, S);
+  } else {
+    if (FWD)
+      z_forward_fast<T, N>(a, tile, ctx, S);
+    else
+      z_backward_fast<T, N>(a, tile, ctx, S);
+  }
+}
+
 template <typename T, int N, Mem STP, bool TWS>
 SB_DEV void y_backward_gather(const YArgs<T>& a, int xt, const cx<T>* stickRow, cx<T>* plane,
                               int nextXt, const cx<T>* nextStickRow, Ctx ctx, cx<T>* S,

@@ -9,17 +9,7 @@ __global__ void __launch_bounds__(FastCfg<T, N>::threads, FastCfg<T, N>::minBloc
   extern __shared__ __align__(16) unsigned char smemRaw[];
   cx<T>* S = reinterpret_cast<cx<T>*>(smemRaw);
   const Ctx ctx{FastCfg<T, N>::threads};
-  if (a.inv) {  // values in stick order: inverse-map (gather) form
-    if (FWD)
-      z_forward_gather<T, N>(a, (int)blockIdx.x, ctx, S);
-    else
-      z_backward_gather<T, N>(a, (int)blockIdx.x, ctx, S);
-  } else {
-    if (FWD)
-      z_forward_fast<T, N>(a, (int)blockIdx.x, ctx, S);
-    else
-      z_backward_fast<T, N>(a, (int)blockIdx.x, ctx, S);
-  }
+  z_fast_any<T, N, FWD>(a, (int)blockIdx.x, ctx, S);
 }
 
 template <typename T, int N>

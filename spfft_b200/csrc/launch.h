@@ -30,6 +30,17 @@ int sb_launch_peer_barrier(int* const* flags, int numRanks, int me, int epoch, v
  * cudaErrorInvalidValue when unsupported) and the launch of one direction. */
 int sb_xy_pipe_config(int isFloat, int n, int numPlanes, int* ring, int* lag, int* numCounters);
 int sb_launch_xy_pipe_f64(int forward, const sb::XYArgs<double>* args, void* stream);
+/* Batched multi-transform (band_kernels.cu): one launch per stage over `numBands` <= sb::kMaxBands
+ * transforms that share the plan in `args`; the table holds the per-band data pointers.
+ * sb_band_kernel_available: does a batched kernel exist for an axis of length n (registerFft: the
+ * axis runs the register-FFT kernels, i.e. its ftw table is set)? */
+int sb_band_kernel_available(int n, int registerFft);
+int sb_launch_z_bands_f64(int forward, const sb::ZArgs<double>* args, const sb::BandTable<double>* table, int numBands, void* stream);
+int sb_launch_z_bands_f32(int forward, const sb::ZArgs<float>* args, const sb::BandTable<float>* table, int numBands, void* stream);
+int sb_launch_y_bands_f64(int forward, const sb::YArgs<double>* args, const sb::BandTable<double>* table, int numBands, void* stream);
+int sb_launch_y_bands_f32(int forward, const sb::YArgs<float>* args, const sb::BandTable<float>* table, int numBands, void* stream);
+int sb_launch_x_bands_f64(int forward, const sb::XArgs<double>* args, const sb::BandTable<double>* table, int numBands, void* stream);
+int sb_launch_x_bands_f32(int forward, const sb::XArgs<float>* args, const sb::BandTable<float>* table, int numBands, void* stream);
 /* total number of kernel launches issued through this file */
 long long sb_launch_count(void);
 void sb_note_launches(int n);

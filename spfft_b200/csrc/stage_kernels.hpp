@@ -142,6 +142,60 @@ struct XArgs {
   int pfDist;           // L2 prefetch distance in blocks, 0 = off; set by the launcher
 };
 
+// -------------------------------------------------------------------------------------------
+// Batched multi-transform (reference: multi_transform_internal.hpp:50-176 runs the transforms one
+// by one, phase-interleaved). Transforms that share one immutable plan (clones: the bands of a
+// plane-wave code) run as ONE launch per stage with blockIdx.y = band; only the data pointers
+// differ per band and travel in this table as a kernel parameter.
+// -------------------------------------------------------------------------------------------
+constexpr int kMaxBands = 32;  // per launch (1.5 KB of kernel parameters)
+
+template <typename T>
+struct BandTable {
+  const cx<T>* valuesIn[kMaxBands];
+  cx<T>* valuesOut[kMaxBands];
+  cx<T>* sticks[kMaxBands];
+  cx<T>* planes[kMaxBands];
+  const void* spaceIn[kMaxBands];
+  void* spaceOut[kMaxBands];
+};
+
+// The arguments of band `band`: the shared ones with this band's pointers (local transforms only:
+// the distributed tables are cleared, which also lets the compiler drop those branches).
+template <typename T>
+SB_DEV ZArgs<T> band_args(const ZArgs<T>& a0, const BandTable<T>& b, int band) {
+  ZArgs<T> a = a0;
+  a.valuesIn = b.valuesIn[band];
+  a.valuesOut = b.valuesOut[band];
+  a.sticks = b.sticks[band];
+  a.rowRank = nullptr;
+  a.rowOff = nullptr;
+  return a;
+}
+template <typename T>
+SB_DEV YArgs<T> band_args(const YArgs<T>& a0, const BandTable<T>& b, int band) {
+  YArgs<T> a = a0;
+  a.sticks = b.sticks[band];
+  a.planes = b.planes[band];
+  a.srcBase = nullptr;
+  a.srcPitch = nullptr;
+  a.tileBase = nullptr;
+  a.tilePitch = nullptr;
+  a.stickRank = nullptr;
+  a.fwdBase = nullptr;
+  a.tileFwdBase = nullptr;
+  a.xtRotate = 0;
+  return a;
+}
+template <typename T>
+SB_DEV XArgs<T> band_args(const XArgs<T>& a0, const BandTable<T>& b, int band) {
+  XArgs<T> a = a0;
+  a.planes = b.planes[band];
+  a.spaceIn = b.spaceIn[band];
+  a.spaceOut = b.spaceOut[band];
+  return a;
+}
+
 // Hermitian completion of one lane of a tile, low index first (reference semantics:
 // src/symmetry/symmetry_host.hpp:47-58,73-90; GPU twin symmetry_kernels.cu:56-78,119-141).
 template <typename T>

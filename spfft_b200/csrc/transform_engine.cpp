@@ -21,6 +21,9 @@ template <typename T>
 struct Launch;
 template <>
 struct Launch<double> {
+  static int zb(int f, const sb::ZArgs<double>& a, const sb::BandTable<double>& t, int n, void* s) { return sb_launch_z_bands_f64(f, &a, &t, n, s); }
+  static int yb(int f, const sb::YArgs<double>& a, const sb::BandTable<double>& t, int n, void* s) { return sb_launch_y_bands_f64(f, &a, &t, n, s); }
+  static int xb(int f, const sb::XArgs<double>& a, const sb::BandTable<double>& t, int n, void* s) { return sb_launch_x_bands_f64(f, &a, &t, n, s); }
   static int z(int f, const sb::ZArgs<double>& a, void* s) { return sb_launch_z_f64(f, &a, s); }
   static int y(int f, const sb::YArgs<double>& a, void* s) { return sb_launch_y_f64(f, &a, s); }
   static int x(int f, const sb::XArgs<double>& a, void* s) { return sb_launch_x_f64(f, &a, s); }
@@ -29,6 +32,9 @@ struct Launch<double> {
 };
 template <>
 struct Launch<float> {
+  static int zb(int f, const sb::ZArgs<float>& a, const sb::BandTable<float>& t, int n, void* s) { return sb_launch_z_bands_f32(f, &a, &t, n, s); }
+  static int yb(int f, const sb::YArgs<float>& a, const sb::BandTable<float>& t, int n, void* s) { return sb_launch_y_bands_f32(f, &a, &t, n, s); }
+  static int xb(int f, const sb::XArgs<float>& a, const sb::BandTable<float>& t, int n, void* s) { return sb_launch_x_bands_f32(f, &a, &t, n, s); }
   static int z(int f, const sb::ZArgs<float>& a, void* s) { return sb_launch_z_f32(f, &a, s); }
   static int y(int f, const sb::YArgs<float>& a, void* s) { return sb_launch_y_f32(f, &a, s); }
   static int x(int f, const sb::XArgs<float>& a, void* s) { return sb_launch_x_f32(f, &a, s); }
@@ -703,6 +709,76 @@ void TransformEngine<T>::enqueue_forward(const T* input, T* output, SpfftScaling
     check_gpu(cudaMemcpyAsync(output, outDev, ne * 2 * sizeof(T), cudaMemcpyDeviceToHost, s));
     record_stage("d2h values");
   }
+}
+
+template <typename T>
+bool TransformEngine<T>::run_batched(bool forward, int n, TransformEngine<T>* const* e, const T* const* in,
+                                     T* const* out, const SpfftScalingType* scaling) {
+  static const bool enabled = [] {
+    const char* v = std::getenv("SPFFT_B200_BATCH");
+    return !(v && std::atoi(v) == 0);
+  }();
+  if (!enabled || n < 2) return false;
+  TransformEngine<T>& e0 = *e[0];
+  if (!e0.plan_ || e0.plan_->distributed || e0.plan_->fusedXY) return false;
+  const IndexMaps& m = *e0.maps_;
+  const size_t ne = static_cast<size_t>(m.num_values());
+  if (static_cast<size_t>(m.dimX) * m.dimY * m.dimZ == 0 || ne == 0 || e0.plan_->numStickTiles == 0) return false;
+  const PlanPointers<T>& pp = e0.plan_->ptrs;
+  if (!sb_band_kernel_available(m.dimX, pp.ftwX != nullptr) || !sb_band_kernel_available(m.dimY, pp.ftwY != nullptr) ||
+      !sb_band_kernel_available(m.dimZ, pp.ftwZ != nullptr))
+    return false;
+  for (int i = 0; i < n; ++i) {
+    const TransformEngine<T>& ei = *e[i];
+    if (ei.plan_ != e0.plan_ || ei.execMode_ != e0.execMode_ || ei.profiling_ ||
+        ei.grid_->device_id() != e0.grid_->device_id())
+      return false;
+    if (!in[i] || !out[i] || !is_device_pointer(in[i]) || !is_device_pointer(out[i])) return false;
+    if (forward && scaling[i] != scaling[0]) return false;
+  }
+  DeviceGuard guard(e0.grid_->device_id());
+  // All bands run on the first transform's stream. Ordering with the other transforms' streams
+  // goes through the default stream like every call (begin_call / synchronize): each of them
+  // waited for its previous work at the end of that call.
+  e0.begin_call();
+  cudaStream_t s = e0.stream_->get();
+  TileMaps geo;
+  geo.numStickTiles = e0.plan_->numStickTiles;
+  geo.pitch = e0.plan_->pitch;
+  geo.numXTiles = e0.plan_->numXTiles;
+  geo.symTile = e0.plan_->symTile;
+  geo.symLane = e0.plan_->symLane;
+  for (int first = 0; first < n; first += sb::kMaxBands) {
+    const int nb = std::min(sb::kMaxBands, n - first);
+    sb::BandTable<T> bt{};
+    for (int b = 0; b < nb; ++b) {
+      TransformEngine<T>& eb = *e[first + b];
+      bt.sticks[b] = eb.sticks();
+      bt.planes[b] = eb.planes();
+      if (forward) {
+        bt.spaceIn[b] = in[first + b];
+        bt.valuesOut[b] = reinterpret_cast<sb::cx<T>*>(out[first + b]);
+      } else {
+        bt.valuesIn[b] = reinterpret_cast<const sb::cx<T>*>(in[first + b]);
+        bt.spaceOut[b] = out[first + b];
+      }
+    }
+    auto za = make_z_args<T>(m, geo, e0.plan_->axes, pp, forward, e0.sticks(), nullptr, nullptr,
+                             forward && scaling[0] == SPFFT_FULL_SCALING);
+    auto ya = make_y_args<T>(m, geo, e0.plan_->axes, pp, e0.sticks(), e0.planes());
+    auto xa = make_x_args<T>(m, e0.plan_->axes, pp, e0.planes(), nullptr, nullptr);
+    if (!forward) {
+      check_launch(Launch<T>::zb(0, za, bt, nb, s));
+      check_launch(Launch<T>::yb(0, ya, bt, nb, s));
+      check_launch(Launch<T>::xb(0, xa, bt, nb, s));
+    } else {
+      check_launch(Launch<T>::xb(1, xa, bt, nb, s));
+      check_launch(Launch<T>::yb(1, ya, bt, nb, s));
+      check_launch(Launch<T>::zb(1, za, bt, nb, s));
+    }
+  }
+  e0.synchronize();
+  return true;
 }
 
 template <typename T>

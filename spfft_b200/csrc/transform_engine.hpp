@@ -148,6 +148,12 @@ public:
   void enqueue_backward(const T* input, T* output);
   void enqueue_forward(const T* input, T* output, SpfftScalingType scaling);
   void synchronize();
+  // Batched multi-transform: all `n` transforms as ONE launch per stage (band_kernels.cu) when they
+  // are clones of one local plan, use device pointers and the same execution mode / scaling.
+  // Returns false (nothing enqueued) when the set does not qualify; the caller then runs the
+  // transforms one by one on their own streams.
+  static bool run_batched(bool forward, int n, TransformEngine<T>* const* engines, const T* const* in,
+                          T* const* out, const SpfftScalingType* scaling);
 
   T* space_domain_data(SpfftProcessingUnitType location);
 

@@ -306,6 +306,59 @@ def test_clone_multi_transform_and_async(torch_cuda, lib, gen):
     assert np.allclose(outs[0].cpu().numpy().view(np.complex128), 1 + 1j, atol=1e-12)
 
 
+@pytest.mark.parametrize("case", [(0, (64, 64, 64), False, 3), (0, (32, 12, 96), True, 5), (1, (96, 32, 13), False, 4),
+                                  (0, (11, 12, 13), False, 35), (1, (192, 64, 32), False, 2), (0, (256, 32, 128), True, 3)],
+                         ids=lambda c: f"{'r2c' if c[0] else 'c2c'}-{'x'.join(map(str, c[1]))}-{'f32' if c[2] else 'f64'}-{c[3]}bands")
+def test_batched_multi_transform(torch_cuda, lib, gen, case):
+    """Clones of one plan through spfft_multi_transform_*_ptr with device pointers run as ONE launch
+    per stage (band_kernels.cu, blockIdx.y = band). Every band must equal the same transform
+    executed on its own (same kernels => bit identical) and the oracle; the launch counter proves
+    that the batched path ran."""
+    from conftest import hermitian_space_values
+    torch = torch_cuda
+    ttype, (nx, ny, nz), single, bands = case
+    trip, vals = gen.make(nx, ny, nz, hermitian=bool(ttype), center=not ttype, stick_fraction=0.5, fill_fraction=0.6)
+    if ttype:
+        vals = hermitian_space_values(orc, nx, ny, nz, trip)
+    param = orc.Parameters(ttype, nx, ny, nz, trip)
+    cdt = np.complex64 if single else np.complex128
+    rdt = torch.float32 if single else torch.float64
+    n = len(trip)
+    t0 = capi.Transform(lib, transform_type=ttype, dim_x=nx, dim_y=ny, dim_z=nz, indices=trip, single=single)
+    ts = [t0] + [t0.clone() for _ in range(bands - 1)]
+    scale = [1.0 + 0.25 * b for b in range(bands)]
+    ins = [_to_dev(torch, (vals * scale[b]).astype(cdt)) for b in range(bands)]
+    nreal = nz * ny * nx * (1 if ttype else 2)
+    spaces = [torch.full((nreal,), float("nan"), dtype=rdt, device="cuda") for _ in range(bands)]
+    outs = [torch.zeros(2 * n, dtype=rdt, device="cuda") for _ in range(bands)]
+    l0 = capi.kernel_launch_count(lib)
+    capi.multi_transform_backward_ptr(ts, ins, spaces)
+    capi.multi_transform_forward_ptr(ts, spaces, outs, [capi.SPFFT_FULL_SCALING] * bands)
+    launches = capi.kernel_launch_count(lib) - l0
+    assert launches == 6 * ((bands + 31) // 32), f"batched path not taken: {launches} launches"
+    # the same transforms one at a time
+    ref_space = torch.empty(nreal, dtype=rdt, device="cuda")
+    ref_out = torch.empty(2 * n, dtype=rdt, device="cuda")
+    sdt = (np.float32 if single else np.float64) if ttype else cdt
+    v0 = vals.astype(np.complex64).astype(np.complex128) if single else vals
+    oracle_space = orc.backward(param, v0)
+    for b in (0, bands // 2, bands - 1):
+        t0.backward_ptr(ins[b], ref_space)
+        t0.forward_ptr(ref_space, ref_out, capi.SPFFT_FULL_SCALING)
+        assert torch.equal(spaces[b], ref_space) and torch.equal(outs[b], ref_out)
+        got = spaces[b].cpu().numpy().view(sdt).reshape(nz, ny, nx)
+        assert orc.rel_l2(got, oracle_space * scale[b]) <= TOL[single]
+    # mixed scaling flags do not qualify for one launch: falls back to the per-transform path, same results
+    if bands >= 2:
+        flags = [capi.SPFFT_FULL_SCALING, capi.SPFFT_NO_SCALING] + [capi.SPFFT_FULL_SCALING] * (bands - 2)
+        outs2 = [torch.zeros(2 * n, dtype=rdt, device="cuda") for _ in range(bands)]
+        capi.multi_transform_forward_ptr(ts, spaces, outs2, flags)
+        assert torch.equal(outs2[0], outs[0])
+        assert float((outs2[1] / (nx * ny * nz) - outs[1]).abs().max()) <= 1e-4 * float(outs[1].abs().max())
+    for t in ts:
+        t.destroy()
+
+
 def test_error_codes_on_device(torch_cuda, lib):
     trip = np.array([[0, 0, 0], [5, 0, 0]], np.int32)
     with pytest.raises(capi.SpfftError) as e:
