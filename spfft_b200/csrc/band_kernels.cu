@@ -59,12 +59,12 @@ __global__ void __launch_bounds__(FastCfg<T, N>::threads, FastCfg<T, N>::minBloc
   else y_backward_fast<T, N>(a, (int)blockIdx.x, Ctx{FastCfg<T, N>::threads}, S);
 }
 template <typename T, int N, bool FWD, bool REAL>
-__global__ void __launch_bounds__(FastCfg<T, N>::threads, FastCfg<T, N>::minBlocks)
+__global__ void __launch_bounds__(FastCfgX<T, N>::threads, FastCfgX<T, N>::minBlocks)
     k_x_fast_b(const __grid_constant__ XArgs<T> a0, const __grid_constant__ BandTable<T> bt) {
   SB_SMEM(T)
   const XArgs<T> a = band_args(a0, bt, (int)blockIdx.y);
-  if (REAL) x_r2c_fast<T, N, !FWD>(a, (int)blockIdx.x, Ctx{FastCfg<T, N>::threads}, S);
-  else x_c2c_fast<T, N, !FWD>(a, (int)blockIdx.x, Ctx{FastCfg<T, N>::threads}, S);
+  if (REAL) x_r2c_fast<T, N, !FWD>(a, (int)blockIdx.x, Ctx{FastCfgX<T, N>::threads}, S);
+  else x_c2c_fast<T, N, !FWD>(a, (int)blockIdx.x, Ctx{FastCfgX<T, N>::threads}, S);
 }
 
 // ---- 3 * 2^k register-FFT kernels --------------------------------------------------------------
@@ -85,12 +85,12 @@ __global__ void __launch_bounds__(Fast3Cfg<T, N>::threads, Fast3Cfg<T, N>::minBl
   else y_backward_fast3<T, N>(a, (int)blockIdx.x, Ctx{Fast3Cfg<T, N>::threads}, S);
 }
 template <typename T, int N, bool FWD, bool REAL>
-__global__ void __launch_bounds__(Fast3Cfg<T, N>::threads, Fast3Cfg<T, N>::minBlocks)
+__global__ void __launch_bounds__(Fast3CfgX<T, N>::threads, Fast3CfgX<T, N>::minBlocks)
     k_x_fast3_b(const __grid_constant__ XArgs<T> a0, const __grid_constant__ BandTable<T> bt) {
   SB_SMEM(T)
   const XArgs<T> a = band_args(a0, bt, (int)blockIdx.y);
-  if (REAL) x_r2c_fast3<T, N, !FWD>(a, (int)blockIdx.x, Ctx{Fast3Cfg<T, N>::threads}, S);
-  else x_c2c_fast3<T, N, !FWD>(a, (int)blockIdx.x, Ctx{Fast3Cfg<T, N>::threads}, S);
+  if (REAL) x_r2c_fast3<T, N, !FWD>(a, (int)blockIdx.x, Ctx{Fast3CfgX<T, N>::threads}, S);
+  else x_c2c_fast3<T, N, !FWD>(a, (int)blockIdx.x, Ctx{Fast3CfgX<T, N>::threads}, S);
 }
 
 // lengths with batched register-FFT kernels
@@ -181,13 +181,13 @@ static int launch_x_bands(int fwd, const XArgs<T>& a, const BandTable<T>& bt, in
 #define POW2(NN)                 \
   {                              \
     constexpr int NN_ = NN;      \
-    using C = FastCfg<T, NN>;    \
+    using C = FastCfgX<T, NN>;   \
     SB_X_CALL(k_x_fast_b, C)     \
   }
 #define THREE(NN)                \
   {                              \
     constexpr int NN_ = NN;      \
-    using C = Fast3Cfg<T, NN>;   \
+    using C = Fast3CfgX<T, NN>;  \
     SB_X_CALL(k_x_fast3_b, C)    \
   }
   SB_BAND_DISPATCH(a.nx, POW2, THREE)

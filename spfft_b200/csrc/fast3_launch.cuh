@@ -27,6 +27,15 @@ struct Fast3Cfg {
   static constexpr size_t smem = (size_t)N * V * sizeof(cx<T>);
 };
 
+template <typename T, int N>
+struct Fast3CfgX {
+  static constexpr int V = 1 << FastLanesX<T, N>::log2V;
+  static constexpr int threads = V * Fast3Plan<N>::T;
+  static constexpr int perSm = Fast3Cfg<T, N>::perSmThreads / threads;
+  static constexpr int minBlocks = perSm > 16 ? 16 : (perSm < 1 ? 1 : perSm);
+  static constexpr size_t smem = (size_t)N * V * sizeof(cx<T>);
+};
+
 #define SB_FAST3_DISPATCH(n, CALL)              \
   switch (n) {                                  \
     case 96: CALL(96); break;                   \

@@ -233,7 +233,7 @@ SB_DEV void scatter_into_tile(cx<T>* S, int elems, const int* slotOf, int e0, in
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      if (base + u * nthr < e1) S[SwzRow::at<LOG2V>(slot[u] >> LOG2V, slot[u] & (V - 1))] = val[u];
+      if (base + u * nthr < e1) S[SwzRow::template at<LOG2V>(slot[u] >> LOG2V, slot[u] & (V - 1))] = val[u];
     }
   }
   SB_PHASE_END
@@ -272,7 +272,7 @@ SB_DEV void z_backward_fast3_impl(const ZArgs<T>& a, int tile, Ctx ctx, cx<T>* S
     cx<T>* v = SB_RP(vAll, 24);
     const LaneJ id = fast_ids<LOG2V, TT, false>(tid);
 #pragma unroll
-    for (int m = 0; m < 24; ++m) v[m] = S[SwzRow::at<LOG2V>(id.j + TT * m, id.lane)];
+    for (int m = 0; m < 24; ++m) v[m] = S[SwzRow::template at<LOG2V>(id.j + TT * m, id.lane)];
     SB_PHASE_END
   }
   fast3_head<T, N, LOG2V, true, Swz, GATHER, false, true>(vAll, S, a.ftw, ctx);
@@ -336,12 +336,12 @@ SB_DEV void z_forward_fast3_impl(const ZArgs<T>& a, int tile, Ctx ctx, cx<T>* S)
     cx<T>* v = SB_RP(vAll, 24);
     const LaneJ id = fast_ids<LOG2V, TT, false>(tid);
 #pragma unroll
-    for (int m = 0; m < 24; ++m) S[SwzRow::at<LOG2V>(id.j + TT * m, id.lane)] = v[m];
+    for (int m = 0; m < 24; ++m) S[SwzRow::template at<LOG2V>(id.j + TT * m, id.lane)] = v[m];
     SB_PHASE_END
     SB_PHASE_BEGIN
     for (int e = e0 + tid; e < e1; e += nthr) {
       const int slot = a.entrySlot[e];
-      cx<T> val = S[SwzRow::at<LOG2V>(slot >> LOG2V, slot & (V - 1))];
+      cx<T> val = S[SwzRow::template at<LOG2V>(slot >> LOG2V, slot & (V - 1))];
       if (a.useScale) val = a.scale * val;
       a.valuesOut[a.entrySrc ? a.entrySrc[e] : e] = val;
     }
@@ -417,7 +417,7 @@ SB_DEV void y_backward_fast3_impl(const YArgs<T>& a, int xt, int zl, const cx<T>
     cx<T>* v = SB_RP(vAll, 24);
     const LaneJ id = fast_ids<LOG2V, TT, false>(tid);
 #pragma unroll
-    for (int m = 0; m < 24; ++m) v[m] = S[SwzRow::at<LOG2V>(id.j + TT * m, id.lane)];
+    for (int m = 0; m < 24; ++m) v[m] = S[SwzRow::template at<LOG2V>(id.j + TT * m, id.lane)];
     SB_PHASE_END
   }
   fast3_head<T, N, LOG2V, true, Swz, GATHER, false, true>(vAll, S, a.ftw, ctx);
@@ -486,13 +486,13 @@ SB_DEV void y_forward_fast3_impl(const YArgs<T>& a, int xt, int zl, cx<T>* stick
     cx<T>* v = SB_RP(vAll, 24);
     const LaneJ id = fast_ids<LOG2V, TT, false>(tid);
 #pragma unroll
-    for (int m = 0; m < 24; ++m) S[SwzRow::at<LOG2V>(id.j + TT * m, id.lane)] = v[m];
+    for (int m = 0; m < 24; ++m) S[SwzRow::template at<LOG2V>(id.j + TT * m, id.lane)] = v[m];
     SB_PHASE_END
     SB_PHASE_BEGIN
     for (int e = e0 + tid; e < e1; e += nthr) {
       const int slot = a.stickSlot[e];
       cx<T>* dst = a.srcBase ? y_dist_stick<T, true>(a, e, zl) : stickRow + e;
-      *dst = S[SwzRow::at<LOG2V>(slot >> LOG2V, slot & (V - 1))];
+      *dst = S[SwzRow::template at<LOG2V>(slot >> LOG2V, slot & (V - 1))];
     }
     SB_PHASE_END_NOSYNC
   }
@@ -560,6 +560,7 @@ SB_DEV void y_forward_fast3(const YArgs<T>& a, int block, Ctx ctx, cx<T>* S) {
 template <typename T, int N, int LOG2V>
 SB_DEV void dit3_to_natural(cx<T>* vAll, cx<T>* S, Ctx ctx) {
   (void)ctx;
+  using SwzCol = SwzX<sizeof(cx<T>)>;
   constexpr int TT = Fast3Plan<N>::T;
   SB_PHASE_BEGIN  // (the caller's last phase ended with a barrier: every thread is done reading S)
   (void)nthr;
@@ -568,7 +569,7 @@ SB_DEV void dit3_to_natural(cx<T>* vAll, cx<T>* S, Ctx ctx) {
 #pragma unroll
   for (int k1 = 0; k1 < 3; ++k1) {
 #pragma unroll
-    for (int m = 0; m < 8; ++m) S[SwzCol::at<LOG2V>(k1 + 3 * (id.j + TT * m), id.lane)] = v[8 * k1 + m];
+    for (int m = 0; m < 8; ++m) S[SwzCol::template at<LOG2V>(k1 + 3 * (id.j + TT * m), id.lane)] = v[8 * k1 + m];
   }
   SB_PHASE_END
   SB_PHASE_BEGIN
@@ -576,13 +577,14 @@ SB_DEV void dit3_to_natural(cx<T>* vAll, cx<T>* S, Ctx ctx) {
   cx<T>* v = SB_RP(vAll, 24);
   const LaneJ id = fast_ids<LOG2V, TT, true>(tid);
 #pragma unroll
-  for (int m = 0; m < 24; ++m) v[m] = S[SwzCol::at<LOG2V>(id.j + TT * m, id.lane)];
+  for (int m = 0; m < 24; ++m) v[m] = S[SwzCol::template at<LOG2V>(id.j + TT * m, id.lane)];
   SB_PHASE_END_NOSYNC
 }
 
 template <typename T, int N, bool BWD>
 SB_DEV void x_c2c_fast3(const XArgs<T>& a, int block, Ctx ctx, cx<T>* S) {
-  constexpr int LOG2V = FastLanes<T>::log2V;
+  constexpr int LOG2V = FastLanesX<T, N>::log2V;
+  using SwzCol = SwzX<sizeof(cx<T>)>;
   constexpr int V = 1 << LOG2V;
   constexpr int TT = Fast3Plan<N>::T;
   constexpr bool DIT = SB_X3_MODE != 1;
@@ -643,7 +645,8 @@ SB_DEV void x_c2c_fast3(const XArgs<T>& a, int block, Ctx ctx, cx<T>* S) {
 // real rows, two per lane (same contract and packing as x_r2c_pair_tile in fast_stage_kernels.hpp)
 template <typename T, int N, bool BWD>
 SB_DEV void x_r2c_fast3(const XArgs<T>& a, int block, Ctx ctx, cx<T>* S) {
-  constexpr int LOG2V = FastLanes<T>::log2V;
+  constexpr int LOG2V = FastLanesX<T, N>::log2V;
+  using SwzCol = SwzX<sizeof(cx<T>)>;
   constexpr int V = 1 << LOG2V;
   constexpr int TT = Fast3Plan<N>::T;
   constexpr int NXF = N / 2 + 1;
@@ -728,7 +731,7 @@ SB_DEV void x_r2c_fast3(const XArgs<T>& a, int block, Ctx ctx, cx<T>* S) {
     (void)validA;
     (void)validB;
 #pragma unroll
-    for (int r = 0; r < 24; ++r) S[SwzCol::at<LOG2V>(SB_OUT_INDEX(r), id.lane)] = v[r];
+    for (int r = 0; r < 24; ++r) S[SwzCol::template at<LOG2V>(SB_OUT_INDEX(r), id.lane)] = v[r];
     SB_PHASE_END
     SB_PHASE_BEGIN
     SB_PAIR_IDS
@@ -738,9 +741,9 @@ SB_DEV void x_r2c_fast3(const XArgs<T>& a, int block, Ctx ctx, cx<T>* S) {
     for (int r = 0; r < 24; ++r) {
       const int k = id.j + TT * r;
       if (k < NXF) {
-        const cx<T> zk = DIT ? S[SwzCol::at<LOG2V>(k, id.lane)] : v[r];
+        const cx<T> zk = DIT ? S[SwzCol::template at<LOG2V>(k, id.lane)] : v[r];
         cx<T> A, B;
-        unpack_half_spectra<T>(zk, S[SwzCol::at<LOG2V>(k == 0 ? 0 : N - k, id.lane)], A, B);
+        unpack_half_spectra<T>(zk, S[SwzCol::template at<LOG2V>(k == 0 ? 0 : N - k, id.lane)], A, B);
         if (validA) dstA[k] = A;
         if (validB) dstB[k] = B;
       }

@@ -4,24 +4,24 @@
 namespace sb {
 
 template <typename T, int N, bool FWD>
-__global__ void __launch_bounds__(Fast3Cfg<T, N>::threads, Fast3Cfg<T, N>::minBlocks)
+__global__ void __launch_bounds__(Fast3CfgX<T, N>::threads, Fast3CfgX<T, N>::minBlocks)
     k_x_fast3(const __grid_constant__ XArgs<T> a) {
   extern __shared__ __align__(16) unsigned char smemRaw[];
   cx<T>* S = reinterpret_cast<cx<T>*>(smemRaw);
-  x_c2c_fast3<T, N, !FWD>(a, (int)blockIdx.x, Ctx{Fast3Cfg<T, N>::threads}, S);
+  x_c2c_fast3<T, N, !FWD>(a, (int)blockIdx.x, Ctx{Fast3CfgX<T, N>::threads}, S);
 }
 
 template <typename T, int N, bool FWD>
-__global__ void __launch_bounds__(Fast3Cfg<T, N>::threads, Fast3Cfg<T, N>::minBlocks)
+__global__ void __launch_bounds__(Fast3CfgX<T, N>::threads, Fast3CfgX<T, N>::minBlocks)
     k_x_real_fast3(const __grid_constant__ XArgs<T> a) {
   extern __shared__ __align__(16) unsigned char smemRaw[];
   cx<T>* S = reinterpret_cast<cx<T>*>(smemRaw);
-  x_r2c_fast3<T, N, !FWD>(a, (int)blockIdx.x, Ctx{Fast3Cfg<T, N>::threads}, S);
+  x_r2c_fast3<T, N, !FWD>(a, (int)blockIdx.x, Ctx{Fast3CfgX<T, N>::threads}, S);
 }
 
 template <typename T, int N>
 static int launch_x3_n(int forward, const XArgs<T>& a, cudaStream_t s) {
-  using C = Fast3Cfg<T, N>;
+  using C = Fast3CfgX<T, N>;
   const long long blocks = (long long)a.numRowTiles * a.numPlanes;
   if (a.r2c)
     return forward ? launch_fast(k_x_real_fast3<T, N, true>, a, blocks, C::threads, C::smem, s)

@@ -32,6 +32,32 @@ __device__ __forceinline__ void trace_mark(int item, int id) {
   if (threadIdx.x == 0 && blockIdx.x < kTraceCtas && item >= 0 && item < kTraceItems)
     g_xy_trace[((size_t)blockIdx.x * kTraceItems + item) * kTraceMarks + id] = clock64();
 }
+// x stage (column mapping on both sides of every exchange), any lane count V <= 128 bytes / element:
+// 128 / ELEM consecutive slots form one 128-byte line = 128 / (ELEM * V) consecutive rows, and the
+// slot inside the line is XOR-permuted by a fold of n. Folds found by exhaustive search with the
+// model of tools/check_swizzle.py: conflict free for N >= 64 in every exchange of the power-of-two
+// plans (and of the 3*2^k plans, whose sub-transforms are power-of-two plans of length N/3).
+// Every fold must keep the map a bijection of the tile (tests/test_emu.py::test_x_stage_swizzle).
+template <int ELEM>
+struct SwzX {
+  template <int LOG2V>
+  static SB_HD int at(int n, int lane) {
+    constexpr int SLOTS = 128 / ELEM;
+    constexpr int V = 1 << LOG2V;
+    static_assert(V <= SLOTS, "at most 128 bytes per tile row");
+    constexpr int ROWS = SLOTS / V;  // rows per line
+    int f;
+    if (ELEM == 16)
+      f = V == 1 ? (n >> 3) : (V == 8 ? (n ^ (n >> 3) ^ (n >> 6) ^ (n >> 9)) : (n ^ (n >> 3)));
+    else
+      f = V == 1 ? ((n >> 1) ^ (n >> 3)) : V == 2 ? (n ^ (n >> 2) ^ (n >> 6))
+                 : (V == 4 ? (n ^ (n >> 1) ^ (n >> 4))
+                           : (V == 8 ? (n ^ (n >> 1) ^ (n >> 3)) : (n ^ (n >> 3) ^ (n >> 4) ^ (n >> 6) ^ (n >> 7) ^ (n >> 8))));
+    const int slot = ((n % ROWS) << LOG2V) | lane;
+    return (n / ROWS) * SLOTS + (slot ^ (f & (SLOTS - 1)));
+  }
+};
+
 }  // namespace sb
 #define SB_MARK(ctx, id) ::sb::trace_mark((ctx).traceItem, id)
 #else
@@ -235,9 +261,16 @@ SB_HD int fast_out_index(int j, int i, int q) {
 //   SwzCol : consecutive threads walk along n with a fixed lane in every stage
 //            (n = j + T*m reads, (b-k)*R + k + q*NS writes): the varying bits of n are 3-bit
 //            groups [0,3), [3,6), [6,9) ..., so fold them down onto the slot bits.
+// 4-lane tiles of 16-byte elements (64-byte rows, experiment builds): two consecutive rows form one
+// 128-byte line of 8 slots, permuted as a whole (conflict free for N = 256, 512 in every thread
+// mapping; searched exhaustively like the 8-lane folds)
+SB_HD int swz_pair_rows(int n, int lane) {
+  return ((n >> 1) << 3) + ((((n & 1) << 2) | lane) ^ ((n ^ (n >> 1) ^ (n >> 2) ^ (n >> 4)) & 7));
+}
 struct SwzRow {
   template <int LOG2V>
   static SB_HD int at(int n, int lane) {
+    if (LOG2V == 2) return swz_pair_rows(n, lane);
     return (n << LOG2V) + (lane ^ (n & ((1 << LOG2V) - 1)));
   }
 };
@@ -246,9 +279,36 @@ struct SwzCol {
   // 8 lanes) and N >= 128 (8-byte elements, 16 lanes)
   template <int LOG2V>
   static SB_HD int at(int n, int lane) {
+    if (LOG2V == 2) return swz_pair_rows(n, lane);
     const int f = LOG2V == 3 ? (n ^ (n >> 3) ^ (n >> 6) ^ (n >> 9))
                              : (n ^ (n >> 3) ^ (n >> 4) ^ (n >> 6) ^ (n >> 7) ^ (n >> 8));
     return (n << LOG2V) + (lane ^ (f & ((1 << LOG2V) - 1)));
+  }
+};
+
+// x stage (column mapping on both sides of every exchange), any lane count V <= 128 bytes / element:
+// 128 / ELEM consecutive slots form one 128-byte line = 128 / (ELEM * V) consecutive rows, and the
+// slot inside the line is XOR-permuted by a fold of n. Folds found by exhaustive search with the
+// model of tools/check_swizzle.py: conflict free for N >= 64 in every exchange of the power-of-two
+// plans (and of the 3*2^k plans, whose sub-transforms are power-of-two plans of length N/3).
+// Every fold must keep the map a bijection of the tile (tests/test_emu.py::test_x_stage_swizzle).
+template <int ELEM>
+struct SwzX {
+  template <int LOG2V>
+  static SB_HD int at(int n, int lane) {
+    constexpr int SLOTS = 128 / ELEM;
+    constexpr int V = 1 << LOG2V;
+    static_assert(V <= SLOTS, "at most 128 bytes per tile row");
+    constexpr int ROWS = SLOTS / V;  // rows per line
+    int f;
+    if (ELEM == 16)
+      f = V == 1 ? (n >> 3) : (V == 8 ? (n ^ (n >> 3) ^ (n >> 6) ^ (n >> 9)) : (n ^ (n >> 3)));
+    else
+      f = V == 1 ? ((n >> 1) ^ (n >> 3)) : V == 2 ? (n ^ (n >> 2) ^ (n >> 6))
+                 : (V == 4 ? (n ^ (n >> 1) ^ (n >> 4))
+                           : (V == 8 ? (n ^ (n >> 1) ^ (n >> 3)) : (n ^ (n >> 3) ^ (n >> 4) ^ (n >> 6) ^ (n >> 7) ^ (n >> 8))));
+    const int slot = ((n % ROWS) << LOG2V) | lane;
+    return (n / ROWS) * SLOTS + (slot ^ (f & (SLOTS - 1)));
   }
 };
 

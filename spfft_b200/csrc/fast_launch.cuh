@@ -18,6 +18,14 @@ struct FastCfg {
   static constexpr size_t smem = (size_t)N * V * sizeof(cx<T>);
 };
 
+// the stand-alone x stage kernels have their own lane count (FastLanesX)
+template <typename T, int N>
+struct FastCfgX {
+  static constexpr int V = 1 << FastLanesX<T, N>::log2V;
+  static constexpr int threads = V * (N / 8);
+  static constexpr int minBlocks = threads >= 1024 ? 1 : (1024 / threads > 16 ? 16 : 1024 / threads);
+  static constexpr size_t smem = (size_t)N * V * sizeof(cx<T>);
+};
 
 template <typename Kernel, typename Args>
 int launch_fast(Kernel kernel, const Args& args, long long blocks, int threads, size_t smemBytes,

@@ -30,7 +30,25 @@ template <typename T>
 struct FastLanes {
   static constexpr int log2V = sizeof(T) == 8 ? SB_LOG2V_F64 : SB_LOG2V_F32;
 };
-
+// Rows per tile of the stand-alone x stage kernels. Rows are contiguous in global memory, so the
+// lane count does not touch coalescing there: it only sets the CTA size (V * threads-per-row
+// threads, N*V elements of shared memory). Small CTAs = many tiles per SM at different phases:
+// measured at 512^3 double (profiles/r01_v4_summary.md) 8 / 4 / 2 / 1 rows = 0.690 / 0.661 / 0.626 /
+// 0.620 ms, at 384^3 0.301 / 0.290 / 0.282 / 0.431 ms -- best around 64-128 threads per CTA, so
+// V = 128 / (N/8) for the power-of-two kernels and 64 / (N/24) for the 3*2^k ones, within 1..8.
+// SB_LOG2VX: build-time override (experiments).
+constexpr int x_lanes_log2(int n) {
+  const int target = n % 3 == 0 ? 1536 / n : 1024 / n;  // rows for the CTA size above
+  return target >= 8 ? 3 : (target >= 4 ? 2 : (target >= 2 ? 1 : 0));
+}
+template <typename T, int N>
+struct FastLanesX {
+#ifdef SB_LOG2VX
+  static constexpr int log2V = SB_LOG2VX;
+#else
+  static constexpr int log2V = x_lanes_log2(N);
+#endif
+};
 
 // gather-form tiles (defined below)
 template <typename T, int N, Mem STP, bool TWS = false>
@@ -188,7 +206,7 @@ SB_DEV void z_backward_fast(const ZArgs<T>& a, int tile, Ctx ctx, cx<T>* S) {
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      if (base + u * nthr < e1) S[SwzRow::at<LOG2V>(slot[u] >> LOG2V, slot[u] & (V - 1))] = val[u];
+      if (base + u * nthr < e1) S[SwzRow::template at<LOG2V>(slot[u] >> LOG2V, slot[u] & (V - 1))] = val[u];
     }
   }
   SB_PHASE_END
@@ -196,7 +214,7 @@ SB_DEV void z_backward_fast(const ZArgs<T>& a, int tile, Ctx ctx, cx<T>* S) {
   SB_PHASE_BEGIN
   SB_ROW_IDS
 #pragma unroll
-  for (int m = 0; m < 8; ++m) v[m] = S[SwzRow::at<LOG2V>(j + TT * m, lane)];
+  for (int m = 0; m < 8; ++m) v[m] = S[SwzRow::template at<LOG2V>(j + TT * m, lane)];
   SB_PHASE_END
   fast_fft_head<T, N, LOG2V, true, SwzRow, false>(vAll, S, a.ftw, ctx);
   SB_PHASE_BEGIN
@@ -235,7 +253,7 @@ SB_DEV void z_forward_fast(const ZArgs<T>& a, int tile, Ctx ctx, cx<T>* S) {
   SB_PHASE_BEGIN
   SB_ROW_IDS
 #pragma unroll
-  for (int m = 0; m < 8; ++m) S[SwzRow::at<LOG2V>(j + TT * m, lane)] = v[m];
+  for (int m = 0; m < 8; ++m) S[SwzRow::template at<LOG2V>(j + TT * m, lane)] = v[m];
   SB_PHASE_END
   SB_PHASE_BEGIN
   constexpr int U = 6;
@@ -252,7 +270,7 @@ SB_DEV void z_forward_fast(const ZArgs<T>& a, int tile, Ctx ctx, cx<T>* S) {
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       if (base + u * nthr < e1) {
-        cx<T> val = S[SwzRow::at<LOG2V>(slot[u] >> LOG2V, slot[u] & (V - 1))];
+        cx<T> val = S[SwzRow::template at<LOG2V>(slot[u] >> LOG2V, slot[u] & (V - 1))];
         if (a.useScale) val = a.scale * val;
         a.valuesOut[dst[u]] = val;
       }
@@ -310,7 +328,7 @@ SB_DEV void y_backward_tile(const YArgs<T>& a, int xt, const cx<T>* stickRow, cx
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      if (base + u * nthr < e1) S[SwzRow::at<LOG2V>(slot[u] >> LOG2V, slot[u] & (V - 1))] = val[u];
+      if (base + u * nthr < e1) S[SwzRow::template at<LOG2V>(slot[u] >> LOG2V, slot[u] & (V - 1))] = val[u];
     }
   }
   SB_PHASE_END
@@ -318,7 +336,7 @@ SB_DEV void y_backward_tile(const YArgs<T>& a, int xt, const cx<T>* stickRow, cx
   SB_PHASE_BEGIN
   SB_ROW_IDS
 #pragma unroll
-  for (int m = 0; m < 8; ++m) v[m] = S[SwzRow::at<LOG2V>(j + TT * m, lane)];
+  for (int m = 0; m < 8; ++m) v[m] = S[SwzRow::template at<LOG2V>(j + TT * m, lane)];
   SB_PHASE_END
   fast_fft_head<T, N, LOG2V, true, SwzRow, false>(vAll, S, a.ftw, ctx);
   SB_PHASE_BEGIN
@@ -359,7 +377,7 @@ SB_DEV void y_forward_tile(const YArgs<T>& a, int xt, const cx<T>* plane, cx<T>*
   SB_PHASE_BEGIN
   SB_ROW_IDS
 #pragma unroll
-  for (int m = 0; m < 8; ++m) S[SwzRow::at<LOG2V>(j + TT * m, lane)] = v[m];
+  for (int m = 0; m < 8; ++m) S[SwzRow::template at<LOG2V>(j + TT * m, lane)] = v[m];
   SB_PHASE_END
   SB_PHASE_BEGIN
   constexpr int U = 6;
@@ -374,7 +392,7 @@ SB_DEV void y_forward_tile(const YArgs<T>& a, int xt, const cx<T>* plane, cx<T>*
       if (base + u * nthr < e1) {
         const int e = base + u * nthr;
         cx<T>* dst = a.srcBase ? y_dist_stick<T, true>(a, e, zl) : stickRow + e;
-        st_g<STS>(dst, S[SwzRow::at<LOG2V>(slot[u] >> LOG2V, slot[u] & (V - 1))]);
+        st_g<STS>(dst, S[SwzRow::template at<LOG2V>(slot[u] >> LOG2V, slot[u] & (V - 1))]);
       }
     }
   }
@@ -682,10 +700,10 @@ SB_DEV void y_forward_gather(const YArgs<T>& a, int xt, const cx<T>* plane, cx<T
 // x stage, complex rows (C2C). Tile = V consecutive rows y0 .. y0+V-1 of one plane;
 // thread = (row lane, j). in / out: the plane's [ny][N] arrays (may be the same memory).
 // -------------------------------------------------------------------------------------------
-template <typename T, int N, bool BWD, Mem LD, Mem ST, bool TWS = false>
+template <typename T, int N, bool BWD, Mem LD, Mem ST, bool TWS = false, int LOG2V = FastLanes<T>::log2V,
+          typename Swz = SwzCol>
 SB_DEV void x_c2c_tile(const cx<T>* in, cx<T>* out, int y0, int ny, const cx<T>* __restrict__ ftw,
                        const cx<T>* nextRows, Ctx ctx, cx<T>* S) {
-  constexpr int LOG2V = FastLanes<T>::log2V;
   constexpr int TT = FastPlan<N>::T;
   SB_REGS(cx<T>, vAll, 8);
 #define SB_COL_IDS                    \
@@ -701,10 +719,10 @@ SB_DEV void x_c2c_tile(const cx<T>* in, cx<T>* out, int y0, int ny, const cx<T>*
   for (int m = 0; m < 8; ++m) v[m] = valid ? ld_g<LD>(src + TT * m) : mk<T>(0, 0);
   if (nextRows) prefetch_l2(nextRows, sizeof(cx<T>) * N * (1 << LOG2V), tid, nthr);
   SB_PHASE_END_NOSYNC  // first use of the tile buffer is the exchange after stage 0
-  fast_fft_head<T, N, LOG2V, BWD, SwzCol, true, true, TWS>(vAll, S, ftw, ctx);
+  fast_fft_head<T, N, LOG2V, BWD, Swz, true, true, TWS>(vAll, S, ftw, ctx);
   SB_PHASE_BEGIN
   SB_COL_IDS
-  fast_fft_tail_read<T, N, LOG2V, SwzCol>(v, S, j, lane);
+  fast_fft_tail_read<T, N, LOG2V, Swz>(v, S, j, lane);
   SB_PHASE_END_IF(TWS)
   SB_MARK(ctx, 8);
   SB_PHASE_BEGIN
@@ -754,7 +772,8 @@ SB_HD void unpack_half_spectra(cx<T> zk, cx<T> zn, cx<T>& A, cx<T>& B) {
 
 template <typename T, int N, bool BWD>
 SB_DEV void x_r2c_pair_tile(const XArgs<T>& a, size_t planeRow0, int y0, Ctx ctx, cx<T>* S) {
-  constexpr int LOG2V = FastLanes<T>::log2V;
+  constexpr int LOG2V = FastLanesX<T, N>::log2V;
+  using SwzCol = SwzX<sizeof(cx<T>)>;  // (shadows the 8-lane fold: this kernel has its own lane count)
   constexpr int TT = FastPlan<N>::T;
   constexpr int NXF = N / 2 + 1;
   SB_REGS(cx<T>, vAll, 8);
@@ -813,7 +832,7 @@ SB_DEV void x_r2c_pair_tile(const XArgs<T>& a, size_t planeRow0, int y0, Ctx ctx
     (void)validA;
     (void)validB;
 #pragma unroll
-    for (int m = 0; m < 8; ++m) S[SwzCol::at<LOG2V>(j + TT * m, lane)] = v[m];
+    for (int m = 0; m < 8; ++m) S[SwzCol::template at<LOG2V>(j + TT * m, lane)] = v[m];
     SB_PHASE_END
     SB_PHASE_BEGIN
     SB_COL_IDS
@@ -824,7 +843,7 @@ SB_DEV void x_r2c_pair_tile(const XArgs<T>& a, size_t planeRow0, int y0, Ctx ctx
       const int k = j + TT * m;
       if (k < NXF) {
         cx<T> A, B;
-        unpack_half_spectra<T>(v[m], S[SwzCol::at<LOG2V>((N - k) & (N - 1), lane)], A, B);
+        unpack_half_spectra<T>(v[m], S[SwzCol::template at<LOG2V>((N - k) & (N - 1), lane)], A, B);
         if (validA) dstA[k] = A;
         if (validB) dstB[k] = B;
       }
@@ -834,29 +853,24 @@ SB_DEV void x_r2c_pair_tile(const XArgs<T>& a, size_t planeRow0, int y0, Ctx ctx
 #undef SB_COL_IDS
 }
 
-// row tiles per plane of the real-row kernels (2*V rows each)
-template <typename T>
-SB_HD int x_pair_row_tiles(int ny) {
-  return (ny + (2 << FastLanes<T>::log2V) - 1) / (2 << FastLanes<T>::log2V);
-}
-
 template <typename T, int N, bool BWD>
 SB_DEV void x_r2c_fast(const XArgs<T>& a, int block, Ctx ctx, cx<T>* S) {
-  constexpr int V = 1 << FastLanes<T>::log2V;
-  const int rt = block % a.numRowTiles;  // numRowTiles = x_pair_row_tiles(ny), stage_args.hpp
+  constexpr int V = 1 << FastLanesX<T, N>::log2V;
+  const int rt = block % a.numRowTiles;  // numRowTiles = ceil(ny / 2V), stage_args.hpp
   const int zl = block / a.numRowTiles;
   x_r2c_pair_tile<T, N, BWD>(a, (size_t)zl * a.ny, rt * 2 * V, ctx, S);
 }
 
 template <typename T, int N, bool BWD>
 SB_DEV void x_c2c_fast(const XArgs<T>& a, int block, Ctx ctx, cx<T>* S) {
-  constexpr int V = 1 << FastLanes<T>::log2V;
+  constexpr int V = 1 << FastLanesX<T, N>::log2V;
   const int rt = block % a.numRowTiles;
   const int zl = block / a.numRowTiles;
   const size_t planeOff = (size_t)zl * a.ny * N;
   const cx<T>* src = (BWD ? a.planes : static_cast<const cx<T>*>(a.spaceIn)) + planeOff;
   cx<T>* dst = (BWD ? static_cast<cx<T>*>(a.spaceOut) : a.planes) + planeOff;
-  x_c2c_tile<T, N, BWD, Mem::Plain, Mem::Plain>(src, dst, rt * V, a.ny, a.ftw, nullptr, ctx, S);
+  x_c2c_tile<T, N, BWD, Mem::Plain, Mem::Plain, false, FastLanesX<T, N>::log2V, SwzX<sizeof(cx<T>)>>(
+      src, dst, rt * V, a.ny, a.ftw, nullptr, ctx, S);
 }
 
 // -------------------------------------------------------------------------------------------

@@ -4,25 +4,25 @@
 namespace sb {
 
 template <typename T, int N, bool FWD>
-__global__ void __launch_bounds__(FastCfg<T, N>::threads, FastCfg<T, N>::minBlocks)
+__global__ void __launch_bounds__(FastCfgX<T, N>::threads, FastCfgX<T, N>::minBlocks)
     k_x_fast(const __grid_constant__ XArgs<T> a) {
   extern __shared__ __align__(16) unsigned char smemRaw[];
   cx<T>* S = reinterpret_cast<cx<T>*>(smemRaw);
-  x_c2c_fast<T, N, !FWD>(a, (int)blockIdx.x, Ctx{FastCfg<T, N>::threads}, S);
+  x_c2c_fast<T, N, !FWD>(a, (int)blockIdx.x, Ctx{FastCfgX<T, N>::threads}, S);
 }
 
 // real rows (R2C forward / C2R backward)
 template <typename T, int N, bool FWD>
-__global__ void __launch_bounds__(FastCfg<T, N>::threads, FastCfg<T, N>::minBlocks)
+__global__ void __launch_bounds__(FastCfgX<T, N>::threads, FastCfgX<T, N>::minBlocks)
     k_x_real_fast(const __grid_constant__ XArgs<T> a) {
   extern __shared__ __align__(16) unsigned char smemRaw[];
   cx<T>* S = reinterpret_cast<cx<T>*>(smemRaw);
-  x_r2c_fast<T, N, !FWD>(a, (int)blockIdx.x, Ctx{FastCfg<T, N>::threads}, S);
+  x_r2c_fast<T, N, !FWD>(a, (int)blockIdx.x, Ctx{FastCfgX<T, N>::threads}, S);
 }
 
 template <typename T, int N>
 static int launch_x_n(int forward, const XArgs<T>& a, cudaStream_t s) {
-  using C = FastCfg<T, N>;
+  using C = FastCfgX<T, N>;
   if constexpr (C::threads > 1024) {
     return (int)cudaErrorInvalidValue;
   } else {

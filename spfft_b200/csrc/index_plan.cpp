@@ -472,6 +472,15 @@ bool fast_path_length(int n, int complexBytes) {
   return lanes * (n / 8) <= 1024;  // threads per CTA
 }
 
+int fast_path_log2_lanes_x(int n) {
+#ifdef SB_LOG2VX
+  (void)n;
+  return SB_LOG2VX;
+#else
+  return sb::x_lanes_log2(n);
+#endif
+}
+
 int fast_path_values_per_thread(int n) { return n % 3 == 0 ? 24 : 8; }
 
 int fast_path_log2_lanes(int complexBytes) {

@@ -241,6 +241,8 @@ void choose_tile_lanes(const IndexMaps& m, int cb, long long smemLimit, AxisPlan
   fastY = fast_path_length(m.dimY, cb);
   fastZ = fast_path_length(m.dimZ, cb);
   const int fastLanes = fast_path_log2_lanes(cb);
+  // (the stand-alone x kernels pick their own row count; build_device_plan sets it once it knows
+  // that the opt-in fused xy kernels, which share one tile shape between y and x, are not used)
   ax.log2Vx = fastX ? fastLanes : choose_log2_lanes(m.dimX, cb, smemLimit);
   ax.log2Vy = fastY ? fastLanes : choose_log2_lanes(m.dimY, cb, smemLimit);
   ax.log2Vz = fastZ ? fastLanes : choose_log2_lanes(m.dimZ, cb, smemLimit);
@@ -303,12 +305,14 @@ std::shared_ptr<DevicePlan<T>> build_device_plan(const IndexMaps& m, long long s
                                       &plan->xyLag, &plan->xyCounters);
     plan->fusedXY = plan->pipeXY = err == 0;
   }
-  if (!plan->fusedXY && allowFused && fastX && fastY && m.dimX == m.dimY && m.type == SPFFT_TRANS_C2C) {
+  if (!plan->fusedXY && allowFused && fastX && fastY && m.dimX == m.dimY && m.type == SPFFT_TRANS_C2C &&
+      ax.log2Vx == ax.log2Vy) {
     // y and x stages as one persistent kernel with the hand-off in L2 (fast_xy.cu)
     const int err = sb_xy_fused_config(sizeof(T) == 4, m.dimX, m.local_planes(), &plan->xyRing,
                                        &plan->xyLag, &plan->xyCounters);
     plan->fusedXY = err == 0;
   }
+  if (!plan->fusedXY && fastX) ax.log2Vx = fast_path_log2_lanes_x(m.dimX);
   TileMaps t = build_tile_maps(m, ax.log2Vz, ax.log2Vy, fastZ, fastY);
   plan->numStickTiles = t.numStickTiles;
   plan->pitch = t.pitch;

@@ -93,7 +93,7 @@ void run_x(bool fwd, const sb::XArgs<T>& a, int b, sb::Ctx ctx, sb::cx<T>* smem)
     return;
   }
   if (sb::is_fast3_length(a.nx)) {
-    sb::Ctx c3{(1 << sb::FastLanes<T>::log2V) * (a.nx / 24)};
+    sb::Ctx c3{(1 << fast_path_log2_lanes_x(a.nx)) * (a.nx / 24)};
 #define CALL(NN)                                                                                       \
   if (a.r2c) {                                                                                         \
     if (fwd) sb::x_r2c_fast3<T, NN, false>(a, b, c3, smem); else sb::x_r2c_fast3<T, NN, true>(a, b, c3, smem); \
@@ -104,7 +104,7 @@ void run_x(bool fwd, const sb::XArgs<T>& a, int b, sb::Ctx ctx, sb::cx<T>* smem)
 #undef CALL
     return;
   }
-  sb::Ctx c{(1 << sb::FastLanes<T>::log2V) * (a.nx / 8)};
+  sb::Ctx c{(1 << fast_path_log2_lanes_x(a.nx)) * (a.nx / 8)};
 #define CALL(NN)                                                                                     \
   if (a.r2c) {                                                                                       \
     if (fwd) sb::x_r2c_fast<T, NN, false>(a, b, c, smem); else sb::x_r2c_fast<T, NN, true>(a, b, c, smem); \
@@ -194,7 +194,9 @@ int run(int type, int dimX, int dimY, int dimZ, int n, const int* triplets, int 
       if (ax.log2Vy > maxLog2V) ax.log2Vy = maxLog2V;
       if (ax.log2Vz > maxLog2V) ax.log2Vz = maxLog2V;
     }
-    if (fastX) ax.log2Vx = fl;
+    // fused xy stage exactly when the product (with its opt-in flag) fuses: one tile shape for y and x
+    const bool fusedShape = fastX && fastY && dimX == dimY && type == SPFFT_TRANS_C2C && dimX % 3 != 0;
+    if (fastX) ax.log2Vx = fusedShape ? fl : fast_path_log2_lanes_x(dimX);
     if (fastY) ax.log2Vy = fl;
     if (fastZ) ax.log2Vz = fl;
     ax.rpX = make_radix_plan(dimX);
@@ -302,6 +304,22 @@ int sb_emu_transform(int isFloat, int type, int dimX, int dimY, int dimZ, int n,
                               nthreads, maxLog2V)
                  : run<double>(type, dimX, dimY, dimZ, n, triplets, forward, in, out, scaling,
                                nthreads, maxLog2V);
+}
+
+// Tile addresses of the x stage swizzle (fast_fft.hpp: SwzX) for every (n, lane): out[n*V + lane].
+int sb_emu_swzx(int elemBytes, int log2V, int n, int* out) {
+  const int V = 1 << log2V;
+  for (int i = 0; i < n; ++i) {
+    for (int lane = 0; lane < V; ++lane) {
+      int a = -1;
+#define SWZ(E, L) if (elemBytes == E && log2V == L) a = sb::SwzX<E>::at<L>(i, lane);
+      SWZ(16, 0) SWZ(16, 1) SWZ(16, 2) SWZ(16, 3)
+      SWZ(8, 0) SWZ(8, 1) SWZ(8, 2) SWZ(8, 3) SWZ(8, 4)
+#undef SWZ
+      out[i * V + lane] = a;
+    }
+  }
+  return 0;
 }
 
 // A single batched 1-D transform through sb::tile_fft (lanes = 1 << log2V sequences of length n,

@@ -106,9 +106,20 @@ def test_emulated_float_and_duplicates(emu, gen):
     assert orc.rel_l2(back[:5], back[-5:]) < 1e-6
 
 
+@pytest.mark.parametrize("elem,log2v", [(16, 0), (16, 1), (16, 2), (16, 3), (8, 0), (8, 1), (8, 2), (8, 3), (8, 4)])
+def test_x_stage_swizzle(emu, elem, log2v):
+    """SwzX (fast_fft.hpp) must be a bijection of the N*V tile for every lane count the x stage kernels
+    can pick (a fold that is conflict free but not injective silently corrupts the exchange)."""
+    for n in (32, 64, 128, 256, 512, 1024, 2048):
+        v = 1 << log2v
+        out = np.full(n * v, -2, dtype=np.int32)
+        assert emu.sb_emu_swzx(elem, log2v, n, _ptr(out)) == 0
+        assert np.array_equal(np.sort(out), np.arange(n * v))
+
+
 # ---- register-FFT ("fast") bodies: power-of-two lengths, mixed with generic axes ---------------
 FAST_SHAPES = [(32, 32, 32), (64, 32, 128), (32, 12, 64), (11, 64, 32), (128, 32, 13), (256, 32, 32),
-               (32, 512, 32), (32, 32, 1024),
+               (32, 512, 32), (32, 32, 1024), (1024, 32, 12), (512, 12, 32),
                # 3 * 2^k lengths (fast3_stage_kernels.hpp), alone and mixed with the other kernel families
                (96, 96, 96), (192, 32, 12), (12, 192, 32), (32, 13, 192), (384, 96, 32), (32, 384, 96),
                (96, 32, 384), (768, 12, 32), (12, 768, 32), (33, 32, 768)]
