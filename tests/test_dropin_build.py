@@ -48,6 +48,42 @@ def test_reference_examples_build_unmodified(built, name, compiler, std):
     _build(compiler, std, src, os.path.join(OUT, "ref_" + name.replace(".", "_")))
 
 
+@pytest.fixture(scope="module")
+def benchmark_exe(built):
+    """tools/spfft_benchmark.cpp: the reference's benchmark CLI (tests/programs/benchmark.cpp) on the public C++ API."""
+    cuda = os.environ.get("CUDA_HOME", "/usr/local/cuda")
+    os.makedirs(OUT, exist_ok=True)
+    exe = os.path.join(OUT, "spfft_benchmark")
+    cmd = [GXX, "-std=c++17", "-O2", "-Wall", "-I" + INC, "-I" + os.path.join(cuda, "include"),
+           os.path.join(ROOT, "tools", "spfft_benchmark.cpp"), "-L" + LIBDIR, "-lspfft_b200",
+           "-L" + os.path.join(cuda, "lib64"), "-lcudart", "-Wl,-rpath," + LIBDIR,
+           "-Wl,-rpath," + os.path.join(cuda, "lib64"), "-o", exe]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    assert res.returncode == 0, " ".join(cmd) + "\n" + res.stdout + res.stderr
+    return exe
+
+
+def test_benchmark_program_builds_and_validates_arguments(benchmark_exe):
+    res = subprocess.run([benchmark_exe, "-d", "8", "8", "8", "-r", "1", "-o", "/dev/null", "-e", "compact", "-p", "cpu"],
+                         capture_output=True, text=True)
+    assert res.returncode == 2 and "no host execution path" in res.stderr
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("args", [["-d", "64", "64", "64", "-r", "3", "-p", "gpu-gpu", "-e", "compact"],
+                                  ["-d", "48", "32", "20", "-r", "2", "-p", "gpu", "-e", "compact", "-t", "r2c", "-s", "0.5"],
+                                  ["-d", "32", "32", "32", "-r", "2", "-p", "gpu-gpu", "-e", "compact", "-m", "3"]],
+                         ids=["c2c-device", "r2c-host-sparse", "multi"])
+def test_benchmark_program_runs(benchmark_exe, tmp_path, args):
+    import json
+    out = tmp_path / "bench.json"
+    res = subprocess.run([benchmark_exe] + args + ["-o", str(out)], capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stdout + res.stderr
+    j = json.loads(out.read_text())
+    assert j["parameters"]["dim_x"] == int(args[1]) and j["parameters"]["num_repeats"] == int(args[5])
+    assert j["timings"]["pairs_per_s"] > 0
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("which", ["c", "cpp"])
 def test_own_consumers_run(callers, which):

@@ -167,6 +167,28 @@ def test_emulated_fast_r2c(emu, gen, shape):
     assert orc.rel_l2(back, orc.forward(param, out, orc.SPFFT_FULL_SCALING)) < 1e-13
 
 
+@pytest.mark.parametrize("shape", [(12, 11, 13), (32, 64, 32), (96, 192, 96), (33, 96, 64)], ids=lambda s: "x".join(map(str, s)))
+def test_emulated_r2c_negative_half_input(emu, gen, shape):
+    """R2C input given at -y on the x = 0 plane and at negative z on stick (0,0) (details.rst:37-40): the
+    gather-form kernels complete the hermitian half while loading (hermitian_combine)."""
+    from conftest import hermitian_space_values
+    nx, ny, nz = shape
+    trip, _ = gen.make(nx, ny, nz, hermitian=True, stick_fraction=1.0, fill_fraction=1.0)
+    trip = trip.copy()
+    sel = (trip[:, 0] == 0) & (trip[:, 1] > 0)
+    trip[sel, 1] = ny - trip[sel, 1]
+    trip[sel, 2] = (nz - trip[sel, 2]) % nz
+    sel0 = (trip[:, 0] == 0) & (trip[:, 1] == 0) & (trip[:, 2] > 0)
+    trip[sel0, 2] = nz - trip[sel0, 2]
+    vals = hermitian_space_values(orc, nx, ny, nz, trip)
+    param = orc.Parameters(orc.SPFFT_TRANS_R2C, nx, ny, nz, trip)
+    out = np.full((nz, ny, nx), np.nan, dtype=np.float64)
+    t = np.ascontiguousarray(trip.reshape(-1))
+    assert emu.sb_emu_transform(0, 1, nx, ny, nz, len(trip), _ptr(t), 0, _ptr(vals), _ptr(out), 0, 32, -1) == 0
+    assert orc.rel_l2(out, orc.backward(param, vals)) < 1e-13
+    assert orc.rel_l2(out, orc.dense_backward(1, nx, ny, nz, trip, vals)) < 1e-13
+
+
 # ---- tile bodies of the pipelined xy kernel (fast_pipe_kernels.hpp): staged input buffers ---------
 @pytest.mark.parametrize("shape", [(32, 32, 32), (64, 64, 9), (128, 128, 5)], ids=lambda s: "x".join(map(str, s)))
 @pytest.mark.parametrize("single", [False, True])

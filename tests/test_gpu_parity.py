@@ -114,11 +114,14 @@ def test_r2c_reference_shapes(torch_cuda, lib, gen, shape):
     assert orc.rel_l2(back, orc.forward(param, ref, orc.SPFFT_FULL_SCALING)) <= TOL[False]
 
 
-def test_r2c_negative_half_input(torch_cuda, lib, gen):
+@pytest.mark.parametrize("shape", [(12, 11, 13), (32, 64, 32), (64, 32, 128), (96, 192, 96), (192, 96, 32), (33, 96, 64)],
+                         ids=lambda s: "x".join(map(str, s)))
+def test_r2c_negative_half_input(torch_cuda, lib, gen, shape):
     """Input given at -y on the x=0 plane / negative z on stick (0,0) (details.rst:37-40): the
-    hermitian fills run in both directions."""
+    hermitian fills run in both directions (generic, power-of-two and 3*2^k kernels: the register-FFT
+    kernels complete the column / the stick while gathering)."""
     from conftest import hermitian_space_values
-    nx, ny, nz = 12, 11, 13
+    nx, ny, nz = shape
     trip, _ = gen.make(nx, ny, nz, hermitian=True, stick_fraction=1.0, fill_fraction=1.0)
     trip = trip.copy()
     sel = (trip[:, 0] == 0) & (trip[:, 1] > 0)
