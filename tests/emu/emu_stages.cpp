@@ -291,9 +291,170 @@ int run(int type, int dimX, int dimY, int dimZ, int n, const int* triplets, int 
   }
 }
 
+
+// Whole DISTRIBUTED transform with all P ranks emulated in this process: every rank's stick buffer A
+// and plane-side buffer Q are host arrays, so the peer-memory form of the exchange (z / y kernels
+// storing straight into the owner's buffer, transform_engine.cpp) runs unchanged with peer[d] =
+// rank d's array; peerMode == 0 runs the block form (what ncclSend / ncclRecv move) with memcpy.
+template <typename T>
+int run_distributed(int type, int dimX, int dimY, int dimZ, int P, const int* numLocal,
+                    const int* const* triplets, const int* planesPerRank, int forward,
+                    const void* const* in, void* const* out, int scaling, int nthreads, int peerMode) {
+  try {
+    std::vector<std::shared_ptr<IndexMaps>> maps(P);
+    std::vector<std::vector<long long>> counts(P, std::vector<long long>(6));
+    std::vector<std::vector<int>> sticks(P);
+    for (int r = 0; r < P; ++r) {
+      maps[r] = make_local_index_maps(static_cast<SpfftTransformType>(type), dimX, dimY, dimZ, numLocal[r],
+                                      SPFFT_INDEX_TRIPLETS, triplets[r]);
+      counts[r] = {dimX, dimY, dimZ, planesPerRank[r], maps[r]->num_sticks(), numLocal[r]};
+      sticks[r] = maps[r]->stickIndices;
+    }
+    for (int r = 0; r < P; ++r) finish_distributed_index_maps(*maps[r], r, counts, sticks);
+    AxisPlans ax;
+    const long long smemLimit = 200 * 1024;
+    const int cb = sizeof(sb::cx<T>);
+    const bool fastX = fast_path_length(dimX, cb), fastY = fast_path_length(dimY, cb),
+               fastZ = fast_path_length(dimZ, cb);
+    const int fl = fast_path_log2_lanes(cb);
+    ax.log2Vx = fastX ? fast_path_log2_lanes_x(dimX) : choose_log2_lanes(dimX, cb, smemLimit);
+    ax.log2Vy = fastY ? fl : choose_log2_lanes(dimY, cb, smemLimit);
+    ax.log2Vz = fastZ ? fl : choose_log2_lanes(dimZ, cb, smemLimit);
+    ax.rpX = make_radix_plan(dimX);
+    ax.rpY = make_radix_plan(dimY);
+    ax.rpZ = make_radix_plan(dimZ);
+    auto twX = make_roots<T>(dimX), twY = make_roots<T>(dimY), twZ = make_roots<T>(dimZ);
+    auto ftwX = make_fast_twiddles<T>(dimX), ftwY = make_fast_twiddles<T>(dimY), ftwZ = make_fast_twiddles<T>(dimZ);
+    std::vector<TileMaps> tiles(P);
+    std::vector<ExchangePlan> exch(P);
+    std::vector<PlanPointers<T>> ptrs(P);
+    std::vector<std::vector<sb::cx<T>>> A(P), Q(P), planes(P);
+    const sb::cx<T> poison = sb::mk<T>(T(1e30), T(-1e30));
+    for (int r = 0; r < P; ++r) {
+      tiles[r] = build_tile_maps(*maps[r], ax.log2Vz, ax.log2Vy, fastZ, fastY);
+      exch[r] = build_exchange_plan(*maps[r], ax.log2Vz, ax.log2Vy, fastY);
+      TileMaps& t = tiles[r];
+      PlanPointers<T>& p = ptrs[r];
+      if (fastX) p.ftwX = ftwX.data();
+      if (fastY) p.ftwY = ftwY.data();
+      if (fastZ) p.ftwZ = ftwZ.data();
+      p.twX = twX.data();
+      p.twY = twY.data();
+      p.twZ = twZ.data();
+      p.tileStart = t.tileStart.data();
+      p.entrySrc = t.identityOrder ? nullptr : t.entrySrc.data();
+      p.entrySlot = t.entrySlot.data();
+      if (t.hasDuplicates) {
+        p.bwdTileStart = t.bwdTileStart.data();
+        p.bwdEntrySrc = t.bwdEntrySrc.data();
+        p.bwdEntrySlot = t.bwdEntrySlot.data();
+      } else {
+        p.bwdTileStart = p.tileStart;
+        p.bwdEntrySrc = p.entrySrc;
+        p.bwdEntrySlot = p.entrySlot;
+      }
+      if (!t.zInv.empty()) p.zInv = t.zInv.data();
+      // y stage over the sticks of ALL ranks (DevicePlan of a distributed transform)
+      t.numXTiles = exch[r].numXTiles;
+      p.xtStart = exch[r].xtStart.data();
+      p.stickSlot = exch[r].stickSlot.data();
+      if (!exch[r].yInv.empty()) p.yInv = exch[r].yInv.data();
+      A[r].assign(static_cast<size_t>(dimZ) * t.pitch + 1, poison);
+      Q[r].assign(static_cast<size_t>(exch[r].planeSideElements) + 1, poison);
+      planes[r].assign(static_cast<size_t>(planesPerRank[r]) * dimY * maps[r]->dimXFreq + 1, poison);
+    }
+    const int maxN = std::max(dimX, std::max(dimY, dimZ));
+    std::vector<sb::cx<T>> smem(2 * static_cast<size_t>(maxN) * 32);
+    sb::Ctx ctx{nthreads};
+    auto y_args = [&](int r, bool fwd) {
+      auto ya = make_y_args<T>(*maps[r], tiles[r], ax, ptrs[r], A[r].data(), planes[r].data());
+      const ExchangePlan& x = exch[r];
+      if (fwd && peerMode) {
+        for (int d = 0; d < P; ++d) ya.peer[d] = A[d].data();
+        ya.stickRank = x.stickRank.data();
+        ya.fwdBase = x.fwdBase.data();
+        ya.tileFwdBase = x.tileFwdBase.data();
+        ya.xtRotate = x.fwdTileRotate;
+      }
+      ya.sticks = Q[r].data();
+      ya.srcBase = x.srcBase.data();
+      ya.srcPitch = x.srcPitch.data();
+      ya.tileBase = x.tileBase.data();
+      ya.tilePitch = x.tilePitch.data();
+      ya.zRowOffset = 0;
+      return ya;
+    };
+    // block form of the exchange: rank r's block for d (stick side) <-> d's block from r (plane side)
+    auto exchange_blocks = [&](bool toPlanes) {
+      for (int r = 0; r < P; ++r)
+        for (int d = 0; d < P; ++d) {
+          const long long n = exch[r].stickCount[d];
+          if (n != exch[d].planeCount[r]) throw spfft::InternalError();
+          sb::cx<T>* a = A[r].data() + exch[r].stickOffset[d];
+          sb::cx<T>* q = Q[d].data() + exch[d].planeOffset[r];
+          if (toPlanes) std::copy(a, a + n, q); else std::copy(q, q + n, a);
+        }
+    };
+    if (!forward) {
+      for (int r = 0; r < P; ++r) {
+        if (tiles[r].numStickTiles == 0) continue;
+        auto za = make_z_args<T>(*maps[r], tiles[r], ax, ptrs[r], false, A[r].data(), static_cast<const T*>(in[r]),
+                                 nullptr, false);
+        if (peerMode) {
+          for (int d = 0; d < P; ++d) za.peer[d] = Q[d].data();
+          za.rowRank = exch[r].rowRank.data();
+          za.rowOff = exch[r].rowOff.data();
+        }
+        for (int b = 0; b < za.numTiles; ++b) run_z<T>(false, za, b, ctx, smem.data());
+      }
+      if (!peerMode) exchange_blocks(true);
+      for (int r = 0; r < P; ++r) {
+        if (planesPerRank[r] == 0) continue;
+        auto ya = y_args(r, false);
+        for (int b = 0; b < ya.numXTiles * ya.numPlanes; ++b) run_y<T>(false, ya, b, ctx, smem.data());
+        auto xa = make_x_args<T>(*maps[r], ax, ptrs[r], planes[r].data(), nullptr, out[r]);
+        for (int b = 0; b < xa.numRowTiles * xa.numPlanes; ++b) run_x<T>(false, xa, b, ctx, smem.data());
+      }
+    } else {
+      for (int r = 0; r < P; ++r) {
+        if (planesPerRank[r] == 0) continue;
+        auto xa = make_x_args<T>(*maps[r], ax, ptrs[r], planes[r].data(), in[r], nullptr);
+        for (int b = 0; b < xa.numRowTiles * xa.numPlanes; ++b) run_x<T>(true, xa, b, ctx, smem.data());
+        if (exch[r].stickSlot.empty()) continue;
+        auto ya = y_args(r, true);
+        for (int b = 0; b < ya.numXTiles * ya.numPlanes; ++b) run_y<T>(true, ya, b, ctx, smem.data());
+      }
+      if (!peerMode) exchange_blocks(false);
+      for (int r = 0; r < P; ++r) {
+        if (tiles[r].numStickTiles == 0 || numLocal[r] == 0) continue;
+        auto za = make_z_args<T>(*maps[r], tiles[r], ax, ptrs[r], true, A[r].data(), nullptr,
+                                 static_cast<T*>(out[r]), scaling != 0);
+        for (int b = 0; b < za.numTiles; ++b) run_z<T>(true, za, b, ctx, smem.data());
+      }
+    }
+    return 0;
+  } catch (const spfft::GenericError& e) {
+    return static_cast<int>(e.error_code());
+  } catch (...) {
+    return 1;
+  }
+}
+
 }  // namespace
 
 extern "C" {
+
+// Distributed transform over P emulated ranks (see run_distributed). in / out: per-rank pointers
+// (forward == 0: values -> slab; else slab -> values).
+int sb_emu_transform_distributed(int isFloat, int type, int dimX, int dimY, int dimZ, int numRanks,
+                                 const int* numLocal, const int* const* triplets, const int* planesPerRank,
+                                 int forward, const void* const* in, void* const* out, int scaling,
+                                 int nthreads, int peerMode) {
+  return isFloat ? run_distributed<float>(type, dimX, dimY, dimZ, numRanks, numLocal, triplets, planesPerRank,
+                                          forward, in, out, scaling, nthreads, peerMode)
+                 : run_distributed<double>(type, dimX, dimY, dimZ, numRanks, numLocal, triplets, planesPerRank,
+                                           forward, in, out, scaling, nthreads, peerMode);
+}
 
 // Whole local transform through the emulated stage kernels. forward == 0: `in` = values
 // (2*n reals), `out` = space (z,y,x); forward != 0: `in` = space, `out` = values.

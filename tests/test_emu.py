@@ -207,3 +207,77 @@ def test_emulated_pipe_xy(emu, gen, shape, single, monkeypatch):
     back = np.zeros(len(trip), dtype=cdt)
     assert emu.sb_emu_transform(int(single), 0, nx, ny, nz, len(trip), _ptr(t), 1, _ptr(out), _ptr(back), 1, 64, -1) == 0
     assert orc.rel_l2(back, vals) < tol
+
+
+# ---- distributed transforms: all ranks emulated in one process, peer-store and block exchange ------
+def _emu_distributed(emu, gen, ttype, shape, world, sdist, pdist, center, single, peer):
+    from conftest import hermitian_space_values
+    nx, ny, nz = shape
+    trips, vals = [], []
+    for r in range(world):
+        t, v = gen.make(nx, ny, nz, hermitian=bool(ttype), center=center, num_ranks=world, rank=r,
+                        stick_distribution=sdist)
+        trips.append(np.ascontiguousarray(t))
+        vals.append(v)
+    if ttype:
+        full = hermitian_space_values(orc, nx, ny, nz, np.concatenate(trips))
+        off = 0
+        for r in range(world):
+            vals[r] = full[off:off + len(trips[r])]
+            off += len(trips[r])
+    planes = gen.plane_split(nz, pdist)
+    params = orc.distributed_parameters(ttype, nx, ny, nz, trips, planes)
+    ref_slabs = orc.backward_distributed(params, vals)
+    ref_back = orc.forward_distributed(params, ref_slabs, orc.SPFFT_FULL_SCALING)
+    cdt = np.complex64 if single else np.complex128
+    sdt = (np.float32 if single else np.float64) if ttype else cdt
+    tol = 3e-6 if single else 1e-13
+    n_loc = (C.c_int * world)(*[len(t) for t in trips])
+    pl = (C.c_int * world)(*planes)
+    flat = [np.ascontiguousarray(t.reshape(-1)) if len(t) else np.zeros(3, np.int32) for t in trips]
+    tp = (C.c_void_p * world)(*[f.ctypes.data for f in flat])
+    vin = [np.ascontiguousarray(v.astype(cdt)) if len(v) else np.zeros(1, cdt) for v in vals]
+    slabs = [np.full(max(planes[r] * ny * nx, 1), np.nan, dtype=sdt) for r in range(world)]
+    pin = (C.c_void_p * world)(*[a.ctypes.data for a in vin])
+    pout = (C.c_void_p * world)(*[a.ctypes.data for a in slabs])
+    assert emu.sb_emu_transform_distributed(int(single), ttype, nx, ny, nz, world, n_loc, tp, pl, 0, pin, pout, 0, 64,
+                                            int(peer)) == 0
+    for r in range(world):
+        if planes[r]:
+            assert orc.rel_l2(slabs[r][:planes[r] * ny * nx].reshape(planes[r], ny, nx), ref_slabs[r]) < tol
+    back = [np.zeros(max(len(v), 1), dtype=cdt) for v in vals]
+    pback = (C.c_void_p * world)(*[a.ctypes.data for a in back])
+    assert emu.sb_emu_transform_distributed(int(single), ttype, nx, ny, nz, world, n_loc, tp, pl, 1, pout, pback, 1, 64,
+                                            int(peer)) == 0
+    for r in range(world):
+        if len(vals[r]):
+            assert orc.rel_l2(back[r][:len(vals[r])], ref_back[r]) < tol
+
+
+DIST_CASES = [
+    (0, (11, 12, 13), "uniform", "uniform", False, False),
+    (0, (12, 13, 11), "first", "uniform", False, False),
+    (0, (13, 11, 12), "first", "last", False, False),
+    (1, (12, 11, 13), "uniform", "uniform", False, False),
+    (0, (32, 32, 32), "uniform", "uniform", True, False),
+    (0, (64, 32, 128), "uniform", "ramp", True, False),
+    (1, (64, 64, 32), "uniform", "uniform", False, False),
+    (0, (32, 64, 32), "uniform", "uniform", True, True),
+    (0, (96, 96, 96), "uniform", "uniform", True, False),
+    (1, (192, 96, 32), "uniform", "ramp", False, False),
+    (0, (32, 192, 96), "first", "last", True, True),
+]
+
+
+@pytest.mark.parametrize("case", DIST_CASES, ids=lambda c: f"{'r2c' if c[0] else 'c2c'}-{'x'.join(map(str, c[1]))}-{c[2]}-{c[3]}")
+@pytest.mark.parametrize("world", [2, 3])
+@pytest.mark.parametrize("peer", [1, 0], ids=["peer-stores", "block-exchange"])
+def test_emulated_distributed(emu, gen, case, world, peer):
+    """The distributed stage kernels (tables of index_plan.cpp::build_exchange_plan, peer stores of the z
+    and y kernels, gather and scatter forms of the distributed y stage) for every kernel family, with the
+    fixtures of the reference's MPI tests (tests/mpi_tests/test_transform.cpp: uniform, all sticks on rank 0,
+    planes on the last rank) -- the same cases tests/dist_gpu_check.py runs on real GPUs."""
+    ttype, shape, sname, pname, center, single = case
+    dists = {"uniform": [1.0] * world, "first": [1.0] + [0.0] * (world - 1), "last": [0.0] * (world - 1) + [1.0],
+             "ramp": [1.0 + r for r in range(world)]}
+    _emu_distributed(emu, gen, ttype, shape, world, dists[sname], dists[pname], center, single, peer)
