@@ -174,6 +174,9 @@ def main():
     ap.add_argument("--bands", type=int, default=1,
                     help="B independent transforms of the same plan (clones, one per band) executed through "
                          "spfft_multi_transform_*: BASELINE.json config 5 (256 bands at 192^3); N=1 only")
+    ap.add_argument("--exchange", choices=["default", "float"], default="default",
+                    help="N > 1, double precision: 'float' = SPFFT_EXCH_COMPACT_BUFFERED_FLOAT, the stick <-> slab exchange "
+                         "in single precision (half the NVLink bytes, accuracy of a float exchange; opt-in like in the reference)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -248,7 +251,9 @@ def main():
         comm = capi.comm_from_torch(lib)
         ns_all = int(len(stick_start))
         max_sticks = ns_all  # generous upper bound for the grid
-        grid = capi.DistributedGrid(lib, comm, n, n, n, max_sticks, (n + world - 1) // world, single=single)
+        exch = capi.SPFFT_EXCH_COMPACT_BUFFERED_FLOAT if args.exchange == "float" else capi.SPFFT_EXCH_DEFAULT
+        grid = capi.DistributedGrid(lib, comm, n, n, n, max_sticks, (n + world - 1) // world, exchange_type=exch,
+                                    single=single)
         t = grid.create_transform(capi.SPFFT_PU_GPU, ttype, n, n, n, nz_local, trip)
     else:
         t = capi.Transform(lib, processing_unit=capi.SPFFT_PU_GPU, transform_type=ttype, dim_x=n, dim_y=n,
@@ -361,7 +366,7 @@ def main():
     # ---------------- NVLink share of the exchange (N > 1) ----------------
     nvlink = None
     if world > 1:
-        c = 8 if single else 16
+        c = 8 if (single or args.exchange == "float") else 16
         sent = c * ns * n * (world - 1) / world  # bytes this rank sends (= receives) per exchange
         peer = capi.peer_exchange(t)
         if peer:
@@ -448,6 +453,8 @@ def main():
                                              f"x ranges) <-> z slabs, one all-to-all per direction "
                                              f"({'fused into the stage kernels over NVLink peer memory' if nvlink and 'fused' in nvlink['collective'] else 'NCCL grouped send/recv'})")
             line["nvlink"] = nvlink
+            line["config"]["exchange"] = ("SPFFT_EXCH_COMPACT_BUFFERED_FLOAT (single-precision wire format)"
+                                          if args.exchange == "float" else "SPFFT_EXCH_DEFAULT (full precision)")
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -174,15 +174,15 @@ SB_DEV void fast3_tail(cx<T>* v, const cx<T>* S, const cx<T>* __restrict__ tw, i
 
 // Inverse-map ("gather") load of the VPT elements j + TT*m of thread (lane, j), column mapping;
 // layout of the map as in fast_stage_kernels.hpp with VPT entries per thread.
-template <typename T, int N, int TT, int VPT>
-SB_DEV void gather_load_v(cx<T>* v, const cx<T>* sparse, const unsigned short* invTile, int tid, int j,
+template <typename T, int N, int TT, int VPT, typename W>
+SB_DEV void gather_load_v(cx<T>* v, const W* sparse, const unsigned short* invTile, int tid, int j,
                           int lane, int hermitianLane) {
   static_assert(VPT % 8 == 0, "whole 16-byte map loads");
 #pragma unroll
   for (int c = 0; c < VPT / 8; ++c) {
     const Inv8 iv = load_inv8(invTile + (size_t)tid * VPT + 8 * c);
 #pragma unroll
-    for (int m = 0; m < 8; ++m) v[8 * c + m] = iv.i[m] != kNoEntry ? sparse[iv.i[m]] : mk<T>(0, 0);
+    for (int m = 0; m < 8; ++m) v[8 * c + m] = iv.i[m] != kNoEntry ? from_wire<T>(sparse[iv.i[m]]) : mk<T>(0, 0);
   }
   if (lane == hermitianLane) {
 #pragma unroll
@@ -190,20 +190,20 @@ SB_DEV void gather_load_v(cx<T>* v, const cx<T>* sparse, const unsigned short* i
       const int n = j + TT * m;
       const int n2 = n == 0 ? 0 : N - n;
       const unsigned short i2 = invTile[((size_t)lane * TT + (n2 % TT)) * VPT + n2 / TT];
-      const cx<T> q = i2 != kNoEntry ? sparse[i2] : mk<T>(0, 0);
+      const cx<T> q = i2 != kNoEntry ? from_wire<T>(sparse[i2]) : mk<T>(0, 0);
       v[m] = hermitian_combine<T>(n, N, v[m], q);
     }
   }
 }
-template <typename T, int VPT>
-SB_DEV void gather_store_v(const cx<T>* v, cx<T>* sparse, const unsigned short* invThread, bool useScale,
+template <typename T, int VPT, typename W>
+SB_DEV void gather_store_v(const cx<T>* v, W* sparse, const unsigned short* invThread, bool useScale,
                            T scale) {
 #pragma unroll
   for (int c = 0; c < VPT / 8; ++c) {
     const Inv8 iv = load_inv8(invThread + 8 * c);
 #pragma unroll
     for (int m = 0; m < 8; ++m) {
-      if (iv.i[m] != kNoEntry) sparse[iv.i[m]] = useScale ? scale * v[8 * c + m] : v[8 * c + m];
+      if (iv.i[m] != kNoEntry) sparse[iv.i[m]] = to_wire<W>(useScale ? scale * v[8 * c + m] : v[8 * c + m]);
     }
   }
 }
@@ -242,7 +242,7 @@ SB_DEV void scatter_into_tile(cx<T>* S, int elems, const int* slotOf, int e0, in
 // -------------------------------------------------------------------------------------------
 // z stage
 // -------------------------------------------------------------------------------------------
-template <typename T, int N, bool GATHER>
+template <typename T, int N, bool GATHER, typename W>
 SB_DEV void z_backward_fast3_impl(const ZArgs<T>& a, int tile, Ctx ctx, cx<T>* S) {
   constexpr int LOG2V = FastLanes<T>::log2V;
   constexpr int V = 1 << LOG2V;
@@ -285,12 +285,12 @@ SB_DEV void z_backward_fast3_impl(const ZArgs<T>& a, int tile, Ctx ctx, cx<T>* S
 #pragma unroll
   for (int k1 = 0; k1 < 3; ++k1) {
 #pragma unroll
-    for (int m = 0; m < 8; ++m) z_row<T>(a, k1 + 3 * (id.j + TT * m))[col] = v[8 * k1 + m];
+    for (int m = 0; m < 8; ++m) z_row<T, W>(a, k1 + 3 * (id.j + TT * m))[col] = to_wire<W>(v[8 * k1 + m]);
   }
   SB_PHASE_END_NOSYNC
 }
 
-template <typename T, int N, bool GATHER>
+template <typename T, int N, bool GATHER, typename W>
 SB_DEV void z_forward_fast3_impl(const ZArgs<T>& a, int tile, Ctx ctx, cx<T>* S) {
   constexpr int LOG2V = FastLanes<T>::log2V;
   constexpr int V = 1 << LOG2V;
@@ -302,15 +302,15 @@ SB_DEV void z_forward_fast3_impl(const ZArgs<T>& a, int tile, Ctx ctx, cx<T>* S)
   SB_PHASE_BEGIN
   cx<T>* v = SB_RP(vAll, 24);
   const LaneJ id = fast_ids<LOG2V, TT, false>(tid);
-  const cx<T>* in = a.sticks + (size_t)tile * V + id.lane;
+  const W* in = reinterpret_cast<const W*>(a.sticks) + (size_t)tile * V + id.lane;
 #pragma unroll
   for (int n1 = 0; n1 < 3; ++n1) {
 #pragma unroll
-    for (int m = 0; m < 8; ++m) v[8 * n1 + m] = in[(size_t)(n1 + 3 * (id.j + TT * m)) * a.pitch];
+    for (int m = 0; m < 8; ++m) v[8 * n1 + m] = from_wire<T>(in[(size_t)(n1 + 3 * (id.j + TT * m)) * a.pitch]);
   }
   if (a.pfDist > 0 && tile + a.pfDist < a.numTiles) {
     for (int r = tid; r < N; r += nthr)
-      prefetch_l2_line(a.sticks + (size_t)(tile + a.pfDist) * V + (size_t)r * a.pitch);
+      prefetch_l2_line(reinterpret_cast<const W*>(a.sticks) + (size_t)(tile + a.pfDist) * V + (size_t)r * a.pitch);
     if (GATHER) prefetch_l2(a.inv + (size_t)(tile + a.pfDist) * THREADS * 24, (size_t)THREADS * 48, tid, nthr);
   }
   SB_PHASE_END_NOSYNC
@@ -351,17 +351,21 @@ SB_DEV void z_forward_fast3_impl(const ZArgs<T>& a, int tile, Ctx ctx, cx<T>* S)
 
 template <typename T, int N>
 SB_DEV void z_backward_fast3(const ZArgs<T>& a, int tile, Ctx ctx, cx<T>* S) {
-  if (a.inv)
-    z_backward_fast3_impl<T, N, true>(a, tile, ctx, S);
-  else
-    z_backward_fast3_impl<T, N, false>(a, tile, ctx, S);
+  with_wire_type<T>(a.wireF32, [&](auto w) {
+    if (a.inv)
+      z_backward_fast3_impl<T, N, true, decltype(w)>(a, tile, ctx, S);
+    else
+      z_backward_fast3_impl<T, N, false, decltype(w)>(a, tile, ctx, S);
+  });
 }
 template <typename T, int N>
 SB_DEV void z_forward_fast3(const ZArgs<T>& a, int tile, Ctx ctx, cx<T>* S) {
-  if (a.inv)
-    z_forward_fast3_impl<T, N, true>(a, tile, ctx, S);
-  else
-    z_forward_fast3_impl<T, N, false>(a, tile, ctx, S);
+  with_wire_type<T>(a.wireF32, [&](auto w) {
+    if (a.inv)
+      z_forward_fast3_impl<T, N, true, decltype(w)>(a, tile, ctx, S);
+    else
+      z_forward_fast3_impl<T, N, false, decltype(w)>(a, tile, ctx, S);
+  });
 }
 
 // -------------------------------------------------------------------------------------------
@@ -370,9 +374,9 @@ SB_DEV void z_forward_fast3(const ZArgs<T>& a, int tile, Ctx ctx, cx<T>* S) {
 //           one source rank's block of a distributed transform) and a.inv holds the inverse map
 //   else  : entry by entry (distributed tiles with sticks from several ranks, or no inverse map)
 // -------------------------------------------------------------------------------------------
-template <typename T, int N, bool GATHER>
-SB_DEV void y_backward_fast3_impl(const YArgs<T>& a, int xt, int zl, const cx<T>* stickRow, int nextXt,
-                                  const cx<T>* nextStickRow, Ctx ctx, cx<T>* S) {
+template <typename T, int N, bool GATHER, typename W>
+SB_DEV void y_backward_fast3_impl(const YArgs<T>& a, int xt, int zl, const W* stickRow, int nextXt,
+                                  const W* nextStickRow, Ctx ctx, cx<T>* S) {
   constexpr int LOG2V = FastLanes<T>::log2V;
   constexpr int V = 1 << LOG2V;
   constexpr int TT = Fast3Plan<N>::T;
@@ -401,14 +405,15 @@ SB_DEV void y_backward_fast3_impl(const YArgs<T>& a, int xt, int zl, const cx<T>
                                 (a.symmetry && xt == 0) ? 0 : -1);
     if (nextXt >= 0) {
       const int p0 = a.xtStart[nextXt], p1 = a.xtStart[nextXt + 1];
-      prefetch_l2(nextStickRow + p0, (size_t)(p1 - p0) * sizeof(cx<T>), tid, nthr);
+      prefetch_l2(nextStickRow + p0, (size_t)(p1 - p0) * sizeof(W), tid, nthr);
     }
     SB_PHASE_END_NOSYNC
   } else {
     scatter_into_tile<T, LOG2V>(
         S, N * V, a.stickSlot, e0, e1,
         [&](int e) {
-          return a.srcBase ? a.sticks[(size_t)a.srcBase[e] + (size_t)zl * a.srcPitch[e]] : stickRow[e];
+          return from_wire<T>(a.srcBase ? reinterpret_cast<const W*>(a.sticks)[(size_t)a.srcBase[e] + (size_t)zl * a.srcPitch[e]]
+                                        : stickRow[e]);
         },
         ctx);
     if (a.symmetry && xt == 0) hermitian_fill_lane_swz<T, LOG2V, SwzRow>(S, N, 0, ctx);
@@ -438,8 +443,8 @@ SB_DEV void y_backward_fast3_impl(const YArgs<T>& a, int xt, int zl, const cx<T>
 }
 
 // stickRow (GATHER): where stick e of this plane is stored (local row, or the owner's buffer)
-template <typename T, int N, bool GATHER>
-SB_DEV void y_forward_fast3_impl(const YArgs<T>& a, int xt, int zl, cx<T>* stickRow, int nextXt,
+template <typename T, int N, bool GATHER, typename W>
+SB_DEV void y_forward_fast3_impl(const YArgs<T>& a, int xt, int zl, W* stickRow, int nextXt,
                                  const cx<T>* nextPlane, Ctx ctx, cx<T>* S) {
   constexpr int LOG2V = FastLanes<T>::log2V;
   constexpr int V = 1 << LOG2V;
@@ -491,37 +496,42 @@ SB_DEV void y_forward_fast3_impl(const YArgs<T>& a, int xt, int zl, cx<T>* stick
     SB_PHASE_BEGIN
     for (int e = e0 + tid; e < e1; e += nthr) {
       const int slot = a.stickSlot[e];
-      cx<T>* dst = a.srcBase ? y_dist_stick<T, true>(a, e, zl) : stickRow + e;
-      *dst = S[SwzRow::template at<LOG2V>(slot >> LOG2V, slot & (V - 1))];
+      W* dst = a.srcBase ? y_dist_stick<T, true, W>(a, e, zl) : stickRow + e;
+      *dst = to_wire<W>(S[SwzRow::template at<LOG2V>(slot >> LOG2V, slot & (V - 1))]);
     }
     SB_PHASE_END_NOSYNC
   }
 }
 
-template <typename T, int N>
-SB_DEV void y_backward_fast3(const YArgs<T>& a, int block, Ctx ctx, cx<T>* S) {
+template <typename T, int N, typename W>
+SB_DEV void y_backward_fast3_w(const YArgs<T>& a, int block, Ctx ctx, cx<T>* S) {
   const int xt = block % a.numXTiles;
   const int zl = block / a.numXTiles;
+  const W* sticks = reinterpret_cast<const W*>(a.sticks);
   int nextXt = -1;
-  const cx<T>* nextRow = nullptr;
+  const W* nextRow = nullptr;
   if (a.pfDist > 0 && !a.srcBase && block + a.pfDist < a.numXTiles * a.numPlanes) {
     nextXt = (block + a.pfDist) % a.numXTiles;
-    nextRow = a.sticks + (size_t)((block + a.pfDist) / a.numXTiles + a.zRowOffset) * a.pitch;
+    nextRow = sticks + (size_t)((block + a.pfDist) / a.numXTiles + a.zRowOffset) * a.pitch;
   }
-  const cx<T>* localRow = a.sticks + (size_t)(zl + a.zRowOffset) * a.pitch;
+  const W* localRow = sticks + (size_t)(zl + a.zRowOffset) * a.pitch;
   if (a.srcBase && a.inv && a.tilePitch[xt] != 0) {
     // distributed, all sticks of this tile from one rank: contiguous inside that rank's block
-    const cx<T>* row = a.sticks + (size_t)a.tileBase[xt] + (size_t)zl * a.tilePitch[xt] - a.xtStart[xt];
-    y_backward_fast3_impl<T, N, true>(a, xt, zl, row, -1, nullptr, ctx, S);
+    const W* row = sticks + (size_t)a.tileBase[xt] + (size_t)zl * a.tilePitch[xt] - a.xtStart[xt];
+    y_backward_fast3_impl<T, N, true, W>(a, xt, zl, row, -1, nullptr, ctx, S);
   } else if (a.inv && !a.srcBase) {
-    y_backward_fast3_impl<T, N, true>(a, xt, zl, localRow, nextXt, nextRow, ctx, S);
+    y_backward_fast3_impl<T, N, true, W>(a, xt, zl, localRow, nextXt, nextRow, ctx, S);
   } else {
-    y_backward_fast3_impl<T, N, false>(a, xt, zl, localRow, -1, nullptr, ctx, S);
+    y_backward_fast3_impl<T, N, false, W>(a, xt, zl, localRow, -1, nullptr, ctx, S);
   }
 }
-
 template <typename T, int N>
-SB_DEV void y_forward_fast3(const YArgs<T>& a, int block, Ctx ctx, cx<T>* S) {
+SB_DEV void y_backward_fast3(const YArgs<T>& a, int block, Ctx ctx, cx<T>* S) {
+  with_wire_type<T>(a.wireF32, [&](auto w) { y_backward_fast3_w<T, N, decltype(w)>(a, block, ctx, S); });
+}
+
+template <typename T, int N, typename W>
+SB_DEV void y_forward_fast3_w(const YArgs<T>& a, int block, Ctx ctx, cx<T>* S) {
   const int xt = (block % a.numXTiles + a.xtRotate) % a.numXTiles;
   const int zl = block / a.numXTiles;
   int nextXt = -1;
@@ -530,15 +540,19 @@ SB_DEV void y_forward_fast3(const YArgs<T>& a, int block, Ctx ctx, cx<T>* S) {
     nextXt = ((block + a.pfDist) % a.numXTiles + a.xtRotate) % a.numXTiles;
     nextPlane = a.planes + (size_t)((block + a.pfDist) / a.numXTiles) * N * a.nxf;
   }
-  cx<T>* localRow = a.sticks + (size_t)(zl + a.zRowOffset) * a.pitch;
+  W* localRow = reinterpret_cast<W*>(a.sticks) + (size_t)(zl + a.zRowOffset) * a.pitch;
   if (a.srcBase && a.inv && a.tilePitch[xt] != 0) {
-    cx<T>* row = y_dist_tile<T, true>(a, xt, zl) - a.xtStart[xt];
-    y_forward_fast3_impl<T, N, true>(a, xt, zl, row, nextXt, nextPlane, ctx, S);
+    W* row = y_dist_tile<T, true, W>(a, xt, zl) - a.xtStart[xt];
+    y_forward_fast3_impl<T, N, true, W>(a, xt, zl, row, nextXt, nextPlane, ctx, S);
   } else if (a.inv && !a.srcBase) {
-    y_forward_fast3_impl<T, N, true>(a, xt, zl, localRow, nextXt, nextPlane, ctx, S);
+    y_forward_fast3_impl<T, N, true, W>(a, xt, zl, localRow, nextXt, nextPlane, ctx, S);
   } else {
-    y_forward_fast3_impl<T, N, false>(a, xt, zl, localRow, nextXt, nextPlane, ctx, S);
+    y_forward_fast3_impl<T, N, false, W>(a, xt, zl, localRow, nextXt, nextPlane, ctx, S);
   }
+}
+template <typename T, int N>
+SB_DEV void y_forward_fast3(const YArgs<T>& a, int block, Ctx ctx, cx<T>* S) {
+  with_wire_type<T>(a.wireF32, [&](auto w) { y_forward_fast3_w<T, N, decltype(w)>(a, block, ctx, S); });
 }
 
 // -------------------------------------------------------------------------------------------

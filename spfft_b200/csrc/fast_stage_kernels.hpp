@@ -51,12 +51,14 @@ struct FastLanesX {
 };
 
 // gather-form tiles (defined below)
-template <typename T, int N, Mem STP, bool TWS = false>
-SB_DEV void y_backward_gather(const YArgs<T>& a, int xt, const cx<T>* stickRow, cx<T>* plane,
-                              int nextXt, const cx<T>* nextStickRow, Ctx ctx, cx<T>* S,
+// (W = element type of the stick buffer: cx<T>, or cx<float> for the single-precision wire format of a
+// distributed double-precision transform; deduced from the row pointer)
+template <typename T, int N, Mem STP, bool TWS = false, typename W = cx<T>>
+SB_DEV void y_backward_gather(const YArgs<T>& a, int xt, const W* stickRow, cx<T>* plane,
+                              int nextXt, const W* nextStickRow, Ctx ctx, cx<T>* S,
                               const cx<T>* tw = nullptr);
-template <typename T, int N, Mem LDP, bool TWS = false>
-SB_DEV void y_forward_gather(const YArgs<T>& a, int xt, const cx<T>* plane, cx<T>* stickRow,
+template <typename T, int N, Mem LDP, bool TWS = false, typename W = cx<T>>
+SB_DEV void y_forward_gather(const YArgs<T>& a, int xt, const cx<T>* plane, W* stickRow,
                              int nextXt, const cx<T>* nextPlane, Ctx ctx, cx<T>* S,
                              const cx<T>* tw = nullptr);
 
@@ -174,7 +176,7 @@ SB_DEV void hermitian_fill_lane_swz(cx<T>* A, int n, int lane, Ctx ctx) {
 // -------------------------------------------------------------------------------------------
 // z stage
 // -------------------------------------------------------------------------------------------
-template <typename T, int N>
+template <typename T, int N, typename W = cx<T>>
 SB_DEV void z_backward_fast(const ZArgs<T>& a, int tile, Ctx ctx, cx<T>* S) {
   constexpr int LOG2V = FastLanes<T>::log2V;
   constexpr int V = 1 << LOG2V;
@@ -222,11 +224,11 @@ SB_DEV void z_backward_fast(const ZArgs<T>& a, int tile, Ctx ctx, cx<T>* S) {
   fast_fft_tail<T, N, LOG2V, true, SwzRow>(v, S, a.ftw, j, lane);
   const size_t col = (size_t)tile * V + lane;
 #pragma unroll
-  for (int m = 0; m < 8; ++m) z_row<T>(a, j + TT * m)[col] = v[m];
+  for (int m = 0; m < 8; ++m) z_row<T, W>(a, j + TT * m)[col] = to_wire<W>(v[m]);
   SB_PHASE_END_NOSYNC
 }
 
-template <typename T, int N>
+template <typename T, int N, typename W = cx<T>>
 SB_DEV void z_forward_fast(const ZArgs<T>& a, int tile, Ctx ctx, cx<T>* S) {
   constexpr int LOG2V = FastLanes<T>::log2V;
   constexpr int V = 1 << LOG2V;
@@ -235,12 +237,12 @@ SB_DEV void z_forward_fast(const ZArgs<T>& a, int tile, Ctx ctx, cx<T>* S) {
   const int e0 = a.tileStart[tile], e1 = a.tileStart[tile + 1];
   SB_PHASE_BEGIN
   SB_ROW_IDS
-  const cx<T>* in = a.sticks + (size_t)tile * V + lane;
+  const W* in = reinterpret_cast<const W*>(a.sticks) + (size_t)tile * V + lane;
 #pragma unroll
-  for (int m = 0; m < 8; ++m) v[m] = in[(size_t)(j + TT * m) * a.pitch];
+  for (int m = 0; m < 8; ++m) v[m] = from_wire<T>(in[(size_t)(j + TT * m) * a.pitch]);
   if (a.pfDist > 0 && tile + a.pfDist < a.numTiles) {
     for (int r = tid; r < N; r += nthr)
-      prefetch_l2_line(a.sticks + (size_t)(tile + a.pfDist) * V + (size_t)r * a.pitch);
+      prefetch_l2_line(reinterpret_cast<const W*>(a.sticks) + (size_t)(tile + a.pfDist) * V + (size_t)r * a.pitch);
     const int p0 = a.tileStart[tile + a.pfDist], p1 = a.tileStart[tile + a.pfDist + 1];
     prefetch_l2(a.entrySlot + p0, (size_t)(p1 - p0) * sizeof(int), tid, nthr);
   }
@@ -284,9 +286,9 @@ SB_DEV void z_forward_fast(const ZArgs<T>& a, int tile, Ctx ctx, cx<T>* S) {
 //   stickRow : row of the plane-major stick buffer that holds this plane (all local sticks)
 //   plane    : the plane's [ny][nxf] array (the plane buffer, or a slot of the L2 scratch ring)
 // -------------------------------------------------------------------------------------------
-template <typename T, int N, Mem LDS, Mem STP>
-SB_DEV void y_backward_tile(const YArgs<T>& a, int xt, const cx<T>* stickRow, cx<T>* plane,
-                            int nextXt, const cx<T>* nextStickRow, Ctx ctx, cx<T>* S, int zl = 0) {
+template <typename T, int N, Mem LDS, Mem STP, typename W = cx<T>>
+SB_DEV void y_backward_tile(const YArgs<T>& a, int xt, const W* stickRow, cx<T>* plane,
+                            int nextXt, const W* nextStickRow, Ctx ctx, cx<T>* S, int zl = 0) {
   constexpr int LOG2V = FastLanes<T>::log2V;
   constexpr int V = 1 << LOG2V;
   constexpr int TT = FastPlan<N>::T;
@@ -308,7 +310,7 @@ SB_DEV void y_backward_tile(const YArgs<T>& a, int xt, const cx<T>* stickRow, cx
   SB_PHASE_BEGIN
   if (nextXt >= 0) {
     const int p0 = a.xtStart[nextXt], p1 = a.xtStart[nextXt + 1];
-    prefetch_l2(nextStickRow + p0, (size_t)(p1 - p0) * sizeof(cx<T>), tid, nthr);
+    prefetch_l2(nextStickRow + p0, (size_t)(p1 - p0) * sizeof(W), tid, nthr);
   }
   for (int i = tid; i < N * V; i += nthr) S[i] = mk<T>(0, 0);
   SB_PHASE_END
@@ -322,8 +324,8 @@ SB_DEV void y_backward_tile(const YArgs<T>& a, int xt, const cx<T>* stickRow, cx
       const int e = base + u * nthr;
       if (e < e1) {
         slot[u] = a.stickSlot[e];
-        val[u] = a.srcBase ? a.sticks[(size_t)a.srcBase[e] + (size_t)zl * a.srcPitch[e]]
-                           : ld_g<LDS>(stickRow + e);
+        val[u] = from_wire<T>(a.srcBase ? reinterpret_cast<const W*>(a.sticks)[(size_t)a.srcBase[e] + (size_t)zl * a.srcPitch[e]]
+                                        : ld_g<LDS>(stickRow + e));
       }
     }
 #pragma unroll
@@ -349,8 +351,8 @@ SB_DEV void y_backward_tile(const YArgs<T>& a, int xt, const cx<T>* stickRow, cx
   SB_PHASE_END_NOSYNC
 }
 
-template <typename T, int N, Mem LDP, Mem STS>
-SB_DEV void y_forward_tile(const YArgs<T>& a, int xt, const cx<T>* plane, cx<T>* stickRow,
+template <typename T, int N, Mem LDP, Mem STS, typename W = cx<T>>
+SB_DEV void y_forward_tile(const YArgs<T>& a, int xt, const cx<T>* plane, W* stickRow,
                            int nextXt, const cx<T>* nextPlane, Ctx ctx, cx<T>* S, int zl = 0) {
   constexpr int LOG2V = FastLanes<T>::log2V;
   constexpr int V = 1 << LOG2V;
@@ -391,41 +393,47 @@ SB_DEV void y_forward_tile(const YArgs<T>& a, int xt, const cx<T>* plane, cx<T>*
     for (int u = 0; u < U; ++u) {
       if (base + u * nthr < e1) {
         const int e = base + u * nthr;
-        cx<T>* dst = a.srcBase ? y_dist_stick<T, true>(a, e, zl) : stickRow + e;
-        st_g<STS>(dst, S[SwzRow::template at<LOG2V>(slot[u] >> LOG2V, slot[u] & (V - 1))]);
+        W* dst = a.srcBase ? y_dist_stick<T, true, W>(a, e, zl) : stickRow + e;
+        st_g<STS>(dst, to_wire<W>(S[SwzRow::template at<LOG2V>(slot[u] >> LOG2V, slot[u] & (V - 1))]));
       }
     }
   }
   SB_PHASE_END_NOSYNC
 }
 
-template <typename T, int N>
-SB_DEV void y_backward_fast(const YArgs<T>& a, int block, Ctx ctx, cx<T>* S) {
+template <typename T, int N, typename W>
+SB_DEV void y_backward_fast_w(const YArgs<T>& a, int block, Ctx ctx, cx<T>* S) {
   const int xt = block % a.numXTiles;
   const int zl = block / a.numXTiles;
+  const W* sticks = reinterpret_cast<const W*>(a.sticks);
   int nextXt = -1;
-  const cx<T>* nextRow = nullptr;
+  const W* nextRow = nullptr;
   if (a.pfDist > 0 && !a.srcBase && block + a.pfDist < a.numXTiles * a.numPlanes) {
     nextXt = (block + a.pfDist) % a.numXTiles;
-    nextRow = a.sticks + (size_t)((block + a.pfDist) / a.numXTiles + a.zRowOffset) * a.pitch;
+    nextRow = sticks + (size_t)((block + a.pfDist) / a.numXTiles + a.zRowOffset) * a.pitch;
   }
   if (a.srcBase && a.inv && a.tilePitch[xt] != 0) {
     // distributed, all sticks of this tile from one rank: contiguous inside that rank's block.
     // The gather form indexes relative to the tile's first stick, so pass row - xtStart[xt].
-    const cx<T>* row = a.sticks + (size_t)a.tileBase[xt] + (size_t)zl * a.tilePitch[xt] - a.xtStart[xt];
-    y_backward_gather<T, N, Mem::Plain>(a, xt, row, a.planes + (size_t)zl * N * a.nxf, -1, nullptr, ctx, S);
+    const W* row = sticks + (size_t)a.tileBase[xt] + (size_t)zl * a.tilePitch[xt] - a.xtStart[xt];
+    y_backward_gather<T, N, Mem::Plain>(a, xt, row, a.planes + (size_t)zl * N * a.nxf, -1, (const W*)nullptr, ctx, S);
   } else if (a.inv && !a.srcBase)
-    y_backward_gather<T, N, Mem::Plain>(a, xt, a.sticks + (size_t)(zl + a.zRowOffset) * a.pitch,
+    y_backward_gather<T, N, Mem::Plain>(a, xt, sticks + (size_t)(zl + a.zRowOffset) * a.pitch,
                                         a.planes + (size_t)zl * N * a.nxf, nextXt, nextRow, ctx, S);
   else
-    y_backward_tile<T, N, Mem::Plain, Mem::Plain>(a, xt, a.sticks + (size_t)(zl + a.zRowOffset) * a.pitch,
+    y_backward_tile<T, N, Mem::Plain, Mem::Plain>(a, xt, sticks + (size_t)(zl + a.zRowOffset) * a.pitch,
                                                   a.planes + (size_t)zl * N * a.nxf, nextXt, nextRow, ctx, S, zl);
 }
-
 template <typename T, int N>
-SB_DEV void y_forward_fast(const YArgs<T>& a, int block, Ctx ctx, cx<T>* S) {
+SB_DEV void y_backward_fast(const YArgs<T>& a, int block, Ctx ctx, cx<T>* S) {
+  with_wire_type<T>(a.wireF32, [&](auto w) { y_backward_fast_w<T, N, decltype(w)>(a, block, ctx, S); });
+}
+
+template <typename T, int N, typename W>
+SB_DEV void y_forward_fast_w(const YArgs<T>& a, int block, Ctx ctx, cx<T>* S) {
   const int xt = (block % a.numXTiles + a.xtRotate) % a.numXTiles;
   const int zl = block / a.numXTiles;
+  W* sticks = reinterpret_cast<W*>(a.sticks);
   int nextXt = -1;
   const cx<T>* nextPlane = nullptr;
   if (a.pfDist > 0 && block + a.pfDist < a.numXTiles * a.numPlanes) {
@@ -433,16 +441,20 @@ SB_DEV void y_forward_fast(const YArgs<T>& a, int block, Ctx ctx, cx<T>* S) {
     nextPlane = a.planes + (size_t)((block + a.pfDist) / a.numXTiles) * N * a.nxf;
   }
   if (a.srcBase && a.inv && a.tilePitch[xt] != 0) {
-    cx<T>* row = y_dist_tile<T, true>(a, xt, zl) - a.xtStart[xt];
+    W* row = y_dist_tile<T, true, W>(a, xt, zl) - a.xtStart[xt];
     y_forward_gather<T, N, Mem::Plain>(a, xt, a.planes + (size_t)zl * N * a.nxf, row, nextXt, nextPlane, ctx, S);
   } else if (a.inv && !a.srcBase)
     y_forward_gather<T, N, Mem::Plain>(a, xt, a.planes + (size_t)zl * N * a.nxf,
-                                       a.sticks + (size_t)(zl + a.zRowOffset) * a.pitch, nextXt, nextPlane,
+                                       sticks + (size_t)(zl + a.zRowOffset) * a.pitch, nextXt, nextPlane,
                                        ctx, S);
   else
     y_forward_tile<T, N, Mem::Plain, Mem::Plain>(a, xt, a.planes + (size_t)zl * N * a.nxf,
-                                                 a.sticks + (size_t)(zl + a.zRowOffset) * a.pitch, nextXt,
+                                                 sticks + (size_t)(zl + a.zRowOffset) * a.pitch, nextXt,
                                                  nextPlane, ctx, S, zl);
+}
+template <typename T, int N>
+SB_DEV void y_forward_fast(const YArgs<T>& a, int block, Ctx ctx, cx<T>* S) {
+  with_wire_type<T>(a.wireF32, [&](auto w) { y_forward_fast_w<T, N, decltype(w)>(a, block, ctx, S); });
 }
 
 
@@ -492,20 +504,20 @@ SB_DEV cx<T> hermitian_combine(int n, int N, cx<T> p, cx<T> q) {
 
 // Loads the 8 elements of thread (lane, j) (column mapping) from `sparse` through the inverse map
 // of this tile (`invTile` = first entry of the tile's map). hermitianLane: complete that lane.
-template <typename T, int N>
-SB_DEV void gather_load(cx<T>* v, const cx<T>* sparse, const unsigned short* invTile, int tid, int j,
+template <typename T, int N, typename W>
+SB_DEV void gather_load(cx<T>* v, const W* sparse, const unsigned short* invTile, int tid, int j,
                         int lane, int hermitianLane) {
   constexpr int TT = FastPlan<N>::T;
   const Inv8 iv = load_inv8(invTile + (size_t)tid * 8);
 #pragma unroll
-  for (int m = 0; m < 8; ++m) v[m] = iv.i[m] != kNoEntry ? sparse[iv.i[m]] : mk<T>(0, 0);
+  for (int m = 0; m < 8; ++m) v[m] = iv.i[m] != kNoEntry ? from_wire<T>(sparse[iv.i[m]]) : mk<T>(0, 0);
   if (lane == hermitianLane) {
 #pragma unroll
     for (int m = 0; m < 8; ++m) {
       const int n = j + TT * m;
       const int n2 = (N - n) & (N - 1);
       const unsigned short i2 = invTile[((size_t)lane * TT + (n2 & (TT - 1))) * 8 + n2 / TT];
-      const cx<T> q = i2 != kNoEntry ? sparse[i2] : mk<T>(0, 0);
+      const cx<T> q = i2 != kNoEntry ? from_wire<T>(sparse[i2]) : mk<T>(0, 0);
       v[m] = hermitian_combine<T>(n, N, v[m], q);
     }
   }
@@ -517,7 +529,7 @@ SB_DEV void gather_load(cx<T>* v, const cx<T>* sparse, const unsigned short* inv
   const int j = tid & (TT - 1);       \
   (void)nthr;
 
-template <typename T, int N>
+template <typename T, int N, typename W = cx<T>>
 SB_DEV void z_backward_gather(const ZArgs<T>& a, int tile, Ctx ctx, cx<T>* S) {
   constexpr int LOG2V = FastLanes<T>::log2V;
   constexpr int V = 1 << LOG2V;
@@ -541,11 +553,11 @@ SB_DEV void z_backward_gather(const ZArgs<T>& a, int tile, Ctx ctx, cx<T>* S) {
   fast_fft_tail<T, N, LOG2V, true, SwzCol>(v, S, a.ftw, j, lane);
   const size_t col = (size_t)tile * V + lane;
 #pragma unroll
-  for (int m = 0; m < 8; ++m) z_row<T>(a, j + TT * m)[col] = v[m];
+  for (int m = 0; m < 8; ++m) z_row<T, W>(a, j + TT * m)[col] = to_wire<W>(v[m]);
   SB_PHASE_END_NOSYNC
 }
 
-template <typename T, int N>
+template <typename T, int N, typename W = cx<T>>
 SB_DEV void z_forward_gather(const ZArgs<T>& a, int tile, Ctx ctx, cx<T>* S) {
   constexpr int LOG2V = FastLanes<T>::log2V;
   constexpr int V = 1 << LOG2V;
@@ -555,12 +567,12 @@ SB_DEV void z_forward_gather(const ZArgs<T>& a, int tile, Ctx ctx, cx<T>* S) {
   const int e0 = a.tileStart[tile];
   SB_PHASE_BEGIN
   SB_ROW_IDS
-  const cx<T>* in = a.sticks + (size_t)tile * V + lane;
+  const W* in = reinterpret_cast<const W*>(a.sticks) + (size_t)tile * V + lane;
 #pragma unroll
-  for (int m = 0; m < 8; ++m) v[m] = in[(size_t)(j + TT * m) * a.pitch];
+  for (int m = 0; m < 8; ++m) v[m] = from_wire<T>(in[(size_t)(j + TT * m) * a.pitch]);
   if (a.pfDist > 0 && tile + a.pfDist < a.numTiles) {
     for (int r = tid; r < N; r += nthr)
-      prefetch_l2_line(a.sticks + (size_t)(tile + a.pfDist) * V + (size_t)r * a.pitch);
+      prefetch_l2_line(reinterpret_cast<const W*>(a.sticks) + (size_t)(tile + a.pfDist) * V + (size_t)r * a.pitch);
     prefetch_l2(a.inv + (size_t)(tile + a.pfDist) * THREADS * 8, (size_t)THREADS * 16, tid, nthr);
   }
   SB_PHASE_END_NOSYNC
@@ -580,22 +592,25 @@ SB_DEV void z_forward_gather(const ZArgs<T>& a, int tile, Ctx ctx, cx<T>* S) {
 // z stage entry: inverse-map (gather) form when the values are in stick order, scatter form otherwise
 template <typename T, int N, bool FWD>
 SB_DEV void z_fast_any(const ZArgs<T>& a, int tile, Ctx ctx, cx<T>* S) {
-  if (a.inv) {
-    if (FWD)
-      z_forward_gather<T, N>(a, tile, ctx, S);
-    else
-      z_backward_gather<T, N>(a, tile, ctx, S);
-  } else {
-    if (FWD)
-      z_forward_fast<T, N>(a, tile, ctx, S);
-    else
-      z_backward_fast<T, N>(a, tile, ctx, S);
-  }
+  with_wire_type<T>(a.wireF32, [&](auto w) {
+    using W = decltype(w);
+    if (a.inv) {
+      if (FWD)
+        z_forward_gather<T, N, W>(a, tile, ctx, S);
+      else
+        z_backward_gather<T, N, W>(a, tile, ctx, S);
+    } else {
+      if (FWD)
+        z_forward_fast<T, N, W>(a, tile, ctx, S);
+      else
+        z_backward_fast<T, N, W>(a, tile, ctx, S);
+    }
+  });
 }
 
-template <typename T, int N, Mem STP, bool TWS>
-SB_DEV void y_backward_gather(const YArgs<T>& a, int xt, const cx<T>* stickRow, cx<T>* plane,
-                              int nextXt, const cx<T>* nextStickRow, Ctx ctx, cx<T>* S,
+template <typename T, int N, Mem STP, bool TWS, typename W>
+SB_DEV void y_backward_gather(const YArgs<T>& a, int xt, const W* stickRow, cx<T>* plane,
+                              int nextXt, const W* nextStickRow, Ctx ctx, cx<T>* S,
                               const cx<T>* tw) {
   if (!TWS) tw = a.ftw;
   constexpr int LOG2V = FastLanes<T>::log2V;
@@ -627,7 +642,7 @@ SB_DEV void y_backward_gather(const YArgs<T>& a, int xt, const cx<T>* stickRow, 
                     (a.symmetry && xt == 0) ? 0 : -1);
   if (nextXt >= 0) {
     const int p0 = a.xtStart[nextXt], p1 = a.xtStart[nextXt + 1];
-    prefetch_l2(nextStickRow + p0, (size_t)(p1 - p0) * sizeof(cx<T>), tid, nthr);
+    prefetch_l2(nextStickRow + p0, (size_t)(p1 - p0) * sizeof(W), tid, nthr);
   }
   SB_PHASE_END_NOSYNC
   fast_fft_head<T, N, LOG2V, true, SwzCol, true, false, TWS>(vAll, S, tw, ctx);
@@ -646,8 +661,8 @@ SB_DEV void y_backward_gather(const YArgs<T>& a, int xt, const cx<T>* stickRow, 
   SB_PHASE_END_NOSYNC
 }
 
-template <typename T, int N, Mem LDP, bool TWS>
-SB_DEV void y_forward_gather(const YArgs<T>& a, int xt, const cx<T>* plane, cx<T>* stickRow,
+template <typename T, int N, Mem LDP, bool TWS, typename W>
+SB_DEV void y_forward_gather(const YArgs<T>& a, int xt, const cx<T>* plane, W* stickRow,
                              int nextXt, const cx<T>* nextPlane, Ctx ctx, cx<T>* S,
                              const cx<T>* tw) {
   if (!TWS) tw = a.ftw;
@@ -687,10 +702,10 @@ SB_DEV void y_forward_gather(const YArgs<T>& a, int xt, const cx<T>* plane, cx<T
   SB_COLMAP_IDS
   fast_stage<T, N, false, FastPlan<N>::numStages - 1, TWS>(v, j, tw);
   const Inv8 iv = load_inv8(a.inv + ((size_t)xt * THREADS + tid) * 8);
-  cx<T>* out = stickRow + e0;
+  W* out = stickRow + e0;
 #pragma unroll
   for (int m = 0; m < 8; ++m) {
-    if (iv.i[m] != kNoEntry) out[iv.i[m]] = v[m];
+    if (iv.i[m] != kNoEntry) out[iv.i[m]] = to_wire<W>(v[m]);
   }
   SB_PHASE_END_NOSYNC
 }

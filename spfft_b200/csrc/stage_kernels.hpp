@@ -58,13 +58,39 @@ struct ZArgs {
   cx<T>* peer[kMaxPeers];
   const unsigned char* rowRank;  // [nz]
   const long long* rowOff;       // [nz] element offset of this rank's row inside the owner's buffer
+  // Distributed double-precision transform with a single-precision wire format
+  // (SPFFT_EXCH_*_FLOAT, reference: complex_conversion.cuh:35-54 inside the pack / unpack kernels of
+  // compact_buffered_kernels.cu:50-52,114-115): the stick buffer holds cx<float>, same element offsets.
+  int wireF32;
 };
 
-// Row z of the stick buffer a z kernel writes (backward) / reads (forward).
-template <typename T>
-SB_DEV cx<T>* z_row(const ZArgs<T>& a, int z) {
-  if (a.rowRank) return a.peer[a.rowRank[z]] + a.rowOff[z];
-  return a.sticks + (size_t)z * a.pitch;
+// Element conversion between the arithmetic type and the type of the exchanged buffers (W = cx<T>,
+// or cx<float> for the single-precision wire format of a double-precision transform).
+template <typename T, typename S>
+SB_HD cx<T> from_wire(cx<S> v) {
+  return mk<T>(static_cast<T>(v.x), static_cast<T>(v.y));
+}
+template <typename W, typename T>
+SB_HD W to_wire(cx<T> v) {
+  W r;
+  r.x = static_cast<decltype(r.x)>(v.x);
+  r.y = static_cast<decltype(r.y)>(v.y);
+  return r;
+}
+// Runs f(tag) with tag = cx<float>{} when the wire format is single precision, cx<T>{} otherwise.
+template <typename T, typename F>
+SB_DEV void with_wire_type(int wireF32, F f) {
+  if (sizeof(T) == 8 && wireF32)
+    f(cx<float>{});
+  else
+    f(cx<T>{});
+}
+
+// Row z of the stick buffer a z kernel writes (backward) / reads (forward), elements of type W.
+template <typename T, typename W = cx<T>>
+SB_DEV W* z_row(const ZArgs<T>& a, int z) {
+  if (a.rowRank) return reinterpret_cast<W*>(a.peer[a.rowRank[z]]) + a.rowOff[z];
+  return reinterpret_cast<W*>(a.sticks) + (size_t)z * a.pitch;
 }
 
 template <typename T>
@@ -108,22 +134,24 @@ struct YArgs {
   // forward kernels visit the x tiles of a plane starting at tile xtRotate: with peer stores
   // every rank then targets a different destination at any time (no ingress hot spot)
   int xtRotate;
+  int wireF32;  // the exchanged buffers (`sticks`, `peer`) hold cx<float> (see ZArgs)
 };
 
 // Where stick e (global sorted list) of local plane zl lives for a distributed y kernel:
 // backward reads the local plane-side buffer, forward writes the owner's stick buffer.
-template <typename T, bool FWD>
-SB_DEV cx<T>* y_dist_stick(const YArgs<T>& a, int e, int zl) {
+template <typename T, bool FWD, typename W = cx<T>>
+SB_DEV W* y_dist_stick(const YArgs<T>& a, int e, int zl) {
   if (FWD && a.stickRank)
-    return a.peer[a.stickRank[e]] + (size_t)a.fwdBase[e] + (size_t)zl * a.srcPitch[e];
-  return a.sticks + (size_t)a.srcBase[e] + (size_t)zl * a.srcPitch[e];
+    return reinterpret_cast<W*>(a.peer[a.stickRank[e]]) + (size_t)a.fwdBase[e] + (size_t)zl * a.srcPitch[e];
+  return reinterpret_cast<W*>(a.sticks) + (size_t)a.srcBase[e] + (size_t)zl * a.srcPitch[e];
 }
 // First stick of single-source tile xt (tilePitch[xt] != 0) at local plane zl.
-template <typename T, bool FWD>
-SB_DEV cx<T>* y_dist_tile(const YArgs<T>& a, int xt, int zl) {
+template <typename T, bool FWD, typename W = cx<T>>
+SB_DEV W* y_dist_tile(const YArgs<T>& a, int xt, int zl) {
   if (FWD && a.stickRank)
-    return a.peer[a.stickRank[a.xtStart[xt]]] + (size_t)a.tileFwdBase[xt] + (size_t)zl * a.tilePitch[xt];
-  return a.sticks + (size_t)a.tileBase[xt] + (size_t)zl * a.tilePitch[xt];
+    return reinterpret_cast<W*>(a.peer[a.stickRank[a.xtStart[xt]]]) + (size_t)a.tileFwdBase[xt] +
+           (size_t)zl * a.tilePitch[xt];
+  return reinterpret_cast<W*>(a.sticks) + (size_t)a.tileBase[xt] + (size_t)zl * a.tilePitch[xt];
 }
 
 template <typename T>
@@ -170,6 +198,7 @@ SB_DEV ZArgs<T> band_args(const ZArgs<T>& a0, const BandTable<T>& b, int band) {
   a.sticks = b.sticks[band];
   a.rowRank = nullptr;
   a.rowOff = nullptr;
+  a.wireF32 = 0;
   return a;
 }
 template <typename T>
@@ -185,6 +214,7 @@ SB_DEV YArgs<T> band_args(const YArgs<T>& a0, const BandTable<T>& b, int band) {
   a.fwdBase = nullptr;
   a.tileFwdBase = nullptr;
   a.xtRotate = 0;
+  a.wireF32 = 0;
   return a;
 }
 template <typename T>
@@ -219,8 +249,8 @@ SB_DEV void hermitian_fill_lane(cx<T>* A, int n, int lane, int log2V, Ctx ctx) {
 // -------------------------------------------------------------------------------------------
 // z stage
 // -------------------------------------------------------------------------------------------
-template <typename T>
-SB_DEV void z_backward_body(const ZArgs<T>& a, int tile, Ctx ctx, cx<T>* smem) {
+template <typename T, typename W>
+SB_DEV void z_backward_body_w(const ZArgs<T>& a, int tile, Ctx ctx, cx<T>* smem) {
   const int V = 1 << a.log2V;
   const int n = a.nz << a.log2V;
   cx<T>* A = smem;
@@ -241,23 +271,27 @@ SB_DEV void z_backward_body(const ZArgs<T>& a, int tile, Ctx ctx, cx<T>* smem) {
   for (int i = tid; i < n; i += nthr) {
     const int z = i >> a.log2V;
     const int lane = i & (V - 1);
-    z_row<T>(a, z)[(size_t)tile * V + lane] = R[i];
+    z_row<T, W>(a, z)[(size_t)tile * V + lane] = to_wire<W>(R[i]);
   }
   SB_PHASE_END
 }
-
 template <typename T>
-SB_DEV void z_forward_body(const ZArgs<T>& a, int tile, Ctx ctx, cx<T>* smem) {
+SB_DEV void z_backward_body(const ZArgs<T>& a, int tile, Ctx ctx, cx<T>* smem) {
+  with_wire_type<T>(a.wireF32, [&](auto w) { z_backward_body_w<T, decltype(w)>(a, tile, ctx, smem); });
+}
+
+template <typename T, typename W>
+SB_DEV void z_forward_body_w(const ZArgs<T>& a, int tile, Ctx ctx, cx<T>* smem) {
   const int V = 1 << a.log2V;
   const int n = a.nz << a.log2V;
   cx<T>* A = smem;
   cx<T>* B = smem + n;
   SB_PHASE_BEGIN
-  const cx<T>* in = a.sticks + (size_t)tile * V;
+  const W* in = reinterpret_cast<const W*>(a.sticks) + (size_t)tile * V;
   for (int i = tid; i < n; i += nthr) {
     const int z = i >> a.log2V;
     const int lane = i & (V - 1);
-    A[i] = in[(size_t)z * a.pitch + lane];
+    A[i] = from_wire<T>(in[(size_t)z * a.pitch + lane]);
   }
   SB_PHASE_END
   cx<T>* R = tile_fft<T, false, false>(A, B, a.rp, a.log2V, a.tw, ctx);
@@ -271,12 +305,16 @@ SB_DEV void z_forward_body(const ZArgs<T>& a, int tile, Ctx ctx, cx<T>* smem) {
   }
   SB_PHASE_END
 }
+template <typename T>
+SB_DEV void z_forward_body(const ZArgs<T>& a, int tile, Ctx ctx, cx<T>* smem) {
+  with_wire_type<T>(a.wireF32, [&](auto w) { z_forward_body_w<T, decltype(w)>(a, tile, ctx, smem); });
+}
 
 // -------------------------------------------------------------------------------------------
 // y stage
 // -------------------------------------------------------------------------------------------
-template <typename T>
-SB_DEV void y_backward_body(const YArgs<T>& a, int block, Ctx ctx, cx<T>* smem) {
+template <typename T, typename W>
+SB_DEV void y_backward_body_w(const YArgs<T>& a, int block, Ctx ctx, cx<T>* smem) {
   const int V = 1 << a.log2V;
   const int n = a.ny << a.log2V;
   const int xt = block % a.numXTiles;
@@ -301,9 +339,10 @@ SB_DEV void y_backward_body(const YArgs<T>& a, int block, Ctx ctx, cx<T>* smem) 
   for (int i = tid; i < n; i += nthr) A[i] = mk<T>(0, 0);
   SB_PHASE_END
   SB_PHASE_BEGIN
-  const cx<T>* row = a.sticks + (size_t)(zl + a.zRowOffset) * a.pitch;
+  const W* base = reinterpret_cast<const W*>(a.sticks);
+  const W* row = base + (size_t)(zl + a.zRowOffset) * a.pitch;
   for (int e = e0 + tid; e < e1; e += nthr)
-    A[a.stickSlot[e]] = a.srcBase ? a.sticks[(size_t)a.srcBase[e] + (size_t)zl * a.srcPitch[e]] : row[e];
+    A[a.stickSlot[e]] = from_wire<T>(a.srcBase ? base[(size_t)a.srcBase[e] + (size_t)zl * a.srcPitch[e]] : row[e]);
   SB_PHASE_END
   if (a.symmetry && xt == 0) hermitian_fill_lane<T>(A, a.ny, 0, a.log2V, ctx);
   cx<T>* R = tile_fft<T, true, false>(A, B, a.rp, a.log2V, a.tw, ctx);
@@ -315,9 +354,13 @@ SB_DEV void y_backward_body(const YArgs<T>& a, int block, Ctx ctx, cx<T>* smem) 
   }
   SB_PHASE_END
 }
-
 template <typename T>
-SB_DEV void y_forward_body(const YArgs<T>& a, int block, Ctx ctx, cx<T>* smem) {
+SB_DEV void y_backward_body(const YArgs<T>& a, int block, Ctx ctx, cx<T>* smem) {
+  with_wire_type<T>(a.wireF32, [&](auto w) { y_backward_body_w<T, decltype(w)>(a, block, ctx, smem); });
+}
+
+template <typename T, typename W>
+SB_DEV void y_forward_body_w(const YArgs<T>& a, int block, Ctx ctx, cx<T>* smem) {
   const int V = 1 << a.log2V;
   const int n = a.ny << a.log2V;
   const int xt = (block % a.numXTiles + a.xtRotate) % a.numXTiles;
@@ -337,14 +380,18 @@ SB_DEV void y_forward_body(const YArgs<T>& a, int block, Ctx ctx, cx<T>* smem) {
   SB_PHASE_END
   cx<T>* R = tile_fft<T, false, false>(A, B, a.rp, a.log2V, a.tw, ctx);
   SB_PHASE_BEGIN
-  cx<T>* row = a.sticks + (size_t)(zl + a.zRowOffset) * a.pitch;
+  W* row = reinterpret_cast<W*>(a.sticks) + (size_t)(zl + a.zRowOffset) * a.pitch;
   for (int e = e0 + tid; e < e1; e += nthr) {
     if (a.srcBase)
-      *y_dist_stick<T, true>(a, e, zl) = R[a.stickSlot[e]];
+      *y_dist_stick<T, true, W>(a, e, zl) = to_wire<W>(R[a.stickSlot[e]]);
     else
-      row[e] = R[a.stickSlot[e]];
+      row[e] = to_wire<W>(R[a.stickSlot[e]]);
   }
   SB_PHASE_END
+}
+template <typename T>
+SB_DEV void y_forward_body(const YArgs<T>& a, int block, Ctx ctx, cx<T>* smem) {
+  with_wire_type<T>(a.wireF32, [&](auto w) { y_forward_body_w<T, decltype(w)>(a, block, ctx, smem); });
 }
 
 // -------------------------------------------------------------------------------------------

@@ -554,6 +554,7 @@ sb::YArgs<T> TransformEngine<T>::make_y_stage_args(const TileMaps& geo, bool for
     ya.tileBase = plan_->tileBase;
     ya.tilePitch = plan_->tilePitch;
     ya.zRowOffset = 0;
+    ya.wireF32 = wire_f32() ? 1 : 0;
   }
   return ya;
 }
@@ -599,6 +600,7 @@ void TransformEngine<T>::enqueue_backward(const T* input, T* output) {
       za.rowRank = plan_->rowRank;
       za.rowOff = plan_->rowOff;
     }
+    za.wireF32 = wire_f32() ? 1 : 0;
     check_launch(Launch<T>::z(0, za, s));
     record_stage(peer ? "z backward + exchange" : "z backward");
   }
@@ -612,7 +614,7 @@ void TransformEngine<T>::enqueue_backward(const T* input, T* output) {
     const ExchangePlan& x = plan_->exchange;
     grid_->communicator()->all_to_all_v(sticks(), x.stickOffset.data(), x.stickCount.data(),
                                         grid_->array_q(), x.planeOffset.data(), x.planeCount.data(),
-                                        static_cast<int>(sizeof(sb::cx<T>)), s);
+                                        static_cast<int>(wire_f32() ? sizeof(sb::cx<float>) : sizeof(sb::cx<T>)), s);
     record_stage("exchange backward");
   }
   if (!haveSpace) return;
@@ -696,7 +698,7 @@ void TransformEngine<T>::enqueue_forward(const T* input, T* output, SpfftScaling
     const ExchangePlan& x = plan_->exchange;
     grid_->communicator()->all_to_all_v(grid_->array_q(), x.planeOffset.data(), x.planeCount.data(),
                                         sticks(), x.stickOffset.data(), x.stickCount.data(),
-                                        static_cast<int>(sizeof(sb::cx<T>)), s);
+                                        static_cast<int>(wire_f32() ? sizeof(sb::cx<float>) : sizeof(sb::cx<T>)), s);
     record_stage("exchange forward");
   }
   if (plan_->numStickTiles == 0 || ne == 0) return;  // no local values to produce
@@ -706,6 +708,7 @@ void TransformEngine<T>::enqueue_forward(const T* input, T* output, SpfftScaling
   {
     auto za = make_z_args<T>(m, geo, plan_->axes, plan_->ptrs, true, sticks(), nullptr, outDev,
                              scaling == SPFFT_FULL_SCALING);
+    za.wireF32 = wire_f32() ? 1 : 0;
     check_launch(Launch<T>::z(1, za, s));
     record_stage("z forward");
   }

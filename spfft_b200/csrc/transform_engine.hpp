@@ -180,6 +180,12 @@ private:
   sb::cx<T>* sticks() const { return static_cast<sb::cx<T>*>(grid_->array_a()); }
   sb::cx<T>* planes() const { return static_cast<sb::cx<T>*>(grid_->array_b()); }
   bool peer_exchange() const { return grid_->peer_exchange() && plan_->rowRank && plan_->stickRank; }
+  // SPFFT_EXCH_*_FLOAT on a distributed double-precision transform: the exchanged buffers hold cx<float>
+  bool wire_f32() const {
+    return sizeof(T) == 8 && plan_ && plan_->distributed &&
+           (grid_->exchange_type() == SPFFT_EXCH_COMPACT_BUFFERED_FLOAT ||
+            grid_->exchange_type() == SPFFT_EXCH_BUFFERED_FLOAT);
+  }
 
   SpfftProcessingUnitType executionUnit_;
   SpfftExecType execMode_ = SPFFT_EXEC_SYNCHRONOUS;

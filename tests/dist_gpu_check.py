@@ -19,6 +19,18 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 
+def cases_float_wire(world):
+    uniform = [1.0] * world
+    return [
+        (0, (11, 12, 13), uniform, uniform, False, False),
+        (1, (12, 11, 13), uniform, uniform, False, False),
+        (0, (64, 32, 128), uniform, [1.0 + r for r in range(world)], True, False),
+        (1, (64, 64, 32), uniform, uniform, False, False),
+        (0, (96, 96, 96), uniform, uniform, True, False),
+        (0, (13, 11, 12), [1.0] + [0.0] * (world - 1), [0.0] * (world - 1) + [1.0], False, False),
+    ]
+
+
 def main():
     import torch
     import torch.distributed as dist
@@ -57,10 +69,14 @@ def main():
     ok = True
     # every case through both exchanges: fused peer-memory stores (default) and NCCL send/recv
     modes = [m for m in os.environ.get("DIST_CHECK_MODES", "1,0").split(",") if m]
-    cases = [c + (mode,) for mode in modes for c in cases]
-    for ttype, (nx, ny, nz), sdist, pdist, center, single, mode in cases:
+    cases = [c + (mode, capi.SPFFT_EXCH_DEFAULT) for mode in modes for c in cases]
+    # SPFFT_EXCH_COMPACT_BUFFERED_FLOAT: double-precision transforms with a single-precision exchange
+    # (every kernel family, both transports); accuracy of a float exchange (details.rst:74)
+    cases += [c + (mode, capi.SPFFT_EXCH_COMPACT_BUFFERED_FLOAT) for mode in modes for c in cases_float_wire(world)]
+    for ttype, (nx, ny, nz), sdist, pdist, center, single, mode, exch in cases:
         os.environ["SPFFT_B200_P2P"] = mode
-        tol = 1e-5 if single else 1e-12
+        wire = exch != capi.SPFFT_EXCH_DEFAULT
+        tol = 1e-5 if single else (2e-6 if wire else 1e-12)
         trips, vals = [], []
         for r in range(world):
             t, v = gen.make(nx, ny, nz, hermitian=bool(ttype), center=center, num_ranks=world, rank=r,
@@ -79,7 +95,7 @@ def main():
         ref_back = orc.forward_distributed(params, ref_slabs, orc.SPFFT_FULL_SCALING)
 
         max_sticks = max(p.num_sticks for p in params)
-        grid = capi.DistributedGrid(lib, comm, nx, ny, nz, max_sticks, max(planes), single=single)
+        grid = capi.DistributedGrid(lib, comm, nx, ny, nz, max_sticks, max(planes), exchange_type=exch, single=single)
         t = grid.create_transform(capi.SPFFT_PU_GPU, ttype, nx, ny, nz, planes[rank], trips[rank])
         assert t.local_z_length() == planes[rank] and t.local_z_offset() == sum(planes[:rank])
         peer = capi.peer_exchange(t)
@@ -111,7 +127,11 @@ def main():
         good = eb <= tol and ef <= tol
         ok = ok and good
         worst = max(worst, eb / tol, ef / tol)
-        print(f"[rank {rank}] {'peer' if peer else 'nccl'} type={ttype} {nx}x{ny}x{nz} sticks={params[rank].num_sticks} planes={planes[rank]} "
+        if wire and world > 1 and nreal and sdist == [1.0] * world:
+            # the exchange really is single precision: a double-precision one would be 1e-15 accurate
+            good = good and eb > 1e-10
+            ok = ok and good
+        print(f"[rank {rank}] {'peer' if peer else 'nccl'}{' f32-wire' if wire else ''} type={ttype} {nx}x{ny}x{nz} sticks={params[rank].num_sticks} planes={planes[rank]} "
               f"bwd={eb:.2e} fwd={ef:.2e} {'ok' if good else 'FAIL'}", flush=True)
         t.destroy()
         grid.destroy()

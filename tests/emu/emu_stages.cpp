@@ -59,12 +59,7 @@ void run_z(bool fwd, const sb::ZArgs<T>& a, int b, sb::Ctx ctx, sb::cx<T>* smem)
     return;
   }
   sb::Ctx c{(1 << sb::FastLanes<T>::log2V) * (a.nz / 8)};
-#define CALL(NN)                                                                         \
-  if (a.inv) {                                                                           \
-    if (fwd) sb::z_forward_gather<T, NN>(a, b, c, smem); else sb::z_backward_gather<T, NN>(a, b, c, smem); \
-  } else {                                                                               \
-    if (fwd) sb::z_forward_fast<T, NN>(a, b, c, smem); else sb::z_backward_fast<T, NN>(a, b, c, smem);     \
-  }
+#define CALL(NN) if (fwd) sb::z_fast_any<T, NN, true>(a, b, c, smem); else sb::z_fast_any<T, NN, false>(a, b, c, smem)
   EMU_DISPATCH(a.nz, CALL)
 #undef CALL
 }
@@ -299,7 +294,8 @@ int run(int type, int dimX, int dimY, int dimZ, int n, const int* triplets, int 
 template <typename T>
 int run_distributed(int type, int dimX, int dimY, int dimZ, int P, const int* numLocal,
                     const int* const* triplets, const int* planesPerRank, int forward,
-                    const void* const* in, void* const* out, int scaling, int nthreads, int peerMode) {
+                    const void* const* in, void* const* out, int scaling, int nthreads, int peerMode,
+                    int wireF32) {
   try {
     std::vector<std::shared_ptr<IndexMaps>> maps(P);
     std::vector<std::vector<long long>> counts(P, std::vector<long long>(6));
@@ -382,6 +378,7 @@ int run_distributed(int type, int dimX, int dimY, int dimZ, int P, const int* nu
       ya.tileBase = x.tileBase.data();
       ya.tilePitch = x.tilePitch.data();
       ya.zRowOffset = 0;
+      ya.wireF32 = wireF32;
       return ya;
     };
     // block form of the exchange: rank r's block for d (stick side) <-> d's block from r (plane side)
@@ -390,6 +387,12 @@ int run_distributed(int type, int dimX, int dimY, int dimZ, int P, const int* nu
         for (int d = 0; d < P; ++d) {
           const long long n = exch[r].stickCount[d];
           if (n != exch[d].planeCount[r]) throw spfft::InternalError();
+          if (wireF32 && sizeof(T) == 8) {  // same element offsets, elements of cx<float>
+            auto* a = reinterpret_cast<sb::cx<float>*>(A[r].data()) + exch[r].stickOffset[d];
+            auto* q = reinterpret_cast<sb::cx<float>*>(Q[d].data()) + exch[d].planeOffset[r];
+            if (toPlanes) std::copy(a, a + n, q); else std::copy(q, q + n, a);
+            continue;
+          }
           sb::cx<T>* a = A[r].data() + exch[r].stickOffset[d];
           sb::cx<T>* q = Q[d].data() + exch[d].planeOffset[r];
           if (toPlanes) std::copy(a, a + n, q); else std::copy(q, q + n, a);
@@ -405,6 +408,7 @@ int run_distributed(int type, int dimX, int dimY, int dimZ, int P, const int* nu
           za.rowRank = exch[r].rowRank.data();
           za.rowOff = exch[r].rowOff.data();
         }
+        za.wireF32 = wireF32;
         for (int b = 0; b < za.numTiles; ++b) run_z<T>(false, za, b, ctx, smem.data());
       }
       if (!peerMode) exchange_blocks(true);
@@ -429,6 +433,7 @@ int run_distributed(int type, int dimX, int dimY, int dimZ, int P, const int* nu
         if (tiles[r].numStickTiles == 0 || numLocal[r] == 0) continue;
         auto za = make_z_args<T>(*maps[r], tiles[r], ax, ptrs[r], true, A[r].data(), nullptr,
                                  static_cast<T*>(out[r]), scaling != 0);
+        za.wireF32 = wireF32;
         for (int b = 0; b < za.numTiles; ++b) run_z<T>(true, za, b, ctx, smem.data());
       }
     }
@@ -449,11 +454,11 @@ extern "C" {
 int sb_emu_transform_distributed(int isFloat, int type, int dimX, int dimY, int dimZ, int numRanks,
                                  const int* numLocal, const int* const* triplets, const int* planesPerRank,
                                  int forward, const void* const* in, void* const* out, int scaling,
-                                 int nthreads, int peerMode) {
+                                 int nthreads, int peerMode, int wireF32) {
   return isFloat ? run_distributed<float>(type, dimX, dimY, dimZ, numRanks, numLocal, triplets, planesPerRank,
-                                          forward, in, out, scaling, nthreads, peerMode)
+                                          forward, in, out, scaling, nthreads, peerMode, wireF32)
                  : run_distributed<double>(type, dimX, dimY, dimZ, numRanks, numLocal, triplets, planesPerRank,
-                                           forward, in, out, scaling, nthreads, peerMode);
+                                           forward, in, out, scaling, nthreads, peerMode, wireF32);
 }
 
 // Whole local transform through the emulated stage kernels. forward == 0: `in` = values

@@ -210,7 +210,7 @@ def test_emulated_pipe_xy(emu, gen, shape, single, monkeypatch):
 
 
 # ---- distributed transforms: all ranks emulated in one process, peer-store and block exchange ------
-def _emu_distributed(emu, gen, ttype, shape, world, sdist, pdist, center, single, peer):
+def _emu_distributed(emu, gen, ttype, shape, world, sdist, pdist, center, single, peer, wire_f32=False):
     from conftest import hermitian_space_values
     nx, ny, nz = shape
     trips, vals = [], []
@@ -231,7 +231,7 @@ def _emu_distributed(emu, gen, ttype, shape, world, sdist, pdist, center, single
     ref_back = orc.forward_distributed(params, ref_slabs, orc.SPFFT_FULL_SCALING)
     cdt = np.complex64 if single else np.complex128
     sdt = (np.float32 if single else np.float64) if ttype else cdt
-    tol = 3e-6 if single else 1e-13
+    tol = 3e-6 if (single or wire_f32) else 1e-13
     n_loc = (C.c_int * world)(*[len(t) for t in trips])
     pl = (C.c_int * world)(*planes)
     flat = [np.ascontiguousarray(t.reshape(-1)) if len(t) else np.zeros(3, np.int32) for t in trips]
@@ -241,14 +241,14 @@ def _emu_distributed(emu, gen, ttype, shape, world, sdist, pdist, center, single
     pin = (C.c_void_p * world)(*[a.ctypes.data for a in vin])
     pout = (C.c_void_p * world)(*[a.ctypes.data for a in slabs])
     assert emu.sb_emu_transform_distributed(int(single), ttype, nx, ny, nz, world, n_loc, tp, pl, 0, pin, pout, 0, 64,
-                                            int(peer)) == 0
+                                            int(peer), int(wire_f32)) == 0
     for r in range(world):
         if planes[r]:
             assert orc.rel_l2(slabs[r][:planes[r] * ny * nx].reshape(planes[r], ny, nx), ref_slabs[r]) < tol
     back = [np.zeros(max(len(v), 1), dtype=cdt) for v in vals]
     pback = (C.c_void_p * world)(*[a.ctypes.data for a in back])
     assert emu.sb_emu_transform_distributed(int(single), ttype, nx, ny, nz, world, n_loc, tp, pl, 1, pout, pback, 1, 64,
-                                            int(peer)) == 0
+                                            int(peer), int(wire_f32)) == 0
     for r in range(world):
         if len(vals[r]):
             assert orc.rel_l2(back[r][:len(vals[r])], ref_back[r]) < tol
@@ -281,3 +281,29 @@ def test_emulated_distributed(emu, gen, case, world, peer):
     dists = {"uniform": [1.0] * world, "first": [1.0] + [0.0] * (world - 1), "last": [0.0] * (world - 1) + [1.0],
              "ramp": [1.0 + r for r in range(world)]}
     _emu_distributed(emu, gen, ttype, shape, world, dists[sname], dists[pname], center, single, peer)
+
+
+@pytest.mark.parametrize("case", [c for c in DIST_CASES if not c[5]],
+                         ids=lambda c: f"{'r2c' if c[0] else 'c2c'}-{'x'.join(map(str, c[1]))}-{c[2]}-{c[3]}")
+@pytest.mark.parametrize("peer", [1, 0], ids=["peer-stores", "block-exchange"])
+def test_emulated_distributed_float_wire(emu, gen, case, peer):
+    """SPFFT_EXCH_*_FLOAT: a double-precision distributed transform whose exchanged buffers hold cx<float>
+    (reference: complex_conversion.cuh:35-54 in the pack / unpack kernels). Accuracy is that of a
+    single-precision exchange (details.rst:74), everything else stays double; and the exchange must really
+    be single precision (the result differs from the double-precision exchange)."""
+    ttype, shape, sname, pname, center, single = case
+    world = 2
+    dists = {"uniform": [1.0] * world, "first": [1.0] + [0.0] * (world - 1), "last": [0.0] * (world - 1) + [1.0],
+             "ramp": [1.0 + r for r in range(world)]}
+    _emu_distributed(emu, gen, ttype, shape, world, dists[sname], dists[pname], center, False, peer, wire_f32=True)
+    if sname == "uniform":  # data really crosses ranks: a double-precision exchange would pass 1e-13
+        with pytest.raises(AssertionError):
+            _emu_distributed_strict(emu, gen, ttype, shape, world, dists[sname], dists[pname], center, peer)
+
+
+def _emu_distributed_strict(emu, gen, ttype, shape, world, sdist, pdist, center, peer):
+    """float wire format checked against the double tolerance (expected to fail)."""
+    import unittest.mock as mock
+    real = orc.rel_l2
+    with mock.patch.object(orc, "rel_l2", lambda a, b: real(a, b) * 1e7):  # 3e-6 * 1e-7 < 1e-12
+        _emu_distributed(emu, gen, ttype, shape, world, sdist, pdist, center, False, peer, wire_f32=True)
