@@ -349,23 +349,19 @@ SB_DEV void z_forward_fast3_impl(const ZArgs<T>& a, int tile, Ctx ctx, cx<T>* S)
   }
 }
 
-template <typename T, int N>
+template <typename T, int N, bool WIRE = false>
 SB_DEV void z_backward_fast3(const ZArgs<T>& a, int tile, Ctx ctx, cx<T>* S) {
-  with_wire_type<T>(a.wireF32, [&](auto w) {
-    if (a.inv)
-      z_backward_fast3_impl<T, N, true, decltype(w)>(a, tile, ctx, S);
-    else
-      z_backward_fast3_impl<T, N, false, decltype(w)>(a, tile, ctx, S);
-  });
+  if (a.inv)
+    z_backward_fast3_impl<T, N, true, WireElem<T, WIRE>>(a, tile, ctx, S);
+  else
+    z_backward_fast3_impl<T, N, false, WireElem<T, WIRE>>(a, tile, ctx, S);
 }
-template <typename T, int N>
+template <typename T, int N, bool WIRE = false>
 SB_DEV void z_forward_fast3(const ZArgs<T>& a, int tile, Ctx ctx, cx<T>* S) {
-  with_wire_type<T>(a.wireF32, [&](auto w) {
-    if (a.inv)
-      z_forward_fast3_impl<T, N, true, decltype(w)>(a, tile, ctx, S);
-    else
-      z_forward_fast3_impl<T, N, false, decltype(w)>(a, tile, ctx, S);
-  });
+  if (a.inv)
+    z_forward_fast3_impl<T, N, true, WireElem<T, WIRE>>(a, tile, ctx, S);
+  else
+    z_forward_fast3_impl<T, N, false, WireElem<T, WIRE>>(a, tile, ctx, S);
 }
 
 // -------------------------------------------------------------------------------------------
@@ -525,9 +521,9 @@ SB_DEV void y_backward_fast3_w(const YArgs<T>& a, int block, Ctx ctx, cx<T>* S) 
     y_backward_fast3_impl<T, N, false, W>(a, xt, zl, localRow, -1, nullptr, ctx, S);
   }
 }
-template <typename T, int N>
+template <typename T, int N, bool WIRE = false>
 SB_DEV void y_backward_fast3(const YArgs<T>& a, int block, Ctx ctx, cx<T>* S) {
-  with_wire_type<T>(a.wireF32, [&](auto w) { y_backward_fast3_w<T, N, decltype(w)>(a, block, ctx, S); });
+  y_backward_fast3_w<T, N, WireElem<T, WIRE>>(a, block, ctx, S);
 }
 
 template <typename T, int N, typename W>
@@ -550,9 +546,9 @@ SB_DEV void y_forward_fast3_w(const YArgs<T>& a, int block, Ctx ctx, cx<T>* S) {
     y_forward_fast3_impl<T, N, false, W>(a, xt, zl, localRow, nextXt, nextPlane, ctx, S);
   }
 }
-template <typename T, int N>
+template <typename T, int N, bool WIRE = false>
 SB_DEV void y_forward_fast3(const YArgs<T>& a, int block, Ctx ctx, cx<T>* S) {
-  with_wire_type<T>(a.wireF32, [&](auto w) { y_forward_fast3_w<T, N, decltype(w)>(a, block, ctx, S); });
+  y_forward_fast3_w<T, N, WireElem<T, WIRE>>(a, block, ctx, S);
 }
 
 // -------------------------------------------------------------------------------------------

@@ -3,16 +3,16 @@
 
 namespace sb {
 
-template <typename T, int N, bool FWD>
+template <typename T, int N, bool FWD, bool WIRE = false>
 __global__ void __launch_bounds__(Fast3Cfg<T, N>::threads, Fast3Cfg<T, N>::minBlocks)
     k_z_fast3(const __grid_constant__ ZArgs<T> a) {
   extern __shared__ __align__(16) unsigned char smemRaw[];
   cx<T>* S = reinterpret_cast<cx<T>*>(smemRaw);
   const Ctx ctx{Fast3Cfg<T, N>::threads};
   if (FWD)
-    z_forward_fast3<T, N>(a, (int)blockIdx.x, ctx, S);
+    z_forward_fast3<T, N, WIRE>(a, (int)blockIdx.x, ctx, S);
   else
-    z_backward_fast3<T, N>(a, (int)blockIdx.x, ctx, S);
+    z_backward_fast3<T, N, WIRE>(a, (int)blockIdx.x, ctx, S);
 }
 
 template <typename T, int N>
@@ -20,6 +20,14 @@ static int launch_z3_n(int forward, const ZArgs<T>& a0, cudaStream_t s) {
   using C = Fast3Cfg<T, N>;
   ZArgs<T> a = a0;
   a.pfDist = (tune_flags() & 1) ? resident_ctas(C::minBlocks) : 0;
+  if (a.wireF32) {  // single-precision wire format of a distributed double-precision transform
+    if constexpr (sizeof(T) == 8) {
+      return forward ? launch_fast(k_z_fast3<T, N, true, true>, a, a.numTiles, C::threads, C::smem, s)
+                     : launch_fast(k_z_fast3<T, N, false, true>, a, a.numTiles, C::threads, C::smem, s);
+    } else {
+      return (int)cudaErrorInvalidValue;
+    }
+  }
   return forward ? launch_fast(k_z_fast3<T, N, true>, a, a.numTiles, C::threads, C::smem, s)
                  : launch_fast(k_z_fast3<T, N, false>, a, a.numTiles, C::threads, C::smem, s);
 }

@@ -50,6 +50,21 @@ struct FastLanesX {
 #endif
 };
 
+// Cache policy of the dense-side global accesses of the stand-alone stage kernels (experiments:
+// -DSB_MEM_YB_ST=Mem::Stream ...). Every stage streams 3-4 GB through the 126 MB L2 once.
+#ifndef SB_MEM_YB_ST
+#define SB_MEM_YB_ST Mem::Plain
+#endif
+#ifndef SB_MEM_YF_LD
+#define SB_MEM_YF_LD Mem::Plain
+#endif
+#ifndef SB_MEM_X_LD
+#define SB_MEM_X_LD Mem::Plain
+#endif
+#ifndef SB_MEM_X_ST
+#define SB_MEM_X_ST Mem::Plain
+#endif
+
 // gather-form tiles (defined below)
 // (W = element type of the stick buffer: cx<T>, or cx<float> for the single-precision wire format of a
 // distributed double-precision transform; deduced from the row pointer)
@@ -416,17 +431,17 @@ SB_DEV void y_backward_fast_w(const YArgs<T>& a, int block, Ctx ctx, cx<T>* S) {
     // distributed, all sticks of this tile from one rank: contiguous inside that rank's block.
     // The gather form indexes relative to the tile's first stick, so pass row - xtStart[xt].
     const W* row = sticks + (size_t)a.tileBase[xt] + (size_t)zl * a.tilePitch[xt] - a.xtStart[xt];
-    y_backward_gather<T, N, Mem::Plain>(a, xt, row, a.planes + (size_t)zl * N * a.nxf, -1, (const W*)nullptr, ctx, S);
+    y_backward_gather<T, N, SB_MEM_YB_ST>(a, xt, row, a.planes + (size_t)zl * N * a.nxf, -1, (const W*)nullptr, ctx, S);
   } else if (a.inv && !a.srcBase)
-    y_backward_gather<T, N, Mem::Plain>(a, xt, sticks + (size_t)(zl + a.zRowOffset) * a.pitch,
+    y_backward_gather<T, N, SB_MEM_YB_ST>(a, xt, sticks + (size_t)(zl + a.zRowOffset) * a.pitch,
                                         a.planes + (size_t)zl * N * a.nxf, nextXt, nextRow, ctx, S);
   else
-    y_backward_tile<T, N, Mem::Plain, Mem::Plain>(a, xt, sticks + (size_t)(zl + a.zRowOffset) * a.pitch,
+    y_backward_tile<T, N, Mem::Plain, SB_MEM_YB_ST>(a, xt, sticks + (size_t)(zl + a.zRowOffset) * a.pitch,
                                                   a.planes + (size_t)zl * N * a.nxf, nextXt, nextRow, ctx, S, zl);
 }
-template <typename T, int N>
+template <typename T, int N, bool WIRE = false>
 SB_DEV void y_backward_fast(const YArgs<T>& a, int block, Ctx ctx, cx<T>* S) {
-  with_wire_type<T>(a.wireF32, [&](auto w) { y_backward_fast_w<T, N, decltype(w)>(a, block, ctx, S); });
+  y_backward_fast_w<T, N, WireElem<T, WIRE>>(a, block, ctx, S);
 }
 
 template <typename T, int N, typename W>
@@ -442,19 +457,19 @@ SB_DEV void y_forward_fast_w(const YArgs<T>& a, int block, Ctx ctx, cx<T>* S) {
   }
   if (a.srcBase && a.inv && a.tilePitch[xt] != 0) {
     W* row = y_dist_tile<T, true, W>(a, xt, zl) - a.xtStart[xt];
-    y_forward_gather<T, N, Mem::Plain>(a, xt, a.planes + (size_t)zl * N * a.nxf, row, nextXt, nextPlane, ctx, S);
+    y_forward_gather<T, N, SB_MEM_YF_LD>(a, xt, a.planes + (size_t)zl * N * a.nxf, row, nextXt, nextPlane, ctx, S);
   } else if (a.inv && !a.srcBase)
-    y_forward_gather<T, N, Mem::Plain>(a, xt, a.planes + (size_t)zl * N * a.nxf,
+    y_forward_gather<T, N, SB_MEM_YF_LD>(a, xt, a.planes + (size_t)zl * N * a.nxf,
                                        sticks + (size_t)(zl + a.zRowOffset) * a.pitch, nextXt, nextPlane,
                                        ctx, S);
   else
-    y_forward_tile<T, N, Mem::Plain, Mem::Plain>(a, xt, a.planes + (size_t)zl * N * a.nxf,
+    y_forward_tile<T, N, SB_MEM_YF_LD, Mem::Plain>(a, xt, a.planes + (size_t)zl * N * a.nxf,
                                                  sticks + (size_t)(zl + a.zRowOffset) * a.pitch, nextXt,
                                                  nextPlane, ctx, S, zl);
 }
-template <typename T, int N>
+template <typename T, int N, bool WIRE = false>
 SB_DEV void y_forward_fast(const YArgs<T>& a, int block, Ctx ctx, cx<T>* S) {
-  with_wire_type<T>(a.wireF32, [&](auto w) { y_forward_fast_w<T, N, decltype(w)>(a, block, ctx, S); });
+  y_forward_fast_w<T, N, WireElem<T, WIRE>>(a, block, ctx, S);
 }
 
 
@@ -590,22 +605,20 @@ SB_DEV void z_forward_gather(const ZArgs<T>& a, int tile, Ctx ctx, cx<T>* S) {
 }
 
 // z stage entry: inverse-map (gather) form when the values are in stick order, scatter form otherwise
-template <typename T, int N, bool FWD>
+template <typename T, int N, bool FWD, bool WIRE = false>
 SB_DEV void z_fast_any(const ZArgs<T>& a, int tile, Ctx ctx, cx<T>* S) {
-  with_wire_type<T>(a.wireF32, [&](auto w) {
-    using W = decltype(w);
-    if (a.inv) {
-      if (FWD)
-        z_forward_gather<T, N, W>(a, tile, ctx, S);
-      else
-        z_backward_gather<T, N, W>(a, tile, ctx, S);
-    } else {
-      if (FWD)
-        z_forward_fast<T, N, W>(a, tile, ctx, S);
-      else
-        z_backward_fast<T, N, W>(a, tile, ctx, S);
-    }
-  });
+  using W = WireElem<T, WIRE>;
+  if (a.inv) {
+    if (FWD)
+      z_forward_gather<T, N, W>(a, tile, ctx, S);
+    else
+      z_backward_gather<T, N, W>(a, tile, ctx, S);
+  } else {
+    if (FWD)
+      z_forward_fast<T, N, W>(a, tile, ctx, S);
+    else
+      z_backward_fast<T, N, W>(a, tile, ctx, S);
+  }
 }
 
 template <typename T, int N, Mem STP, bool TWS, typename W>
@@ -884,7 +897,7 @@ SB_DEV void x_c2c_fast(const XArgs<T>& a, int block, Ctx ctx, cx<T>* S) {
   const size_t planeOff = (size_t)zl * a.ny * N;
   const cx<T>* src = (BWD ? a.planes : static_cast<const cx<T>*>(a.spaceIn)) + planeOff;
   cx<T>* dst = (BWD ? static_cast<cx<T>*>(a.spaceOut) : a.planes) + planeOff;
-  x_c2c_tile<T, N, BWD, Mem::Plain, Mem::Plain, false, FastLanesX<T, N>::log2V, SwzX<sizeof(cx<T>)>>(
+  x_c2c_tile<T, N, BWD, SB_MEM_X_LD, SB_MEM_X_ST, false, FastLanesX<T, N>::log2V, SwzX<sizeof(cx<T>)>>(
       src, dst, rt * V, a.ny, a.ftw, nullptr, ctx, S);
 }
 

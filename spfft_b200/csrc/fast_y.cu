@@ -3,15 +3,15 @@
 
 namespace sb {
 
-template <typename T, int N, bool FWD>
+template <typename T, int N, bool FWD, bool WIRE = false>
 __global__ void __launch_bounds__(FastCfg<T, N>::threads, FastCfg<T, N>::minBlocks)
     k_y_fast(const __grid_constant__ YArgs<T> a) {
   extern __shared__ __align__(16) unsigned char smemRaw[];
   cx<T>* S = reinterpret_cast<cx<T>*>(smemRaw);
   if (FWD)
-    y_forward_fast<T, N>(a, (int)blockIdx.x, Ctx{FastCfg<T, N>::threads}, S);
+    y_forward_fast<T, N, WIRE>(a, (int)blockIdx.x, Ctx{FastCfg<T, N>::threads}, S);
   else
-    y_backward_fast<T, N>(a, (int)blockIdx.x, Ctx{FastCfg<T, N>::threads}, S);
+    y_backward_fast<T, N, WIRE>(a, (int)blockIdx.x, Ctx{FastCfg<T, N>::threads}, S);
 }
 
 template <typename T, int N>
@@ -22,6 +22,14 @@ static int launch_y_n(int forward, const YArgs<T>& a0, cudaStream_t s) {
   if constexpr (C::threads > 1024) {
     return (int)cudaErrorInvalidValue;
   } else {
+    if (a.wireF32) {  // single-precision wire format of a distributed double-precision transform
+      if constexpr (sizeof(T) == 8) {
+        return forward ? launch_fast(k_y_fast<T, N, true, true>, a, (long long)a.numXTiles * a.numPlanes, C::threads, C::smem, s)
+                       : launch_fast(k_y_fast<T, N, false, true>, a, (long long)a.numXTiles * a.numPlanes, C::threads, C::smem, s);
+      } else {
+        return (int)cudaErrorInvalidValue;
+      }
+    }
     return forward ? launch_fast(k_y_fast<T, N, true>, a, (long long)a.numXTiles * a.numPlanes, C::threads, C::smem, s)
                    : launch_fast(k_y_fast<T, N, false>, a, (long long)a.numXTiles * a.numPlanes, C::threads, C::smem, s);
   }

@@ -3,13 +3,13 @@
 
 namespace sb {
 
-template <typename T, int N, bool FWD>
+template <typename T, int N, bool FWD, bool WIRE = false>
 __global__ void __launch_bounds__(FastCfg<T, N>::threads, FastCfg<T, N>::minBlocks)
     k_z_fast(const __grid_constant__ ZArgs<T> a) {
   extern __shared__ __align__(16) unsigned char smemRaw[];
   cx<T>* S = reinterpret_cast<cx<T>*>(smemRaw);
   const Ctx ctx{FastCfg<T, N>::threads};
-  z_fast_any<T, N, FWD>(a, (int)blockIdx.x, ctx, S);
+  z_fast_any<T, N, FWD, WIRE>(a, (int)blockIdx.x, ctx, S);
 }
 
 template <typename T, int N>
@@ -20,6 +20,14 @@ static int launch_z_n(int forward, const ZArgs<T>& a0, cudaStream_t s) {
   if constexpr (C::threads > 1024) {
     return (int)cudaErrorInvalidValue;
   } else {
+    if (a.wireF32) {  // single-precision wire format of a distributed double-precision transform
+      if constexpr (sizeof(T) == 8) {
+        return forward ? launch_fast(k_z_fast<T, N, true, true>, a, a.numTiles, C::threads, C::smem, s)
+                       : launch_fast(k_z_fast<T, N, false, true>, a, a.numTiles, C::threads, C::smem, s);
+      } else {
+        return (int)cudaErrorInvalidValue;
+      }
+    }
     return forward ? launch_fast(k_z_fast<T, N, true>, a, a.numTiles, C::threads, C::smem, s)
                    : launch_fast(k_z_fast<T, N, false>, a, a.numTiles, C::threads, C::smem, s);
   }

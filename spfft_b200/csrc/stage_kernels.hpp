@@ -77,7 +77,21 @@ SB_HD W to_wire(cx<T> v) {
   r.y = static_cast<decltype(r.y)>(v.y);
   return r;
 }
-// Runs f(tag) with tag = cx<float>{} when the wire format is single precision, cx<T>{} otherwise.
+// Compile-time choice of the exchanged element type: the register-FFT kernels are instantiated once per
+// wire format (a run-time branch inside one kernel cost registers: +4 % on the y stage at 512^3).
+template <typename T, bool WIRE>
+struct WireElemOf {
+  using type = cx<T>;
+};
+template <>
+struct WireElemOf<double, true> {
+  using type = cx<float>;
+};
+template <typename T, bool WIRE>
+using WireElem = typename WireElemOf<T, WIRE>::type;
+
+// Runs f(tag) with tag = cx<float>{} when the wire format is single precision, cx<T>{} otherwise
+// (generic kernels only: one kernel serves both formats).
 template <typename T, typename F>
 SB_DEV void with_wire_type(int wireF32, F f) {
   if (sizeof(T) == 8 && wireF32)

@@ -53,13 +53,17 @@ void run_z(bool fwd, const sb::ZArgs<T>& a, int b, sb::Ctx ctx, sb::cx<T>* smem)
   }
   if (sb::is_fast3_length(a.nz)) {
     sb::Ctx c3{(1 << sb::FastLanes<T>::log2V) * (a.nz / 24)};
-#define CALL(NN) if (fwd) sb::z_forward_fast3<T, NN>(a, b, c3, smem); else sb::z_backward_fast3<T, NN>(a, b, c3, smem)
+#define CALL(NN)                                                                                               \
+  if (a.wireF32) { if (fwd) sb::z_forward_fast3<T, NN, true>(a, b, c3, smem); else sb::z_backward_fast3<T, NN, true>(a, b, c3, smem); } \
+  else { if (fwd) sb::z_forward_fast3<T, NN>(a, b, c3, smem); else sb::z_backward_fast3<T, NN>(a, b, c3, smem); }
     EMU_DISPATCH3(a.nz, CALL)
 #undef CALL
     return;
   }
   sb::Ctx c{(1 << sb::FastLanes<T>::log2V) * (a.nz / 8)};
-#define CALL(NN) if (fwd) sb::z_fast_any<T, NN, true>(a, b, c, smem); else sb::z_fast_any<T, NN, false>(a, b, c, smem)
+#define CALL(NN)                                                                                               \
+  if (a.wireF32) { if (fwd) sb::z_fast_any<T, NN, true, true>(a, b, c, smem); else sb::z_fast_any<T, NN, false, true>(a, b, c, smem); } \
+  else { if (fwd) sb::z_fast_any<T, NN, true>(a, b, c, smem); else sb::z_fast_any<T, NN, false>(a, b, c, smem); }
   EMU_DISPATCH(a.nz, CALL)
 #undef CALL
 }
@@ -71,13 +75,17 @@ void run_y(bool fwd, const sb::YArgs<T>& a, int b, sb::Ctx ctx, sb::cx<T>* smem)
   }
   if (sb::is_fast3_length(a.ny)) {
     sb::Ctx c3{(1 << sb::FastLanes<T>::log2V) * (a.ny / 24)};
-#define CALL(NN) if (fwd) sb::y_forward_fast3<T, NN>(a, b, c3, smem); else sb::y_backward_fast3<T, NN>(a, b, c3, smem)
+#define CALL(NN)                                                                                               \
+  if (a.wireF32) { if (fwd) sb::y_forward_fast3<T, NN, true>(a, b, c3, smem); else sb::y_backward_fast3<T, NN, true>(a, b, c3, smem); } \
+  else { if (fwd) sb::y_forward_fast3<T, NN>(a, b, c3, smem); else sb::y_backward_fast3<T, NN>(a, b, c3, smem); }
     EMU_DISPATCH3(a.ny, CALL)
 #undef CALL
     return;
   }
   sb::Ctx c{(1 << sb::FastLanes<T>::log2V) * (a.ny / 8)};
-#define CALL(NN) if (fwd) sb::y_forward_fast<T, NN>(a, b, c, smem); else sb::y_backward_fast<T, NN>(a, b, c, smem)
+#define CALL(NN)                                                                                               \
+  if (a.wireF32) { if (fwd) sb::y_forward_fast<T, NN, true>(a, b, c, smem); else sb::y_backward_fast<T, NN, true>(a, b, c, smem); } \
+  else { if (fwd) sb::y_forward_fast<T, NN>(a, b, c, smem); else sb::y_backward_fast<T, NN>(a, b, c, smem); }
   EMU_DISPATCH(a.ny, CALL)
 #undef CALL
 }
