@@ -70,7 +70,11 @@ SB_DEV void dit3_front(cx<T>* v, int j, const cx<T>* __restrict__ tw) {
     cx<T> a[3] = {v[m], v[8 + m], v[16 + m]};
     Butterfly<T, BWD, 3>::run(a);
     const int n2 = j + P::T * m;
+#if SB_TW_DERIVE
+    const cx<T> w1 = ld_ro(tw + n2), w2 = w1 * w1;  // one table read per element instead of two
+#else
     const cx<T> w1 = ld_ro(tw + n2), w2 = ld_ro(tw + P::M + n2);
+#endif
     v[m] = a[0];
     v[8 + m] = a[1] * (BWD ? conj(w1) : w1);
     v[16 + m] = a[2] * (BWD ? conj(w2) : w2);
@@ -83,7 +87,11 @@ SB_DEV void dif3_back(cx<T>* v, int j, const cx<T>* __restrict__ tw) {
 #pragma unroll
   for (int m = 0; m < 8; ++m) {
     const int k2 = j + P::T * m;
+#if SB_TW_DERIVE
+    const cx<T> w1 = ld_ro(tw + k2), w2 = w1 * w1;
+#else
     const cx<T> w1 = ld_ro(tw + k2), w2 = ld_ro(tw + P::M + k2);
+#endif
     cx<T> a[3] = {v[m], v[8 + m] * (BWD ? conj(w1) : w1), v[16 + m] * (BWD ? conj(w2) : w2)};
     Butterfly<T, BWD, 3>::run(a);
     v[m] = a[0];

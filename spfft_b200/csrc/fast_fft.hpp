@@ -64,6 +64,11 @@ struct SwzX {
 #define SB_MARK(ctx, id)
 #endif
 
+// 1: derive w^3, w^5, w^6, w^7 of a radix-8 stage from w^1, w^2, w^4 instead of reading them
+#ifndef SB_TW_DERIVE
+#define SB_TW_DERIVE 1
+#endif
+
 namespace sb {
 
 constexpr int ilog2_c(int n) { return n <= 1 ? 0 : 1 + ilog2_c(n >> 1); }
@@ -226,11 +231,28 @@ SB_DEV void fast_stage(cx<T>* v, int j, const cx<T>* __restrict__ tw) {
   if (S > 0) {  // R == 8 here
     const int k = j & (NS - 1);
     const cx<T>* t = tw + P::tw_offset(S) + k;
+#if SB_TW_DERIVE
+    // w^1, w^2, w^4 from the table, the other four powers by one or two multiplications: the L1 /
+    // shared-memory data pipe is the busiest unit of every stage kernel (ncu: 70-91 %) and the seven
+    // table reads of a thread cost as many wavefronts as its eight data loads; the fp64 pipe has room.
+    // Error of a derived power: ~2 ulp, far inside the 1e-12 budget of a length-N transform.
+    cx<T> w[8];
+    w[1] = TWS ? t[0] : ld_ro(t);
+    w[2] = TWS ? t[NS] : ld_ro(t + NS);
+    w[4] = TWS ? t[3 * NS] : ld_ro(t + 3 * NS);
+    w[3] = w[1] * w[2];
+    w[5] = w[4] * w[1];
+    w[6] = w[4] * w[2];
+    w[7] = w[4] * w[3];
+#pragma unroll
+    for (int r = 1; r < 8; ++r) v[r] = v[r] * (BWD ? conj(w[r]) : w[r]);
+#else
 #pragma unroll
     for (int r = 1; r < 8; ++r) {
       const cx<T> w = TWS ? t[(r - 1) * NS] : ld_ro(t + (r - 1) * NS);
       v[r] = v[r] * (BWD ? conj(w) : w);
     }
+#endif
   }
 #pragma unroll
   for (int i = 0; i < M; ++i) {
