@@ -32,6 +32,27 @@ __device__ __forceinline__ void trace_mark(int item, int id) {
   if (threadIdx.x == 0 && blockIdx.x < kTraceCtas && item >= 0 && item < kTraceItems)
     g_xy_trace[((size_t)blockIdx.x * kTraceItems + item) * kTraceMarks + id] = clock64();
 }
+// Dense-side stores through the tile buffer and one bulk copy (cp.async.bulk, async proxy) per tile row
+// instead of STG.128 per element: a 128-bit global store moves 64 bytes per wavefront of the L1 data pipe,
+// a shared-memory store 128, and the bulk copy none (profiles/r01_v4_summary.md). Experiment switch:
+// measured SLOWER (z backward 0.55 -> 0.64 ms, y backward 0.77 -> 0.89 ms at 512^3, r01_v4_bulk_store.log):
+// the two extra barriers and the wait on the bulk group cost more than the pipe work they save.
+#ifndef SB_BULK_STORE
+#define SB_BULK_STORE 0
+#endif
+#if SB_ON_GPU
+SB_DEV void bulk_store_row(void* gdst, const void* ssrc, unsigned bytes) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(ssrc);
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(sa), "r"(bytes)
+               : "memory");
+}
+SB_DEV void bulk_store_fence() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+SB_DEV void bulk_store_commit_wait() {
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+#endif
+
 // x stage (column mapping on both sides of every exchange), any lane count V <= 128 bytes / element:
 // 128 / ELEM consecutive slots form one 128-byte line = 128 / (ELEM * V) consecutive rows, and the
 // slot inside the line is XOR-permuted by a fold of n. Folds found by exhaustive search with the
@@ -307,6 +328,27 @@ struct SwzCol {
     return (n << LOG2V) + (lane ^ (f & ((1 << LOG2V) - 1)));
   }
 };
+
+// Dense-side stores through the tile buffer and one bulk copy (cp.async.bulk, async proxy) per tile row
+// instead of STG.128 per element: a 128-bit global store moves 64 bytes per wavefront of the L1 data pipe,
+// a shared-memory store 128, and the bulk copy none (profiles/r01_v4_summary.md). Experiment switch:
+// measured SLOWER (z backward 0.55 -> 0.64 ms, y backward 0.77 -> 0.89 ms at 512^3, r01_v4_bulk_store.log):
+// the two extra barriers and the wait on the bulk group cost more than the pipe work they save.
+#ifndef SB_BULK_STORE
+#define SB_BULK_STORE 0
+#endif
+#if SB_ON_GPU
+SB_DEV void bulk_store_row(void* gdst, const void* ssrc, unsigned bytes) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(ssrc);
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(sa), "r"(bytes)
+               : "memory");
+}
+SB_DEV void bulk_store_fence() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+SB_DEV void bulk_store_commit_wait() {
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+#endif
 
 // x stage (column mapping on both sides of every exchange), any lane count V <= 128 bytes / element:
 // 128 / ELEM consecutive slots form one 128-byte line = 128 / (ELEM * V) consecutive rows, and the

@@ -563,6 +563,27 @@ SB_DEV void z_backward_gather(const ZArgs<T>& a, int tile, Ctx ctx, cx<T>* S) {
   }
   SB_PHASE_END_NOSYNC
   fast_fft_head<T, N, LOG2V, true, SwzCol, true, false>(vAll, S, a.ftw, ctx);
+#if SB_ON_GPU && SB_BULK_STORE
+  {
+    W* R = reinterpret_cast<W*>(S);  // the finished tile, natural layout [row][lane]
+    SB_PHASE_BEGIN
+    SB_ROW_IDS
+    fast_fft_tail<T, N, LOG2V, true, SwzCol>(v, S, a.ftw, j, lane);
+    SB_PHASE_END  // every thread has read its inputs of the last stage
+    SB_PHASE_BEGIN
+    SB_ROW_IDS
+#pragma unroll
+    for (int m = 0; m < 8; ++m) R[((j + TT * m) << LOG2V) + lane] = to_wire<W>(v[m]);
+    bulk_store_fence();
+    SB_PHASE_END
+    SB_PHASE_BEGIN
+    for (int r = tid; r < N; r += nthr)
+      bulk_store_row(z_row<T, W>(a, r) + (size_t)tile * V, R + ((size_t)r << LOG2V), V * sizeof(W));
+    bulk_store_commit_wait();
+    SB_PHASE_END_NOSYNC
+    return;
+  }
+#endif
   SB_PHASE_BEGIN
   SB_ROW_IDS
   fast_fft_tail<T, N, LOG2V, true, SwzCol>(v, S, a.ftw, j, lane);
@@ -667,6 +688,19 @@ SB_DEV void y_backward_gather(const YArgs<T>& a, int xt, const W* stickRow, cx<T
   SB_PHASE_BEGIN
   SB_ROW_IDS
   fast_stage<T, N, true, FastPlan<N>::numStages - 1, TWS>(v, j, tw);
+#if SB_ON_GPU && SB_BULK_STORE
+  if (!TWS && ((a.nxf * sizeof(cx<T>)) & 15) == 0) {
+    // (every thread is past its last read of the tile buffer only after a barrier)
+    group_sync(ctx);
+#pragma unroll
+    for (int m = 0; m < 8; ++m) S[((j + TT * m) << LOG2V) + lane] = v[m];
+    bulk_store_fence();
+    group_sync(ctx);
+    for (int r = tid; r < N; r += nthr)
+      bulk_store_row(planeTile + (size_t)r * a.nxf, S + ((size_t)r << LOG2V), lanesValid * sizeof(cx<T>));
+    bulk_store_commit_wait();
+  } else
+#endif
   if (lane < lanesValid) {
 #pragma unroll
     for (int m = 0; m < 8; ++m) st_g<STP>(planeTile + (size_t)(j + TT * m) * a.nxf + lane, v[m]);
