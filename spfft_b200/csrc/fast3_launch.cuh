@@ -22,7 +22,9 @@ template <typename T, int N>
 struct Fast3Cfg {
   static constexpr int V = 1 << FastLanes<T>::log2V;
   static constexpr int threads = V * Fast3Plan<N>::T;
-  static constexpr int perSmThreads = sizeof(T) == 8 ? (N <= 192 ? SB_F3_PSM_F64 : 384) : (N <= 192 ? SB_F3_PSM_F32 : 512);
+  // (5 * 2^k: 40 values per thread -> no register cap for double, 168 for float)
+  static constexpr int perSmThreads = N % 5 == 0 ? (sizeof(T) == 8 ? 256 : 384)
+                                                 : (sizeof(T) == 8 ? (N <= 192 ? SB_F3_PSM_F64 : 384) : (N <= 192 ? SB_F3_PSM_F32 : 512));
   static constexpr int minBlocks = perSmThreads / threads > 16 ? 16 : (perSmThreads / threads < 1 ? 1 : perSmThreads / threads);
   static constexpr size_t smem = (size_t)N * V * sizeof(cx<T>);
 };
@@ -42,6 +44,9 @@ struct Fast3CfgX {
     case 192: CALL(192); break;                 \
     case 384: CALL(384); break;                 \
     case 768: CALL(768); break;                 \
+    case 160: CALL(160); break;                 \
+    case 320: CALL(320); break;                 \
+    case 640: CALL(640); break;                 \
     default: return (int)cudaErrorInvalidValue; \
   }
 

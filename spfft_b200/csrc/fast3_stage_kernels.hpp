@@ -1,7 +1,9 @@
 // fast3_stage_kernels.hpp -- register-FFT stage kernel bodies for transform lengths N = 3 * 2^k
 // (96, 192, 384, 768: the 2^a*3 grid sizes plane-wave codes pick between the powers of two, e.g.
-// the 192^3 band batches of BASELINE.json config 5). Same layouts, argument structs and semantics
-// as fast_stage_kernels.hpp (power-of-two lengths) and stage_kernels.hpp (any length).
+// the 192^3 band batches of BASELINE.json config 5) and, with G = 5 groups instead of 3 (a radix-5
+// step, 40 values per thread), N = 5 * 2^k (160, 320, 640). Same layouts, argument structs and
+// semantics as fast_stage_kernels.hpp (power-of-two lengths) and stage_kernels.hpp (any length).
+// The comments below describe G = 3; read "3" as G and "24" as 8*G.
 //
 // Every thread keeps 24 complex values = 3 groups of 8 in registers; a transform of length
 // N = 3*M is done by T = M/8 threads:
@@ -31,18 +33,22 @@
 
 namespace sb {
 
+// G = 3 or 5 groups: N = G * 2^k (the same scheme with a radix-5 step serves 160, 320, 640)
+constexpr int fast_group_count(int n) { return n % 5 == 0 ? 5 : 3; }
+
 template <int N>
 struct Fast3Plan {
-  static_assert(N % 3 == 0, "N = 3 * 2^k");
-  static constexpr int M = N / 3;
+  static constexpr int G = fast_group_count(N);
+  static_assert(N % G == 0, "N = 3 * 2^k or 5 * 2^k");
+  static constexpr int M = N / G;
   using Sub = FastPlan<M>;
-  static constexpr int T = M / 8;       // threads per transform
-  static constexpr int VPT = 24;        // values per thread
-  static constexpr int subTw = 2 * M;   // offset of the sub-transform stage twiddles
+  static constexpr int T = M / 8;             // threads per transform
+  static constexpr int VPT = 8 * G;           // values per thread
+  static constexpr int subTw = (G - 1) * M;   // offset of the sub-transform stage twiddles
   static_assert(Sub::numStages >= 2 && Sub::numStages <= 3, "32 <= M <= 512");
 };
 
-constexpr bool is_fast3_length(int n) { return n % 3 == 0; }
+constexpr bool is_fast3_length(int n) { return n % 3 == 0 || n % 5 == 0; }
 
 struct LaneJ {
   int lane, j;
@@ -61,42 +67,59 @@ SB_HD LaneJ fast_ids(int tid) {
   return r;
 }
 
-// radix-3 step + twiddles in front of the sub-transforms (DIT3)
+// w^r, r = 1 .. G-1, of one element: table [r-1][k], or w and its powers (SB_TW_DERIVE: one table read
+// per element; the L1 data pipe is the bottleneck unit, the fp64 pipe has room)
+template <typename T, int N, bool BWD>
+SB_DEV void group_twiddles(cx<T>* w, int k, const cx<T>* __restrict__ tw) {
+  using P = Fast3Plan<N>;
+#if SB_TW_DERIVE
+  w[1] = ld_ro(tw + k);
+  w[2] = w[1] * w[1];
+  if (P::G > 3) {
+    w[3] = w[2] * w[1];
+    w[4] = w[2] * w[2];
+  }
+#else
+#pragma unroll
+  for (int r = 1; r < P::G; ++r) w[r] = ld_ro(tw + (r - 1) * P::M + k);
+#endif
+  if (BWD) {
+#pragma unroll
+    for (int r = 1; r < P::G; ++r) w[r] = conj(w[r]);
+  }
+}
+// radix-G step + twiddles in front of the sub-transforms (DIT)
 template <typename T, int N, bool BWD>
 SB_DEV void dit3_front(cx<T>* v, int j, const cx<T>* __restrict__ tw) {
   using P = Fast3Plan<N>;
+  constexpr int G = P::G;
 #pragma unroll
   for (int m = 0; m < 8; ++m) {
-    cx<T> a[3] = {v[m], v[8 + m], v[16 + m]};
-    Butterfly<T, BWD, 3>::run(a);
-    const int n2 = j + P::T * m;
-#if SB_TW_DERIVE
-    const cx<T> w1 = ld_ro(tw + n2), w2 = w1 * w1;  // one table read per element instead of two
-#else
-    const cx<T> w1 = ld_ro(tw + n2), w2 = ld_ro(tw + P::M + n2);
-#endif
+    cx<T> a[G], w[G];
+#pragma unroll
+    for (int g = 0; g < G; ++g) a[g] = v[8 * g + m];
+    Butterfly<T, BWD, G>::run(a);
+    group_twiddles<T, N, BWD>(w, j + P::T * m, tw);
     v[m] = a[0];
-    v[8 + m] = a[1] * (BWD ? conj(w1) : w1);
-    v[16 + m] = a[2] * (BWD ? conj(w2) : w2);
+#pragma unroll
+    for (int g = 1; g < G; ++g) v[8 * g + m] = a[g] * w[g];
   }
 }
-// twiddles + radix-3 step behind the sub-transforms (DIF3)
+// twiddles + radix-G step behind the sub-transforms (DIF)
 template <typename T, int N, bool BWD>
 SB_DEV void dif3_back(cx<T>* v, int j, const cx<T>* __restrict__ tw) {
   using P = Fast3Plan<N>;
+  constexpr int G = P::G;
 #pragma unroll
   for (int m = 0; m < 8; ++m) {
-    const int k2 = j + P::T * m;
-#if SB_TW_DERIVE
-    const cx<T> w1 = ld_ro(tw + k2), w2 = w1 * w1;
-#else
-    const cx<T> w1 = ld_ro(tw + k2), w2 = ld_ro(tw + P::M + k2);
-#endif
-    cx<T> a[3] = {v[m], v[8 + m] * (BWD ? conj(w1) : w1), v[16 + m] * (BWD ? conj(w2) : w2)};
-    Butterfly<T, BWD, 3>::run(a);
-    v[m] = a[0];
-    v[8 + m] = a[1];
-    v[16 + m] = a[2];
+    cx<T> a[G], w[G];
+    group_twiddles<T, N, BWD>(w, j + P::T * m, tw);
+    a[0] = v[m];
+#pragma unroll
+    for (int g = 1; g < G; ++g) a[g] = v[8 * g + m] * w[g];
+    Butterfly<T, BWD, G>::run(a);
+#pragma unroll
+    for (int g = 0; g < G; ++g) v[8 * g + m] = a[g];
   }
 }
 
@@ -129,15 +152,18 @@ SB_DEV void fast3_head(cx<T>* vAll, cx<T>* S, const cx<T>* __restrict__ tw, Ctx 
   using P3 = Fast3Plan<N>;
   using P = typename P3::Sub;
   constexpr int M = P3::M;
+  constexpr int G = P3::G;
+  constexpr int VPT = 8 * G;
+  (void)VPT;
   constexpr int V = 1 << LOG2V;
   const cx<T>* stw = tw + P3::subTw;
   SB_PHASE_BEGIN
   (void)nthr;
-  cx<T>* v = SB_RP(vAll, 24);
+  cx<T>* v = SB_RP(vAll, VPT);
   const LaneJ id = fast_ids<LOG2V, P3::T, COL0>(tid);
   if (DIT) dit3_front<T, N, BWD>(v, id.j, tw);
 #pragma unroll
-  for (int g = 0; g < 3; ++g) {
+  for (int g = 0; g < G; ++g) {
     fast_stage<T, M, BWD, 0>(v + 8 * g, id.j, stw);
     sub_write<T, M, LOG2V, Swz, 0>(v + 8 * g, S + g * M * V, id.j, id.lane);
   }
@@ -145,20 +171,20 @@ SB_DEV void fast3_head(cx<T>* vAll, cx<T>* S, const cx<T>* __restrict__ tw, Ctx 
   if constexpr (P::numStages > 2) {
     SB_PHASE_BEGIN
     (void)nthr;
-    cx<T>* v = SB_RP(vAll, 24);
+    cx<T>* v = SB_RP(vAll, VPT);
     const LaneJ id = fast_ids<LOG2V, P3::T, COL>(tid);
 #pragma unroll
-    for (int g = 0; g < 3; ++g) {
+    for (int g = 0; g < G; ++g) {
       sub_read<T, M, LOG2V, Swz>(v + 8 * g, S + g * M * V, id.j, id.lane);
       fast_stage<T, M, BWD, 1>(v + 8 * g, id.j, stw);
     }
     SB_PHASE_END
     SB_PHASE_BEGIN
     (void)nthr;
-    cx<T>* v = SB_RP(vAll, 24);
+    cx<T>* v = SB_RP(vAll, VPT);
     const LaneJ id = fast_ids<LOG2V, P3::T, COL>(tid);
 #pragma unroll
-    for (int g = 0; g < 3; ++g) sub_write<T, M, LOG2V, Swz, 1>(v + 8 * g, S + g * M * V, id.j, id.lane);
+    for (int g = 0; g < G; ++g) sub_write<T, M, LOG2V, Swz, 1>(v + 8 * g, S + g * M * V, id.j, id.lane);
     SB_PHASE_END
   }
 }
@@ -170,10 +196,13 @@ SB_DEV void fast3_tail(cx<T>* v, const cx<T>* S, const cx<T>* __restrict__ tw, i
   using P3 = Fast3Plan<N>;
   using P = typename P3::Sub;
   constexpr int M = P3::M;
+  constexpr int G = P3::G;
+  constexpr int VPT = 8 * G;
+  (void)VPT;
   constexpr int V = 1 << LOG2V;
   const cx<T>* stw = tw + P3::subTw;
 #pragma unroll
-  for (int g = 0; g < 3; ++g) {
+  for (int g = 0; g < G; ++g) {
     sub_read<T, M, LOG2V, Swz>(v + 8 * g, S + g * M * V, j, lane);
     fast_stage<T, M, BWD, P::numStages - 1>(v + 8 * g, j, stw);
   }
@@ -255,20 +284,23 @@ SB_DEV void z_backward_fast3_impl(const ZArgs<T>& a, int tile, Ctx ctx, cx<T>* S
   constexpr int LOG2V = FastLanes<T>::log2V;
   constexpr int V = 1 << LOG2V;
   constexpr int TT = Fast3Plan<N>::T;
+  constexpr int G = Fast3Plan<N>::G;
+  constexpr int VPT = 8 * G;
+  (void)G;
   constexpr int THREADS = V * TT;
   using Swz = typename std::conditional<GATHER, SwzCol, SwzRow>::type;
-  SB_REGS(cx<T>, vAll, 24);
+  SB_REGS(cx<T>, vAll, VPT);
   const int e0 = a.tileStart[tile], e1 = a.tileStart[tile + 1];
   if (GATHER) {
     SB_PHASE_BEGIN
-    cx<T>* v = SB_RP(vAll, 24);
+    cx<T>* v = SB_RP(vAll, VPT);
     const LaneJ id = fast_ids<LOG2V, TT, true>(tid);
-    gather_load_v<T, N, TT, 24>(v, a.valuesIn + e0, a.inv + (size_t)tile * THREADS * 24, tid, id.j, id.lane,
+    gather_load_v<T, N, TT, VPT>(v, a.valuesIn + e0, a.inv + (size_t)tile * THREADS * VPT, tid, id.j, id.lane,
                                 tile == a.symTile ? a.symLane : -1);
     if (a.pfDist > 0 && tile + a.pfDist < a.numTiles) {
       const int p0 = a.tileStart[tile + a.pfDist], p1 = a.tileStart[tile + a.pfDist + 1];
       prefetch_l2(a.valuesIn + p0, (size_t)(p1 - p0) * sizeof(cx<T>), tid, nthr);
-      prefetch_l2(a.inv + (size_t)(tile + a.pfDist) * THREADS * 24, (size_t)THREADS * 48, tid, nthr);
+      prefetch_l2(a.inv + (size_t)(tile + a.pfDist) * THREADS * VPT, (size_t)THREADS * 2 * VPT, tid, nthr);
     }
     SB_PHASE_END_NOSYNC
   } else {
@@ -277,23 +309,23 @@ SB_DEV void z_backward_fast3_impl(const ZArgs<T>& a, int tile, Ctx ctx, cx<T>* S
     if (tile == a.symTile) hermitian_fill_lane_swz<T, LOG2V, SwzRow>(S, N, a.symLane, ctx);
     SB_PHASE_BEGIN
     (void)nthr;
-    cx<T>* v = SB_RP(vAll, 24);
+    cx<T>* v = SB_RP(vAll, VPT);
     const LaneJ id = fast_ids<LOG2V, TT, false>(tid);
 #pragma unroll
-    for (int m = 0; m < 24; ++m) v[m] = S[SwzRow::template at<LOG2V>(id.j + TT * m, id.lane)];
+    for (int m = 0; m < VPT; ++m) v[m] = S[SwzRow::template at<LOG2V>(id.j + TT * m, id.lane)];
     SB_PHASE_END
   }
   fast3_head<T, N, LOG2V, true, Swz, GATHER, false, true>(vAll, S, a.ftw, ctx);
   SB_PHASE_BEGIN
   (void)nthr;
-  cx<T>* v = SB_RP(vAll, 24);
+  cx<T>* v = SB_RP(vAll, VPT);
   const LaneJ id = fast_ids<LOG2V, TT, false>(tid);
   fast3_tail<T, N, LOG2V, true, Swz, true>(v, S, a.ftw, id.j, id.lane);
   const size_t col = (size_t)tile * V + id.lane;
 #pragma unroll
-  for (int k1 = 0; k1 < 3; ++k1) {
+  for (int k1 = 0; k1 < G; ++k1) {
 #pragma unroll
-    for (int m = 0; m < 8; ++m) z_row<T, W>(a, k1 + 3 * (id.j + TT * m))[col] = to_wire<W>(v[8 * k1 + m]);
+    for (int m = 0; m < 8; ++m) z_row<T, W>(a, k1 + G * (id.j + TT * m))[col] = to_wire<W>(v[8 * k1 + m]);
   }
   SB_PHASE_END_NOSYNC
 }
@@ -303,48 +335,51 @@ SB_DEV void z_forward_fast3_impl(const ZArgs<T>& a, int tile, Ctx ctx, cx<T>* S)
   constexpr int LOG2V = FastLanes<T>::log2V;
   constexpr int V = 1 << LOG2V;
   constexpr int TT = Fast3Plan<N>::T;
+  constexpr int G = Fast3Plan<N>::G;
+  constexpr int VPT = 8 * G;
+  (void)G;
   constexpr int THREADS = V * TT;
   using Swz = typename std::conditional<GATHER, SwzCol, SwzRow>::type;
-  SB_REGS(cx<T>, vAll, 24);
+  SB_REGS(cx<T>, vAll, VPT);
   const int e0 = a.tileStart[tile], e1 = a.tileStart[tile + 1];
   SB_PHASE_BEGIN
-  cx<T>* v = SB_RP(vAll, 24);
+  cx<T>* v = SB_RP(vAll, VPT);
   const LaneJ id = fast_ids<LOG2V, TT, false>(tid);
   const W* in = reinterpret_cast<const W*>(a.sticks) + (size_t)tile * V + id.lane;
 #pragma unroll
-  for (int n1 = 0; n1 < 3; ++n1) {
+  for (int n1 = 0; n1 < G; ++n1) {
 #pragma unroll
-    for (int m = 0; m < 8; ++m) v[8 * n1 + m] = from_wire<T>(in[(size_t)(n1 + 3 * (id.j + TT * m)) * a.pitch]);
+    for (int m = 0; m < 8; ++m) v[8 * n1 + m] = from_wire<T>(in[(size_t)(n1 + G * (id.j + TT * m)) * a.pitch]);
   }
   if (a.pfDist > 0 && tile + a.pfDist < a.numTiles) {
     for (int r = tid; r < N; r += nthr)
       prefetch_l2_line(reinterpret_cast<const W*>(a.sticks) + (size_t)(tile + a.pfDist) * V + (size_t)r * a.pitch);
-    if (GATHER) prefetch_l2(a.inv + (size_t)(tile + a.pfDist) * THREADS * 24, (size_t)THREADS * 48, tid, nthr);
+    if (GATHER) prefetch_l2(a.inv + (size_t)(tile + a.pfDist) * THREADS * VPT, (size_t)THREADS * 2 * VPT, tid, nthr);
   }
   SB_PHASE_END_NOSYNC
   fast3_head<T, N, LOG2V, false, Swz, false, GATHER, false>(vAll, S, a.ftw, ctx);
   if (GATHER) {
     SB_PHASE_BEGIN
     (void)nthr;
-    cx<T>* v = SB_RP(vAll, 24);
+    cx<T>* v = SB_RP(vAll, VPT);
     const LaneJ id = fast_ids<LOG2V, TT, true>(tid);
     fast3_tail<T, N, LOG2V, false, Swz, false>(v, S, a.ftw, id.j, id.lane);
-    gather_store_v<T, 24>(v, a.valuesOut + e0, a.inv + ((size_t)tile * THREADS + tid) * 24, a.useScale != 0,
+    gather_store_v<T, VPT>(v, a.valuesOut + e0, a.inv + ((size_t)tile * THREADS + tid) * VPT, a.useScale != 0,
                           a.scale);
     SB_PHASE_END_NOSYNC
   } else {
     SB_PHASE_BEGIN
     (void)nthr;
-    cx<T>* v = SB_RP(vAll, 24);
+    cx<T>* v = SB_RP(vAll, VPT);
     const LaneJ id = fast_ids<LOG2V, TT, false>(tid);
     fast3_tail<T, N, LOG2V, false, Swz, false>(v, S, a.ftw, id.j, id.lane);
     SB_PHASE_END  // every thread has read its inputs of the last stage
     SB_PHASE_BEGIN
     (void)nthr;
-    cx<T>* v = SB_RP(vAll, 24);
+    cx<T>* v = SB_RP(vAll, VPT);
     const LaneJ id = fast_ids<LOG2V, TT, false>(tid);
 #pragma unroll
-    for (int m = 0; m < 24; ++m) S[SwzRow::template at<LOG2V>(id.j + TT * m, id.lane)] = v[m];
+    for (int m = 0; m < VPT; ++m) S[SwzRow::template at<LOG2V>(id.j + TT * m, id.lane)] = v[m];
     SB_PHASE_END
     SB_PHASE_BEGIN
     for (int e = e0 + tid; e < e1; e += nthr) {
@@ -384,6 +419,9 @@ SB_DEV void y_backward_fast3_impl(const YArgs<T>& a, int xt, int zl, const W* st
   constexpr int LOG2V = FastLanes<T>::log2V;
   constexpr int V = 1 << LOG2V;
   constexpr int TT = Fast3Plan<N>::T;
+  constexpr int G = Fast3Plan<N>::G;
+  constexpr int VPT = 8 * G;
+  (void)G;
   constexpr int THREADS = V * TT;
   using Swz = typename std::conditional<GATHER, SwzCol, SwzRow>::type;
   const int e0 = a.xtStart[xt], e1 = a.xtStart[xt + 1];
@@ -400,12 +438,12 @@ SB_DEV void y_backward_fast3_impl(const YArgs<T>& a, int xt, int zl, const W* st
     SB_PHASE_END_NOSYNC
     return;
   }
-  SB_REGS(cx<T>, vAll, 24);
+  SB_REGS(cx<T>, vAll, VPT);
   if (GATHER) {
     SB_PHASE_BEGIN
-    cx<T>* v = SB_RP(vAll, 24);
+    cx<T>* v = SB_RP(vAll, VPT);
     const LaneJ id = fast_ids<LOG2V, TT, true>(tid);
-    gather_load_v<T, N, TT, 24>(v, stickRow + e0, a.inv + (size_t)xt * THREADS * 24, tid, id.j, id.lane,
+    gather_load_v<T, N, TT, VPT>(v, stickRow + e0, a.inv + (size_t)xt * THREADS * VPT, tid, id.j, id.lane,
                                 (a.symmetry && xt == 0) ? 0 : -1);
     if (nextXt >= 0) {
       const int p0 = a.xtStart[nextXt], p1 = a.xtStart[nextXt + 1];
@@ -423,24 +461,24 @@ SB_DEV void y_backward_fast3_impl(const YArgs<T>& a, int xt, int zl, const W* st
     if (a.symmetry && xt == 0) hermitian_fill_lane_swz<T, LOG2V, SwzRow>(S, N, 0, ctx);
     SB_PHASE_BEGIN
     (void)nthr;
-    cx<T>* v = SB_RP(vAll, 24);
+    cx<T>* v = SB_RP(vAll, VPT);
     const LaneJ id = fast_ids<LOG2V, TT, false>(tid);
 #pragma unroll
-    for (int m = 0; m < 24; ++m) v[m] = S[SwzRow::template at<LOG2V>(id.j + TT * m, id.lane)];
+    for (int m = 0; m < VPT; ++m) v[m] = S[SwzRow::template at<LOG2V>(id.j + TT * m, id.lane)];
     SB_PHASE_END
   }
   fast3_head<T, N, LOG2V, true, Swz, GATHER, false, true>(vAll, S, a.ftw, ctx);
   SB_PHASE_BEGIN
   (void)nthr;
-  cx<T>* v = SB_RP(vAll, 24);
+  cx<T>* v = SB_RP(vAll, VPT);
   const LaneJ id = fast_ids<LOG2V, TT, false>(tid);
   fast3_tail<T, N, LOG2V, true, Swz, true>(v, S, a.ftw, id.j, id.lane);
   if (id.lane < lanesValid) {
 #pragma unroll
-    for (int k1 = 0; k1 < 3; ++k1) {
+    for (int k1 = 0; k1 < G; ++k1) {
 #pragma unroll
       for (int m = 0; m < 8; ++m)
-        planeTile[(size_t)(k1 + 3 * (id.j + TT * m)) * a.nxf + id.lane] = v[8 * k1 + m];
+        planeTile[(size_t)(k1 + G * (id.j + TT * m)) * a.nxf + id.lane] = v[8 * k1 + m];
     }
   }
   SB_PHASE_END_NOSYNC
@@ -453,21 +491,24 @@ SB_DEV void y_forward_fast3_impl(const YArgs<T>& a, int xt, int zl, W* stickRow,
   constexpr int LOG2V = FastLanes<T>::log2V;
   constexpr int V = 1 << LOG2V;
   constexpr int TT = Fast3Plan<N>::T;
+  constexpr int G = Fast3Plan<N>::G;
+  constexpr int VPT = 8 * G;
+  (void)G;
   constexpr int THREADS = V * TT;
   using Swz = typename std::conditional<GATHER, SwzCol, SwzRow>::type;
   const int e0 = a.xtStart[xt], e1 = a.xtStart[xt + 1];
   if (e0 == e1) return;  // no stick needs these columns
   const cx<T>* planeTile = a.planes + (size_t)zl * N * a.nxf + (size_t)xt * V;
   const int lanesValid = (a.nxf - xt * V) < V ? (a.nxf - xt * V) : V;
-  SB_REGS(cx<T>, vAll, 24);
+  SB_REGS(cx<T>, vAll, VPT);
   SB_PHASE_BEGIN
-  cx<T>* v = SB_RP(vAll, 24);
+  cx<T>* v = SB_RP(vAll, VPT);
   const LaneJ id = fast_ids<LOG2V, TT, false>(tid);
 #pragma unroll
-  for (int n1 = 0; n1 < 3; ++n1) {
+  for (int n1 = 0; n1 < G; ++n1) {
 #pragma unroll
     for (int m = 0; m < 8; ++m)
-      v[8 * n1 + m] = id.lane < lanesValid ? planeTile[(size_t)(n1 + 3 * (id.j + TT * m)) * a.nxf + id.lane]
+      v[8 * n1 + m] = id.lane < lanesValid ? planeTile[(size_t)(n1 + G * (id.j + TT * m)) * a.nxf + id.lane]
                                            : mk<T>(0, 0);
   }
   if (nextXt >= 0) {
@@ -478,24 +519,24 @@ SB_DEV void y_forward_fast3_impl(const YArgs<T>& a, int xt, int zl, W* stickRow,
   if (GATHER) {
     SB_PHASE_BEGIN
     (void)nthr;
-    cx<T>* v = SB_RP(vAll, 24);
+    cx<T>* v = SB_RP(vAll, VPT);
     const LaneJ id = fast_ids<LOG2V, TT, true>(tid);
     fast3_tail<T, N, LOG2V, false, Swz, false>(v, S, a.ftw, id.j, id.lane);
-    gather_store_v<T, 24>(v, stickRow + e0, a.inv + ((size_t)xt * THREADS + tid) * 24, false, T(1));
+    gather_store_v<T, VPT>(v, stickRow + e0, a.inv + ((size_t)xt * THREADS + tid) * VPT, false, T(1));
     SB_PHASE_END_NOSYNC
   } else {
     SB_PHASE_BEGIN
     (void)nthr;
-    cx<T>* v = SB_RP(vAll, 24);
+    cx<T>* v = SB_RP(vAll, VPT);
     const LaneJ id = fast_ids<LOG2V, TT, false>(tid);
     fast3_tail<T, N, LOG2V, false, Swz, false>(v, S, a.ftw, id.j, id.lane);
     SB_PHASE_END
     SB_PHASE_BEGIN
     (void)nthr;
-    cx<T>* v = SB_RP(vAll, 24);
+    cx<T>* v = SB_RP(vAll, VPT);
     const LaneJ id = fast_ids<LOG2V, TT, false>(tid);
 #pragma unroll
-    for (int m = 0; m < 24; ++m) S[SwzRow::template at<LOG2V>(id.j + TT * m, id.lane)] = v[m];
+    for (int m = 0; m < VPT; ++m) S[SwzRow::template at<LOG2V>(id.j + TT * m, id.lane)] = v[m];
     SB_PHASE_END
     SB_PHASE_BEGIN
     for (int e = e0 + tid; e < e1; e += nthr) {
@@ -580,22 +621,25 @@ SB_DEV void dit3_to_natural(cx<T>* vAll, cx<T>* S, Ctx ctx) {
   (void)ctx;
   using SwzCol = SwzX<sizeof(cx<T>)>;
   constexpr int TT = Fast3Plan<N>::T;
+  constexpr int G = Fast3Plan<N>::G;
+  constexpr int VPT = 8 * G;
+  (void)G;
   SB_PHASE_BEGIN  // (the caller's last phase ended with a barrier: every thread is done reading S)
   (void)nthr;
-  cx<T>* v = SB_RP(vAll, 24);
+  cx<T>* v = SB_RP(vAll, VPT);
   const LaneJ id = fast_ids<LOG2V, TT, true>(tid);
 #pragma unroll
-  for (int k1 = 0; k1 < 3; ++k1) {
+  for (int k1 = 0; k1 < G; ++k1) {
 #pragma unroll
-    for (int m = 0; m < 8; ++m) S[SwzCol::template at<LOG2V>(k1 + 3 * (id.j + TT * m), id.lane)] = v[8 * k1 + m];
+    for (int m = 0; m < 8; ++m) S[SwzCol::template at<LOG2V>(k1 + G * (id.j + TT * m), id.lane)] = v[8 * k1 + m];
   }
   SB_PHASE_END
   SB_PHASE_BEGIN
   (void)nthr;
-  cx<T>* v = SB_RP(vAll, 24);
+  cx<T>* v = SB_RP(vAll, VPT);
   const LaneJ id = fast_ids<LOG2V, TT, true>(tid);
 #pragma unroll
-  for (int m = 0; m < 24; ++m) v[m] = S[SwzCol::template at<LOG2V>(id.j + TT * m, id.lane)];
+  for (int m = 0; m < VPT; ++m) v[m] = S[SwzCol::template at<LOG2V>(id.j + TT * m, id.lane)];
   SB_PHASE_END_NOSYNC
 }
 
@@ -605,6 +649,9 @@ SB_DEV void x_c2c_fast3(const XArgs<T>& a, int block, Ctx ctx, cx<T>* S) {
   using SwzCol = SwzX<sizeof(cx<T>)>;
   constexpr int V = 1 << LOG2V;
   constexpr int TT = Fast3Plan<N>::T;
+  constexpr int G = Fast3Plan<N>::G;
+  constexpr int VPT = 8 * G;
+  (void)G;
   constexpr bool DIT = SB_X3_MODE != 1;
   const int rt = block % a.numRowTiles;
   const int zl = block / a.numRowTiles;
@@ -612,28 +659,28 @@ SB_DEV void x_c2c_fast3(const XArgs<T>& a, int block, Ctx ctx, cx<T>* S) {
   const cx<T>* in = (BWD ? a.planes : static_cast<const cx<T>*>(a.spaceIn)) + planeOff;
   cx<T>* out = (BWD ? static_cast<cx<T>*>(a.spaceOut) : a.planes) + planeOff;
   const int y0 = rt * V;
-  SB_REGS(cx<T>, vAll, 24);
+  SB_REGS(cx<T>, vAll, VPT);
   SB_PHASE_BEGIN
   (void)nthr;
-  cx<T>* v = SB_RP(vAll, 24);
+  cx<T>* v = SB_RP(vAll, VPT);
   const LaneJ id = fast_ids<LOG2V, TT, true>(tid);
   const bool valid = y0 + id.lane < a.ny;
   const cx<T>* src = in + (size_t)(y0 + id.lane) * N;
   if (DIT) {
 #pragma unroll
-    for (int m = 0; m < 24; ++m) v[m] = valid ? src[id.j + TT * m] : mk<T>(0, 0);
+    for (int m = 0; m < VPT; ++m) v[m] = valid ? src[id.j + TT * m] : mk<T>(0, 0);
   } else {
 #pragma unroll
     for (int m = 0; m < 8; ++m) {
 #pragma unroll
-      for (int n1 = 0; n1 < 3; ++n1) v[8 * n1 + m] = valid ? src[n1 + 3 * (id.j + TT * m)] : mk<T>(0, 0);
+      for (int n1 = 0; n1 < G; ++n1) v[8 * n1 + m] = valid ? src[n1 + G * (id.j + TT * m)] : mk<T>(0, 0);
     }
   }
   SB_PHASE_END_NOSYNC
   fast3_head<T, N, LOG2V, BWD, SwzCol, true, true, DIT>(vAll, S, a.ftw, ctx);
   SB_PHASE_BEGIN
   (void)nthr;
-  cx<T>* v = SB_RP(vAll, 24);
+  cx<T>* v = SB_RP(vAll, VPT);
   const LaneJ id = fast_ids<LOG2V, TT, true>(tid);
   fast3_tail<T, N, LOG2V, BWD, SwzCol, DIT>(v, S, a.ftw, id.j, id.lane);
   if (SB_X3_MODE == 0 && y0 + id.lane < a.ny) {
@@ -641,7 +688,7 @@ SB_DEV void x_c2c_fast3(const XArgs<T>& a, int block, Ctx ctx, cx<T>* S) {
 #pragma unroll
     for (int m = 0; m < 8; ++m) {
 #pragma unroll
-      for (int k1 = 0; k1 < 3; ++k1) dst[k1 + 3 * (id.j + TT * m)] = v[8 * k1 + m];
+      for (int k1 = 0; k1 < G; ++k1) dst[k1 + G * (id.j + TT * m)] = v[8 * k1 + m];
     }
   }
   SB_PHASE_END_IF(SB_X3_MODE == 2)
@@ -649,12 +696,12 @@ SB_DEV void x_c2c_fast3(const XArgs<T>& a, int block, Ctx ctx, cx<T>* S) {
     if (SB_X3_MODE == 2) dit3_to_natural<T, N, LOG2V>(vAll, S, ctx);
     SB_PHASE_BEGIN
     (void)nthr;
-    cx<T>* v = SB_RP(vAll, 24);
+    cx<T>* v = SB_RP(vAll, VPT);
     const LaneJ id = fast_ids<LOG2V, TT, true>(tid);
     if (y0 + id.lane < a.ny) {
       cx<T>* dst = out + (size_t)(y0 + id.lane) * N + id.j;
 #pragma unroll
-      for (int m = 0; m < 24; ++m) dst[TT * m] = v[m];
+      for (int m = 0; m < VPT; ++m) dst[TT * m] = v[m];
     }
     SB_PHASE_END_NOSYNC
   }
@@ -667,30 +714,33 @@ SB_DEV void x_r2c_fast3(const XArgs<T>& a, int block, Ctx ctx, cx<T>* S) {
   using SwzCol = SwzX<sizeof(cx<T>)>;
   constexpr int V = 1 << LOG2V;
   constexpr int TT = Fast3Plan<N>::T;
+  constexpr int G = Fast3Plan<N>::G;
+  constexpr int VPT = 8 * G;
+  (void)G;
   constexpr int NXF = N / 2 + 1;
   constexpr bool DIT = SB_X3_MODE != 1;
   const int rt = block % a.numRowTiles;  // numRowTiles = ceil(ny / 2V), stage_args.hpp
   const int zl = block / a.numRowTiles;
   const int y0 = rt * 2 * V;
   const size_t planeRow0 = (size_t)zl * a.ny;
-  SB_REGS(cx<T>, vAll, 24);
+  SB_REGS(cx<T>, vAll, VPT);
 #define SB_PAIR_IDS                                          \
-  cx<T>* v = SB_RP(vAll, 24);                                \
+  cx<T>* v = SB_RP(vAll, VPT);                                \
   const LaneJ id = fast_ids<LOG2V, TT, true>(tid);           \
   const int yA = y0 + 2 * id.lane;                           \
   const bool validA = yA < a.ny;                             \
   const bool validB = yA + 1 < a.ny;                         \
   (void)nthr;
   // element held in register r before the transform / after it
-#define SB_IN_INDEX(r) (DIT ? id.j + TT * (r) : (r) / 8 + 3 * (id.j + TT * ((r) % 8)))
-#define SB_OUT_INDEX(r) (DIT ? (r) / 8 + 3 * (id.j + TT * ((r) % 8)) : id.j + TT * (r))
+#define SB_IN_INDEX(r) (DIT ? id.j + TT * (r) : (r) / 8 + G * (id.j + TT * ((r) % 8)))
+#define SB_OUT_INDEX(r) (DIT ? (r) / 8 + G * (id.j + TT * ((r) % 8)) : id.j + TT * (r))
   SB_PHASE_BEGIN
   SB_PAIR_IDS
   if (BWD) {
     const cx<T>* srcA = a.planes + (planeRow0 + yA) * NXF;
     const cx<T>* srcB = srcA + NXF;
 #pragma unroll
-    for (int r = 0; r < 24; ++r) {
+    for (int r = 0; r < VPT; ++r) {
       const int n = SB_IN_INDEX(r);
       const bool hi = n >= NXF;
       const int x = hi ? N - n : n;
@@ -702,7 +752,7 @@ SB_DEV void x_r2c_fast3(const XArgs<T>& a, int block, Ctx ctx, cx<T>* S) {
     const T* srcA = static_cast<const T*>(a.spaceIn) + (planeRow0 + yA) * N;
     const T* srcB = srcA + N;
 #pragma unroll
-    for (int r = 0; r < 24; ++r) {
+    for (int r = 0; r < VPT; ++r) {
       const int n = SB_IN_INDEX(r);
       v[r] = mk<T>(validA ? srcA[n] : T(0), validB ? srcB[n] : T(0));
     }
@@ -717,7 +767,7 @@ SB_DEV void x_r2c_fast3(const XArgs<T>& a, int block, Ctx ctx, cx<T>* S) {
       T* dstA = static_cast<T*>(a.spaceOut) + (planeRow0 + yA) * N;
       T* dstB = dstA + N;
 #pragma unroll
-      for (int r = 0; r < 24; ++r) {
+      for (int r = 0; r < VPT; ++r) {
         const int k = SB_OUT_INDEX(r);
         if (validA) dstA[k] = v[r].x;
         if (validB) dstB[k] = v[r].y;
@@ -731,7 +781,7 @@ SB_DEV void x_r2c_fast3(const XArgs<T>& a, int block, Ctx ctx, cx<T>* S) {
       T* dstA = static_cast<T*>(a.spaceOut) + (planeRow0 + yA) * N;
       T* dstB = dstA + N;
 #pragma unroll
-      for (int r = 0; r < 24; ++r) {
+      for (int r = 0; r < VPT; ++r) {
         if (validA) dstA[id.j + TT * r] = v[r].x;
         if (validB) dstB[id.j + TT * r] = v[r].y;
       }
@@ -749,14 +799,14 @@ SB_DEV void x_r2c_fast3(const XArgs<T>& a, int block, Ctx ctx, cx<T>* S) {
     (void)validA;
     (void)validB;
 #pragma unroll
-    for (int r = 0; r < 24; ++r) S[SwzCol::template at<LOG2V>(SB_OUT_INDEX(r), id.lane)] = v[r];
+    for (int r = 0; r < VPT; ++r) S[SwzCol::template at<LOG2V>(SB_OUT_INDEX(r), id.lane)] = v[r];
     SB_PHASE_END
     SB_PHASE_BEGIN
     SB_PAIR_IDS
     cx<T>* dstA = a.planes + (planeRow0 + yA) * NXF;
     cx<T>* dstB = dstA + NXF;
 #pragma unroll
-    for (int r = 0; r < 24; ++r) {
+    for (int r = 0; r < VPT; ++r) {
       const int k = id.j + TT * r;
       if (k < NXF) {
         const cx<T> zk = DIT ? S[SwzCol::template at<LOG2V>(k, id.lane)] : v[r];

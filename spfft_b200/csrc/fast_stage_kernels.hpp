@@ -38,7 +38,7 @@ struct FastLanes {
 // V = 128 / (N/8) for the power-of-two kernels and 64 / (N/24) for the 3*2^k ones, within 1..8.
 // SB_LOG2VX: build-time override (experiments).
 constexpr int x_lanes_log2(int n) {
-  const int target = n % 3 == 0 ? 1536 / n : 1024 / n;  // rows for the CTA size above
+  const int target = n % 5 == 0 ? 2560 / n : (n % 3 == 0 ? 1536 / n : 1024 / n);  // rows for the CTA size above
   return target >= 8 ? 3 : (target >= 4 ? 2 : (target >= 2 ? 1 : 0));
 }
 template <typename T, int N>

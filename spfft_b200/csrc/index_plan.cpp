@@ -463,6 +463,10 @@ template std::vector<sb::cx<float>> make_roots<float>(int);
 template std::vector<sb::cx<double>> make_roots<double>(int);
 
 bool fast_path_length(int n, int complexBytes) {
+  if (n % 5 == 0) {  // 5 * 2^k: 160, 320, 640 (fast3_stage_kernels.hpp, 40 values per thread)
+    const int m = n / 5;
+    return m >= 32 && m <= 128 && (m & (m - 1)) == 0;
+  }
   if (n % 3 == 0) {  // 3 * 2^k, sub-transforms of 32 .. 256 (fast3_stage_kernels.hpp)
     const int m = n / 3;
     return m >= 32 && m <= 256 && (m & (m - 1)) == 0;
@@ -481,7 +485,7 @@ int fast_path_log2_lanes_x(int n) {
 #endif
 }
 
-int fast_path_values_per_thread(int n) { return n % 3 == 0 ? 24 : 8; }
+int fast_path_values_per_thread(int n) { return n % 5 == 0 ? 40 : (n % 3 == 0 ? 24 : 8); }
 
 int fast_path_log2_lanes(int complexBytes) {
   return complexBytes == 16 ? sb::FastLanes<double>::log2V : sb::FastLanes<float>::log2V;
@@ -491,10 +495,11 @@ template <typename T>
 std::vector<sb::cx<T>> make_fast_twiddles(int n) {
   std::vector<sb::cx<T>> w;
   const long double twoPiL = 6.283185307179586476925286766559005768L;
-  if (n > 0 && n % 3 == 0) {
-    // N = 3*M: [r-1][k] = exp(-2*pi*i*r*k/N), r = 1,2, k < M, then the stage twiddles of length M
-    const int m = n / 3;
-    for (int r = 1; r <= 2; ++r) {
+  if (n > 0 && (n % 3 == 0 || n % 5 == 0)) {
+    // N = G*M: [r-1][k] = exp(-2*pi*i*r*k/N), r = 1 .. G-1, k < M, then the stage twiddles of length M
+    const int groups = n % 5 == 0 ? 5 : 3;
+    const int m = n / groups;
+    for (int r = 1; r < groups; ++r) {
       for (int k = 0; k < m; ++k) {
         const long double a = twoPiL * static_cast<long double>(r * k) / static_cast<long double>(n);
         sb::cx<T> v;

@@ -64,6 +64,7 @@ def main():
         (0, (96, 96, 96), uniform, uniform, True, False),
         (1, (192, 96, 32), uniform, [1.0 + r for r in range(world)], False, False),
         (0, (32, 192, 96), first, last, True, True),
+        (0, (160, 32, 160), uniform, [1.0 + r for r in range(world)], True, False),
     ]
     worst = 0.0
     ok = True

@@ -42,6 +42,9 @@ namespace {
     case 192: CALL(192); break; \
     case 384: CALL(384); break; \
     case 768: CALL(768); break; \
+    case 160: CALL(160); break; \
+    case 320: CALL(320); break; \
+    case 640: CALL(640); break; \
     default: throw spfft::InternalError(); \
   }
 
@@ -52,7 +55,7 @@ void run_z(bool fwd, const sb::ZArgs<T>& a, int b, sb::Ctx ctx, sb::cx<T>* smem)
     return;
   }
   if (sb::is_fast3_length(a.nz)) {
-    sb::Ctx c3{(1 << sb::FastLanes<T>::log2V) * (a.nz / 24)};
+    sb::Ctx c3{(1 << sb::FastLanes<T>::log2V) * (a.nz / fast_path_values_per_thread(a.nz))};
 #define CALL(NN)                                                                                               \
   if (a.wireF32) { if (fwd) sb::z_forward_fast3<T, NN, true>(a, b, c3, smem); else sb::z_backward_fast3<T, NN, true>(a, b, c3, smem); } \
   else { if (fwd) sb::z_forward_fast3<T, NN>(a, b, c3, smem); else sb::z_backward_fast3<T, NN>(a, b, c3, smem); }
@@ -74,7 +77,7 @@ void run_y(bool fwd, const sb::YArgs<T>& a, int b, sb::Ctx ctx, sb::cx<T>* smem)
     return;
   }
   if (sb::is_fast3_length(a.ny)) {
-    sb::Ctx c3{(1 << sb::FastLanes<T>::log2V) * (a.ny / 24)};
+    sb::Ctx c3{(1 << sb::FastLanes<T>::log2V) * (a.ny / fast_path_values_per_thread(a.ny))};
 #define CALL(NN)                                                                                               \
   if (a.wireF32) { if (fwd) sb::y_forward_fast3<T, NN, true>(a, b, c3, smem); else sb::y_backward_fast3<T, NN, true>(a, b, c3, smem); } \
   else { if (fwd) sb::y_forward_fast3<T, NN>(a, b, c3, smem); else sb::y_backward_fast3<T, NN>(a, b, c3, smem); }
@@ -96,7 +99,7 @@ void run_x(bool fwd, const sb::XArgs<T>& a, int b, sb::Ctx ctx, sb::cx<T>* smem)
     return;
   }
   if (sb::is_fast3_length(a.nx)) {
-    sb::Ctx c3{(1 << fast_path_log2_lanes_x(a.nx)) * (a.nx / 24)};
+    sb::Ctx c3{(1 << fast_path_log2_lanes_x(a.nx)) * (a.nx / fast_path_values_per_thread(a.nx))};
 #define CALL(NN)                                                                                       \
   if (a.r2c) {                                                                                         \
     if (fwd) sb::x_r2c_fast3<T, NN, false>(a, b, c3, smem); else sb::x_r2c_fast3<T, NN, true>(a, b, c3, smem); \
@@ -198,7 +201,7 @@ int run(int type, int dimX, int dimY, int dimZ, int n, const int* triplets, int 
       if (ax.log2Vz > maxLog2V) ax.log2Vz = maxLog2V;
     }
     // fused xy stage exactly when the product (with its opt-in flag) fuses: one tile shape for y and x
-    const bool fusedShape = fastX && fastY && dimX == dimY && type == SPFFT_TRANS_C2C && dimX % 3 != 0;
+    const bool fusedShape = fastX && fastY && dimX == dimY && type == SPFFT_TRANS_C2C && dimX % 3 != 0 && dimX % 5 != 0;
     if (fastX) ax.log2Vx = fusedShape ? fl : fast_path_log2_lanes_x(dimX);
     if (fastY) ax.log2Vy = fl;
     if (fastZ) ax.log2Vz = fl;
@@ -243,7 +246,7 @@ int run(int type, int dimX, int dimY, int dimZ, int n, const int* triplets, int 
     sb::Ctx ctx{nthreads};
 
     // fused xy stage exactly when the product fuses; a small ring / lag exercises slot reuse
-    const bool fused = fastX && fastY && dimX == dimY && type == SPFFT_TRANS_C2C && dimX % 3 != 0;
+    const bool fused = fastX && fastY && dimX == dimY && type == SPFFT_TRANS_C2C && dimX % 3 != 0 && dimX % 5 != 0;
     const int ring = dimZ > 3 ? 3 : dimZ, lag = dimZ > 3 ? 2 : 1;
     std::vector<sb::cx<T>> scratch(static_cast<size_t>(ring) * dimX * dimY + 1,
                                    sb::mk<T>(T(1e30), T(-1e30)));

@@ -122,7 +122,9 @@ FAST_SHAPES = [(32, 32, 32), (64, 32, 128), (32, 12, 64), (11, 64, 32), (128, 32
                (32, 512, 32), (32, 32, 1024), (1024, 32, 12), (512, 12, 32),
                # 3 * 2^k lengths (fast3_stage_kernels.hpp), alone and mixed with the other kernel families
                (96, 96, 96), (192, 32, 12), (12, 192, 32), (32, 13, 192), (384, 96, 32), (32, 384, 96),
-               (96, 32, 384), (768, 12, 32), (12, 768, 32), (33, 32, 768)]
+               (96, 32, 384), (768, 12, 32), (12, 768, 32), (33, 32, 768),
+               # 5 * 2^k lengths (same kernels, radix-5 step, 40 values per thread)
+               (160, 160, 32), (12, 320, 32), (32, 13, 640), (320, 96, 64), (640, 12, 160)]
 
 
 @pytest.mark.parametrize("shape", FAST_SHAPES, ids=lambda s: "x".join(map(str, s)))
@@ -149,7 +151,8 @@ def test_emulated_fast_c2c(emu, gen, shape, single, shuffle):
 
 
 @pytest.mark.parametrize("shape", [(32, 32, 32), (64, 128, 32), (12, 32, 64), (33, 64, 32), (96, 96, 96), (192, 32, 96),
-                                   (32, 192, 12), (384, 96, 32), (33, 96, 192), (768, 12, 96)],
+                                   (32, 192, 12), (384, 96, 32), (33, 96, 192), (768, 12, 96),
+                                   (160, 160, 32), (320, 12, 160), (33, 640, 32)],
                          ids=lambda s: "x".join(map(str, s)))
 def test_emulated_fast_r2c(emu, gen, shape):
     from conftest import hermitian_space_values
@@ -167,7 +170,8 @@ def test_emulated_fast_r2c(emu, gen, shape):
     assert orc.rel_l2(back, orc.forward(param, out, orc.SPFFT_FULL_SCALING)) < 1e-13
 
 
-@pytest.mark.parametrize("shape", [(12, 11, 13), (32, 64, 32), (96, 192, 96), (33, 96, 64)], ids=lambda s: "x".join(map(str, s)))
+@pytest.mark.parametrize("shape", [(12, 11, 13), (32, 64, 32), (96, 192, 96), (33, 96, 64), (160, 320, 32)],
+                         ids=lambda s: "x".join(map(str, s)))
 def test_emulated_r2c_negative_half_input(emu, gen, shape):
     """R2C input given at -y on the x = 0 plane and at negative z on stick (0,0) (details.rst:37-40): the
     gather-form kernels complete the hermitian half while loading (hermitian_combine)."""
@@ -266,6 +270,7 @@ DIST_CASES = [
     (0, (96, 96, 96), "uniform", "uniform", True, False),
     (1, (192, 96, 32), "uniform", "ramp", False, False),
     (0, (32, 192, 96), "first", "last", True, True),
+    (0, (160, 32, 160), "uniform", "ramp", True, False),
 ]
 
 

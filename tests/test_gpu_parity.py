@@ -487,13 +487,14 @@ def test_power_of_two_fast_path(torch_cuda, lib, gen, shape, single, ttype):
 
 
 @pytest.mark.parametrize("shape", [(96, 96, 96), (192, 32, 12), (12, 192, 32), (32, 13, 192), (384, 96, 32), (32, 384, 96),
-                                   (96, 32, 384), (768, 12, 32), (12, 768, 32), (33, 32, 768), (192, 192, 192)],
+                                   (96, 32, 384), (768, 12, 32), (12, 768, 32), (33, 32, 768), (192, 192, 192),
+                                   (160, 160, 32), (12, 320, 32), (32, 13, 640), (320, 96, 64), (640, 12, 160)],
                          ids=lambda s: "x".join(map(str, s)))
 @pytest.mark.parametrize("single", [False, True])
 @pytest.mark.parametrize("ttype", [0, 1])
 @pytest.mark.parametrize("shuffle", [False, True])
 def test_three_times_power_of_two_fast_path(torch_cuda, lib, gen, shape, single, ttype, shuffle):
-    """Register-FFT kernels for N = 3 * 2^k axes (fast3_stage_kernels.hpp) mixed with the other kernel
+    """Register-FFT kernels for N = 3 * 2^k and 5 * 2^k axes (fast3_stage_kernels.hpp) mixed with the other kernel
     families, both precisions; shuffle = values in arbitrary user order (scatter-form z kernels)."""
     from conftest import hermitian_space_values
     nx, ny, nz = shape
