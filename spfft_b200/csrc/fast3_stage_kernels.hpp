@@ -577,12 +577,12 @@ SB_DEV void y_backward_fast3(const YArgs<T>& a, int block, Ctx ctx, cx<T>* S) {
 
 template <typename T, int N, typename W>
 SB_DEV void y_forward_fast3_w(const YArgs<T>& a, int block, Ctx ctx, cx<T>* S) {
-  const int xt = (block % a.numXTiles + a.xtRotate) % a.numXTiles;
+  const int xt = y_forward_tile_at<T>(a, block % a.numXTiles);
   const int zl = block / a.numXTiles;
   int nextXt = -1;
   const cx<T>* nextPlane = nullptr;
   if (a.pfDist > 0 && block + a.pfDist < a.numXTiles * a.numPlanes) {
-    nextXt = ((block + a.pfDist) % a.numXTiles + a.xtRotate) % a.numXTiles;
+    nextXt = y_forward_tile_at<T>(a, (block + a.pfDist) % a.numXTiles);
     nextPlane = a.planes + (size_t)((block + a.pfDist) / a.numXTiles) * N * a.nxf;
   }
   W* localRow = reinterpret_cast<W*>(a.sticks) + (size_t)(zl + a.zRowOffset) * a.pitch;

@@ -265,6 +265,25 @@ ExchangePlan build_exchange_plan(const IndexMaps& m, int log2Vz, int log2Vy, boo
       }
     }
   }
+  if (!x.stickRank.empty() && P > 1) {
+    std::vector<std::vector<int>> byOwner(P);
+    std::vector<int> empty;
+    for (int t = 0; t < x.numXTiles; ++t) {
+      if (x.xtStart[t] < x.xtStart[t + 1])
+        byOwner[x.stickRank[x.xtStart[t]]].push_back(t);
+      else
+        empty.push_back(t);
+    }
+    size_t longest = 0;
+    for (const auto& v : byOwner) longest = std::max(longest, v.size());
+    x.fwdTileOrder.reserve(x.numXTiles);
+    for (size_t i = 0; i < longest; ++i)
+      for (int k = 1; k <= P; ++k) {
+        const auto& v = byOwner[(me + k) % P];
+        if (i < v.size()) x.fwdTileOrder.push_back(v[i]);
+      }
+    x.fwdTileOrder.insert(x.fwdTileOrder.end(), empty.begin(), empty.end());
+  }
   if (fastY && !all.empty()) {
     const int ny = m.dimY;
     const int vpt = fast_path_values_per_thread(ny);

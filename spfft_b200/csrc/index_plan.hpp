@@ -93,6 +93,9 @@ struct ExchangePlan {
   std::vector<int> fwdBase;             // [NsTotal]
   std::vector<int> tileFwdBase;         // [numXTiles]
   int fwdTileRotate = 0;                // first x tile owned by the next rank (forward visiting order)
+  // forward visiting order of the x tiles: destination ranks interleaved round robin, starting with the
+  // next rank (a tile belongs to the owner of its first stick; tiles without sticks go last)
+  std::vector<int> fwdTileOrder;        // [numXTiles]
 };
 
 ExchangePlan build_exchange_plan(const IndexMaps& maps, int log2Vz, int log2Vy, bool fastY = false);

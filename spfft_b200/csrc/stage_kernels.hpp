@@ -148,8 +148,19 @@ struct YArgs {
   // forward kernels visit the x tiles of a plane starting at tile xtRotate: with peer stores
   // every rank then targets a different destination at any time (no ingress hot spot)
   int xtRotate;
+  // ... or in the order xtOrder[0 .. numXTiles) when set: the tiles of the destination ranks interleaved
+  // (next rank first), so that the NVLink stores and the local stores of a plane overlap instead of coming
+  // in two bursts, and every rank still addresses all destinations evenly
+  const int* xtOrder;
   int wireF32;  // the exchanged buffers (`sticks`, `peer`) hold cx<float> (see ZArgs)
 };
+
+// x tile the forward y kernels work on in position `pos` of a plane's visiting order
+template <typename T>
+SB_DEV int y_forward_tile_at(const YArgs<T>& a, int pos) {
+  if (a.xtOrder) return a.xtOrder[pos];
+  return (pos + a.xtRotate) % a.numXTiles;
+}
 
 // Where stick e (global sorted list) of local plane zl lives for a distributed y kernel:
 // backward reads the local plane-side buffer, forward writes the owner's stick buffer.
@@ -228,6 +239,7 @@ SB_DEV YArgs<T> band_args(const YArgs<T>& a0, const BandTable<T>& b, int band) {
   a.fwdBase = nullptr;
   a.tileFwdBase = nullptr;
   a.xtRotate = 0;
+  a.xtOrder = nullptr;
   a.wireF32 = 0;
   return a;
 }
@@ -377,7 +389,7 @@ template <typename T, typename W>
 SB_DEV void y_forward_body_w(const YArgs<T>& a, int block, Ctx ctx, cx<T>* smem) {
   const int V = 1 << a.log2V;
   const int n = a.ny << a.log2V;
-  const int xt = (block % a.numXTiles + a.xtRotate) % a.numXTiles;
+  const int xt = y_forward_tile_at<T>(a, block % a.numXTiles);
   const int zl = block / a.numXTiles;
   const int e0 = a.xtStart[xt], e1 = a.xtStart[xt + 1];
   if (e0 == e1) return;  // no stick needs these columns

@@ -362,6 +362,11 @@ std::shared_ptr<DevicePlan<T>> build_device_plan(const IndexMaps& m, long long s
     plan->stickRank = upload(st, total, plan->exchange.stickRank);
     plan->fwdBase = upload(st, total, plan->exchange.fwdBase);
     plan->tileFwdBase = upload(st, total, plan->exchange.tileFwdBase);
+    // SPFFT_B200_FWD_ORDER=1: destination ranks interleaved tile by tile instead of the rotated order
+    // (experiment: no difference on 2 GPUs, 0.689 ms for the forward exchange kernel either way;
+    // the rotated order is the one measured on 4 and 8 GPUs, so it stays the default)
+    const char* ord = std::getenv("SPFFT_B200_FWD_ORDER");
+    if (ord && std::atoi(ord) == 1) plan->fwdTileOrder = upload(st, total, plan->exchange.fwdTileOrder);
     plan->fusedXY = false;
   } else {
     p.xtStart = upload(st, total, t.xtStart);
@@ -544,6 +549,7 @@ sb::YArgs<T> TransformEngine<T>::make_y_stage_args(const TileMaps& geo, bool for
     ya.stickRank = plan_->stickRank;
     ya.fwdBase = plan_->fwdBase;
     ya.tileFwdBase = plan_->tileFwdBase;
+    ya.xtOrder = plan_->fwdTileOrder;
     ya.xtRotate = plan_->exchange.fwdTileRotate;
   }
   if (plan_->distributed) {

@@ -121,6 +121,7 @@ struct DevicePlan {
   const unsigned char* stickRank = nullptr;
   const int* fwdBase = nullptr;
   const int* tileFwdBase = nullptr;
+  const int* fwdTileOrder = nullptr;
   std::vector<DeviceBuffer> storage;
   size_t deviceBytes = 0;
 };

@@ -382,6 +382,7 @@ int run_distributed(int type, int dimX, int dimY, int dimZ, int P, const int* nu
         ya.fwdBase = x.fwdBase.data();
         ya.tileFwdBase = x.tileFwdBase.data();
         ya.xtRotate = x.fwdTileRotate;
+        if (!x.fwdTileOrder.empty()) ya.xtOrder = x.fwdTileOrder.data();
       }
       ya.sticks = Q[r].data();
       ya.srcBase = x.srcBase.data();
