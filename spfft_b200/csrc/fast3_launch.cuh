@@ -20,7 +20,7 @@ namespace sb {
 #endif
 template <typename T, int N>
 struct Fast3Cfg {
-  static constexpr int V = 1 << FastLanes<T>::log2V;
+  static constexpr int V = 1 << Fast3Lanes<T, N>::log2V;
   static constexpr int threads = V * Fast3Plan<N>::T;
   // (5 * 2^k: 40 values per thread -> no register cap for double, 168 for float)
   static constexpr int perSmThreads = N % 5 == 0 ? (sizeof(T) == 8 ? 256 : 384)

@@ -50,6 +50,17 @@ struct Fast3Plan {
 
 constexpr bool is_fast3_length(int n) { return n % 3 == 0 || n % 5 == 0; }
 
+// Lanes per z / y tile of this kernel family: the common choice (FastLanes), except single precision at
+// N = 96, 192 where 16 lanes (128-byte rows, still only 64 / 128 threads per CTA) measured 3-6 % faster
+// (profiles/r01_v4_float_lanes16.log: 64 bands at 192^3 single 9548 -> 10130 pairs/s; at 384 it loses).
+constexpr int fast3_lanes_log2(int n, int complexBytes, int common) {
+  return (complexBytes == 8 && n % 3 == 0 && n <= 192) ? 4 : common;
+}
+template <typename T, int N>
+struct Fast3Lanes {
+  static constexpr int log2V = fast3_lanes_log2(N, (int)sizeof(cx<T>), FastLanes<T>::log2V);
+};
+
 struct LaneJ {
   int lane, j;
 };
@@ -281,7 +292,7 @@ SB_DEV void scatter_into_tile(cx<T>* S, int elems, const int* slotOf, int e0, in
 // -------------------------------------------------------------------------------------------
 template <typename T, int N, bool GATHER, typename W>
 SB_DEV void z_backward_fast3_impl(const ZArgs<T>& a, int tile, Ctx ctx, cx<T>* S) {
-  constexpr int LOG2V = FastLanes<T>::log2V;
+  constexpr int LOG2V = Fast3Lanes<T, N>::log2V;
   constexpr int V = 1 << LOG2V;
   constexpr int TT = Fast3Plan<N>::T;
   constexpr int G = Fast3Plan<N>::G;
@@ -332,7 +343,7 @@ SB_DEV void z_backward_fast3_impl(const ZArgs<T>& a, int tile, Ctx ctx, cx<T>* S
 
 template <typename T, int N, bool GATHER, typename W>
 SB_DEV void z_forward_fast3_impl(const ZArgs<T>& a, int tile, Ctx ctx, cx<T>* S) {
-  constexpr int LOG2V = FastLanes<T>::log2V;
+  constexpr int LOG2V = Fast3Lanes<T, N>::log2V;
   constexpr int V = 1 << LOG2V;
   constexpr int TT = Fast3Plan<N>::T;
   constexpr int G = Fast3Plan<N>::G;
@@ -416,7 +427,7 @@ SB_DEV void z_forward_fast3(const ZArgs<T>& a, int tile, Ctx ctx, cx<T>* S) {
 template <typename T, int N, bool GATHER, typename W>
 SB_DEV void y_backward_fast3_impl(const YArgs<T>& a, int xt, int zl, const W* stickRow, int nextXt,
                                   const W* nextStickRow, Ctx ctx, cx<T>* S) {
-  constexpr int LOG2V = FastLanes<T>::log2V;
+  constexpr int LOG2V = Fast3Lanes<T, N>::log2V;
   constexpr int V = 1 << LOG2V;
   constexpr int TT = Fast3Plan<N>::T;
   constexpr int G = Fast3Plan<N>::G;
@@ -488,7 +499,7 @@ SB_DEV void y_backward_fast3_impl(const YArgs<T>& a, int xt, int zl, const W* st
 template <typename T, int N, bool GATHER, typename W>
 SB_DEV void y_forward_fast3_impl(const YArgs<T>& a, int xt, int zl, W* stickRow, int nextXt,
                                  const cx<T>* nextPlane, Ctx ctx, cx<T>* S) {
-  constexpr int LOG2V = FastLanes<T>::log2V;
+  constexpr int LOG2V = Fast3Lanes<T, N>::log2V;
   constexpr int V = 1 << LOG2V;
   constexpr int TT = Fast3Plan<N>::T;
   constexpr int G = Fast3Plan<N>::G;

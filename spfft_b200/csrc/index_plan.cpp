@@ -6,6 +6,7 @@
 #include <cstdint>
 #include <numeric>
 
+#include "fast3_stage_kernels.hpp"
 #include "fast_stage_kernels.hpp"
 #include "spfft/exceptions.hpp"
 
@@ -491,7 +492,7 @@ bool fast_path_length(int n, int complexBytes) {
     return m >= 32 && m <= 256 && (m & (m - 1)) == 0;
   }
   if (n < 32 || (n & (n - 1)) != 0) return false;
-  const int lanes = 1 << fast_path_log2_lanes(complexBytes);
+  const int lanes = 1 << fast_path_log2_lanes(complexBytes, n);
   return lanes * (n / 8) <= 1024;  // threads per CTA
 }
 
@@ -506,8 +507,9 @@ int fast_path_log2_lanes_x(int n) {
 
 int fast_path_values_per_thread(int n) { return n % 5 == 0 ? 40 : (n % 3 == 0 ? 24 : 8); }
 
-int fast_path_log2_lanes(int complexBytes) {
-  return complexBytes == 16 ? sb::FastLanes<double>::log2V : sb::FastLanes<float>::log2V;
+int fast_path_log2_lanes(int complexBytes, int n) {
+  const int common = complexBytes == 16 ? sb::FastLanes<double>::log2V : sb::FastLanes<float>::log2V;
+  return (n > 0 && sb::is_fast3_length(n)) ? sb::fast3_lanes_log2(n, complexBytes, common) : common;
 }
 
 template <typename T>

@@ -143,7 +143,7 @@ bool fast_path_length(int n, int complexBytes);
 // complex values a thread of the fast path holds (8, or 24 for 3 * 2^k): the inverse maps are laid
 // out [tile][thread = lane*(n/vpt) + j][vpt]
 int fast_path_values_per_thread(int n);
-int fast_path_log2_lanes(int complexBytes);
+int fast_path_log2_lanes(int complexBytes, int n = 0);  // z / y tiles of an axis of length n on the fast path
 int fast_path_log2_lanes_x(int n);  // log2 rows per tile of the stand-alone x stage kernels of length n
 // Stage twiddles of the register FFT: for every stage s >= 1 (radix 8, stride ns) the entries
 // [r-1][k] = exp(-2*pi*i*r*k/(8*ns)), r = 1..7, k < ns; rounded from long double.

@@ -244,8 +244,8 @@ void choose_tile_lanes(const IndexMaps& m, int cb, long long smemLimit, AxisPlan
   // (the stand-alone x kernels pick their own row count; build_device_plan sets it once it knows
   // that the opt-in fused xy kernels, which share one tile shape between y and x, are not used)
   ax.log2Vx = fastX ? fastLanes : choose_log2_lanes(m.dimX, cb, smemLimit);
-  ax.log2Vy = fastY ? fastLanes : choose_log2_lanes(m.dimY, cb, smemLimit);
-  ax.log2Vz = fastZ ? fastLanes : choose_log2_lanes(m.dimZ, cb, smemLimit);
+  ax.log2Vy = fastY ? fast_path_log2_lanes(cb, m.dimY) : choose_log2_lanes(m.dimY, cb, smemLimit);
+  ax.log2Vz = fastZ ? fast_path_log2_lanes(cb, m.dimZ) : choose_log2_lanes(m.dimZ, cb, smemLimit);
   // a transform length whose two tile buffers exceed shared memory is not supported
   if (ax.log2Vx < 0 || ax.log2Vy < 0 || ax.log2Vz < 0) throw InvalidParameterError();
 }

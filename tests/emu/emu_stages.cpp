@@ -55,7 +55,7 @@ void run_z(bool fwd, const sb::ZArgs<T>& a, int b, sb::Ctx ctx, sb::cx<T>* smem)
     return;
   }
   if (sb::is_fast3_length(a.nz)) {
-    sb::Ctx c3{(1 << sb::FastLanes<T>::log2V) * (a.nz / fast_path_values_per_thread(a.nz))};
+    sb::Ctx c3{(1 << a.log2V) * (a.nz / fast_path_values_per_thread(a.nz))};
 #define CALL(NN)                                                                                               \
   if (a.wireF32) { if (fwd) sb::z_forward_fast3<T, NN, true>(a, b, c3, smem); else sb::z_backward_fast3<T, NN, true>(a, b, c3, smem); } \
   else { if (fwd) sb::z_forward_fast3<T, NN>(a, b, c3, smem); else sb::z_backward_fast3<T, NN>(a, b, c3, smem); }
@@ -77,7 +77,7 @@ void run_y(bool fwd, const sb::YArgs<T>& a, int b, sb::Ctx ctx, sb::cx<T>* smem)
     return;
   }
   if (sb::is_fast3_length(a.ny)) {
-    sb::Ctx c3{(1 << sb::FastLanes<T>::log2V) * (a.ny / fast_path_values_per_thread(a.ny))};
+    sb::Ctx c3{(1 << a.log2V) * (a.ny / fast_path_values_per_thread(a.ny))};
 #define CALL(NN)                                                                                               \
   if (a.wireF32) { if (fwd) sb::y_forward_fast3<T, NN, true>(a, b, c3, smem); else sb::y_backward_fast3<T, NN, true>(a, b, c3, smem); } \
   else { if (fwd) sb::y_forward_fast3<T, NN>(a, b, c3, smem); else sb::y_backward_fast3<T, NN>(a, b, c3, smem); }
@@ -203,8 +203,8 @@ int run(int type, int dimX, int dimY, int dimZ, int n, const int* triplets, int 
     // fused xy stage exactly when the product (with its opt-in flag) fuses: one tile shape for y and x
     const bool fusedShape = fastX && fastY && dimX == dimY && type == SPFFT_TRANS_C2C && dimX % 3 != 0 && dimX % 5 != 0;
     if (fastX) ax.log2Vx = fusedShape ? fl : fast_path_log2_lanes_x(dimX);
-    if (fastY) ax.log2Vy = fl;
-    if (fastZ) ax.log2Vz = fl;
+    if (fastY) ax.log2Vy = fast_path_log2_lanes(cb, dimY);
+    if (fastZ) ax.log2Vz = fast_path_log2_lanes(cb, dimZ);
     ax.rpX = make_radix_plan(dimX);
     ax.rpY = make_radix_plan(dimY);
     ax.rpZ = make_radix_plan(dimZ);
@@ -325,8 +325,9 @@ int run_distributed(int type, int dimX, int dimY, int dimZ, int P, const int* nu
                fastZ = fast_path_length(dimZ, cb);
     const int fl = fast_path_log2_lanes(cb);
     ax.log2Vx = fastX ? fast_path_log2_lanes_x(dimX) : choose_log2_lanes(dimX, cb, smemLimit);
-    ax.log2Vy = fastY ? fl : choose_log2_lanes(dimY, cb, smemLimit);
-    ax.log2Vz = fastZ ? fl : choose_log2_lanes(dimZ, cb, smemLimit);
+    ax.log2Vy = fastY ? fast_path_log2_lanes(cb, dimY) : choose_log2_lanes(dimY, cb, smemLimit);
+    ax.log2Vz = fastZ ? fast_path_log2_lanes(cb, dimZ) : choose_log2_lanes(dimZ, cb, smemLimit);
+    (void)fl;
     ax.rpX = make_radix_plan(dimX);
     ax.rpY = make_radix_plan(dimY);
     ax.rpZ = make_radix_plan(dimZ);
