@@ -1,4 +1,4 @@
-# usage: bash tools/gpu_dist2.sh N   (under gpurun --gpus N): distributed parity check + sharded benches
+# usage: bash tools/sessions/gpu_dist2.sh N   (under gpurun --gpus N): distributed parity check + sharded benches
 N=${1:-2}
 mkdir -p gpurun_out
 timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 tests/dist_gpu_check.py > gpurun_out/dist_check_$N.log 2>&1; echo "dist check exit $?" >> gpurun_out/dist_check_$N.log

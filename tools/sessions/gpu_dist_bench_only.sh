@@ -1,4 +1,4 @@
-# usage: bash tools/gpu_dist_bench_only.sh N   (under gpurun --gpus N)
+# usage: bash tools/sessions/gpu_dist_bench_only.sh N   (under gpurun --gpus N)
 N=${1:-8}
 mkdir -p gpurun_out
 for cfg in "--size 512" "--size 256 --type r2c" "--size 512 --type r2c"; do
