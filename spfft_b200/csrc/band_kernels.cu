@@ -22,6 +22,7 @@ constexpr int kBandThreads = 256;  // generic kernels (same as kernels.cu)
 // ---- generic kernels ---------------------------------------------------------------------------
 template <typename T, bool FWD>
 __global__ void __launch_bounds__(kBandThreads) k_z_stage_b(const __grid_constant__ ZArgs<T> a0, const __grid_constant__ BandTable<T> bt) {
+  pdl_prologue();
   SB_SMEM(T)
   const ZArgs<T> a = band_args(a0, bt, (int)blockIdx.y);
   if (FWD) z_forward_body<T>(a, (int)blockIdx.x, Ctx{kBandThreads}, S);
@@ -29,6 +30,7 @@ __global__ void __launch_bounds__(kBandThreads) k_z_stage_b(const __grid_constan
 }
 template <typename T, bool FWD>
 __global__ void __launch_bounds__(kBandThreads) k_y_stage_b(const __grid_constant__ YArgs<T> a0, const __grid_constant__ BandTable<T> bt) {
+  pdl_prologue();
   SB_SMEM(T)
   const YArgs<T> a = band_args(a0, bt, (int)blockIdx.y);
   if (FWD) y_forward_body<T>(a, (int)blockIdx.x, Ctx{kBandThreads}, S);
@@ -36,6 +38,7 @@ __global__ void __launch_bounds__(kBandThreads) k_y_stage_b(const __grid_constan
 }
 template <typename T, bool FWD>
 __global__ void __launch_bounds__(kBandThreads) k_x_stage_b(const __grid_constant__ XArgs<T> a0, const __grid_constant__ BandTable<T> bt) {
+  pdl_prologue();
   SB_SMEM(T)
   const XArgs<T> a = band_args(a0, bt, (int)blockIdx.y);
   if (FWD) x_forward_body<T>(a, (int)blockIdx.x, Ctx{kBandThreads}, S);
@@ -46,6 +49,7 @@ __global__ void __launch_bounds__(kBandThreads) k_x_stage_b(const __grid_constan
 template <typename T, int N, bool FWD>
 __global__ void __launch_bounds__(FastCfg<T, N>::threads, FastCfg<T, N>::minBlocks)
     k_z_fast_b(const __grid_constant__ ZArgs<T> a0, const __grid_constant__ BandTable<T> bt) {
+  pdl_prologue();
   SB_SMEM(T)
   const ZArgs<T> a = band_args(a0, bt, (int)blockIdx.y);
   z_fast_any<T, N, FWD>(a, (int)blockIdx.x, Ctx{FastCfg<T, N>::threads}, S);
@@ -53,6 +57,7 @@ __global__ void __launch_bounds__(FastCfg<T, N>::threads, FastCfg<T, N>::minBloc
 template <typename T, int N, bool FWD>
 __global__ void __launch_bounds__(FastCfg<T, N>::threads, FastCfg<T, N>::minBlocks)
     k_y_fast_b(const __grid_constant__ YArgs<T> a0, const __grid_constant__ BandTable<T> bt) {
+  pdl_prologue();
   SB_SMEM(T)
   const YArgs<T> a = band_args(a0, bt, (int)blockIdx.y);
   if (FWD) y_forward_fast<T, N>(a, (int)blockIdx.x, Ctx{FastCfg<T, N>::threads}, S);
@@ -61,6 +66,7 @@ __global__ void __launch_bounds__(FastCfg<T, N>::threads, FastCfg<T, N>::minBloc
 template <typename T, int N, bool FWD, bool REAL>
 __global__ void __launch_bounds__(FastCfgX<T, N>::threads, FastCfgX<T, N>::minBlocks)
     k_x_fast_b(const __grid_constant__ XArgs<T> a0, const __grid_constant__ BandTable<T> bt) {
+  pdl_prologue();
   SB_SMEM(T)
   const XArgs<T> a = band_args(a0, bt, (int)blockIdx.y);
   if (REAL) x_r2c_fast<T, N, !FWD>(a, (int)blockIdx.x, Ctx{FastCfgX<T, N>::threads}, S);
@@ -71,6 +77,7 @@ __global__ void __launch_bounds__(FastCfgX<T, N>::threads, FastCfgX<T, N>::minBl
 template <typename T, int N, bool FWD>
 __global__ void __launch_bounds__(Fast3Cfg<T, N>::threads, Fast3Cfg<T, N>::minBlocks)
     k_z_fast3_b(const __grid_constant__ ZArgs<T> a0, const __grid_constant__ BandTable<T> bt) {
+  pdl_prologue();
   SB_SMEM(T)
   const ZArgs<T> a = band_args(a0, bt, (int)blockIdx.y);
   if (FWD) z_forward_fast3<T, N>(a, (int)blockIdx.x, Ctx{Fast3Cfg<T, N>::threads}, S);
@@ -79,6 +86,7 @@ __global__ void __launch_bounds__(Fast3Cfg<T, N>::threads, Fast3Cfg<T, N>::minBl
 template <typename T, int N, bool FWD>
 __global__ void __launch_bounds__(Fast3Cfg<T, N>::threads, Fast3Cfg<T, N>::minBlocks)
     k_y_fast3_b(const __grid_constant__ YArgs<T> a0, const __grid_constant__ BandTable<T> bt) {
+  pdl_prologue();
   SB_SMEM(T)
   const YArgs<T> a = band_args(a0, bt, (int)blockIdx.y);
   if (FWD) y_forward_fast3<T, N>(a, (int)blockIdx.x, Ctx{Fast3Cfg<T, N>::threads}, S);
@@ -87,6 +95,7 @@ __global__ void __launch_bounds__(Fast3Cfg<T, N>::threads, Fast3Cfg<T, N>::minBl
 template <typename T, int N, bool FWD, bool REAL>
 __global__ void __launch_bounds__(Fast3CfgX<T, N>::threads, Fast3CfgX<T, N>::minBlocks)
     k_x_fast3_b(const __grid_constant__ XArgs<T> a0, const __grid_constant__ BandTable<T> bt) {
+  pdl_prologue();
   SB_SMEM(T)
   const XArgs<T> a = band_args(a0, bt, (int)blockIdx.y);
   if (REAL) x_r2c_fast3<T, N, !FWD>(a, (int)blockIdx.x, Ctx{Fast3CfgX<T, N>::threads}, S);

@@ -6,6 +6,7 @@ namespace sb {
 template <typename T, int N, bool FWD>
 __global__ void __launch_bounds__(Fast3CfgX<T, N>::threads, Fast3CfgX<T, N>::minBlocks)
     k_x_fast3(const __grid_constant__ XArgs<T> a) {
+  pdl_prologue();
   extern __shared__ __align__(16) unsigned char smemRaw[];
   cx<T>* S = reinterpret_cast<cx<T>*>(smemRaw);
   x_c2c_fast3<T, N, !FWD>(a, (int)blockIdx.x, Ctx{Fast3CfgX<T, N>::threads}, S);
@@ -14,6 +15,7 @@ __global__ void __launch_bounds__(Fast3CfgX<T, N>::threads, Fast3CfgX<T, N>::min
 template <typename T, int N, bool FWD>
 __global__ void __launch_bounds__(Fast3CfgX<T, N>::threads, Fast3CfgX<T, N>::minBlocks)
     k_x_real_fast3(const __grid_constant__ XArgs<T> a) {
+  pdl_prologue();
   extern __shared__ __align__(16) unsigned char smemRaw[];
   cx<T>* S = reinterpret_cast<cx<T>*>(smemRaw);
   x_r2c_fast3<T, N, !FWD>(a, (int)blockIdx.x, Ctx{Fast3CfgX<T, N>::threads}, S);

@@ -53,6 +53,17 @@ SB_DEV void bulk_store_commit_wait() {
 }
 #endif
 
+// Programmatic dependent launch: every stage kernel starts with this. `wait` returns once the preceding
+// kernel of the stream has completed (no-op for a normal launch); `launch_dependents` lets the NEXT stage
+// kernel's CTAs become resident while this grid drains, where they block in their own `wait`. Removes the
+// launch gap and the ramp-up between the six dependent kernels of a transform (what bounds 64^3-128^3).
+#if SB_ON_GPU
+SB_DEV void pdl_prologue() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+#endif
+
 // x stage (column mapping on both sides of every exchange), any lane count V <= 128 bytes / element:
 // 128 / ELEM consecutive slots form one 128-byte line = 128 / (ELEM * V) consecutive rows, and the
 // slot inside the line is XOR-permuted by a fold of n. Folds found by exhaustive search with the
@@ -347,6 +358,17 @@ SB_DEV void bulk_store_fence() { asm volatile("fence.proxy.async.shared::cta;" :
 SB_DEV void bulk_store_commit_wait() {
   asm volatile("cp.async.bulk.commit_group;" ::: "memory");
   asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+#endif
+
+// Programmatic dependent launch: every stage kernel starts with this. `wait` returns once the preceding
+// kernel of the stream has completed (no-op for a normal launch); `launch_dependents` lets the NEXT stage
+// kernel's CTAs become resident while this grid drains, where they block in their own `wait`. Removes the
+// launch gap and the ramp-up between the six dependent kernels of a transform (what bounds 64^3-128^3).
+#if SB_ON_GPU
+SB_DEV void pdl_prologue() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 }
 #endif
 

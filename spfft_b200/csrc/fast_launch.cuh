@@ -27,6 +27,29 @@ struct FastCfgX {
   static constexpr size_t smem = (size_t)N * V * sizeof(cx<T>);
 };
 
+// Programmatic dependent launch of the stage kernels (pdl_prologue, fast_fft.hpp); SPFFT_B200_PDL=0 disables.
+inline bool pdl_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("SPFFT_B200_PDL");
+    return !(e && atoi(e) == 0);
+  }();
+  return on;
+}
+template <typename Kernel, typename... A>
+int launch_stage_kernel(Kernel kernel, dim3 grid, int threads, size_t smemBytes, cudaStream_t stream, const A&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3((unsigned)threads);
+  cfg.dynamicSmemBytes = smemBytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return (int)cudaLaunchKernelEx(&cfg, kernel, args...);
+}
+
 template <typename Kernel, typename Args>
 int launch_fast(Kernel kernel, const Args& args, long long blocks, int threads, size_t smemBytes,
                 cudaStream_t stream) {
@@ -37,8 +60,7 @@ int launch_fast(Kernel kernel, const Args& args, long long blocks, int threads, 
                                          (int)smemBytes);
     if (e != cudaSuccess) return (int)e;
   }
-  kernel<<<(unsigned)blocks, threads, smemBytes, stream>>>(args);
-  return (int)cudaGetLastError();
+  return launch_stage_kernel(kernel, dim3((unsigned)blocks), threads, smemBytes, stream, args);
 }
 
 // one launch over `bands` transforms of the same plan: grid (blocks, bands)
@@ -52,8 +74,7 @@ int launch_bands(Kernel kernel, const Args& args, const Table& table, long long 
                                          (int)smemBytes);
     if (e != cudaSuccess) return (int)e;
   }
-  kernel<<<dim3((unsigned)blocks, (unsigned)bands), threads, smemBytes, stream>>>(args, table);
-  return (int)cudaGetLastError();
+  return launch_stage_kernel(kernel, dim3((unsigned)blocks, (unsigned)bands), threads, smemBytes, stream, args, table);
 }
 
 // Debug / tuning knob: environment variable SPFFT_B200_TUNE (integer bit mask, default 1).

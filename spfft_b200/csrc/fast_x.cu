@@ -6,6 +6,7 @@ namespace sb {
 template <typename T, int N, bool FWD>
 __global__ void __launch_bounds__(FastCfgX<T, N>::threads, FastCfgX<T, N>::minBlocks)
     k_x_fast(const __grid_constant__ XArgs<T> a) {
+  pdl_prologue();
   extern __shared__ __align__(16) unsigned char smemRaw[];
   cx<T>* S = reinterpret_cast<cx<T>*>(smemRaw);
   x_c2c_fast<T, N, !FWD>(a, (int)blockIdx.x, Ctx{FastCfgX<T, N>::threads}, S);
@@ -15,6 +16,7 @@ __global__ void __launch_bounds__(FastCfgX<T, N>::threads, FastCfgX<T, N>::minBl
 template <typename T, int N, bool FWD>
 __global__ void __launch_bounds__(FastCfgX<T, N>::threads, FastCfgX<T, N>::minBlocks)
     k_x_real_fast(const __grid_constant__ XArgs<T> a) {
+  pdl_prologue();
   extern __shared__ __align__(16) unsigned char smemRaw[];
   cx<T>* S = reinterpret_cast<cx<T>*>(smemRaw);
   x_r2c_fast<T, N, !FWD>(a, (int)blockIdx.x, Ctx{FastCfgX<T, N>::threads}, S);

@@ -6,6 +6,7 @@ namespace sb {
 template <typename T, int N, bool FWD, bool WIRE = false>
 __global__ void __launch_bounds__(FastCfg<T, N>::threads, FastCfg<T, N>::minBlocks)
     k_z_fast(const __grid_constant__ ZArgs<T> a) {
+  pdl_prologue();
   extern __shared__ __align__(16) unsigned char smemRaw[];
   cx<T>* S = reinterpret_cast<cx<T>*>(smemRaw);
   const Ctx ctx{FastCfg<T, N>::threads};

@@ -14,6 +14,7 @@ constexpr int kThreads = 256;
 
 template <typename T, bool FWD>
 __global__ void __launch_bounds__(kThreads) k_z_stage(const __grid_constant__ ZArgs<T> a) {
+  pdl_prologue();
   extern __shared__ __align__(16) unsigned char smemRaw[];
   cx<T>* smem = reinterpret_cast<cx<T>*>(smemRaw);
   if (FWD)
@@ -24,6 +25,7 @@ __global__ void __launch_bounds__(kThreads) k_z_stage(const __grid_constant__ ZA
 
 template <typename T, bool FWD>
 __global__ void __launch_bounds__(kThreads) k_y_stage(const __grid_constant__ YArgs<T> a) {
+  pdl_prologue();
   extern __shared__ __align__(16) unsigned char smemRaw[];
   cx<T>* smem = reinterpret_cast<cx<T>*>(smemRaw);
   if (FWD)
@@ -34,6 +36,7 @@ __global__ void __launch_bounds__(kThreads) k_y_stage(const __grid_constant__ YA
 
 template <typename T, bool FWD>
 __global__ void __launch_bounds__(kThreads) k_x_stage(const __grid_constant__ XArgs<T> a) {
+  pdl_prologue();
   extern __shared__ __align__(16) unsigned char smemRaw[];
   cx<T>* smem = reinterpret_cast<cx<T>*>(smemRaw);
   if (FWD)
@@ -83,9 +86,8 @@ static int launch(Kernel kernel, const Args& args, long long blocks, size_t smem
                                          (int)smemBytes);
     if (e != cudaSuccess) return (int)e;
   }
-  kernel<<<(unsigned)blocks, kThreads, smemBytes, stream>>>(args);
   g_launches.fetch_add(1, std::memory_order_relaxed);
-  return (int)cudaGetLastError();
+  return launch_stage_kernel(kernel, dim3((unsigned)blocks), kThreads, smemBytes, stream, args);
 }
 
 template <typename T>
