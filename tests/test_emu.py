@@ -117,6 +117,28 @@ def test_x_stage_swizzle(emu, elem, log2v):
         assert np.array_equal(np.sort(out), np.arange(n * v))
 
 
+@pytest.mark.parametrize("shape", [(32, 32, 32), (96, 32, 64), (64, 32, 160), (12, 192, 32)], ids=lambda s: "x".join(map(str, s)))
+@pytest.mark.parametrize("single", [False, True])
+def test_emulated_duplicates_on_register_fft_axes(emu, gen, shape, single):
+    """Duplicate triplets (legal: last one wins on backward, all receive the value on forward,
+    compression_host.hpp:88-91) switch the z stage of the register-FFT kernels to the scatter form."""
+    nx, ny, nz = shape
+    trip, vals = gen.make(nx, ny, nz, center=True, stick_fraction=0.5, fill_fraction=0.6)
+    trip = np.concatenate([trip, trip[:7]], axis=0)
+    vals = np.concatenate([vals, vals[:7] * 3.0])
+    param = orc.Parameters(orc.SPFFT_TRANS_C2C, nx, ny, nz, trip)
+    cdt = np.complex64 if single else np.complex128
+    tol = 3e-6 if single else 1e-13
+    v = vals.astype(cdt)
+    out = np.full((nz, ny, nx), np.nan, dtype=cdt)
+    t = np.ascontiguousarray(trip.reshape(-1))
+    assert emu.sb_emu_transform(int(single), 0, nx, ny, nz, len(trip), _ptr(t), 0, _ptr(v), _ptr(out), 0, 64, -1) == 0
+    assert orc.rel_l2(out, orc.backward(param, vals)) < tol
+    back = np.zeros(len(trip), dtype=cdt)
+    assert emu.sb_emu_transform(int(single), 0, nx, ny, nz, len(trip), _ptr(t), 1, _ptr(out), _ptr(back), 1, 64, -1) == 0
+    assert orc.rel_l2(back[:7], back[-7:]) < tol
+
+
 # ---- register-FFT ("fast") bodies: power-of-two lengths, mixed with generic axes ---------------
 FAST_SHAPES = [(32, 32, 32), (64, 32, 128), (32, 12, 64), (11, 64, 32), (128, 32, 13), (256, 32, 32),
                (32, 512, 32), (32, 32, 1024), (1024, 32, 12), (512, 12, 32),
