@@ -202,6 +202,23 @@ def test_grid_shared_by_transforms_and_smaller_transform(torch_cuda, lib, gen):
     assert e.value.code == capi.SPFFT_INVALID_PARAMETER_ERROR
 
 
+def test_grid_with_both_processing_unit_bits(torch_cuda, lib, gen):
+    """A Grid may be created for SPFFT_PU_HOST | SPFFT_PU_GPU (grid_internal.cpp:76-99); a transform picks
+    exactly one unit (transform_internal.cpp:71-80) -- here only the GPU one exists."""
+    both = capi.SPFFT_PU_HOST | capi.SPFFT_PU_GPU
+    grid = capi.Grid(lib, 12, 12, 12, 144, both, -1)
+    assert grid.processing_unit() == both
+    nx, ny, nz = 12, 11, 12
+    trip, vals = gen.make(nx, ny, nz)
+    param = orc.Parameters(0, nx, ny, nz, trip)
+    space, back = _run_pair(torch_cuda, lib, 0, nx, ny, nz, trip, vals, grid=grid)
+    assert orc.rel_l2(space, orc.backward(param, vals)) <= TOL[False]
+    for bad in (both, capi.SPFFT_PU_HOST, 0):
+        with pytest.raises(capi.SpfftError) as e:
+            grid.create_transform(bad, 0, nx, ny, nz, nz, trip)
+        assert e.value.code == capi.SPFFT_INVALID_PARAMETER_ERROR
+
+
 def test_empty_and_degenerate(torch_cuda, lib):
     # no elements at all: legal, output is zero (SURVEY Appendix C)
     t = capi.Transform(lib, transform_type=0, dim_x=4, dim_y=5, dim_z=6, indices=np.zeros((0, 3), np.int32))
