@@ -334,3 +334,53 @@ def _emu_distributed_strict(emu, gen, ttype, shape, world, sdist, pdist, center,
     real = orc.rel_l2
     with mock.patch.object(orc, "rel_l2", lambda a, b: real(a, b) * 1e7):  # 3e-6 * 1e-7 < 1e-12
         _emu_distributed(emu, gen, ttype, shape, world, sdist, pdist, center, False, peer, wire_f32=True)
+
+
+@pytest.mark.parametrize("elem,log2v,sizes", [(16, 0, (1024,)), (16, 1, (512, 1024)), (16, 2, (256, 512)), (16, 3, (64, 128, 256)),
+                                              (8, 0, (1024,)), (8, 1, (512,)), (8, 2, (256,)), (8, 3, (64, 128, 256))])
+def test_x_stage_swizzle_is_conflict_free(emu, elem, log2v, sizes):
+    """Bank-conflict model of tools/check_swizzle.py (32 banks x 4 bytes; 16-byte accesses in phases of 8
+    threads, 8-byte ones in phases of 16) on the real SwzX addresses, for the (length, rows per tile)
+    combinations the x stage kernels pick (x_lanes_log2): every exchange write and read of the
+    power-of-two plan must take one wavefront per phase."""
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location(
+        "check_swizzle", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools", "check_swizzle.py"))
+    cs = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(cs)
+    v = 1 << log2v
+    phase = 8 if elem == 16 else 16
+    slots = 128 // elem
+    for n in sizes:
+        table = np.zeros(n * v, dtype=np.int32)
+        assert emu.sb_emu_swzx(elem, log2v, n, _ptr(table)) == 0
+        t = n // 8
+        radix, ns = cs.plan(n)
+        worst = 1
+
+        def check(addresses):
+            seen = {}
+            for a in addresses:
+                seen.setdefault(a % slots, set()).add(a)
+            return max(len(s) for s in seen.values())
+
+        threads = t * v
+        for s in range(len(radix) - 1):
+            r, nss = radix[s], ns[s]
+            m = 8 // r
+            for i in range(m):
+                for q in range(r):
+                    for w0 in range(0, threads, phase):
+                        addrs = []
+                        for tid in range(w0, min(w0 + phase, threads)):
+                            j, lane = tid % t, tid // t
+                            b = j + i * t
+                            k = b % nss
+                            addrs.append(int(table[((b - k) * r + k + q * nss) * v + lane]))
+                        worst = max(worst, check(addrs))
+            for mm in range(8):
+                for w0 in range(0, threads, phase):
+                    addrs = [int(table[((tid % t) + t * mm) * v + tid // t]) for tid in range(w0, min(w0 + phase, threads))]
+                    worst = max(worst, check(addrs))
+        assert worst == 1, f"N={n} V={v} elem={elem}: {worst} wavefronts per phase"
