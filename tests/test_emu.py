@@ -21,7 +21,8 @@ def _ptr(a):
     return a.ctypes.data_as(C.c_void_p)
 
 
-@pytest.mark.parametrize("n", [1, 2, 3, 4, 5, 7, 8, 11, 12, 13, 16, 25, 49, 60, 64, 100, 128, 192, 210])
+@pytest.mark.parametrize("n", [1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 15, 16, 18, 20, 25, 30, 36, 45, 49, 50, 60, 64, 75, 90, 100,
+                               120, 128, 144, 150, 192, 200, 210, 225, 240, 250, 360, 400, 450, 625, 720, 2048])
 @pytest.mark.parametrize("backward", [0, 1])
 def test_tile_fft_double(emu, n, backward):
     rng = np.random.default_rng(n)
