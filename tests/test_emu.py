@@ -385,3 +385,81 @@ def test_x_stage_swizzle_is_conflict_free(emu, elem, log2v, sizes):
                     addrs = [int(table[((tid % t) + t * mm) * v + tid // t]) for tid in range(w0, min(w0 + phase, threads))]
                     worst = max(worst, check(addrs))
         assert worst == 1, f"N={n} V={v} elem={elem}: {worst} wavefronts per phase"
+
+
+def _fuzz_cases(count, seed):
+    rng = np.random.default_rng(seed)
+    dims = [1, 2, 3, 5, 8, 12, 13, 20, 32, 33, 64, 96, 100, 128, 160, 192]
+    cases = []
+    while len(cases) < count:
+        shape = tuple(int(rng.choice(dims)) for _ in range(3))
+        if shape[0] * shape[1] * shape[2] > 700_000:
+            continue
+        cases.append((shape, int(rng.integers(0, 2)), bool(rng.integers(0, 2)), bool(rng.integers(0, 2)),
+                      float(rng.choice([0.2, 0.6, 1.0])), float(rng.choice([0.3, 0.7, 1.0])), bool(rng.integers(0, 2)),
+                      int(rng.integers(0, 1 << 30))))
+    return cases
+
+
+@pytest.mark.parametrize("case", _fuzz_cases(40, 2024),
+                         ids=lambda c: f"{'x'.join(map(str, c[0]))}-{'r2c' if c[1] else 'c2c'}-{'f32' if c[2] else 'f64'}"
+                                       f"{'-centered' if c[3] else ''}{'-shuffled' if c[6] else ''}")
+def test_emulated_random_mix(emu, gen, case):
+    """Random mixes of the kernel families along the three axes (generic, 2^k, 3*2^k, 5*2^k, degenerate lengths),
+    transform type, precision, centering, sparsity and value order against the oracle."""
+    from conftest import hermitian_space_values
+    (nx, ny, nz), ttype, single, center, sf, ff, shuffle, seed = case
+    center = center and not ttype
+    trip, vals = gen.make(nx, ny, nz, hermitian=bool(ttype), center=center, stick_fraction=sf, fill_fraction=ff,
+                          seed=seed % 100000)
+    if len(trip) == 0:
+        pytest.skip("empty index set")
+    if ttype:
+        vals = hermitian_space_values(orc, nx, ny, nz, trip)
+    if shuffle:
+        perm = np.random.default_rng(seed).permutation(len(trip))
+        trip, vals = np.ascontiguousarray(trip[perm]), np.ascontiguousarray(vals[perm])
+    param = orc.Parameters(ttype, nx, ny, nz, trip)
+    cdt = np.complex64 if single else np.complex128
+    sdt = (np.float32 if single else np.float64) if ttype else cdt
+    tol = 5e-6 if single else 1e-13
+    v = np.ascontiguousarray(vals.astype(cdt))
+    out = np.full((nz, ny, nx), np.nan, dtype=sdt)
+    t = np.ascontiguousarray(trip.reshape(-1))
+    assert emu.sb_emu_transform(int(single), ttype, nx, ny, nz, len(trip), _ptr(t), 0, _ptr(v), _ptr(out), 0, 64, -1) == 0
+    ref = orc.backward(param, vals.astype(cdt).astype(np.complex128))
+    assert orc.rel_l2(out, ref) < tol
+    back = np.zeros(len(trip), dtype=cdt)
+    assert emu.sb_emu_transform(int(single), ttype, nx, ny, nz, len(trip), _ptr(t), 1, _ptr(out), _ptr(back), 1, 64, -1) == 0
+    assert orc.rel_l2(back, orc.forward(param, ref, orc.SPFFT_FULL_SCALING)) < tol
+
+
+def _fuzz_dist_cases(count, seed):
+    rng = np.random.default_rng(seed)
+    dims = [2, 5, 8, 12, 13, 32, 33, 64, 96, 160]
+    cases = []
+    while len(cases) < count:
+        shape = tuple(int(rng.choice(dims)) for _ in range(3))
+        if shape[0] * shape[1] * shape[2] > 400_000:
+            continue
+        world = int(rng.integers(2, 6))
+        sdist = [float(x) for x in rng.choice([0.0, 1.0, 2.0, 3.0], size=world)]
+        pdist = [float(x) for x in rng.choice([0.0, 1.0, 2.0], size=world)]
+        if sum(sdist) == 0:
+            sdist[int(rng.integers(0, world))] = 1.0
+        if sum(pdist) == 0:
+            pdist[int(rng.integers(0, world))] = 1.0
+        cases.append((int(rng.integers(0, 2)), shape, world, sdist, pdist, bool(rng.integers(0, 2)), bool(rng.integers(0, 2)),
+                      int(rng.integers(0, 2)), bool(rng.integers(0, 4) == 0)))
+    return cases
+
+
+@pytest.mark.parametrize("case", _fuzz_dist_cases(24, 99),
+                         ids=lambda c: f"{'r2c' if c[0] else 'c2c'}-{'x'.join(map(str, c[1]))}-P{c[2]}-{'peer' if c[7] else 'block'}"
+                                       f"{'-f32' if c[6] else ''}{'-wire' if c[8] else ''}")
+def test_emulated_distributed_random_mix(emu, gen, case):
+    """Random rank counts (2-5), stick / plane distributions (ranks without sticks or planes included), kernel
+    families, precisions, exchange forms and wire formats against the distributed oracle."""
+    ttype, shape, world, sdist, pdist, center, single, peer, wire = case
+    _emu_distributed(emu, gen, ttype, shape, world, sdist, pdist, center and not ttype, single, peer,
+                     wire_f32=wire and not single)
