@@ -186,3 +186,46 @@ def test_spherical_workload_counts():
         assert len(si) == ns_expected
         assert np.array_equal(bench.spherical_triplets(n, herm), t)
     assert np.array_equal(bench.spherical_triplets(32, True), orc.spherical_cutoff_triplets(32, hermitian=True))
+
+
+def test_index_maps_random_triplets_vs_reference(lib, ref_indices):
+    """Randomised: arbitrary triplet lists (any order, duplicates, negative = centered, sometimes out of
+    range, hermitian or not, degenerate dimensions) through the reference's own convert_index_triplets
+    (src/compression/indices.hpp:120-186) and through the product: same error code, or bit-identical
+    valueIndices / stickIndices."""
+    rng = np.random.default_rng(12345)
+    ok = bad = 0
+    for _ in range(300):
+        nx, ny, nz = (int(rng.choice([1, 2, 3, 4, 7, 8, 12, 16])) for _ in range(3))
+        herm = bool(rng.integers(0, 2))
+        n = int(rng.integers(0, min(nx * ny * nz, 60) + 1))
+        mode = rng.integers(0, 4)  # 0: storage indices, 1: centered, 2: occasionally out of range, 3: mixed signs
+        t = np.zeros((n, 3), np.int32)
+        for d, dim in enumerate((nx, ny, nz)):
+            if mode == 0:
+                t[:, d] = rng.integers(0, dim, n)
+            elif mode == 1:
+                t[:, d] = rng.integers(dim // 2 - dim + 1, dim // 2 + 1, n)
+            elif mode == 2:
+                t[:, d] = rng.integers(-dim, dim + 1, n)
+            else:
+                t[:, d] = rng.integers(-(dim // 2), dim, n)
+        if herm and mode in (0, 1) and n:
+            t[:, 0] = np.abs(t[:, 0]) % (nx // 2 + 1)
+        vi = np.zeros(max(n, 1), np.int32)
+        si = np.zeros(nx * ny + 1, np.int32)
+        ns = C.c_int()
+        tt = np.ascontiguousarray(t.reshape(-1)) if n else np.zeros(3, np.int32)
+        code = ref_indices.spfft_ref_convert_index_triplets(int(herm), nx, ny, nz, n, tt.ctypes.data_as(C.c_void_p),
+                                                            vi.ctypes.data_as(C.c_void_p),
+                                                            si.ctypes.data_as(C.c_void_p), C.byref(ns))
+        if code:
+            bad += 1
+            with pytest.raises(capi.SpfftError) as e:
+                capi.convert_index_triplets(lib, herm, nx, ny, nz, t)
+            assert e.value.code == code, (herm, nx, ny, nz, t.tolist())
+        else:
+            ok += 1
+            pvi, psi = capi.convert_index_triplets(lib, herm, nx, ny, nz, t)
+            assert np.array_equal(pvi, vi[:n]) and np.array_equal(psi, si[:ns.value]), (herm, nx, ny, nz, t.tolist())
+    assert ok > 50 and bad > 20
