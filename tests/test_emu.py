@@ -463,3 +463,34 @@ def test_emulated_distributed_random_mix(emu, gen, case):
     ttype, shape, world, sdist, pdist, center, single, peer, wire = case
     _emu_distributed(emu, gen, ttype, shape, world, sdist, pdist, center and not ttype, single, peer,
                      wire_f32=wire and not single)
+
+
+@pytest.mark.parametrize("case", _fuzz_cases(12, 31337), ids=lambda c: f"{'x'.join(map(str, c[0]))}-{'r2c' if c[1] else 'c2c'}")
+def test_emulated_kernels_vs_reference_host_library(emu, gen, ref_lib, case):
+    """The kernel bodies against the REFERENCE itself: the unmodified reference host pipeline
+    (oracle/_ref/libspfft_ref.so, SPFFT_PU_HOST, its own C ABI) on the same random inputs, double precision."""
+    from conftest import hermitian_space_values
+    from spfft_b200 import capi
+    (nx, ny, nz), ttype, _single, center, sf, ff, _shuffle, seed = case
+    center = center and not ttype
+    trip, vals = gen.make(nx, ny, nz, hermitian=bool(ttype), center=center, stick_fraction=sf, fill_fraction=ff,
+                          seed=seed % 100000)
+    if len(trip) == 0:
+        pytest.skip("empty index set")
+    if ttype:
+        vals = hermitian_space_values(orc, nx, ny, nz, trip)
+    rt = capi.Transform(ref_lib, processing_unit=capi.SPFFT_PU_HOST, transform_type=ttype, dim_x=nx, dim_y=ny,
+                        dim_z=nz, indices=trip)
+    rt.backward(np.ascontiguousarray(vals), capi.SPFFT_PU_HOST)
+    ref_space = rt.space_domain_host_view(ttype).copy()
+    ref_back = np.zeros(len(trip), np.complex128)
+    rt.forward(capi.SPFFT_PU_HOST, ref_back, capi.SPFFT_FULL_SCALING)
+    rt.destroy()
+    out = np.full((nz, ny, nx), np.nan, dtype=np.float64 if ttype else np.complex128)
+    t = np.ascontiguousarray(trip.reshape(-1))
+    v = np.ascontiguousarray(vals.astype(np.complex128))
+    assert emu.sb_emu_transform(0, ttype, nx, ny, nz, len(trip), _ptr(t), 0, _ptr(v), _ptr(out), 0, 64, -1) == 0
+    assert orc.rel_l2(out, ref_space) <= 1e-12
+    back = np.zeros(len(trip), dtype=np.complex128)
+    assert emu.sb_emu_transform(0, ttype, nx, ny, nz, len(trip), _ptr(t), 1, _ptr(out), _ptr(back), 1, 64, -1) == 0
+    assert orc.rel_l2(back, ref_back) <= 1e-12
