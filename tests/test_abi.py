@@ -127,3 +127,30 @@ def test_product_does_not_reference_the_oracle():
                 assert not re.search(r"^\s*(from|import)\s+oracle|#include\s+\"[^\"]*oracle/|libspfft_ref", text, flags=re.M), f
     out = subprocess.run(["ldd", os.path.join(pkg, "lib", "libspfft_b200.so")], capture_output=True, text=True).stdout
     assert "oracle" not in out and "spfft_ref" not in out and "fftw" not in out.lower()
+
+
+def test_fortran_module_matches_the_c_api(built):
+    """include/spfft/spfft.f90 (generated by tools/gen_fortran_module.py; no Fortran compiler in the image):
+    up to date with the generator, every bind(C) interface names a symbol the library exports, and its
+    dummy-argument list is exactly the argument list of the C declaration."""
+    import importlib.util
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("gen_fortran_module", os.path.join(root, "tools", "gen_fortran_module.py"))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    text, count = gen.generate()
+    committed = open(os.path.join(root, "include", "spfft", "spfft.f90")).read()
+    assert committed == text, "run python tools/gen_fortran_module.py"
+    lib = C.CDLL(built.LIB)
+    joined = re.sub(r"&\s*\n\s*", "", committed)
+    found = re.findall(r"integer\(c_int\) function (\w+)\(([^)]*)\) bind\(C\)", joined)
+    assert len(found) == count == 72
+    protos = {name: [a for _, a in args] for name, args in gen.prototypes()}
+    for name, args in found:
+        assert hasattr(lib, name), name
+        base = name.replace("spfft_float_", "").replace("spfft_", "", 1) if name.startswith("spfft_float_") else name[len("spfft_"):]
+        assert [a.strip() for a in args.split(",")] == protos[base], name
+    # structure: balanced blocks, no line beyond the free-form limit
+    assert committed.count("end function") == count and committed.count("\ninterface\n") == 1
+    assert max(len(l) for l in committed.splitlines()) <= 132
