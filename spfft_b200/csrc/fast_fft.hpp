@@ -32,64 +32,6 @@ __device__ __forceinline__ void trace_mark(int item, int id) {
   if (threadIdx.x == 0 && blockIdx.x < kTraceCtas && item >= 0 && item < kTraceItems)
     g_xy_trace[((size_t)blockIdx.x * kTraceItems + item) * kTraceMarks + id] = clock64();
 }
-// Dense-side stores through the tile buffer and one bulk copy (cp.async.bulk, async proxy) per tile row
-// instead of STG.128 per element: a 128-bit global store moves 64 bytes per wavefront of the L1 data pipe,
-// a shared-memory store 128, and the bulk copy none (profiles/r01_v4_summary.md). Experiment switch:
-// measured SLOWER (z backward 0.55 -> 0.64 ms, y backward 0.77 -> 0.89 ms at 512^3, r01_v4_bulk_store.log):
-// the two extra barriers and the wait on the bulk group cost more than the pipe work they save.
-#ifndef SB_BULK_STORE
-#define SB_BULK_STORE 0
-#endif
-#if SB_ON_GPU
-SB_DEV void bulk_store_row(void* gdst, const void* ssrc, unsigned bytes) {
-  const unsigned sa = (unsigned)__cvta_generic_to_shared(ssrc);
-  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(sa), "r"(bytes)
-               : "memory");
-}
-SB_DEV void bulk_store_fence() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-SB_DEV void bulk_store_commit_wait() {
-  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-}
-#endif
-
-// Programmatic dependent launch: every stage kernel starts with this. `wait` returns once the preceding
-// kernel of the stream has completed (no-op for a normal launch); `launch_dependents` lets the NEXT stage
-// kernel's CTAs become resident while this grid drains, where they block in their own `wait`. Removes the
-// launch gap and the ramp-up between the six dependent kernels of a transform (what bounds 64^3-128^3).
-#if SB_ON_GPU
-SB_DEV void pdl_prologue() {
-  asm volatile("griddepcontrol.wait;" ::: "memory");
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-}
-#endif
-
-// x stage (column mapping on both sides of every exchange), any lane count V <= 128 bytes / element:
-// 128 / ELEM consecutive slots form one 128-byte line = 128 / (ELEM * V) consecutive rows, and the
-// slot inside the line is XOR-permuted by a fold of n. Folds found by exhaustive search with the
-// model of tools/check_swizzle.py: conflict free for N >= 64 in every exchange of the power-of-two
-// plans (and of the 3*2^k plans, whose sub-transforms are power-of-two plans of length N/3).
-// Every fold must keep the map a bijection of the tile (tests/test_emu.py::test_x_stage_swizzle).
-template <int ELEM>
-struct SwzX {
-  template <int LOG2V>
-  static SB_HD int at(int n, int lane) {
-    constexpr int SLOTS = 128 / ELEM;
-    constexpr int V = 1 << LOG2V;
-    static_assert(V <= SLOTS, "at most 128 bytes per tile row");
-    constexpr int ROWS = SLOTS / V;  // rows per line
-    int f;
-    if (ELEM == 16)
-      f = V == 1 ? (n >> 3) : (V == 8 ? (n ^ (n >> 3) ^ (n >> 6) ^ (n >> 9)) : (n ^ (n >> 3)));
-    else
-      f = V == 1 ? ((n >> 1) ^ (n >> 3)) : V == 2 ? (n ^ (n >> 2) ^ (n >> 6))
-                 : (V == 4 ? (n ^ (n >> 1) ^ (n >> 4))
-                           : (V == 8 ? (n ^ (n >> 1) ^ (n >> 3)) : (n ^ (n >> 3) ^ (n >> 4) ^ (n >> 6) ^ (n >> 7) ^ (n >> 8))));
-    const int slot = ((n % ROWS) << LOG2V) | lane;
-    return (n / ROWS) * SLOTS + (slot ^ (f & (SLOTS - 1)));
-  }
-};
-
 }  // namespace sb
 #define SB_MARK(ctx, id) ::sb::trace_mark((ctx).traceItem, id)
 #else

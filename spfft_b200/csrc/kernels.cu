@@ -50,9 +50,14 @@ __global__ void __launch_bounds__(kThreads) k_x_stage(const __grid_constant__ XA
 // for rank r's epoch in the local slot. Launched after the kernel whose peer stores it publishes
 // (stream order = kernel boundary, so those stores are complete), it replaces the
 // cudaStreamSynchronize + MPI_Alltoallv pair of transpose_mpi_compact_buffered_gpu.cpp:186-217.
+// Like MPI_Alltoallv the barrier simply WAITS for late peers (it spins with __nanosleep; a rank may
+// enter a transform arbitrarily later than the others). Debug knob SPFFT_B200_BARRIER_TIMEOUT_S=<s>
+// (> 0, opt-in, default off): trap after that many seconds instead of spinning on, to turn a lost
+// rank into an error while debugging.
 struct PeerBarrierArgs {
   int* flags[kMaxPeers];  // flags[r] = rank r's flag array (mapped), flags[me] local
   int numRanks, me, epoch;
+  unsigned long long timeoutNs;  // 0 = wait for ever (default)
 };
 
 __global__ void k_peer_barrier(const __grid_constant__ PeerBarrierArgs a) {
@@ -69,7 +74,7 @@ __global__ void k_peer_barrier(const __grid_constant__ PeerBarrierArgs a) {
     if (v - a.epoch >= 0) break;  // wrap-safe comparison
     unsigned long long t1;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-    if (t1 - t0 > 30ull * 1000000000ull) __trap();  // a peer never arrived: fail instead of hanging
+    if (a.timeoutNs != 0 && t1 - t0 > a.timeoutNs) __trap();  // opt-in debug knob only
     __nanosleep(200);
   }
 }
@@ -151,6 +156,12 @@ int sb_launch_peer_barrier(int* const* flags, int numRanks, int me, int epoch, v
   a.numRanks = numRanks;
   a.me = me;
   a.epoch = epoch;
+  static const unsigned long long timeoutNs = [] {
+    const char* e = getenv("SPFFT_B200_BARRIER_TIMEOUT_S");
+    const double sec = e ? atof(e) : 0.0;
+    return sec > 0.0 ? (unsigned long long)(sec * 1e9) : 0ull;
+  }();
+  a.timeoutNs = timeoutNs;
   sb::k_peer_barrier<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(a);
   sb::g_launches.fetch_add(1, std::memory_order_relaxed);
   return (int)cudaGetLastError();

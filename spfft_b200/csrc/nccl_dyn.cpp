@@ -121,16 +121,21 @@ void Communicator::all_to_all_v(const void* sendBuf, const long long* sendOffset
   if (size_ == 1) return;
   const Api& a = api();
   check_nccl(a.GroupStart());
-  for (int r = 0; r < size_; ++r) {
+  // the group is ALWAYS closed, also when a send / recv fails in between (an open group would
+  // swallow every later NCCL call of this thread)
+  int firstError = kNcclSuccess;
+  for (int r = 0; r < size_ && firstError == kNcclSuccess; ++r) {
     if (r == rank_) continue;
     if (sendCount[r] > 0)
-      check_nccl(a.Send(sb + sendOffset[r] * elemBytes, static_cast<size_t>(sendCount[r]) * elemBytes,
-                        kNcclInt8, r, comm_, stream));
-    if (recvCount[r] > 0)
-      check_nccl(a.Recv(rb + recvOffset[r] * elemBytes, static_cast<size_t>(recvCount[r]) * elemBytes,
-                        kNcclInt8, r, comm_, stream));
+      firstError = a.Send(sb + sendOffset[r] * elemBytes, static_cast<size_t>(sendCount[r]) * elemBytes,
+                          kNcclInt8, r, comm_, stream);
+    if (firstError == kNcclSuccess && recvCount[r] > 0)
+      firstError = a.Recv(rb + recvOffset[r] * elemBytes, static_cast<size_t>(recvCount[r]) * elemBytes,
+                          kNcclInt8, r, comm_, stream);
   }
-  check_nccl(a.GroupEnd());
+  const int endError = a.GroupEnd();
+  check_nccl(firstError);
+  check_nccl(endError);
 }
 
 }  // namespace b200

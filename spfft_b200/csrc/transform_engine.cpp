@@ -250,16 +250,66 @@ void choose_tile_lanes(const IndexMaps& m, int cb, long long smemLimit, AxisPlan
   if (ax.log2Vx < 0 || ax.log2Vy < 0 || ax.log2Vz < 0) throw InvalidParameterError();
 }
 
+void throw_error_code(int code) {
+  switch (code) {
+    case SPFFT_SUCCESS: return;
+    case SPFFT_OVERFLOW_ERROR: throw OverflowError();
+    case SPFFT_ALLOCATION_ERROR: throw HostAllocationError();
+    case SPFFT_INVALID_PARAMETER_ERROR: throw InvalidParameterError();
+    case SPFFT_DUPLICATE_INDICES_ERROR: throw DuplicateIndicesError();
+    case SPFFT_INVALID_INDICES_ERROR: throw InvalidIndicesError();
+    case SPFFT_MPI_ERROR: throw MPIError();
+    case SPFFT_MPI_PARAMETER_MISMATCH_ERROR: throw MPIParameterMismatchError();
+    case SPFFT_FFTW_ERROR: throw InternalError();
+    case SPFFT_GPU_ALLOCATION_ERROR: throw GPUAllocationError();
+    case SPFFT_GPU_LAUNCH_ERROR: throw GPULaunchError();
+    case SPFFT_GPU_INVALID_VALUE_ERROR: throw GPUInvalidValueError();
+    case SPFFT_GPU_ERROR: throw GPUError();
+    default: throw GenericError();
+  }
+}
+
+void agree_on_error(Communicator& comm, int localCode) {
+  // rank-local failures of a collective construction become the same error on EVERY rank (the
+  // lowest failing rank's code) instead of leaving the other ranks waiting in the next collective
+  const std::vector<int> all = comm.all_gather_ints(&localCode, 1);
+  for (int c : all)
+    if (c != SPFFT_SUCCESS) throw_error_code(c);
+}
+
+namespace {
+template <typename F>
+int error_code_of(F&& f) {
+  try {
+    f();
+  } catch (const GenericError& e) {
+    return static_cast<int>(e.error_code());
+  } catch (const std::bad_alloc&) {
+    return static_cast<int>(SPFFT_ALLOCATION_ERROR);
+  } catch (...) {
+    return static_cast<int>(SPFFT_UNKNOWN_ERROR);
+  }
+  return static_cast<int>(SPFFT_SUCCESS);
+}
+}  // namespace
+
 std::shared_ptr<IndexMaps> make_distributed_index_maps(Communicator& comm, SpfftTransformType type,
                                                        int dimX, int dimY, int dimZ, int localZLength,
                                                        int numLocalElements,
                                                        SpfftIndexFormatType indexFormat,
                                                        const int* indices) {
-  // local part exactly as for a single rank (index conversion, zeroZeroStickIndex)
-  auto m = make_local_index_maps(type, dimX, dimY, dimZ, numLocalElements, indexFormat, indices);
+  // local part exactly as for a single rank (index conversion, zeroZeroStickIndex); a rank whose
+  // indices are invalid still takes part in the collectives below and reports its error code there
+  std::shared_ptr<IndexMaps> m;
+  const int localError = error_code_of(
+      [&] { m = make_local_index_maps(type, dimX, dimY, dimZ, numLocalElements, indexFormat, indices); });
   const int P = comm.size();
-  const int mine[6] = {dimX, dimY, dimZ, localZLength, m->num_sticks(), numLocalElements};
-  const std::vector<int> all = comm.all_gather_ints(mine, 6);  // parameters.cpp:89
+  const int mine[7] = {dimX, dimY, dimZ, localZLength, m ? m->num_sticks() : 0, numLocalElements, localError};
+  const std::vector<int> all7 = comm.all_gather_ints(mine, 7);  // parameters.cpp:89
+  for (int r = 0; r < P; ++r) throw_error_code(all7[7 * r + 6]);
+  std::vector<int> all(static_cast<size_t>(6) * P);
+  for (int r = 0; r < P; ++r)
+    for (int k = 0; k < 6; ++k) all[6 * r + k] = all7[7 * r + k];
   std::vector<std::vector<long long>> counts(P, std::vector<long long>(6));
   int maxSticks = 0;
   for (int r = 0; r < P; ++r) {
@@ -276,7 +326,7 @@ std::shared_ptr<IndexMaps> make_distributed_index_maps(Communicator& comm, Spfft
       sticks[r].assign(gathered.begin() + static_cast<size_t>(r) * maxSticks,
                        gathered.begin() + static_cast<size_t>(r) * maxSticks + all[6 * r + 4]);
   }
-  finish_distributed_index_maps(*m, comm.rank(), counts, std::move(sticks));
+  agree_on_error(comm, error_code_of([&] { finish_distributed_index_maps(*m, comm.rank(), counts, std::move(sticks)); }));
   return m;
 }
 
@@ -390,8 +440,9 @@ TransformEngine<T>::TransformEngine(SpfftProcessingUnitType executionUnit,
       grid_(std::move(grid)),
       maps_(std::move(maps)),
       plan_(std::move(plan)) {
-  // transform_internal.cpp:52-80
   if (!grid_) throw InvalidParameterError();
+  auto construct = [&] {
+  // transform_internal.cpp:52-80
   if (maps_->local_planes() > grid_->max_num_local_xy_planes()) throw InvalidParameterError();
   if (grid_->local() && maps_->dimZ != maps_->local_planes()) throw InvalidParameterError();
   if (!grid_->local() && (grid_->communicator()->size() != maps_->commSize ||
@@ -421,6 +472,17 @@ TransformEngine<T>::TransformEngine(SpfftProcessingUnitType executionUnit,
   if (plan_->distributed &&
       sizeof(sb::cx<T>) * static_cast<size_t>(plan_->exchange.planeSideElements) > grid_->bytes_q())
     throw InvalidParameterError();
+  // array B also stages the frequency values of host-pointer calls; duplicate triplets can make
+  // numLocalElements larger than every grid-derived size (indices.hpp:124 only bounds it by the volume)
+  if (sizeof(sb::cx<T>) * static_cast<size_t>(maps_->num_values()) > grid_->bytes_b())
+    throw InvalidParameterError();
+  };
+  // distributed: every rank reports, all ranks throw the same error (plan construction can fail on
+  // one rank only: table overflow, shared-memory limit, buffer sizes)
+  if (grid_->local())
+    construct();
+  else
+    agree_on_error(*grid_->communicator(), error_code_of(construct));
   stream_.reset(new Stream());
   startEvent_.reset(new Event());
   endEvent_.reset(new Event());

@@ -206,6 +206,11 @@ std::shared_ptr<DevicePlan<T>> build_device_plan(const IndexMaps& maps, long lon
 
 // Parameters of a distributed transform (parameters.cpp:43-140): local index conversion, then the
 // stick lists and plane counts of all ranks gathered over the communicator (collective call).
+// Throws the exception type of a C error code (no-op for SPFFT_SUCCESS).
+void throw_error_code(int code);
+// Collective: all ranks pass their local error code; if any is not SPFFT_SUCCESS every rank throws it.
+void agree_on_error(Communicator& comm, int localCode);
+
 std::shared_ptr<IndexMaps> make_distributed_index_maps(Communicator& comm, SpfftTransformType type,
                                                        int dimX, int dimY, int dimZ, int localZLength,
                                                        int numLocalElements,
