@@ -1,0 +1,236 @@
+// wfft.hpp -- warp-autonomous register FFT: 16 complex values per lane, ONE shared-memory exchange
+// per transform that never leaves the warp (no CTA barrier anywhere inside a transform).
+//
+//   N = 512 : one warp (32 lanes x 16 values) per transform
+//             stage A = radix 32 = radix-16 DFT inside the lane  +  radix-2 across the lane pair
+//             (L, L^16) with the compile-time twiddles w32^q, exchanged with 8 shuffles per lane;
+//             exchange through the warp's private 8 KB (double) region of shared memory;
+//             stage B = radix 16 with the per-lane twiddles w512^(r*L).
+//   N = 256 : half a warp (16 lanes x 16 values) per transform, two transforms per warp
+//             stage A = radix 16, exchange, stage B = radix 16 with w256^(r*j).
+//
+// Input and output are both in natural "lane-strided" order: lane L (of the T lanes of a transform)
+// holds x[L + T*m] in register m before and X[L + T*m] after the transform. Consecutive lanes hold
+// consecutive elements, so global loads / stores of rows are coalesced and a transposed store into
+// an 8-lane tile [n][lane] with the 128-byte XOR pattern of a TMA tensor map is conflict free.
+//
+// Compared with the 8-values-per-thread plan of fast_fft.hpp (two CTA-wide exchanges, three barriers
+// per tile) this halves the shared-memory wavefronts per point and removes every CTA barrier from
+// the transform itself; what a tile still needs is ONE barrier / mbarrier wait on the side where
+// eight transforms share 128-byte global segments (z / y stages).
+//
+// Index algebra (Stockham autosort, as in fast_fft.hpp): stage with radix R, stride NS, butterfly b:
+//   inputs n = b + r*N/R, twiddled by w_{NS*R}^{r*(b mod NS)};  outputs (b-k)*R + k + q*NS, k = b mod NS.
+// N = 512: stage A (R = 32, NS = 1): b = j = L & 15, input r' = 2m + h with h = L >> 4, i.e. element
+//   j + 16*(2m + h) = L + 32 m; output slot 32 j + k'. Stage B (R = 16, NS = 32): b = L, inputs L + 32 r,
+//   twiddle w512^(r L), outputs L + 32 q.
+//
+// The arithmetic bodies are SB_HD (host + device) so that tests/emu can run the identical index
+// algebra lane by lane on the CPU; only the exchange primitives (shuffle, __syncwarp) are device code.
+//
+// Replaces the cuFFT plans of the reference (src/fft/transform_1d_gpu.hpp:52-141,
+// src/fft/transform_2d_gpu.hpp:51-140): unnormalised DFT, sign + backward / - forward.
+#pragma once
+#include "cx.hpp"
+#include "fft_tile.hpp"
+
+namespace sb {
+
+// v * (c + s*i*sn), s = +1 (BWD) / -1 (forward)
+template <bool BWD, typename T>
+SB_HD cx<T> mul_w(cx<T> v, T c, T sn) {
+  const T si = BWD ? sn : -sn;
+  return mk<T>(v.x * c - v.y * si, v.x * si + v.y * c);
+}
+
+// 16-point DFT in registers, natural order in and out (4 x 4 decomposition, 8 radix-4 butterflies).
+template <typename T, bool BWD>
+SB_HD void dft16(cx<T>* v) {
+  const T h = T(0.70710678118654752440084436210485);   // cos(pi/4)
+  const T c1 = T(0.92387953251128675612818318939679);  // cos(pi/8)
+  const T s1 = T(0.38268343236508977172845998403040);  // sin(pi/8)
+  // A[n0][k1] = sum_n1 x[n0 + 4 n1] w4^(n1 k1), stored at v[n0 + 4 k1]
+#pragma unroll
+  for (int n0 = 0; n0 < 4; ++n0) dft4<T, BWD>(v[n0], v[n0 + 4], v[n0 + 8], v[n0 + 12]);
+  // A[n0][k1] *= w16^(n0 k1)
+  v[1 + 4 * 1] = mul_w<BWD, T>(v[1 + 4 * 1], c1, s1);    // e = 1
+  v[2 + 4 * 1] = mul_w<BWD, T>(v[2 + 4 * 1], h, h);      // e = 2
+  v[3 + 4 * 1] = mul_w<BWD, T>(v[3 + 4 * 1], s1, c1);    // e = 3
+  v[1 + 4 * 2] = mul_w<BWD, T>(v[1 + 4 * 2], h, h);      // e = 2
+  v[2 + 4 * 2] = mul_si<BWD, T>(v[2 + 4 * 2]);           // e = 4
+  v[3 + 4 * 2] = mul_w<BWD, T>(v[3 + 4 * 2], -h, h);     // e = 6
+  v[1 + 4 * 3] = mul_w<BWD, T>(v[1 + 4 * 3], s1, c1);    // e = 3
+  v[2 + 4 * 3] = mul_w<BWD, T>(v[2 + 4 * 3], -h, h);     // e = 6
+  v[3 + 4 * 3] = mul_w<BWD, T>(v[3 + 4 * 3], -c1, -s1);  // e = 9
+  // X[k1 + 4 k2] = sum_n0 A[n0][k1] w4^(n0 k2): now v[4 k1 + k2] = X[k1 + 4 k2]
+#pragma unroll
+  for (int k1 = 0; k1 < 4; ++k1) dft4<T, BWD>(v[4 * k1], v[4 * k1 + 1], v[4 * k1 + 2], v[4 * k1 + 3]);
+  // natural order (register renaming only: every index is a compile-time constant)
+  cx<T> t;
+#define SB_SWAP16(a, b) t = v[a]; v[a] = v[b]; v[b] = t;
+  SB_SWAP16(1, 4) SB_SWAP16(2, 8) SB_SWAP16(3, 12) SB_SWAP16(6, 9) SB_SWAP16(7, 13) SB_SWAP16(11, 14)
+#undef SB_SWAP16
+}
+
+// cos / sin of 2*pi*q/32, q = 0..15 (radix-2 step across the lane pair of the N = 512 plan)
+template <typename T>
+SB_HD void w32_const(int q, T& c, T& s) {
+  constexpr double C[16] = {1.0,
+                            0.98078528040323044912618223613424,
+                            0.92387953251128675612818318939679,
+                            0.83146961230254523707878837761791,
+                            0.70710678118654752440084436210485,
+                            0.55557023301960222474283081394853,
+                            0.38268343236508977172845998403040,
+                            0.19509032201612826784828486847702,
+                            0.0,
+                            -0.19509032201612826784828486847702,
+                            -0.38268343236508977172845998403040,
+                            -0.55557023301960222474283081394853,
+                            -0.70710678118654752440084436210485,
+                            -0.83146961230254523707878837761791,
+                            -0.92387953251128675612818318939679,
+                            -0.98078528040323044912618223613424};
+  c = T(C[q]);
+  s = T(C[q >= 8 ? q - 8 : 8 - q]);  // sin(t) = cos(t - pi/2) = cos(2 pi |q - 8| / 32)
+}
+
+template <typename T, int N>
+struct WPlan;
+
+// --------------------------------------------------------------------------------------------
+// N = 512
+// --------------------------------------------------------------------------------------------
+template <typename T>
+struct WPlan<T, 512> {
+  static constexpr int N = 512;
+  static constexpr int LANES = 32;          // lanes per transform
+  static constexpr int PER_WARP = 1;        // transforms per warp
+  static constexpr int TW = 15 * 32;        // stage-B twiddle table entries: tw[(r-1)*32 + L] = w512^(r L)
+  // slot of element n'' of the exchange, XOR-swizzled so that the stage-A writes (32 j + k', lanes
+  // along j) and the stage-B reads (L + 32 r, lanes along L) are both bank-conflict free
+  static SB_HD int slot(int n) {
+    return sizeof(T) == 8 ? (n ^ ((n >> 5) & 7)) : (n ^ ((n >> 5) & 15));
+  }
+  // exchange write: register i of lane L after stage A
+  static SB_HD int xw(int L, int i) {
+    const int j = L & 15, h = L >> 4;
+    const int kp = (i & 7) + 8 * h + ((i & 8) << 1);
+    return slot(32 * j + kp);
+  }
+  // exchange read: input r of stage B
+  static SB_HD int xr(int L, int r) { return slot(L + 32 * r); }
+
+  // Stage A, part 1 (inside the lane): DFT16 over the lane's 16 inputs. Lanes of the upper half warp
+  // (h = 1) produce their outputs rotated by 8 registers (odd inputs negated) and multiplied by
+  // w32^q', so that afterwards EVERY lane keeps registers 0..7 and sends registers 8..15.
+  template <bool BWD>
+  static SB_HD void stage_a_local(cx<T>* v, int L) {
+    const int h = L >> 4;
+    if (h) {
+#pragma unroll
+      for (int m = 1; m < 16; m += 2) v[m] = mk<T>(-v[m].x, -v[m].y);
+    }
+    dft16<T, BWD>(v);
+    if (h) {
+      // register q holds E1[q'] with q' = (q + 8) & 15: multiply by w32^(q')
+#pragma unroll
+      for (int q = 0; q < 16; ++q) {
+        const int qp = (q + 8) & 15;
+        if (qp == 0) continue;
+        T c, s;
+        w32_const<T>(qp, c, s);
+        v[q] = qp == 8 ? mul_si<BWD, T>(v[q]) : mul_w<BWD, T>(v[q], c, s);
+      }
+    }
+  }
+  // Stage A, part 2: `recv` = register 8 + i of the partner lane L ^ 16. In place: register i gets
+  // k' = i + 8 h, register 8 + i gets k' = i + 8 h + 16.
+  static SB_HD void stage_a_combine(cx<T>& keep, cx<T>& hi, cx<T> recv, int L) {
+    const cx<T> lo = keep + recv;
+    const cx<T> d = keep - recv;  // h = 0: E0 - T;  h = 1: T - E0 = -(E0 - T)
+    keep = lo;
+    hi = (L >> 4) ? mk<T>(-d.x, -d.y) : d;
+  }
+  // Stage B: twiddles + DFT16; afterwards v[q] = X[L + 32 q]. tw: forward table (conjugated for BWD)
+  template <bool BWD, typename TWP>
+  static SB_HD void stage_b(cx<T>* v, int L, TWP tw) {
+#pragma unroll
+    for (int r = 1; r < 16; ++r) {
+      const cx<T> w = tw[(r - 1) * 32 + L];
+      v[r] = v[r] * (BWD ? conj(w) : w);
+    }
+    dft16<T, BWD>(v);
+  }
+};
+
+// --------------------------------------------------------------------------------------------
+// N = 256: half a warp per transform
+// --------------------------------------------------------------------------------------------
+template <typename T>
+struct WPlan<T, 256> {
+  static constexpr int N = 256;
+  static constexpr int LANES = 16;
+  static constexpr int PER_WARP = 2;
+  static constexpr int TW = 15 * 16;  // tw[(r-1)*16 + j] = w256^(r j)
+  // n'' in 0..255 of transform t (0/1) of the warp: writes 16 j + q (lanes along j), reads j + 16 r
+  static SB_HD int slot(int n) {
+    return sizeof(T) == 8 ? (n ^ ((n >> 4) & 7)) : (n ^ ((n >> 4) & 15));
+  }
+  static SB_HD int xw(int L, int i) { return ((L >> 4) << 8) + slot(16 * (L & 15) + i); }
+  static SB_HD int xr(int L, int r) { return ((L >> 4) << 8) + slot((L & 15) + 16 * r); }
+  template <bool BWD>
+  static SB_HD void stage_a_local(cx<T>* v, int) {
+    dft16<T, BWD>(v);
+  }
+  template <bool BWD, typename TWP>
+  static SB_HD void stage_b(cx<T>* v, int L, TWP tw) {
+    const int j = L & 15;
+#pragma unroll
+    for (int r = 1; r < 16; ++r) {
+      const cx<T> w = tw[(r - 1) * 16 + j];
+      v[r] = v[r] * (BWD ? conj(w) : w);
+    }
+    dft16<T, BWD>(v);
+  }
+};
+
+// number of table entries / fill (host side, long double roots like make_fast_twiddles)
+inline int wfft_tw_size(int n) { return n == 512 ? 15 * 32 : (n == 256 ? 15 * 16 : 0); }
+inline bool wfft_length(int n) { return n == 512 || n == 256; }
+
+#if SB_ON_GPU
+// complex shuffle
+template <typename T>
+SB_DEV cx<T> shfl_xor_cx(cx<T> v, int mask) {
+  if constexpr (sizeof(T) == 8) {
+    return mk<T>(__shfl_xor_sync(0xffffffffu, v.x, mask), __shfl_xor_sync(0xffffffffu, v.y, mask));
+  } else {
+    return mk<T>(__shfl_xor_sync(0xffffffffu, v.x, mask), __shfl_xor_sync(0xffffffffu, v.y, mask));
+  }
+}
+
+// The whole transform of one warp: v[m] = x[L + T m] in, v[q] = X[L + T q] out. `X` = the warp's private
+// exchange region (N * PER_WARP elements), `tw` = stage-B table (shared or global memory).
+template <typename T, int N, bool BWD, typename TWP>
+SB_DEV void warp_fft(cx<T>* v, cx<T>* X, TWP tw, int L) {
+  using P = WPlan<T, N>;
+  P::template stage_a_local<BWD>(v, L);
+  if constexpr (N == 512) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const cx<T> recv = shfl_xor_cx<T>(v[8 + i], 16);
+      P::stage_a_combine(v[i], v[8 + i], recv, L);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 16; ++i) X[P::xw(L, i)] = v[i];
+  __syncwarp();
+#pragma unroll
+  for (int r = 0; r < 16; ++r) v[r] = X[P::xr(L, r)];
+  __syncwarp();  // the region may be rewritten by the warp's next transform
+  P::template stage_b<BWD>(v, L, tw);
+}
+#endif
+
+}  // namespace sb
