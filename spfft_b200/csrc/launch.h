@@ -30,6 +30,13 @@ int sb_launch_peer_barrier(int* const* flags, int numRanks, int me, int epoch, v
  * cudaErrorInvalidValue when unsupported) and the launch of one direction. */
 int sb_xy_pipe_config(int isFloat, int n, int numPlanes, int* ring, int* lag, int* numCounters);
 int sb_launch_xy_pipe_f64(int forward, const sb::XYArgs<double>* args, void* stream);
+/* Warp-FFT kernels (wfft_xy.cu, wfft_z.cu: one warp per transform, TMA-staged tiles; double precision,
+ * transform length 512). sb_wxy_config: plan-time query like sb_xy_fused_config for the fused xy stage
+ * (C2C, dimX == dimY == 512, local slab); sb_wz_available: z stage (dimZ == 512, values in stick order). */
+int sb_wxy_config(int isFloat, int n, int numPlanes, int* ring, int* lag, int* numCounters);
+int sb_launch_wxy_f64(int forward, const sb::XYArgs<double>* args, void* stream);
+int sb_wz_available(int isFloat, int nz);
+int sb_launch_wz_f64(int forward, const sb::ZArgs<double>* args, void* stream);
 /* Batched multi-transform (band_kernels.cu): one launch per stage over `numBands` <= sb::kMaxBands
  * transforms that share the plan in `args`; the table holds the per-band data pointers.
  * sb_band_kernel_available: does a batched kernel exist for an axis of length n (registerFft: the

@@ -42,8 +42,10 @@ inline int make_tile_map(TensorMap* map, void* base, int elemBytes, long long co
   const cuuint32_t box[3] = {(cuuint32_t)(2 * boxCols), (cuuint32_t)boxRows, 1};
   const cuuint32_t estr[3] = {1, 1, 1};
   const int rowBytes = 2 * boxCols * sb;
-  const CUtensorMapSwizzle swz = rowBytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
-                                                 : (rowBytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE);
+  const CUtensorMapSwizzle swz = rowBytes == 128  ? CU_TENSOR_MAP_SWIZZLE_128B
+                                 : rowBytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                 : rowBytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B
+                                                  : CU_TENSOR_MAP_SWIZZLE_NONE;
   const CUresult r = encode(map, dt, 3, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
                             CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? 0 : (int)cudaErrorInvalidValue;

@@ -29,6 +29,8 @@ struct Launch<double> {
   static int x(int f, const sb::XArgs<double>& a, void* s) { return sb_launch_x_f64(f, &a, s); }
   static int xy(int f, const sb::XYArgs<double>& a, void* s) { return sb_launch_xy_f64(f, &a, s); }
   static int xy_pipe(int f, const sb::XYArgs<double>& a, void* s) { return sb_launch_xy_pipe_f64(f, &a, s); }
+  static int wxy(int f, const sb::XYArgs<double>& a, void* s) { return sb_launch_wxy_f64(f, &a, s); }
+  static int wz(int f, const sb::ZArgs<double>& a, void* s) { return sb_launch_wz_f64(f, &a, s); }
 };
 template <>
 struct Launch<float> {
@@ -40,6 +42,8 @@ struct Launch<float> {
   static int x(int f, const sb::XArgs<float>& a, void* s) { return sb_launch_x_f32(f, &a, s); }
   static int xy(int f, const sb::XYArgs<float>& a, void* s) { return sb_launch_xy_f32(f, &a, s); }
   static int xy_pipe(int, const sb::XYArgs<float>&, void*) { return static_cast<int>(cudaErrorInvalidValue); }
+  static int wxy(int, const sb::XYArgs<float>&, void*) { return static_cast<int>(cudaErrorInvalidValue); }
+  static int wz(int, const sb::ZArgs<float>&, void*) { return static_cast<int>(cudaErrorInvalidValue); }
 };
 
 inline void check_launch(int err) {
@@ -362,8 +366,18 @@ std::shared_ptr<DevicePlan<T>> build_device_plan(const IndexMaps& m, long long s
                                        &plan->xyLag, &plan->xyCounters);
     plan->fusedXY = err == 0;
   }
+  // Warp-FFT kernels (default where they exist; SPFFT_B200_WFFT=0 selects the round-1 kernels, bit 0 =
+  // fused xy stage, bit 1 = z stage): one warp per transform, tiles staged by TMA, y <-> x hand-off in L2.
+  const char* wEnv = std::getenv("SPFFT_B200_WFFT");
+  const int wMask = wEnv ? std::atoi(wEnv) : 3;
+  if (!plan->fusedXY && (wMask & 1) && sizeof(T) == 8 && fastX && fastY && m.dimX == m.dimY &&
+      m.type == SPFFT_TRANS_C2C && m.commSize == 1 && m.num_sticks() > 0 && ax.log2Vy == 3) {
+    const int err = sb_wxy_config(0, m.dimX, m.local_planes(), &plan->xyRing, &plan->xyLag, &plan->xyCounters);
+    plan->fusedXY = plan->wfftXY = err == 0;
+  }
   if (!plan->fusedXY && fastX) ax.log2Vx = fast_path_log2_lanes_x(m.dimX);
   TileMaps t = build_tile_maps(m, ax.log2Vz, ax.log2Vy, fastZ, fastY);
+  plan->wfftZ = (wMask & 2) && fastZ && ax.log2Vz == 3 && sb_wz_available(sizeof(T) == 4, m.dimZ) && !t.zInv.empty();
   plan->numStickTiles = t.numStickTiles;
   plan->pitch = t.pitch;
   plan->numXTiles = t.numXTiles;
@@ -418,6 +432,7 @@ std::shared_ptr<DevicePlan<T>> build_device_plan(const IndexMaps& m, long long s
     const char* ord = std::getenv("SPFFT_B200_FWD_ORDER");
     if (ord && std::atoi(ord) == 1) plan->fwdTileOrder = upload(st, total, plan->exchange.fwdTileOrder);
     plan->fusedXY = false;
+    plan->wfftXY = false;
   } else {
     p.xtStart = upload(st, total, t.xtStart);
     p.stickSlot = upload(st, total, t.stickSlot);
@@ -669,7 +684,7 @@ void TransformEngine<T>::enqueue_backward(const T* input, T* output) {
       za.rowOff = plan_->rowOff;
     }
     za.wireF32 = wire_f32() ? 1 : 0;
-    check_launch(Launch<T>::z(0, za, s));
+    check_launch(plan_->wfftZ && !peer && !za.wireF32 ? Launch<T>::wz(0, za, s) : Launch<T>::z(0, za, s));
     record_stage(peer ? "z backward + exchange" : "z backward");
   }
   // ---- exchange: every rank sends, for every peer, the rows of that peer's slab (one contiguous
@@ -690,8 +705,9 @@ void TransformEngine<T>::enqueue_backward(const T* input, T* output) {
   T* outDev = outOnDevice ? output : device_space();
   if (plan_->fusedXY) {
     // ---- fused xy stage: y tiles and x tiles in one persistent kernel, hand-off through L2
-    check_launch(plan_->pipeXY ? Launch<T>::xy_pipe(0, make_xy_args(geo, nullptr, outDev), s)
-                               : Launch<T>::xy(0, make_xy_args(geo, nullptr, outDev), s));
+    check_launch(plan_->wfftXY ? Launch<T>::wxy(0, make_xy_args(geo, nullptr, outDev), s)
+                 : plan_->pipeXY ? Launch<T>::xy_pipe(0, make_xy_args(geo, nullptr, outDev), s)
+                                 : Launch<T>::xy(0, make_xy_args(geo, nullptr, outDev), s));
     record_stage("xy backward");
   } else {
     // ---- y stage: stick gather + plane symmetry + y-FFT (execution_gpu.cpp:371-390)
@@ -744,8 +760,9 @@ void TransformEngine<T>::enqueue_forward(const T* input, T* output, SpfftScaling
     }
     if (plan_->fusedXY) {
       if (anySticks) {
-        check_launch(plan_->pipeXY ? Launch<T>::xy_pipe(1, make_xy_args(geo, src, nullptr), s)
-                                   : Launch<T>::xy(1, make_xy_args(geo, src, nullptr), s));
+        check_launch(plan_->wfftXY ? Launch<T>::wxy(1, make_xy_args(geo, src, nullptr), s)
+                     : plan_->pipeXY ? Launch<T>::xy_pipe(1, make_xy_args(geo, src, nullptr), s)
+                                     : Launch<T>::xy(1, make_xy_args(geo, src, nullptr), s));
         record_stage("xy forward");
       }
     } else {
@@ -777,7 +794,7 @@ void TransformEngine<T>::enqueue_forward(const T* input, T* output, SpfftScaling
     auto za = make_z_args<T>(m, geo, plan_->axes, plan_->ptrs, true, sticks(), nullptr, outDev,
                              scaling == SPFFT_FULL_SCALING);
     za.wireF32 = wire_f32() ? 1 : 0;
-    check_launch(Launch<T>::z(1, za, s));
+    check_launch(plan_->wfftZ && !za.wireF32 ? Launch<T>::wz(1, za, s) : Launch<T>::z(1, za, s));
     record_stage("z forward");
   }
   if (!outOnDevice) {

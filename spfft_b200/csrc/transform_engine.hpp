@@ -106,6 +106,9 @@ struct DevicePlan {
   bool fusedXY = false;
   bool pipeXY = false;  // fusedXY through the pipelined kernel (fast_pipe.cu) instead of fast_xy.cu
   int xyRing = 0, xyLag = 0, xyCounters = 0;
+  // warp-FFT kernels (wfft_xy.cu / wfft_z.cu): fused xy stage (implies fusedXY) / z stage
+  bool wfftXY = false;
+  bool wfftZ = false;
   // distributed transforms: the stick <-> slab exchange (host offsets/counts) and the y-stage
   // tables over all ranks' sticks
   bool distributed = false;

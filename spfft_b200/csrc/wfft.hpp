@@ -31,6 +31,8 @@
 // Replaces the cuFFT plans of the reference (src/fft/transform_1d_gpu.hpp:52-141,
 // src/fft/transform_2d_gpu.hpp:51-140): unnormalised DFT, sign + backward / - forward.
 #pragma once
+#include <cmath>
+
 #include "cx.hpp"
 #include "fft_tile.hpp"
 
@@ -41,6 +43,25 @@ template <bool BWD, typename T>
 SB_HD cx<T> mul_w(cx<T> v, T c, T sn) {
   const T si = BWD ? sn : -sn;
   return mk<T>(v.x * c - v.y * si, v.x * si + v.y * c);
+}
+
+// -v if `flip` (lane-dependent), v otherwise: an integer XOR of the sign bits on the GPU (ALU pipe, no
+// branch, no select) instead of a negation on the fp64 pipe behind a divergent branch.
+template <typename T>
+SB_HD T flip_sign(T x, unsigned mask /* 0 or 0x80000000 */) {
+#if SB_ON_GPU
+  if constexpr (sizeof(T) == 8) {
+    return __hiloint2double(__double2hiint(x) ^ (int)mask, __double2loint(x));
+  } else {
+    return __int_as_float(__float_as_int(x) ^ (int)mask);
+  }
+#else
+  return mask ? -x : x;
+#endif
+}
+template <typename T>
+SB_HD cx<T> flip_sign(cx<T> v, unsigned mask) {
+  return mk<T>(flip_sign<T>(v.x, mask), flip_sign<T>(v.y, mask));
 }
 
 // 16-point DFT in registers, natural order in and out (4 x 4 decomposition, 8 radix-4 butterflies).
@@ -127,10 +148,9 @@ struct WPlan<T, 512> {
   template <bool BWD>
   static SB_HD void stage_a_local(cx<T>* v, int L) {
     const int h = L >> 4;
-    if (h) {
+    const unsigned mask = (unsigned)h << 31;
 #pragma unroll
-      for (int m = 1; m < 16; m += 2) v[m] = mk<T>(-v[m].x, -v[m].y);
-    }
+    for (int m = 1; m < 16; m += 2) v[m] = flip_sign<T>(v[m], mask);
     dft16<T, BWD>(v);
     if (h) {
       // register q holds E1[q'] with q' = (q + 8) & 15: multiply by w32^(q')
@@ -150,7 +170,7 @@ struct WPlan<T, 512> {
     const cx<T> lo = keep + recv;
     const cx<T> d = keep - recv;  // h = 0: E0 - T;  h = 1: T - E0 = -(E0 - T)
     keep = lo;
-    hi = (L >> 4) ? mk<T>(-d.x, -d.y) : d;
+    hi = flip_sign<T>(d, (unsigned)(L >> 4) << 31);
   }
   // Stage B: twiddles + DFT16; afterwards v[q] = X[L + 32 q]. tw: forward table (conjugated for BWD)
   template <bool BWD, typename TWP>
@@ -194,6 +214,53 @@ struct WPlan<T, 256> {
     dft16<T, BWD>(v);
   }
 };
+
+// Lane twiddles kept in registers for the whole kernel: w^1, w^2, w^4, w^8 of w = w_N^(lane index),
+// forward sign. The other eleven powers of a radix-16 stage are products of these (11 complex
+// multiplications on the fp64 / fp32 pipe instead of 15 table reads through the L1 data pipe, which is
+// the busier unit of the stage kernels).
+template <typename T>
+struct LaneTw {
+  cx<T> w1, w2, w4, w8;
+};
+
+// v[r] *= w^r (r = 1..15), conjugated for the backward transform, then the 16-point DFT.
+template <typename T, bool BWD>
+SB_HD void twiddle_dft16(cx<T>* v, const LaneTw<T>& t) {
+  const cx<T> w1 = BWD ? conj(t.w1) : t.w1;
+  const cx<T> w2 = BWD ? conj(t.w2) : t.w2;
+  const cx<T> w4 = BWD ? conj(t.w4) : t.w4;
+  const cx<T> w8 = BWD ? conj(t.w8) : t.w8;
+  const cx<T> w3 = w2 * w1;
+  v[1] = v[1] * w1;
+  v[2] = v[2] * w2;
+  v[3] = v[3] * w3;
+  v[4] = v[4] * w4;
+  const cx<T> w5 = w4 * w1, w6 = w4 * w2, w7 = w4 * w3;
+  v[5] = v[5] * w5;
+  v[6] = v[6] * w6;
+  v[7] = v[7] * w7;
+  v[8] = v[8] * w8;
+  v[9] = v[9] * (w8 * w1);
+  v[10] = v[10] * (w8 * w2);
+  v[11] = v[11] * (w8 * w3);
+  v[12] = v[12] * (w8 * w4);
+  v[13] = v[13] * (w8 * w5);
+  v[14] = v[14] * (w8 * w6);
+  v[15] = v[15] * (w8 * w7);
+  dft16<T, BWD>(v);
+}
+
+// host side: the four lane twiddles w_n^(2^i * lane), i = 0..3, lane = 0..lanes-1, forward sign
+template <typename T>
+inline void wfft_lane_twiddles(int n, int lanes, cx<T>* out /* [4][lanes] */) {
+  const long double pi2 = 6.283185307179586476925286766559005768L;
+  for (int i = 0; i < 4; ++i)
+    for (int L = 0; L < lanes; ++L) {
+      const long double a = -pi2 * (long double)(((1 << i) * L) % n) / (long double)n;
+      out[i * lanes + L] = mk<T>((T)cosl(a), (T)sinl(a));
+    }
+}
 
 // number of table entries / fill (host side, long double roots like make_fast_twiddles)
 inline int wfft_tw_size(int n) { return n == 512 ? 15 * 32 : (n == 256 ? 15 * 16 : 0); }

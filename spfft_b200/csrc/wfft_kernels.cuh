@@ -1,0 +1,169 @@
+// wfft_kernels.cuh -- device building blocks of the warp-FFT stage kernels (wfft_xy.cu, wfft_z.cu),
+// sm_100a, double precision, transform length 512.
+//
+// One warp = one transform (wfft.hpp: 16 values per lane, radix 32 = in-lane DFT16 + one shuffle step,
+// ONE exchange through shared memory that never leaves the warp, radix 16 with lane twiddles held in
+// registers). One CTA = 8 warps = one tile of 8 transforms and ONE 64 KB tile buffer S laid out
+// [512 rows][8 x 16-byte chunks] with the 128-byte XOR pattern of a TMA tensor map
+// (CU_TENSOR_MAP_SWIZZLE_128B): chunk c of row r sits at chunk c ^ (r & 7). Warp w owns "column" w of
+// S: it is its private exchange region AND the place where the transposed side of a y / z tile is
+// handed to / taken from the TMA engine, so the only CTA-wide synchronisation of a tile is around the
+// bulk tensor copy itself.
+//
+// Replaces the cuFFT plans of the reference (src/fft/transform_1d_gpu.hpp:52-141,
+// src/fft/transform_2d_gpu.hpp:51-140) together with its transpose / compression kernels
+// (src/transpose/gpu_kernels/local_transpose_kernels.cu:48-201,
+// src/compression/gpu_kernels/compression_kernels.cu:40-150).
+#pragma once
+#include <cuda_runtime.h>
+
+#include "stage_kernels.hpp"
+#include "tma_util.hpp"
+#include "wfft.hpp"
+
+namespace sb {
+
+constexpr int kWN = 512;        // transform length of this kernel family
+constexpr int kWWarps = 8;      // transforms per tile
+constexpr int kWThreads = 256;
+constexpr size_t kWTileBytes = (size_t)kWN * kWWarps * sizeof(cx<double>);  // 64 KB
+
+// w[i][L] = w_512^(2^i * L), forward sign; travels as a kernel parameter (2 KB)
+template <typename T>
+struct WTw4 {
+  cx<T> w[4][32];
+};
+
+// The lane twiddles live in shared memory (2 KB, staged once per CTA) and are re-read for every transform:
+// as registers they would cost 16 of the 128, and read straight from the parameter bank (lane-dependent
+// index) every access replays once per lane (ncu: LDC + short-scoreboard stalls, 20 % of all samples).
+template <typename T>
+__device__ __forceinline__ void w_stage_twiddles(cx<T>* sTw, const WTw4<T>& twp) {
+  for (int i = threadIdx.x; i < 4 * 32; i += blockDim.x) sTw[i] = twp.w[i >> 5][i & 31];
+}
+template <typename T>
+__device__ __forceinline__ LaneTw<T> w_lane_twiddles(const cx<T>* sTw, int L) {
+  LaneTw<T> t;
+  t.w1 = sTw[L];
+  t.w2 = sTw[32 + L];
+  t.w4 = sTw[64 + L];
+  t.w8 = sTw[96 + L];
+  return t;
+}
+
+template <typename T>
+__device__ __forceinline__ cx<T>* wcol(cx<T>* S, int s, int w) {
+  return S + (s << 3) + (w ^ (s & 7));
+}
+
+__device__ __forceinline__ int w_ld_acquire(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void w_fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+__device__ __forceinline__ void w_tma_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+template <typename T>
+__device__ __forceinline__ cx<T> w_ldcg(const cx<T>* p) {
+  const double2 q = __ldcg(reinterpret_cast<const double2*>(p));
+  return mk<T>(q.x, q.y);
+}
+template <typename T>
+__device__ __forceinline__ void w_stcg(cx<T>* p, cx<T> v) {
+  __stcg(reinterpret_cast<double2*>(p), make_double2(v.x, v.y));
+}
+template <typename T>
+__device__ __forceinline__ cx<T> w_ldcs(const cx<T>* p) {
+  const double2 q = __ldcs(reinterpret_cast<const double2*>(p));
+  return mk<T>(q.x, q.y);
+}
+template <typename T>
+__device__ __forceinline__ void w_stcs(cx<T>* p, cx<T> v) {
+  __stcs(reinterpret_cast<double2*>(p), make_double2(v.x, v.y));
+}
+
+// Stage A of the length-512 plan: v[m] = x[L + 32 m] in.
+template <typename T, bool BWD>
+__device__ __forceinline__ void w512_head(cx<T>* v, int L) {
+  using P = WPlan<T, 512>;
+  P::template stage_a_local<BWD>(v, L);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const cx<T> recv = shfl_xor_cx<T>(v[8 + i], 16);
+    P::stage_a_combine(v[i], v[8 + i], recv, L);
+  }
+}
+// Byte offsets inside S of everything lane L of warp w touches, in a form that costs ONE xor per access:
+//   natural element n = L + 32 m of column w        : nat + (m << 12)
+//   exchange write, register i (slot xw(L, i))      : (xwBase ^ ((i & 7) * 0x90)) + ((i >> 3) << 11)
+//   exchange read, input r (slot xr(L, r))          : (nat ^ ((r & 7) * 0x90)) + (r << 12)
+// (slot s of column w lives at byte (s << 7) | ((w ^ (s & 7)) << 4); the slots of WPlan<T, 512> differ from
+// lane-constant bases only in their low three bits, which enter the address as the xor pattern q * 0x90.)
+struct WAddr {
+  unsigned nat, xwBase;
+};
+__device__ __forceinline__ WAddr w_addr(int w, int L) {
+  WAddr a;
+  a.nat = ((unsigned)L << 7) | ((unsigned)(w ^ (L & 7)) << 4);
+  const unsigned j = L & 15, h = L >> 4, q = j & 7;
+  a.xwBase = ((32u * j + 8u * h) << 7) | (q << 7) | ((unsigned)(w ^ q) << 4);
+  return a;
+}
+template <typename T>
+__device__ __forceinline__ cx<T>* w_at(cx<T>* S, unsigned byteOff) {
+  return reinterpret_cast<cx<T>*>(reinterpret_cast<char*>(S) + byteOff);
+}
+// The exchange inside column w of S (private to the warp).
+template <typename T>
+__device__ __forceinline__ void w512_exchange(cx<T>* v, cx<T>* S, const WAddr& ad) {
+  static_assert(sizeof(cx<T>) == 16, "double precision tile layout");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) *w_at(S, (ad.xwBase ^ ((i & 7) * 0x90u)) + ((unsigned)(i >> 3) << 11)) = v[i];
+  __syncwarp();
+#pragma unroll
+  for (int r = 0; r < 16; ++r) v[r] = *w_at(S, (ad.nat ^ ((r & 7) * 0x90u)) + ((unsigned)r << 12));
+  __syncwarp();
+}
+// natural-order access of the warp's column (tile side)
+template <typename T>
+__device__ __forceinline__ void w512_col_load(cx<T>* v, cx<T>* S, const WAddr& ad) {
+#pragma unroll
+  for (int m = 0; m < 16; ++m) v[m] = *w_at(S, ad.nat + ((unsigned)m << 12));
+}
+template <typename T>
+__device__ __forceinline__ void w512_col_store(const cx<T>* v, cx<T>* S, const WAddr& ad) {
+#pragma unroll
+  for (int m = 0; m < 16; ++m) *w_at(S, ad.nat + ((unsigned)m << 12)) = v[m];
+}
+// Stage B: afterwards v[q] = X[L + 32 q].
+template <typename T, bool BWD>
+__device__ __forceinline__ void w512_tail(cx<T>* v, const cx<T>* sTw, int L) {
+  const LaneTw<T> tw = w_lane_twiddles<T>(sTw, L);
+  twiddle_dft16<T, BWD>(v, tw);
+}
+
+// The 16 inverse-map entries of lane L of column w of a tile (maps of index_plan.cpp, layout
+// [tile][lane_of_tile * 64 + (n & 63)][n >> 6], n = position along the transform): entry m belongs to
+// n = L + 32 m. 0xFFFF = no sparse element at n.
+struct WInv16 {
+  unsigned short i[16];
+};
+__device__ __forceinline__ WInv16 w_load_inv(const unsigned short* inv, long long tile, int w, int L) {
+  const unsigned short* p = inv + ((size_t)tile * 512 + (size_t)w * 64 + L) * 8;
+  const uint4 q0 = __ldg(reinterpret_cast<const uint4*>(p));
+  const uint4 q1 = __ldg(reinterpret_cast<const uint4*>(p + 32 * 8));
+  WInv16 r;
+  r.i[0] = q0.x & 0xFFFF;  r.i[2] = q0.x >> 16;
+  r.i[4] = q0.y & 0xFFFF;  r.i[6] = q0.y >> 16;
+  r.i[8] = q0.z & 0xFFFF;  r.i[10] = q0.z >> 16;
+  r.i[12] = q0.w & 0xFFFF; r.i[14] = q0.w >> 16;
+  r.i[1] = q1.x & 0xFFFF;  r.i[3] = q1.x >> 16;
+  r.i[5] = q1.y & 0xFFFF;  r.i[7] = q1.y >> 16;
+  r.i[9] = q1.z & 0xFFFF;  r.i[11] = q1.z >> 16;
+  r.i[13] = q1.w & 0xFFFF; r.i[15] = q1.w >> 16;
+  return r;
+}
+constexpr unsigned short kWNone = 0xFFFF;
+
+}  // namespace sb

@@ -574,6 +574,41 @@ def test_fused_xy_kernel(torch_cuda, lib, gen, tune):
             os.environ["SPFFT_B200_TUNE"] = old
 
 
+@pytest.mark.parametrize("case", [(0, (512, 512, 3)), (0, (512, 512, 24)), (0, (512, 512, 45)), (0, (32, 32, 512)), (1, (64, 12, 512)),
+                                  (0, (512, 512, 512))],
+                         ids=lambda c: ("r2c" if c[0] else "c2c") + "x".join(map(str, c[1])))
+def test_warp_fft_kernels(torch_cuda, lib, ref_lib, gen, case):
+    """Warp-FFT kernels (wfft_xy.cu: fused xy stage with the hand-off in L2, ring slots reused from 11 planes on;
+    wfft_z.cu: z stage incl. the hermitian completion of stick (0,0)), double precision, length 512: against the
+    numpy oracle and, at 512^3 (the BASELINE headline shape, spherical cutoff), value by value against the
+    reference's own host library on the same inputs."""
+    from conftest import hermitian_space_values
+    ttype, (nx, ny, nz) = case
+    if nx * ny * nz >= 512 ** 3:
+        trip = orc.spherical_cutoff_triplets(nx)
+        rng = np.random.default_rng(42)
+        vals = rng.uniform(-1, 1, len(trip)) + 1j * rng.uniform(-1, 1, len(trip))
+        rt = capi.Transform(ref_lib, processing_unit=capi.SPFFT_PU_HOST, transform_type=ttype, dim_x=nx,
+                            dim_y=ny, dim_z=nz, indices=trip)
+        rt.backward(np.ascontiguousarray(vals), capi.SPFFT_PU_HOST)
+        ref = rt.space_domain_host_view(ttype).copy()
+        ref_back = np.zeros(len(trip), np.complex128)
+        rt.forward(capi.SPFFT_PU_HOST, ref_back, capi.SPFFT_FULL_SCALING)
+        rt.destroy()
+        space, back = _run_pair(torch_cuda, lib, ttype, nx, ny, nz, trip, vals, twice=False)
+        assert orc.rel_l2(space, ref) <= TOL[False]
+        assert orc.rel_l2(back, ref_back) <= TOL[False]
+        return
+    trip, vals = gen.make(nx, ny, nz, hermitian=bool(ttype), center=not ttype, stick_fraction=0.6, fill_fraction=0.7)
+    if ttype:
+        vals = hermitian_space_values(orc, nx, ny, nz, trip)
+    param = orc.Parameters(ttype, nx, ny, nz, trip)
+    space, back = _run_pair(torch_cuda, lib, ttype, nx, ny, nz, trip, vals)
+    ref = orc.backward(param, vals)
+    assert orc.rel_l2(space, ref) <= TOL[False]
+    assert orc.rel_l2(back, orc.forward(param, ref, orc.SPFFT_FULL_SCALING)) <= TOL[False]
+
+
 def test_distributed_two_gpus(torch_cuda):
     """One process per GPU over NCCL (tests/dist_gpu_check.py); skipped on a single-GPU box."""
     import subprocess
