@@ -51,11 +51,6 @@ __device__ __forceinline__ LaneTw<T> w_lane_twiddles(const cx<T>* sTw, int L) {
   return t;
 }
 
-template <typename T>
-__device__ __forceinline__ cx<T>* wcol(cx<T>* S, int s, int w) {
-  return S + (s << 3) + (w ^ (s & 7));
-}
-
 __device__ __forceinline__ int w_ld_acquire(const int* p) {
   int v;
   asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -83,6 +78,32 @@ __device__ __forceinline__ void w_stcs(cx<T>* p, cx<T> v) {
   __stcs(reinterpret_cast<double2*>(p), make_double2(v.x, v.y));
 }
 
+// L2 prefetch of [base, base + bytes) by the CTA (no registers held, no wait): the inputs of the CTA's NEXT
+// item, so that its demand loads pay the L2 latency instead of the HBM latency (16 warps per SM hide neither).
+__device__ __forceinline__ void w_prefetch_l2(const void* base, size_t bytes) {
+  const char* p = static_cast<const char*>(base);
+  const size_t mis = reinterpret_cast<size_t>(p) & 127;
+  p -= mis;
+  bytes += mis;
+  for (size_t off = (size_t)threadIdx.x * 128; off < bytes; off += (size_t)blockDim.x * 128)
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p + off));
+}
+// L2 prefetch of a tile of a tensor map (one thread)
+__device__ __forceinline__ void w_prefetch_tile(const TensorMap* map, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global [%0, {%1, %2, %3}];" ::"l"(map), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+
+// 16-byte asynchronous copy global -> shared (LDGSTS): no register holds the data while it is in flight
+__device__ __forceinline__ void w_cp_async16(void* smemDst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr(smemDst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void w_cp_async_wait() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+// completion counter += 1 with release semantics at gpu scope (cumulative over what the thread observed
+// through the preceding CTA / group barrier)
+__device__ __forceinline__ void w_red_release(int* counter) {
+  asm volatile("red.release.gpu.global.add.s32 [%0], 1;" ::"l"(counter) : "memory");
+}
+
 // Stage A of the length-512 plan: v[m] = x[L + 32 m] in.
 template <typename T, bool BWD>
 __device__ __forceinline__ void w512_head(cx<T>* v, int L) {
@@ -94,47 +115,78 @@ __device__ __forceinline__ void w512_head(cx<T>* v, int L) {
     P::stage_a_combine(v[i], v[8 + i], recv, L);
   }
 }
-// Byte offsets inside S of everything lane L of warp w touches, in a form that costs ONE xor per access:
-//   natural element n = L + 32 m of column w        : nat + (m << 12)
-//   exchange write, register i (slot xw(L, i))      : (xwBase ^ ((i & 7) * 0x90)) + ((i >> 3) << 11)
-//   exchange read, input r (slot xr(L, r))          : (nat ^ ((r & 7) * 0x90)) + (r << 12)
-// (slot s of column w lives at byte (s << 7) | ((w ^ (s & 7)) << 4); the slots of WPlan<T, 512> differ from
-// lane-constant bases only in their low three bits, which enter the address as the xor pattern q * 0x90.)
+// Sub-tiles. The 8 warps of a CTA form 8 / W independent groups of W warps; a group owns W adjacent columns of
+// the CTA's 8-column tile and its own sub-tile buffer [512 rows][W x 16-byte chunks] (TMA swizzle of the row
+// width: 128B / 64B / 32B), synchronises on its own named barrier and never waits for the other groups: with
+// W = 2 (pairs) four groups per CTA drift through load / fp64 / exchange / store phases independently, which is
+// what lets the SM overlap them (one 8-warp tile per CTA ran in lock step: ncu barrier stalls 29 % of all samples).
+template <int W>
+struct WGeom {
+  static_assert(W == 2 || W == 4 || W == 8, "columns per group");
+  static constexpr int kGroups = kWWarps / W;
+  static constexpr int kGroupThreads = W * 32;
+  static constexpr unsigned kRowBytes = 16u * W;
+  static constexpr size_t kSubBytes = (size_t)kWN * kRowBytes;
+  static constexpr int kLog2RowsPer128 = W == 8 ? 0 : (W == 4 ? 1 : 2);
+  // chunk permutation of row s: chunk c sits at c ^ fold(s)
+  __host__ __device__ static constexpr unsigned fold(unsigned s) { return (s >> kLog2RowsPer128) & (W - 1); }
+  // xor pattern of the low three slot bits q
+  __host__ __device__ static constexpr unsigned pat(unsigned q) { return (q * kRowBytes) | (fold(q) << 4); }
+};
+template <int W>
+__device__ __forceinline__ void w_group_sync(int g) {
+  if constexpr (W == 8) {
+    __syncthreads();
+  } else {
+    asm volatile("bar.sync %0, %1;" ::"r"(g + 1), "n"(W * 32) : "memory");
+  }
+}
+
+// Byte offsets inside the group's sub-tile of everything lane L of its warp wl touches, in a form that costs ONE
+// xor per access (RB = row bytes = 16 W):
+//   natural element n = L + 32 m of column wl        : nat + m * 32 RB
+//   exchange write, register i (slot xw(L, i))       : (xwBase ^ pat(i & 7)) + (i >> 3) * 16 RB
+//   exchange read, input r (slot xr(L, r))           : (nat ^ pat(r & 7)) + r * 32 RB
+// (slot s of column wl lives at byte s * RB + ((wl ^ fold(s)) << 4); the slots of WPlan<T, 512> differ from
+// lane-constant bases only in their low three bits q, which enter the address as the xor pattern pat(q).)
 struct WAddr {
   unsigned nat, xwBase;
 };
-__device__ __forceinline__ WAddr w_addr(int w, int L) {
+template <int W>
+__device__ __forceinline__ WAddr w_addr(int wl, int L) {
+  using G = WGeom<W>;
   WAddr a;
-  a.nat = ((unsigned)L << 7) | ((unsigned)(w ^ (L & 7)) << 4);
+  a.nat = ((unsigned)L * G::kRowBytes) | ((unsigned)(wl ^ G::fold(L & 7)) << 4);
   const unsigned j = L & 15, h = L >> 4, q = j & 7;
-  a.xwBase = ((32u * j + 8u * h) << 7) | (q << 7) | ((unsigned)(w ^ q) << 4);
+  a.xwBase = ((32u * j + 8u * h) * G::kRowBytes) | (q * G::kRowBytes) | ((unsigned)(wl ^ G::fold(q)) << 4);
   return a;
 }
 template <typename T>
 __device__ __forceinline__ cx<T>* w_at(cx<T>* S, unsigned byteOff) {
   return reinterpret_cast<cx<T>*>(reinterpret_cast<char*>(S) + byteOff);
 }
-// The exchange inside column w of S (private to the warp).
-template <typename T>
+// The exchange inside the warp's column of the sub-tile (private to the warp).
+template <typename T, int W>
 __device__ __forceinline__ void w512_exchange(cx<T>* v, cx<T>* S, const WAddr& ad) {
   static_assert(sizeof(cx<T>) == 16, "double precision tile layout");
+  using G = WGeom<W>;
 #pragma unroll
-  for (int i = 0; i < 16; ++i) *w_at(S, (ad.xwBase ^ ((i & 7) * 0x90u)) + ((unsigned)(i >> 3) << 11)) = v[i];
+  for (int i = 0; i < 16; ++i) *w_at(S, (ad.xwBase ^ G::pat(i & 7)) + (unsigned)(i >> 3) * 16u * G::kRowBytes) = v[i];
   __syncwarp();
 #pragma unroll
-  for (int r = 0; r < 16; ++r) v[r] = *w_at(S, (ad.nat ^ ((r & 7) * 0x90u)) + ((unsigned)r << 12));
+  for (int r = 0; r < 16; ++r) v[r] = *w_at(S, (ad.nat ^ G::pat(r & 7)) + (unsigned)r * 32u * G::kRowBytes);
   __syncwarp();
 }
 // natural-order access of the warp's column (tile side)
-template <typename T>
+template <typename T, int W>
 __device__ __forceinline__ void w512_col_load(cx<T>* v, cx<T>* S, const WAddr& ad) {
 #pragma unroll
-  for (int m = 0; m < 16; ++m) v[m] = *w_at(S, ad.nat + ((unsigned)m << 12));
+  for (int m = 0; m < 16; ++m) v[m] = *w_at(S, ad.nat + (unsigned)m * 32u * WGeom<W>::kRowBytes);
 }
-template <typename T>
+template <typename T, int W>
 __device__ __forceinline__ void w512_col_store(const cx<T>* v, cx<T>* S, const WAddr& ad) {
 #pragma unroll
-  for (int m = 0; m < 16; ++m) *w_at(S, ad.nat + ((unsigned)m << 12)) = v[m];
+  for (int m = 0; m < 16; ++m) *w_at(S, ad.nat + (unsigned)m * 32u * WGeom<W>::kRowBytes) = v[m];
 }
 // Stage B: afterwards v[q] = X[L + 32 q].
 template <typename T, bool BWD>
@@ -149,10 +201,10 @@ __device__ __forceinline__ void w512_tail(cx<T>* v, const cx<T>* sTw, int L) {
 struct WInv16 {
   unsigned short i[16];
 };
-__device__ __forceinline__ WInv16 w_load_inv(const unsigned short* inv, long long tile, int w, int L) {
-  const unsigned short* p = inv + ((size_t)tile * 512 + (size_t)w * 64 + L) * 8;
-  const uint4 q0 = __ldg(reinterpret_cast<const uint4*>(p));
-  const uint4 q1 = __ldg(reinterpret_cast<const uint4*>(p + 32 * 8));
+__device__ __forceinline__ const unsigned short* w_inv_ptr(const unsigned short* inv, long long tile, int w, int L) {
+  return inv + ((size_t)tile * 512 + (size_t)w * 64 + L) * 8;  // second half: + 32 * 8
+}
+__device__ __forceinline__ WInv16 w_unpack_inv(uint4 q0, uint4 q1) {
   WInv16 r;
   r.i[0] = q0.x & 0xFFFF;  r.i[2] = q0.x >> 16;
   r.i[4] = q0.y & 0xFFFF;  r.i[6] = q0.y >> 16;
@@ -163,6 +215,10 @@ __device__ __forceinline__ WInv16 w_load_inv(const unsigned short* inv, long lon
   r.i[9] = q1.z & 0xFFFF;  r.i[11] = q1.z >> 16;
   r.i[13] = q1.w & 0xFFFF; r.i[15] = q1.w >> 16;
   return r;
+}
+__device__ __forceinline__ WInv16 w_load_inv(const unsigned short* inv, long long tile, int w, int L) {
+  const unsigned short* p = w_inv_ptr(inv, tile, w, L);
+  return w_unpack_inv(__ldg(reinterpret_cast<const uint4*>(p)), __ldg(reinterpret_cast<const uint4*>(p + 32 * 8)));
 }
 constexpr unsigned short kWNone = 0xFFFF;
 

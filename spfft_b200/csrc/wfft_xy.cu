@@ -9,13 +9,15 @@
 // and its transposing unpack / pack kernels (src/transpose/gpu_kernels/local_transpose_kernels.cu).
 //
 // Schedule: items in the order of xy_decode (fast_stage_kernels.hpp): for step u, the A tiles of
-// plane u, then the B tiles of plane u - lag. Item i belongs to CTA i mod gridDim (static, no
-// claim counter); the grid is launched cooperatively, so every CTA is resident and waiting on an
-// earlier item cannot deadlock. A B tile waits until all A tiles of its plane are complete, an A
-// tile until the B tiles of the plane that used its ring slot before are complete. Completion of
-// item k is published while item k+1 of the same CTA runs (after the CTA barrier that item needs
-// anyway), and the dependency of item k+1 is polled while the loads of item k are in flight, so in
-// the steady state no warp ever waits on a flag.
+// plane u, then the B tiles of plane u - lag; an item = 8 columns (y tile) or 8 rows (x tile) of one
+// plane. Item i belongs to CTA i mod gridDim (static, no claim counter); the grid is launched
+// cooperatively, so every CTA is resident and waiting on an earlier item cannot deadlock. Inside a CTA
+// the 8 / W groups of W warps (WGeom) each take W columns / rows of the item and run on their own: own
+// sub-tile buffer, own named barrier, own flags. A group's B part waits until all A parts of its plane
+// are complete, an A part until the B parts of the plane that used its ring slot before are complete
+// (counters count group parts). Completion of a group's part k is published while its part k+1 runs
+// (after the group barrier that part needs anyway), and the dependency of part k+1 is polled while the
+// loads of part k are in flight, so in the steady state no warp ever waits on a flag.
 #include <cstdlib>
 
 #include "fast_launch.cuh"
@@ -24,88 +26,182 @@
 
 namespace sb {
 
+#ifdef SB_WTRACE
+// experiment builds only (-DSB_WTRACE): clock64 per phase of the backward kernel, summed by lane 0 of warp 0 of
+// every CTA: g_wtrace[role][phase] (cycles), g_wtrace[role][15] = number of parts
+__device__ unsigned long long g_wtrace[2][16];
+#define W_TRACE_DECL long long tr_prev = clock64(); const bool tr_on = threadIdx.x == 0;
+#define W_TRACE(role, ph)                                                       \
+  if (tr_on) {                                                                  \
+    const long long now_ = clock64();                                           \
+    atomicAdd(&g_wtrace[role][ph], (unsigned long long)(now_ - tr_prev));       \
+    tr_prev = now_;                                                             \
+  }
+#define W_TRACE_COUNT(role) if (tr_on) atomicAdd(&g_wtrace[role][15], 1ULL);
+#define W_TRACE_SLOW(role) if (tr_on) atomicAdd(&g_wtrace[role][14], 1ULL);
+#define W_TRACE_USE(v)                                                          \
+  _Pragma("unroll") for (int m_ = 0; m_ < 16; ++m_) asm volatile("" ::"d"((v)[m_].x), "d"((v)[m_].y));
+#else
+#define W_TRACE_DECL
+#define W_TRACE(role, ph)
+#define W_TRACE_COUNT(role)
+#define W_TRACE_SLOW(role)
+#define W_TRACE_USE(v)
+#endif
+
 namespace {
 
-template <typename T>
+// Flags. Completion counters are incremented with red.release.gpu after the data of a part has been written;
+// they are POLLED with relaxed loads (an acquire load would be followed by an L1 invalidation that stalls the
+// polling warp for the whole L2 round trip, ncu: CCTL.IVALL). That is sufficient here because every read of
+// hand-off data that follows a successful poll is an L2 access (ld.global.cg / bulk tensor copy), issued after
+// the poll in program order, and the GPU does not speculate loads.
+__device__ __forceinline__ int w_ld_relaxed(const int* p) {
+  int v;
+  asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
 struct WxyCounters {
   int* aDone;
   int* bDone;
   int nA, nB, ring;
+  // counter and threshold of a part's dependency (nullptr: none)
+  __device__ __forceinline__ const int* dep_counter(const XYItem& it, int& need) const {
+    if (it.roleA) {
+      need = nB;
+      return it.plane < ring ? nullptr : &bDone[it.plane - ring];
+    }
+    need = nA;
+    return &aDone[it.plane];
+  }
   __device__ __forceinline__ bool ready(const XYItem& it) const {
-    if (it.roleA) return it.plane < ring || w_ld_acquire(&bDone[it.plane - ring]) >= nB;
-    return w_ld_acquire(&aDone[it.plane]) >= nA;
+    int need;
+    const int* c = dep_counter(it, need);
+    return !c || w_ld_relaxed(c) >= need;
   }
 };
+
+// Items of a plane: 64 y tiles + 64 x tiles (N = 512, 8 columns / rows each); xy_decode with shifts.
+template <bool BWD>
+__device__ __forceinline__ XYItem w_decode(int item, int numPlanes, int lag) {
+  constexpr int kTiles = kWN / kWWarps;  // 64
+  const int u = item / (2 * kTiles);
+  const int r = item % (2 * kTiles);
+  XYItem it;
+  it.roleA = r < kTiles;
+  it.plane = it.roleA ? u : u - lag;
+  it.tile = r & (kTiles - 1);
+  it.valid = it.roleA ? (u < numPlanes) : (it.plane >= 0);
+  return it;
+}
 
 // first valid item of this CTA's sequence at or after `i`
 template <typename T, bool BWD>
 __device__ __forceinline__ long long w_next_valid(const XYArgs<T>& a, long long i, long long total, XYItem& it) {
   while (i < total) {
-    it = xy_decode<T, BWD>(a, (int)i);
+    it = w_decode<BWD>((int)i, a.y.numPlanes, a.lag);
     if (it.valid) break;
     i += gridDim.x;
   }
   return i;
 }
 
+__device__ __forceinline__ void w_publish(int* counter) { w_red_release(counter); }
+
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------
-// backward: A = y tile (8 columns of one plane: gather -> FFT -> transposed into S -> TMA store into
-// the ring), B = x tile (8 rows of one plane, one per warp: ring -> FFT -> space domain)
+// Duties inside a group of W warps (lane 0 of ...):
+//   warp 0      "leader"    issues and awaits the group's bulk tensor copies
+//   warp 1      "poller"    looks at the dependency of the NEXT part while this part's loads are in flight and
+//                           posts the answer after its tail (the L2 round trip hides behind the butterflies)
+//   warp W - 1  "publisher" publishes the group's PREVIOUS part right after the group barrier of this part
+// so that no warp carries more than one flag round trip per part and none of them in front of a barrier.
 // ------------------------------------------------------------------------------------------------
-template <typename T>
+
+// ------------------------------------------------------------------------------------------------
+// backward: A = y tile (gather -> FFT -> transposed into the sub-tile -> TMA store into the ring),
+//           B = x tile (one row per warp: ring -> FFT -> space domain)
+// ------------------------------------------------------------------------------------------------
+template <typename T, int W>
 __global__ void __launch_bounds__(kWThreads, 2)
     k_wxy_bwd(const __grid_constant__ XYArgs<T> a, const __grid_constant__ TensorMap ringMap,
               const __grid_constant__ WTw4<T> twp) {
   constexpr int N = kWN;
+  using G = WGeom<W>;
   extern __shared__ __align__(1024) unsigned char smemRaw[];
-  cx<T>* S = reinterpret_cast<cx<T>*>(smemRaw);
-  __shared__ int sReady[2];
-  const int tid = threadIdx.x;
-  const int w = tid >> 5, L = tid & 31;
-  const WAddr ad = w_addr(w, L);
+  __shared__ int sReadySeq[G::kGroups];  // (k << 1) | ready: dependency of the group's part k seen satisfied
   __shared__ __align__(16) cx<T> sTw[4 * 32];
+  // inverse-map entries of the thread's NEXT y part, fetched asynchronously one part ahead (no registers,
+  // no exposed round trip in front of the gather)
+  __shared__ __align__(16) uint4 sInv[2][kWThreads][2];  // [parity of the part][thread][half]
+  const int tid = threadIdx.x;
+  const int w = tid >> 5, L = tid & 31;  // w: column / row of the item
+  const int g = w / W, wl = w % W;       // group, warp inside the group
+  const bool leader = L == 0 && wl == 0;
+  const bool poller = L == 0 && wl == 1;
+  const bool publisher = L == 0 && wl == W - 1;
+  cx<T>* S = reinterpret_cast<cx<T>*>(smemRaw + (size_t)g * G::kSubBytes);
+  const WAddr ad = w_addr<W>(wl, L);
   w_stage_twiddles<T>(sTw, twp);
   __syncthreads();
   const int P = a.y.numPlanes;
-  WxyCounters<T> dep;
+  WxyCounters dep;
   dep.aDone = a.counters + 1;
   dep.bDone = a.counters + 1 + P;
-  dep.nA = a.y.numXTiles;
-  dep.nB = N / kWWarps;
+  dep.nA = (N / kWWarps) * G::kGroups;
+  dep.nB = (N / kWWarps) * G::kGroups;
   dep.ring = a.ring;
   const long long total = xy_total_items<T, true>(a);
   const size_t planeElems = (size_t)N * N;
 
-  int* pend = nullptr;   // counter of the previous item, not yet published (CTA-uniform)
-  bool pendTma = false;  // ... whose output is a bulk tensor store issued by thread 0
+  int* pend = nullptr;   // counter of the group's previous part, not yet published (group-uniform)
+  bool pendTma = false;  // ... whose output is a bulk tensor store issued by the group leader
   XYItem it, nx;
   long long cur = w_next_valid<T, true>(a, blockIdx.x, total, it);
+  bool invAhead = false;
+  int e0 = (cur < total && it.roleA) ? a.y.xtStart[it.tile] : 0;  // first stick of the part's x tile
+  W_TRACE_DECL
   for (int k = 0; cur < total; ++k) {
     const long long nxt = w_next_valid<T, true>(a, cur + gridDim.x, total, nx);
-    // ---- dependency of this item: normally seen satisfied one item ago
-    if (k == 0 || !sReady[k & 1]) {
-      __syncthreads();
-      if (tid == 0) {
+    const int trRole = it.roleA ? 0 : 1;
+    (void)trRole;
+    W_TRACE(trRole, 0)  // previous part's stores issued + decode
+    // ---- dependency of this part: normally seen satisfied one part ago
+    bool depSeen = false;
+    if (k > 0) {
+      // posted by the poller behind its tail of the previous part (sequence number: no barrier needed)
+      int rs;
+      do {
+        rs = reinterpret_cast<volatile int*>(sReadySeq)[g];
+      } while ((rs >> 1) != k);
+      depSeen = rs & 1;
+    }
+    if (!depSeen) {
+      W_TRACE_SLOW(trRole)
+      w_group_sync<W>(g);
+      if (leader) {
         if (pendTma) w_tma_wait_all();
-        if (pend) {
-          __threadfence();
-          atomicAdd(pend, 1);
-        }
-        while (!dep.ready(it)) __nanosleep(100);
+        if (pend) w_publish(pend);
+        while (!dep.ready(it)) __nanosleep(64);
       }
       pend = nullptr;
       pendTma = false;
-      __syncthreads();
+      w_group_sync<W>(g);
     }
+    W_TRACE(trRole, 1)  // dependency (slow path)
     // ---- loads
     cx<T> v[16];
     const int slot = it.plane % a.ring;
     if (it.roleA) {
-      const int e0 = a.y.xtStart[it.tile];
       const cx<T>* row = a.y.sticks + (size_t)(it.plane + a.y.zRowOffset) * a.y.pitch + e0;
-      const WInv16 iv = w_load_inv(a.y.inv, it.tile, w, L);
+      WInv16 iv;
+      if (invAhead) {
+        w_cp_async_wait();
+        iv = w_unpack_inv(sInv[k & 1][tid][0], sInv[k & 1][tid][1]);
+      } else {
+        iv = w_load_inv(a.y.inv, it.tile, w, L);
+      }
 #pragma unroll
       for (int m = 0; m < 16; ++m) {
         v[m] = mk<T>(0, 0);
@@ -116,8 +212,21 @@ __global__ void __launch_bounds__(kWThreads, 2)
 #pragma unroll
       for (int m = 0; m < 16; ++m) v[m] = w_ldcg(src + 32 * m);
     }
-    if (tid == 0) sReady[(k + 1) & 1] = nxt < total ? (dep.ready(nx) ? 1 : 0) : 1;
+    // ---- in flight behind this part's work: inverse map and first stick of the next y part, flag of the next part
+    invAhead = nxt < total && nx.roleA;
+    int e0Next = 0;
+    if (invAhead) {
+      const unsigned short* p = w_inv_ptr(a.y.inv, nx.tile, w, L);
+      w_cp_async16(&sInv[(k + 1) & 1][tid][0], p);
+      w_cp_async16(&sInv[(k + 1) & 1][tid][1], p + 32 * 8);
+      e0Next = a.y.xtStart[nx.tile];
+    }
+    W_TRACE(trRole, 2)  // loads issued (incl. inverse map wait)
+    W_TRACE_USE(v)
+    W_TRACE(trRole, 3)  // loads arrived
     w512_head<T, true>(v, L);
+    W_TRACE_USE(v)
+    W_TRACE(trRole, 5)  // head
     if (!it.roleA) {
       // the consumed hand-off row (8 KB, fully read by now) is dropped from L2, not written back
       const char* rowBytes = reinterpret_cast<const char*>(a.scratch + (size_t)slot * planeElems +
@@ -125,24 +234,39 @@ __global__ void __launch_bounds__(kWThreads, 2)
       asm volatile("discard.global.L2 [%0], 128;" ::"l"(rowBytes + (size_t)L * 128) : "memory");
       asm volatile("discard.global.L2 [%0], 128;" ::"l"(rowBytes + (size_t)(L + 32) * 128) : "memory");
     }
-    // ---- S is free once the previous tile's tensor store has read it; publish the previous item
-    if (tid == 0 && pendTma) w_tma_wait_all();
-    __syncthreads();
-    if (tid == 0 && pend) {
-      __threadfence();
-      atomicAdd(pend, 1);
+    // ---- the sub-tile is free (and the previous part complete) once its tensor store has finished; it was
+    // issued a gather + head ago
+    if (leader && pendTma) w_tma_wait_all();
+    W_TRACE(trRole, 6)  // discard + wait for the tensor store + flag of the next part
+    w_group_sync<W>(g);
+    W_TRACE(trRole, 7)  // group barrier
+    if (publisher && pend) w_publish(pend);  // all stores of the previous part precede the barrier
+    w512_exchange<T, W>(v, S, ad);
+    W_TRACE_USE(v)
+    W_TRACE(trRole, 8)  // exchange (+ publish)
+    // flag of the next part: looked at as late as possible, the round trip hides behind the tail
+    int pollNeed = 0, pollSeen = 0;
+    if (poller && nxt < total) {
+      const int* c = dep.dep_counter(nx, pollNeed);
+      if (c) pollSeen = w_ld_relaxed(c); else pollNeed = 0;
     }
-    w512_exchange<T>(v, S, ad);
     w512_tail<T, true>(v, sTw, L);
+    W_TRACE_USE(v)
+    W_TRACE(trRole, 9)  // tail
+    if (poller) reinterpret_cast<volatile int*>(sReadySeq)[g] = ((k + 1) << 1) | (pollSeen >= pollNeed ? 1 : 0);
     if (it.roleA) {
-      w512_col_store<T>(v, S, ad);
+      w512_col_store<T, W>(v, S, ad);
       fence_async_smem();
-      __syncthreads();
-      if (tid == 0) {
-        tma_store_3d(&ringMap, it.tile * 16, 0, slot, S);
-        tma_store_3d(&ringMap, it.tile * 16, 256, slot, S + 256 * 8);
+      W_TRACE(trRole, 10)  // column store
+      w_group_sync<W>(g);
+      W_TRACE(trRole, 11)  // group barrier before the tensor store
+      if (leader) {
+        const int c0 = (it.tile * kWWarps + g * W) * 2;
+        tma_store_3d(&ringMap, c0, 0, slot, S);
+        tma_store_3d(&ringMap, c0, 256, slot, S + 256 * W);
         tma_store_commit();
       }
+      W_TRACE(trRole, 12)  // tensor store issue
       pend = &dep.aDone[it.plane];
       pendTma = true;
     } else {
@@ -150,76 +274,80 @@ __global__ void __launch_bounds__(kWThreads, 2)
                    (size_t)(it.tile * kWWarps + w) * N + L;
 #pragma unroll
       for (int m = 0; m < 16; ++m) dst[32 * m] = v[m];
+      W_TRACE(trRole, 12)  // stores
       pend = &dep.bDone[it.plane];
       pendTma = false;
     }
+    W_TRACE_COUNT(trRole)
     cur = nxt;
     it = nx;
+    e0 = e0Next;
   }
-  // publish the CTA's last item (tiles of other CTAs may wait for it); the bulk store of the last y
-  // tile must have read S before the CTA exits
-  __syncthreads();
-  if (tid == 0) {
+  // publish the group's last part (parts of other CTAs may wait for it); the bulk store of the last y
+  // tile must have read the sub-tile before the CTA exits
+  w_group_sync<W>(g);
+  if (leader) {
     if (pendTma) w_tma_wait_all();
-    if (pend) {
-      __threadfence();
-      atomicAdd(pend, 1);
-    }
+    if (pend) w_publish(pend);
   }
 }
 
 // ------------------------------------------------------------------------------------------------
-// forward: A = x tile (8 rows: space -> FFT -> ring), B = y tile (TMA load of 8 ring columns into S ->
-// FFT -> scatter into the stick rows)
+// forward: A = x tile (one row per warp: space -> FFT -> ring), B = y tile (TMA load of the group's ring
+// columns into its sub-tile -> FFT -> scatter into the stick rows)
 // ------------------------------------------------------------------------------------------------
-template <typename T>
+template <typename T, int W>
 __global__ void __launch_bounds__(kWThreads, 2)
     k_wxy_fwd(const __grid_constant__ XYArgs<T> a, const __grid_constant__ TensorMap ringMap,
               const __grid_constant__ WTw4<T> twp) {
   constexpr int N = kWN;
+  using G = WGeom<W>;
   extern __shared__ __align__(1024) unsigned char smemRaw[];
-  cx<T>* S = reinterpret_cast<cx<T>*>(smemRaw);
-  __shared__ int sReady[2];
-  __shared__ __align__(8) uint64_t full;
+  __shared__ int sReady[G::kGroups][2];
+  __shared__ __align__(8) uint64_t full[G::kGroups];
+  __shared__ __align__(16) cx<T> sTw[4 * 32];
+  __shared__ __align__(16) uint4 sInv[2][kWThreads][2];  // inverse-map entries of the thread's current y part, by parity
   const int tid = threadIdx.x;
   const int w = tid >> 5, L = tid & 31;
-  const WAddr ad = w_addr(w, L);
-  __shared__ __align__(16) cx<T> sTw[4 * 32];
+  const int g = w / W, wl = w % W;
+  const bool leader = L == 0 && wl == 0;
+  const bool poller = L == 0 && wl == 1;
+  const bool publisher = L == 0 && wl == W - 1;
+  cx<T>* S = reinterpret_cast<cx<T>*>(smemRaw + (size_t)g * G::kSubBytes);
+  const WAddr ad = w_addr<W>(wl, L);
   w_stage_twiddles<T>(sTw, twp);
-  __syncthreads();
-  if (tid == 0) {
-    mbar_init(&full, 1);
+  if (leader) {
+    mbar_init(&full[g], 1);
     mbar_fence_init();
   }
+  __syncthreads();
   const int P = a.y.numPlanes;
-  WxyCounters<T> dep;
+  WxyCounters dep;
   dep.aDone = a.counters + 1;
   dep.bDone = a.counters + 1 + P;
-  dep.nA = N / kWWarps;
-  dep.nB = a.y.numXTiles;
+  dep.nA = (N / kWWarps) * G::kGroups;
+  dep.nB = (N / kWWarps) * G::kGroups;
   dep.ring = a.ring;
   const long long total = xy_total_items<T, false>(a);
   const size_t planeElems = (size_t)N * N;
+  constexpr uint32_t kSubBytes = (uint32_t)G::kSubBytes;
 
   int* pend = nullptr;
   uint32_t phase = 0;
-  bool preloaded = false;  // the tile of the current (B) item is already on its way into S
+  bool preloaded = false;  // the sub-tile of the current (B) part is already on its way into S
   XYItem it, nx;
   long long cur = w_next_valid<T, false>(a, blockIdx.x, total, it);
-  __syncthreads();
+  int e0 = (cur < total && !it.roleA) ? a.y.xtStart[it.tile] : 0;
   for (int k = 0; cur < total; ++k) {
     const long long nxt = w_next_valid<T, false>(a, cur + gridDim.x, total, nx);
-    if (k == 0 || !sReady[k & 1]) {
-      __syncthreads();
-      if (tid == 0) {
-        if (pend) {
-          __threadfence();
-          atomicAdd(pend, 1);
-        }
-        while (!dep.ready(it)) __nanosleep(100);
+    if (k == 0 || !sReady[g][k & 1]) {
+      w_group_sync<W>(g);
+      if (leader) {
+        if (pend) w_publish(pend);
+        while (!dep.ready(it)) __nanosleep(64);
       }
       pend = nullptr;
-      __syncthreads();
+      w_group_sync<W>(g);
     }
     cx<T> v[16];
     const int slot = it.plane % a.ring;
@@ -228,42 +356,53 @@ __global__ void __launch_bounds__(kWThreads, 2)
                          (size_t)(it.tile * kWWarps + w) * N + L;
 #pragma unroll
       for (int m = 0; m < 16; ++m) v[m] = src[32 * m];
-      if (tid == 0) sReady[(k + 1) & 1] = nxt < total ? (dep.ready(nx) ? 1 : 0) : 1;
     } else {
-      // every warp is past the barrier of the previous item, i.e. past its last access of S
-      if (!preloaded && tid == 0) {
+      // every warp of the group is past the barrier of the previous part, i.e. past its last access of S
+      if (!preloaded && leader) {
         w_fence_proxy_async();
-        mbar_expect_tx(&full, (uint32_t)kWTileBytes);
-        tma_load_3d(S, &ringMap, it.tile * 16, 0, slot, &full);
-        tma_load_3d(S + 256 * 8, &ringMap, it.tile * 16, 256, slot, &full);
+        const int c0 = (it.tile * kWWarps + g * W) * 2;
+        mbar_expect_tx(&full[g], kSubBytes);
+        tma_load_3d(S, &ringMap, c0, 0, slot, &full[g]);
+        tma_load_3d(S + 256 * W, &ringMap, c0, 256, slot, &full[g]);
       }
-      if (tid == 0) sReady[(k + 1) & 1] = nxt < total ? (dep.ready(nx) ? 1 : 0) : 1;
-      mbar_wait(&full, phase);
+      const unsigned short* p = w_inv_ptr(a.y.inv, it.tile, w, L);
+      w_cp_async16(&sInv[k & 1][tid][0], p);
+      w_cp_async16(&sInv[k & 1][tid][1], p + 32 * 8);
+    }
+    // in flight behind this part's work: first stick of the next y part, flag of the next part
+    const int e0Next = (nxt < total && !nx.roleA) ? a.y.xtStart[nx.tile] : 0;
+    int pollNeed = 0, pollSeen = 0;
+    if (poller && nxt < total) {
+      const int* c = dep.dep_counter(nx, pollNeed);
+      if (c) pollSeen = w_ld_relaxed(c); else pollNeed = 0;
+    }
+    if (!it.roleA) {
+      mbar_wait(&full[g], phase);
       phase ^= 1;
-      w512_col_load<T>(v, S, ad);
+      w512_col_load<T, W>(v, S, ad);
       __syncwarp();
-      // the consumed column segments (one 128-byte line per row) are dropped from L2
-      const char* tileBytes = reinterpret_cast<const char*>(a.scratch + (size_t)slot * planeElems + (size_t)it.tile * kWWarps);
-      asm volatile("discard.global.L2 [%0], 128;" ::"l"(tileBytes + (size_t)tid * N * sizeof(cx<T>)) : "memory");
-      asm volatile("discard.global.L2 [%0], 128;" ::"l"(tileBytes + (size_t)(tid + 256) * N * sizeof(cx<T>)) : "memory");
+      // the consumed column segments are dropped from L2 where the group consumes whole 128-byte lines
+      // (W == 8); narrower groups share their lines with the other groups of the CTA
+      if constexpr (W == 8) {
+        const char* tileBytes = reinterpret_cast<const char*>(a.scratch + (size_t)slot * planeElems + (size_t)it.tile * kWWarps);
+        asm volatile("discard.global.L2 [%0], 128;" ::"l"(tileBytes + (size_t)tid * N * sizeof(cx<T>)) : "memory");
+        asm volatile("discard.global.L2 [%0], 128;" ::"l"(tileBytes + (size_t)(tid + 256) * N * sizeof(cx<T>)) : "memory");
+      }
     }
     w512_head<T, false>(v, L);
-    w512_exchange<T>(v, S, ad);
-    // ---- every warp is done with S; all stores of the previous item were issued before this point
-    __syncthreads();
-    preloaded = nxt < total && !nx.roleA && sReady[(k + 1) & 1];
-    if (tid == 0) {
-      if (pend) {
-        __threadfence();
-        atomicAdd(pend, 1);
-      }
-      if (preloaded) {
-        w_fence_proxy_async();
-        const int nslot = nx.plane % a.ring;
-        mbar_expect_tx(&full, (uint32_t)kWTileBytes);
-        tma_load_3d(S, &ringMap, nx.tile * 16, 0, nslot, &full);
-        tma_load_3d(S + 256 * 8, &ringMap, nx.tile * 16, 256, nslot, &full);
-      }
+    if (poller) sReady[g][(k + 1) & 1] = pollSeen >= pollNeed;
+    w512_exchange<T, W>(v, S, ad);
+    // ---- every warp of the group is done with S; all stores of the previous part were issued before this point
+    w_group_sync<W>(g);
+    if (publisher && pend) w_publish(pend);
+    preloaded = nxt < total && !nx.roleA && sReady[g][(k + 1) & 1];
+    if (leader && preloaded) {
+      w_fence_proxy_async();
+      const int nslot = nx.plane % a.ring;
+      const int c0 = (nx.tile * kWWarps + g * W) * 2;
+      mbar_expect_tx(&full[g], kSubBytes);
+      tma_load_3d(S, &ringMap, c0, 0, nslot, &full[g]);
+      tma_load_3d(S + 256 * W, &ringMap, c0, 256, nslot, &full[g]);
     }
     w512_tail<T, false>(v, sTw, L);
     if (it.roleA) {
@@ -272,9 +411,9 @@ __global__ void __launch_bounds__(kWThreads, 2)
       for (int m = 0; m < 16; ++m) w_stcg(dst + 32 * m, v[m]);
       pend = &dep.aDone[it.plane];
     } else {
-      const int e0 = a.y.xtStart[it.tile];
       cx<T>* row = a.y.sticks + (size_t)(it.plane + a.y.zRowOffset) * a.y.pitch + e0;
-      const WInv16 iv = w_load_inv(a.y.inv, it.tile, w, L);
+      w_cp_async_wait();
+      const WInv16 iv = w_unpack_inv(sInv[k & 1][tid][0], sInv[k & 1][tid][1]);
 #pragma unroll
       for (int m = 0; m < 16; ++m)
         if (iv.i[m] != kWNone) row[iv.i[m]] = v[m];
@@ -282,13 +421,11 @@ __global__ void __launch_bounds__(kWThreads, 2)
     }
     cur = nxt;
     it = nx;
+    e0 = e0Next;
   }
-  // publish the CTA's last item (tiles of other CTAs may wait for it)
-  __syncthreads();
-  if (tid == 0 && pend) {
-    __threadfence();
-    atomicAdd(pend, 1);
-  }
+  // publish the group's last part (parts of other CTAs may wait for it)
+  w_group_sync<W>(g);
+  if (leader && pend) w_publish(pend);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -296,20 +433,41 @@ __global__ void __launch_bounds__(kWThreads, 2)
 // ------------------------------------------------------------------------------------------------
 namespace {
 
-int wxy_grid(int* gridOut) {
+// columns per group: backward 4, forward 8 (the forward y tiles can drop their consumed hand-off lines from L2
+// only when one group consumes whole 128-byte lines); SPFFT_B200_WGROUP = 2 / 4 / 8 overrides both (experiments)
+int wxy_group(int forward) {
+  static const int w = [] {
+    const char* e = getenv("SPFFT_B200_WGROUP");
+    const int v = e ? atoi(e) : 0;
+    return (v == 2 || v == 4 || v == 8) ? v : 0;
+  }();
+  return w ? w : (forward ? 8 : 4);
+}
+
+// experiment: SPFFT_B200_WPAD = extra dynamic shared memory in KB (forces fewer CTAs per SM)
+size_t wxy_smem() {
+  static const size_t pad = [] {
+    const char* e = getenv("SPFFT_B200_WPAD");
+    return e ? (size_t)atoi(e) * 1024 : (size_t)0;
+  }();
+  return kWTileBytes + pad;
+}
+
+template <int W>
+int wxy_grid_w(int* gridOut) {
   static int cached = 0;
   if (cached > 0) {
     *gridOut = cached;
     return 0;
   }
-  cudaError_t e = cudaFuncSetAttribute(k_wxy_bwd<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWTileBytes);
+  cudaError_t e = cudaFuncSetAttribute(k_wxy_bwd<double, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wxy_smem());
   if (e != cudaSuccess) return (int)e;
-  e = cudaFuncSetAttribute(k_wxy_fwd<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWTileBytes);
+  e = cudaFuncSetAttribute(k_wxy_fwd<double, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wxy_smem());
   if (e != cudaSuccess) return (int)e;
   int b0 = 0, b1 = 0, dev = 0, sms = 0;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b0, k_wxy_bwd<double>, kWThreads, kWTileBytes);
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b0, k_wxy_bwd<double, W>, kWThreads, wxy_smem());
   if (e != cudaSuccess) return (int)e;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b1, k_wxy_fwd<double>, kWThreads, kWTileBytes);
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b1, k_wxy_fwd<double, W>, kWThreads, wxy_smem());
   if (e != cudaSuccess) return (int)e;
   e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return (int)e;
@@ -324,6 +482,19 @@ int wxy_grid(int* gridOut) {
   *gridOut = cached;
   return 0;
 }
+int wxy_grid(int* gridOut) {
+  // (same launch bounds and shared memory for every W: one occupancy figure)
+  int ga = 0, gb = 0;
+  int err = wxy_grid_w<8>(&ga);
+  if (err) return err;
+  err = wxy_grid_w<4>(&gb);
+  if (err) return err;
+  int gc = 0;
+  err = wxy_grid_w<2>(&gc);
+  if (err) return err;
+  *gridOut = ga < gb ? (ga < gc ? ga : gc) : (gb < gc ? gb : gc);
+  return 0;
+}
 
 template <typename Kernel>
 int wxy_launch(Kernel kernel, int grid, const XYArgs<double>& a, const TensorMap& map, const WTw4<double>& tw,
@@ -331,7 +502,7 @@ int wxy_launch(Kernel kernel, int grid, const XYArgs<double>& a, const TensorMap
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)grid);
   cfg.blockDim = dim3(kWThreads);
-  cfg.dynamicSmemBytes = kWTileBytes;
+  cfg.dynamicSmemBytes = wxy_smem();
   cfg.stream = s;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeCooperative;
@@ -341,10 +512,29 @@ int wxy_launch(Kernel kernel, int grid, const XYArgs<double>& a, const TensorMap
   return (int)cudaLaunchKernelEx(&cfg, kernel, a, map, tw);
 }
 
+template <int W>
+int wxy_launch_w(int forward, int grid, const XYArgs<double>& a, const WTw4<double>& tw, cudaStream_t s) {
+  TensorMap map;
+  const int err = make_tile_map(&map, a.scratch, sizeof(cx<double>), kWN, kWN, kWN, a.ring, (long long)kWN * kWN, W, 256);
+  if (err) return err;
+  return forward ? wxy_launch(k_wxy_fwd<double, W>, grid, a, map, tw, s) : wxy_launch(k_wxy_bwd<double, W>, grid, a, map, tw, s);
+}
+
 }  // namespace
 }  // namespace sb
 
 extern "C" {
+
+#ifdef SB_WTRACE
+__attribute__((visibility("default"))) int sb_wxy_trace_read(unsigned long long* host /* [2][16] */, int reset) {
+  if (cudaMemcpyFromSymbol(host, sb::g_wtrace, sizeof(unsigned long long) * 32) != cudaSuccess) return -1;
+  if (reset) {
+    unsigned long long z[32] = {0};
+    if (cudaMemcpyToSymbol(sb::g_wtrace, z, sizeof z) != cudaSuccess) return -2;
+  }
+  return 0;
+}
+#endif
 
 int sb_wxy_config(int isFloat, int n, int numPlanes, int* ring, int* lag, int* numCounters) {
   if (isFloat || n != sb::kWN) return (int)cudaErrorInvalidValue;
@@ -352,9 +542,14 @@ int sb_wxy_config(int isFloat, int n, int numPlanes, int* ring, int* lag, int* n
   const int err = sb::wxy_grid(&grid);
   if (err) return err;
   const int perStep = 2 * (n / sb::kWWarps);
-  int l = (grid + perStep - 1) / perStep + 1;
-  int r = 2 * l + 2;
+  // A part is published one part later than it ran and polled one part before it is needed, and the CTAs drift
+  // apart by about one part: the B parts of a plane follow its A parts by the parts in flight (grid / perStep
+  // steps) + 5 steps. Measured at 512^3 (profiles/r02_wfft_summary.md): lag 6 / 8 / 10 / 12 = 1.29+1.36 /
+  // 1.33+1.31 / 1.38+1.37 / 1.39+1.44 ms (backward + forward), ring = 2 lag + 2; a ring of lag + 4 makes the A
+  // parts wait for their slot (1.46+1.44 ms at lag 8).
+  int l = (grid + perStep - 1) / perStep + 5;
   if (const char* e = getenv("SPFFT_B200_XY_LAG")) l = atoi(e) > 0 ? atoi(e) : l;
+  int r = 2 * l + 2;
   if (const char* e = getenv("SPFFT_B200_XY_RING")) r = atoi(e) > l ? atoi(e) : l + 1;
   if (numPlanes <= r) r = numPlanes > 0 ? numPlanes : 1;  // every plane has its own slot: no reuse waits
   *ring = r;
@@ -368,7 +563,9 @@ int sb_launch_wxy_f64(int forward, const sb::XYArgs<double>* args, void* stream)
   const XYArgs<double>& a = *args;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (a.y.numPlanes <= 0) return 0;
-  if (a.x.nx != kWN || a.y.ny != kWN || a.y.nxf != kWN || !a.y.inv || a.y.srcBase) return (int)cudaErrorInvalidValue;
+  if (a.x.nx != kWN || a.y.ny != kWN || a.y.nxf != kWN || !a.y.inv || a.y.srcBase || a.y.numXTiles != kWN / kWWarps ||
+      a.x.numRowTiles != kWN / kWWarps)
+    return (int)cudaErrorInvalidValue;
   int grid = 0;
   int err = wxy_grid(&grid);
   if (err) return err;
@@ -380,12 +577,13 @@ int sb_launch_wxy_f64(int forward, const sb::XYArgs<double>* args, void* stream)
     wfft_lane_twiddles<double>(kWN, 32, &t.w[0][0]);
     return t;
   }();
-  TensorMap map;
-  err = make_tile_map(&map, a.scratch, sizeof(cx<double>), kWN, kWN, kWN, a.ring, (long long)kWN * kWN, 8, 256);
-  if (err) return err;
   cudaError_t e = cudaMemsetAsync(a.counters, 0, sizeof(int) * (1 + 2 * (size_t)a.y.numPlanes), s);
   if (e != cudaSuccess) return (int)e;
   sb_note_launches(1);
-  return forward ? wxy_launch(k_wxy_fwd<double>, grid, a, map, tw, s) : wxy_launch(k_wxy_bwd<double>, grid, a, map, tw, s);
+  switch (wxy_group(forward)) {
+    case 8: return wxy_launch_w<8>(forward, grid, a, tw, s);
+    case 4: return wxy_launch_w<4>(forward, grid, a, tw, s);
+    default: return wxy_launch_w<2>(forward, grid, a, tw, s);
+  }
 }
 }

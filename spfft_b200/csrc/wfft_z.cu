@@ -24,7 +24,7 @@ __global__ void __launch_bounds__(kWThreads, 2)
   cx<T>* S = reinterpret_cast<cx<T>*>(smemRaw);
   const int tid = threadIdx.x;
   const int w = tid >> 5, L = tid & 31;
-  const WAddr ad = w_addr(w, L);
+  const WAddr ad = w_addr<8>(w, L);
   __shared__ __align__(16) cx<T> sTw[4 * 32];
   w_stage_twiddles<T>(sTw, twp);
   __syncthreads();
@@ -54,9 +54,9 @@ __global__ void __launch_bounds__(kWThreads, 2)
     w512_head<T, true>(v, L);
     if (tid == 0) tma_store_wait_read();  // the previous tile's store has read S
     __syncthreads();
-    w512_exchange<T>(v, S, ad);
+    w512_exchange<T, 8>(v, S, ad);
     w512_tail<T, true>(v, sTw, L);
-    w512_col_store<T>(v, S, ad);
+    w512_col_store<T, 8>(v, S, ad);
     fence_async_smem();
     __syncthreads();
     if (tid == 0) {
@@ -77,7 +77,7 @@ __global__ void __launch_bounds__(kWThreads, 2)
   __shared__ __align__(8) uint64_t full;
   const int tid = threadIdx.x;
   const int w = tid >> 5, L = tid & 31;
-  const WAddr ad = w_addr(w, L);
+  const WAddr ad = w_addr<8>(w, L);
   __shared__ __align__(16) cx<T> sTw[4 * 32];
   w_stage_twiddles<T>(sTw, twp);
   __syncthreads();
@@ -100,10 +100,10 @@ __global__ void __launch_bounds__(kWThreads, 2)
     mbar_wait(&full, phase);
     phase ^= 1;
     cx<T> v[16];
-    w512_col_load<T>(v, S, ad);
+    w512_col_load<T, 8>(v, S, ad);
     __syncwarp();
     w512_head<T, false>(v, L);
-    w512_exchange<T>(v, S, ad);
+    w512_exchange<T, 8>(v, S, ad);
     __syncthreads();  // every warp is done with S
     const int next = tile + gridDim.x;
     if (next < a.numTiles && tid == 0) {
