@@ -936,10 +936,10 @@ SB_DEV void x_c2c_fast(const XArgs<T>& a, int block, Ctx ctx, cx<T>* S) {
 }
 
 // -------------------------------------------------------------------------------------------
-// Fused xy stage: y tiles and x tiles of every plane as items of ONE persistent kernel, the y<->x
-// hand-off going through a small ring of scratch planes that stays resident in the 126 MB L2
+// Fused xy stage (wfft_xy.cu): y tiles and x tiles of every plane as items of ONE persistent kernel, the
+// y<->x hand-off going through a small ring of scratch planes that stays resident in the 126 MB L2
 // instead of a full-size plane buffer in HBM (replaces the two passes of the reference's
-// cufftMakePlanMany 2-D plans, src/fft/transform_2d_gpu.hpp:51-140).
+// cufftMakePlanMany 2-D plans, src/fft/transform_2d_gpu.hpp:51-140). Argument struct and item order:
 //
 // Item order (handed out by an atomic counter): for step u = 0 .. P+lag-1:
 //     the A tiles of plane u (if u < P), then the B tiles of plane u-lag (if u >= lag)
@@ -987,52 +987,6 @@ SB_HD XYItem xy_decode(const XYArgs<T>& a, int item) {
   it.tile = it.roleA ? r : r - nA;
   it.valid = it.roleA ? (u < a.y.numPlanes) : (it.plane >= 0);
   return it;
-}
-
-// The tile work of one item (no waiting / signalling: the caller does that). `nx` is the item
-// this CTA runs next (or an invalid one): its HBM-resident input is prefetched into L2.
-// `tws`: the stage twiddle table (same for x and y: both have length N) in shared memory.
-template <typename T, int N, bool BWD>
-SB_DEV void xy_run_item(const XYArgs<T>& a, const XYItem& it, const XYItem& nx, const cx<T>* tws,
-                        Ctx ctx, cx<T>* S) {
-  constexpr int V = 1 << FastLanes<T>::log2V;
-  const size_t planeElems = (size_t)N * N;
-  cx<T>* slot = a.scratch + (size_t)(it.plane % a.ring) * planeElems;
-  cx<T>* stickRow = a.y.sticks + (size_t)(it.plane + a.y.zRowOffset) * a.y.pitch;
-  const bool pfA = nx.valid && nx.roleA;  // only A tiles read from HBM
-  if (BWD) {
-    const cx<T>* nextRow = a.y.sticks + (size_t)(nx.plane + a.y.zRowOffset) * a.y.pitch;
-    if (it.roleA) {
-      y_backward_gather<T, N, Mem::L2Only, true>(a.y, it.tile, stickRow, slot, pfA ? nx.tile : -1,
-                                                 nextRow, ctx, S, tws);
-    } else {
-      if (pfA) {
-        SB_PHASE_BEGIN
-        const int p0 = a.y.xtStart[nx.tile], p1 = a.y.xtStart[nx.tile + 1];
-        prefetch_l2(nextRow + p0, (size_t)(p1 - p0) * sizeof(cx<T>), tid, nthr);
-        SB_PHASE_END_NOSYNC
-      }
-      x_c2c_tile<T, N, true, Mem::L2Only, Mem::Plain, true>(
-          slot, static_cast<cx<T>*>(a.x.spaceOut) + (size_t)it.plane * planeElems, it.tile * V, N,
-          tws, nullptr, ctx, S);
-    }
-  } else {
-    const cx<T>* nextRows =
-        pfA ? static_cast<const cx<T>*>(a.x.spaceIn) + (size_t)nx.plane * planeElems + (size_t)nx.tile * V * N
-            : nullptr;
-    if (it.roleA) {
-      x_c2c_tile<T, N, false, Mem::Plain, Mem::L2Only, true>(
-          static_cast<const cx<T>*>(a.x.spaceIn) + (size_t)it.plane * planeElems, slot, it.tile * V,
-          N, tws, nextRows, ctx, S);
-    } else {
-      if (nextRows) {
-        SB_PHASE_BEGIN
-        prefetch_l2(nextRows, sizeof(cx<T>) * N * V, tid, nthr);
-        SB_PHASE_END_NOSYNC
-      }
-      y_forward_gather<T, N, Mem::L2Only, true>(a.y, it.tile, slot, stickRow, -1, nullptr, ctx, S, tws);
-    }
-  }
 }
 
 #undef SB_ROW_IDS

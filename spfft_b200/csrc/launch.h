@@ -15,24 +15,13 @@ int sb_launch_y_f32(int forward, const sb::YArgs<float>* args, void* stream);
 /* x stage on every (row tile, local plane). */
 int sb_launch_x_f64(int forward, const sb::XArgs<double>* args, void* stream);
 int sb_launch_x_f32(int forward, const sb::XArgs<float>* args, void* stream);
-/* Fused xy stage (C2C, dimX == dimY, power of two): plan-time query of the scratch ring
- * (planes), the item lag and the number of int counters the kernel needs, for `numPlanes` local
- * planes of n x n. Returns cudaErrorInvalidValue if no fused kernel exists for n. */
-int sb_xy_fused_config(int isFloat, int n, int numPlanes, int* ring, int* lag, int* numCounters);
-/* One direction of the fused xy stage. `counters` must be zero (the launcher enqueues the memset). */
-int sb_launch_xy_f64(int forward, const sb::XYArgs<double>* args, void* stream);
-int sb_launch_xy_f32(int forward, const sb::XYArgs<float>* args, void* stream);
 /* Barrier over the ranks of a distributed transform through peer-mapped flag arrays
  * (flags[r] = rank r's array of numRanks ints, zero-initialised; epoch increases by one per call). */
 int sb_launch_peer_barrier(int* const* flags, int numRanks, int me, int epoch, void* stream);
-/* Pipelined persistent xy stage (fast_pipe.cu: TMA-staged tiles, warp groups; double precision,
- * C2C, dimX == dimY == n in {128, 256, 512}): plan-time query like sb_xy_fused_config (returns
- * cudaErrorInvalidValue when unsupported) and the launch of one direction. */
-int sb_xy_pipe_config(int isFloat, int n, int numPlanes, int* ring, int* lag, int* numCounters);
-int sb_launch_xy_pipe_f64(int forward, const sb::XYArgs<double>* args, void* stream);
 /* Warp-FFT kernels (wfft_xy.cu, wfft_z.cu: one warp per transform, TMA-staged tiles; double precision,
- * transform length 512). sb_wxy_config: plan-time query like sb_xy_fused_config for the fused xy stage
- * (C2C, dimX == dimY == 512, local slab); sb_wz_available: z stage (dimZ == 512, values in stick order). */
+ * transform length 512). sb_wxy_config: plan-time query of the fused xy stage (C2C, dimX == dimY == 512,
+ * local slab): scratch ring (planes), item lag and number of int counters the kernel needs (which must be zero at
+ * launch: the launcher enqueues the memset); sb_wz_available: z stage (dimZ == 512, values in stick order). */
 int sb_wxy_config(int isFloat, int n, int numPlanes, int* ring, int* lag, int* numCounters);
 int sb_launch_wxy_f64(int forward, const sb::XYArgs<double>* args, void* stream);
 int sb_wz_available(int isFloat, int nz);

@@ -27,8 +27,6 @@ struct Launch<double> {
   static int z(int f, const sb::ZArgs<double>& a, void* s) { return sb_launch_z_f64(f, &a, s); }
   static int y(int f, const sb::YArgs<double>& a, void* s) { return sb_launch_y_f64(f, &a, s); }
   static int x(int f, const sb::XArgs<double>& a, void* s) { return sb_launch_x_f64(f, &a, s); }
-  static int xy(int f, const sb::XYArgs<double>& a, void* s) { return sb_launch_xy_f64(f, &a, s); }
-  static int xy_pipe(int f, const sb::XYArgs<double>& a, void* s) { return sb_launch_xy_pipe_f64(f, &a, s); }
   static int wxy(int f, const sb::XYArgs<double>& a, void* s) { return sb_launch_wxy_f64(f, &a, s); }
   static int wz(int f, const sb::ZArgs<double>& a, void* s) { return sb_launch_wz_f64(f, &a, s); }
 };
@@ -40,8 +38,6 @@ struct Launch<float> {
   static int z(int f, const sb::ZArgs<float>& a, void* s) { return sb_launch_z_f32(f, &a, s); }
   static int y(int f, const sb::YArgs<float>& a, void* s) { return sb_launch_y_f32(f, &a, s); }
   static int x(int f, const sb::XArgs<float>& a, void* s) { return sb_launch_x_f32(f, &a, s); }
-  static int xy(int f, const sb::XYArgs<float>& a, void* s) { return sb_launch_xy_f32(f, &a, s); }
-  static int xy_pipe(int, const sb::XYArgs<float>&, void*) { return static_cast<int>(cudaErrorInvalidValue); }
   static int wxy(int, const sb::XYArgs<float>&, void*) { return static_cast<int>(cudaErrorInvalidValue); }
   static int wz(int, const sb::ZArgs<float>&, void*) { return static_cast<int>(cudaErrorInvalidValue); }
 };
@@ -345,27 +341,6 @@ std::shared_ptr<DevicePlan<T>> build_device_plan(const IndexMaps& m, long long s
   ax.rpX = make_radix_plan(m.dimX);
   ax.rpY = make_radix_plan(m.dimY);
   ax.rpZ = make_radix_plan(m.dimZ);
-  // SPFFT_B200_TUNE bit 2 (value 4) selects the fused xy kernel. It moves only the algorithmic
-  // bytes (hand-off kept in L2, dirty lines discarded) but its per-item acquire/release overhead
-  // currently makes it slower than the separate y and x kernels (profiles/r01_summary.md), so the
-  // separate kernels are the default.
-  const char* tuneEnv = std::getenv("SPFFT_B200_TUNE");
-  const bool allowFused = tuneEnv && (std::atoi(tuneEnv) & 4);
-  const bool allowPipe = tuneEnv && (std::atoi(tuneEnv) & 8);
-  if (allowPipe && fastX && fastY && m.dimX == m.dimY && m.type == SPFFT_TRANS_C2C && m.commSize == 1 &&
-      ax.log2Vx == ax.log2Vy) {
-    // y and x stages as one pipelined persistent kernel (fast_pipe.cu)
-    const int err = sb_xy_pipe_config(sizeof(T) == 4, m.dimX, m.local_planes(), &plan->xyRing,
-                                      &plan->xyLag, &plan->xyCounters);
-    plan->fusedXY = plan->pipeXY = err == 0;
-  }
-  if (!plan->fusedXY && allowFused && fastX && fastY && m.dimX == m.dimY && m.type == SPFFT_TRANS_C2C &&
-      ax.log2Vx == ax.log2Vy) {
-    // y and x stages as one persistent kernel with the hand-off in L2 (fast_xy.cu)
-    const int err = sb_xy_fused_config(sizeof(T) == 4, m.dimX, m.local_planes(), &plan->xyRing,
-                                       &plan->xyLag, &plan->xyCounters);
-    plan->fusedXY = err == 0;
-  }
   // Warp-FFT kernels (default where they exist; SPFFT_B200_WFFT=0 selects the round-1 kernels, bit 0 =
   // fused xy stage, bit 1 = z stage): one warp per transform, tiles staged by TMA, y <-> x hand-off in L2.
   const char* wEnv = std::getenv("SPFFT_B200_WFFT");
@@ -703,11 +678,12 @@ void TransformEngine<T>::enqueue_backward(const T* input, T* output) {
   if (!haveSpace) return;
   const bool outOnDevice = is_device_pointer(output);
   T* outDev = outOnDevice ? output : device_space();
-  if (plan_->fusedXY) {
+  // (the warp-FFT kernels move rows with 16-byte bulk copies / vector accesses: a space pointer that is only
+  // aligned to its scalar type takes the separate y and x kernels)
+  const bool fusedHere = plan_->fusedXY && !(plan_->wfftXY && (reinterpret_cast<size_t>(outDev) & 15) != 0);
+  if (fusedHere) {
     // ---- fused xy stage: y tiles and x tiles in one persistent kernel, hand-off through L2
-    check_launch(plan_->wfftXY ? Launch<T>::wxy(0, make_xy_args(geo, nullptr, outDev), s)
-                 : plan_->pipeXY ? Launch<T>::xy_pipe(0, make_xy_args(geo, nullptr, outDev), s)
-                                 : Launch<T>::xy(0, make_xy_args(geo, nullptr, outDev), s));
+    check_launch(Launch<T>::wxy(0, make_xy_args(geo, nullptr, outDev), s));
     record_stage("xy backward");
   } else {
     // ---- y stage: stick gather + plane symmetry + y-FFT (execution_gpu.cpp:371-390)
@@ -758,11 +734,10 @@ void TransformEngine<T>::enqueue_forward(const T* input, T* output, SpfftScaling
       src = device_space();
       record_stage("h2d space");
     }
-    if (plan_->fusedXY) {
+    const bool fusedHere = plan_->fusedXY && !(plan_->wfftXY && (reinterpret_cast<size_t>(src) & 15) != 0);
+    if (fusedHere) {
       if (anySticks) {
-        check_launch(plan_->wfftXY ? Launch<T>::wxy(1, make_xy_args(geo, src, nullptr), s)
-                     : plan_->pipeXY ? Launch<T>::xy_pipe(1, make_xy_args(geo, src, nullptr), s)
-                                     : Launch<T>::xy(1, make_xy_args(geo, src, nullptr), s));
+        check_launch(Launch<T>::wxy(1, make_xy_args(geo, src, nullptr), s));
         record_stage("xy forward");
       }
     } else {

@@ -102,9 +102,8 @@ struct DevicePlan {
   PlanPointers<T> ptrs;
   // tile geometry (host copies of the scalars of TileMaps)
   int numStickTiles = 0, pitch = 0, numXTiles = 0, symTile = -1, symLane = -1;
-  // fused xy stage (fast_xy.cu): scratch ring geometry, 0 planes = separate y and x kernels
+  // fused xy stage (wfft_xy.cu): scratch ring geometry; false = separate y and x kernels
   bool fusedXY = false;
-  bool pipeXY = false;  // fusedXY through the pipelined kernel (fast_pipe.cu) instead of fast_xy.cu
   int xyRing = 0, xyLag = 0, xyCounters = 0;
   // warp-FFT kernels (wfft_xy.cu / wfft_z.cu): fused xy stage (implies fusedXY) / z stage
   bool wfftXY = false;

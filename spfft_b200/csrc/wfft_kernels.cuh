@@ -177,6 +177,33 @@ __device__ __forceinline__ void w512_exchange(cx<T>* v, cx<T>* S, const WAddr& a
   for (int r = 0; r < 16; ++r) v[r] = *w_at(S, (ad.nat ^ G::pat(r & 7)) + (unsigned)r * 32u * G::kRowBytes);
   __syncwarp();
 }
+// The same exchange in a FLAT private region of 512 elements (a row that a bulk copy landed in natural order):
+// slot(n) = n ^ ((n >> 5) & 7) (WPlan<T, 512>::slot), i.e. natural element L + 32 m at (L << 4) + m * 512 bytes,
+// exchange write at (xwFlat ^ (q << 4)) + (i >> 3) * 256, exchange read at ((L << 4) ^ (q << 4)) + r * 512.
+template <typename T>
+__device__ __forceinline__ void w512_exchange_flat(cx<T>* v, cx<T>* R, int L) {
+  const unsigned nat = (unsigned)L << 4;
+  const unsigned j = L & 15, h = L >> 4;
+  const unsigned xwFlat = ((32u * j + 8u * h) << 4) | ((j & 7) << 4);
+#pragma unroll
+  for (int i = 0; i < 16; ++i) *w_at(R, (xwFlat ^ ((unsigned)(i & 7) << 4)) + (unsigned)(i >> 3) * 256u) = v[i];
+  __syncwarp();
+#pragma unroll
+  for (int r = 0; r < 16; ++r) v[r] = *w_at(R, (nat ^ ((unsigned)(r & 7) << 4)) + (unsigned)r * 512u);
+  __syncwarp();
+}
+template <typename T>
+__device__ __forceinline__ void w512_flat_load(cx<T>* v, const cx<T>* R, int L) {
+#pragma unroll
+  for (int m = 0; m < 16; ++m) v[m] = R[L + 32 * m];
+}
+// global -> shared bulk copy (contiguous bytes, multiple of 16), completes on `bar`
+__device__ __forceinline__ void w_bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(dst)),
+               "l"(src), "r"(bytes), "r"(smem_addr(bar))
+               : "memory");
+}
+
 // natural-order access of the warp's column (tile side)
 template <typename T, int W>
 __device__ __forceinline__ void w512_col_load(cx<T>* v, cx<T>* S, const WAddr& ad) {

@@ -351,20 +351,22 @@ __global__ void __launch_bounds__(kWThreads, 2)
     }
     cx<T> v[16];
     const int slot = it.plane % a.ring;
-    if (it.roleA) {
-      const cx<T>* src = static_cast<const cx<T>*>(a.x.spaceIn) + (size_t)it.plane * planeElems +
-                         (size_t)(it.tile * kWWarps + w) * N + L;
-#pragma unroll
-      for (int m = 0; m < 16; ++m) v[m] = src[32 * m];
-    } else {
-      // every warp of the group is past the barrier of the previous part, i.e. past its last access of S
-      if (!preloaded && leader) {
-        w_fence_proxy_async();
+    cx<T>* R = S + (size_t)wl * N;  // x parts: the warp's flat private region of the sub-tile
+    // every warp of the group is past the barrier of the previous part, i.e. past its last access of S
+    if (!preloaded && leader) {
+      w_fence_proxy_async();
+      mbar_expect_tx(&full[g], kSubBytes);
+      if (it.roleA) {
+        // the W rows of the group are contiguous in the space domain: one bulk copy
+        w_bulk_load(S, static_cast<const cx<T>*>(a.x.spaceIn) + (size_t)it.plane * planeElems + (size_t)(it.tile * kWWarps + g * W) * N,
+                    kSubBytes, &full[g]);
+      } else {
         const int c0 = (it.tile * kWWarps + g * W) * 2;
-        mbar_expect_tx(&full[g], kSubBytes);
         tma_load_3d(S, &ringMap, c0, 0, slot, &full[g]);
         tma_load_3d(S + 256 * W, &ringMap, c0, 256, slot, &full[g]);
       }
+    }
+    if (!it.roleA) {
       const unsigned short* p = w_inv_ptr(a.y.inv, it.tile, w, L);
       w_cp_async16(&sInv[k & 1][tid][0], p);
       w_cp_async16(&sInv[k & 1][tid][1], p + 32 * 8);
@@ -376,9 +378,12 @@ __global__ void __launch_bounds__(kWThreads, 2)
       const int* c = dep.dep_counter(nx, pollNeed);
       if (c) pollSeen = w_ld_relaxed(c); else pollNeed = 0;
     }
-    if (!it.roleA) {
-      mbar_wait(&full[g], phase);
-      phase ^= 1;
+    mbar_wait(&full[g], phase);
+    phase ^= 1;
+    if (it.roleA) {
+      w512_flat_load<T>(v, R, L);
+      __syncwarp();
+    } else {
       w512_col_load<T, W>(v, S, ad);
       __syncwarp();
       // the consumed column segments are dropped from L2 where the group consumes whole 128-byte lines
@@ -391,18 +396,28 @@ __global__ void __launch_bounds__(kWThreads, 2)
     }
     w512_head<T, false>(v, L);
     if (poller) sReady[g][(k + 1) & 1] = pollSeen >= pollNeed;
-    w512_exchange<T, W>(v, S, ad);
+    if (it.roleA)
+      w512_exchange_flat<T>(v, R, L);
+    else
+      w512_exchange<T, W>(v, S, ad);
     // ---- every warp of the group is done with S; all stores of the previous part were issued before this point
     w_group_sync<W>(g);
     if (publisher && pend) w_publish(pend);
-    preloaded = nxt < total && !nx.roleA && sReady[g][(k + 1) & 1];
+    // the input of the next part flows into S behind the tail and the stores of this one: the rows of an x part
+    // come from the space domain (always there), the ring columns of a y part once their plane is complete
+    preloaded = nxt < total && (nx.roleA || sReady[g][(k + 1) & 1]);
     if (leader && preloaded) {
       w_fence_proxy_async();
-      const int nslot = nx.plane % a.ring;
-      const int c0 = (nx.tile * kWWarps + g * W) * 2;
       mbar_expect_tx(&full[g], kSubBytes);
-      tma_load_3d(S, &ringMap, c0, 0, nslot, &full[g]);
-      tma_load_3d(S + 256 * W, &ringMap, c0, 256, nslot, &full[g]);
+      if (nx.roleA) {
+        w_bulk_load(S, static_cast<const cx<T>*>(a.x.spaceIn) + (size_t)nx.plane * planeElems + (size_t)(nx.tile * kWWarps + g * W) * N,
+                    kSubBytes, &full[g]);
+      } else {
+        const int nslot = nx.plane % a.ring;
+        const int c0 = (nx.tile * kWWarps + g * W) * 2;
+        tma_load_3d(S, &ringMap, c0, 0, nslot, &full[g]);
+        tma_load_3d(S + 256 * W, &ringMap, c0, 256, nslot, &full[g]);
+      }
     }
     w512_tail<T, false>(v, sTw, L);
     if (it.roleA) {

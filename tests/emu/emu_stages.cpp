@@ -15,7 +15,6 @@
 #include "../../spfft_b200/csrc/stage_args.hpp"
 #include "../../spfft_b200/csrc/fast_stage_kernels.hpp"
 #include "../../spfft_b200/csrc/fast3_stage_kernels.hpp"
-#include "../../spfft_b200/csrc/fast_pipe_kernels.hpp"
 #include "../../spfft_b200/csrc/stage_kernels.hpp"
 #include "spfft/exceptions.hpp"
 
@@ -121,62 +120,6 @@ void run_x(bool fwd, const sb::XArgs<T>& a, int b, sb::Ctx ctx, sb::cx<T>* smem)
 #undef CALL
 }
 
-// fused xy stage: the items in hand-out order, one after the other (every dependency of an item
-// is an earlier item, so sequential execution satisfies all waits of the GPU kernel)
-// pipelined xy stage (fast_pipe.cu): same item order; the bulk copy that stages a tile is a memcpy
-// into a poisoned buffer, then the tile body runs on it
-template <typename T>
-void run_xy_pipe(bool fwd, const sb::XYArgs<T>& a) {
-  const int n = a.x.nx;
-  const int V = 1 << sb::FastLanes<T>::log2V;
-  sb::Ctx c{V * (n / 8)};
-  std::vector<sb::cx<T>> buf(static_cast<size_t>(n) * V);
-  const long long total = fwd ? sb::xy_total_items<T, false>(a) : sb::xy_total_items<T, true>(a);
-  for (long long item = 0; item < total; ++item) {
-    const sb::XYItem it = fwd ? sb::xy_decode<T, false>(a, (int)item) : sb::xy_decode<T, true>(a, (int)item);
-    if (!it.valid) continue;
-    std::fill(buf.begin(), buf.end(), sb::mk<T>(T(1e30), T(-1e30)));
-#define CALL(NN)                                                                                    \
-  {                                                                                                 \
-    unsigned bytes = 0;                                                                             \
-    const sb::cx<T>* src = fwd ? sb::pipe_item_source<T, NN, false>(a, it, &bytes)                  \
-                               : sb::pipe_item_source<T, NN, true>(a, it, &bytes);                  \
-    if (bytes > buf.size() * sizeof(sb::cx<T>)) throw spfft::InternalError();                       \
-    if (bytes) std::memcpy(buf.data(), src, bytes);                                                 \
-    if (fwd) sb::pipe_run_item<T, NN, false>(a, it, buf.data(), a.x.ftw, c);                        \
-    else sb::pipe_run_item<T, NN, true>(a, it, buf.data(), a.x.ftw, c);                             \
-  }
-    EMU_DISPATCH(n, CALL)
-#undef CALL
-  }
-}
-
-template <typename T>
-void run_xy(bool fwd, const sb::XYArgs<T>& a, sb::cx<T>* smem) {
-  if (getenv("SB_EMU_PIPE")) return run_xy_pipe<T>(fwd, a);
-  sb::Ctx c{(1 << sb::FastLanes<T>::log2V) * (a.x.nx / 8)};
-  std::vector<int> aDone(a.y.numPlanes, 0), bDone(a.y.numPlanes, 0);
-  const long long total = fwd ? sb::xy_total_items<T, false>(a) : sb::xy_total_items<T, true>(a);
-  for (long long item = 0; item < total; ++item) {
-    const sb::XYItem it = fwd ? sb::xy_decode<T, false>(a, (int)item) : sb::xy_decode<T, true>(a, (int)item);
-    if (!it.valid) continue;
-    const int nA = fwd ? sb::xy_tiles_a<T, false>(a) : sb::xy_tiles_a<T, true>(a);
-    const int nB = fwd ? sb::xy_tiles_b<T, false>(a) : sb::xy_tiles_b<T, true>(a);
-    if (it.roleA) {
-      if (it.plane >= a.ring && bDone[it.plane - a.ring] != nB) throw spfft::InternalError();
-    } else if (aDone[it.plane] != nA) {
-      throw spfft::InternalError();
-    }
-    sb::XYItem nx;
-    nx.valid = false;
-    if (item + 1 < total) nx = fwd ? sb::xy_decode<T, false>(a, (int)item + 1) : sb::xy_decode<T, true>(a, (int)item + 1);
-#define CALL(NN) if (fwd) sb::xy_run_item<T, NN, false>(a, it, nx, a.x.ftw, c, smem); else sb::xy_run_item<T, NN, true>(a, it, nx, a.x.ftw, c, smem)
-    EMU_DISPATCH(a.x.nx, CALL)
-#undef CALL
-    ++(it.roleA ? aDone : bDone)[it.plane];
-  }
-}
-
 template <typename T>
 int run(int type, int dimX, int dimY, int dimZ, int n, const int* triplets, int forward,
         const void* in, void* out, int scaling, int nthreads, int maxLog2V) {
@@ -200,8 +143,9 @@ int run(int type, int dimX, int dimY, int dimZ, int n, const int* triplets, int 
       if (ax.log2Vy > maxLog2V) ax.log2Vy = maxLog2V;
       if (ax.log2Vz > maxLog2V) ax.log2Vz = maxLog2V;
     }
-    // fused xy stage exactly when the product (with its opt-in flag) fuses: one tile shape for y and x
-    const bool fusedShape = fastX && fastY && dimX == dimY && type == SPFFT_TRANS_C2C && dimX % 3 != 0 && dimX % 5 != 0;
+    // same x tile shape as the product, which keeps 8-row x tiles where its fused xy stage applies (wfft_xy.cu:
+    // double precision C2C with dimX == dimY == 512; the emulation runs the separate y and x kernels there)
+    const bool fusedShape = fastX && fastY && dimX == dimY && dimX == 512 && cb == 16 && type == SPFFT_TRANS_C2C;
     if (fastX) ax.log2Vx = fusedShape ? fl : fast_path_log2_lanes_x(dimX);
     if (fastY) ax.log2Vy = fast_path_log2_lanes(cb, dimY);
     if (fastZ) ax.log2Vz = fast_path_log2_lanes(cb, dimZ);
@@ -245,46 +189,23 @@ int run(int type, int dimX, int dimY, int dimZ, int n, const int* triplets, int 
     std::vector<sb::cx<T>> smem(2 * static_cast<size_t>(maxN) * 32);
     sb::Ctx ctx{nthreads};
 
-    // fused xy stage exactly when the product fuses; a small ring / lag exercises slot reuse
-    const bool fused = fastX && fastY && dimX == dimY && type == SPFFT_TRANS_C2C && dimX % 3 != 0 && dimX % 5 != 0;
-    const int ring = dimZ > 3 ? 3 : dimZ, lag = dimZ > 3 ? 2 : 1;
-    std::vector<sb::cx<T>> scratch(static_cast<size_t>(ring) * dimX * dimY + 1,
-                                   sb::mk<T>(T(1e30), T(-1e30)));
-    auto make_xy = [&](const void* spaceIn, void* spaceOut) {
-      sb::XYArgs<T> a{};
-      a.y = make_y_args<T>(*maps, t, ax, p, sticks.data(), static_cast<sb::cx<T>*>(nullptr));
-      a.x = make_x_args<T>(*maps, ax, p, static_cast<sb::cx<T>*>(nullptr), spaceIn, spaceOut);
-      a.scratch = scratch.data();
-      a.ring = ring;
-      a.lag = lag;
-      a.counters = nullptr;
-      return a;
-    };
     if (!forward) {
       auto za = make_z_args<T>(*maps, t, ax, p, false, sticks.data(), static_cast<const T*>(in),
                                nullptr, false);
       for (int b = 0; b < za.numTiles; ++b) run_z<T>(false, za, b, ctx, smem.data());
-      if (fused) {
-        run_xy<T>(false, make_xy(nullptr, out), smem.data());
-      } else {
-        auto ya = make_y_args<T>(*maps, t, ax, p, sticks.data(), planes.data());
-        for (int b = 0; b < ya.numXTiles * ya.numPlanes; ++b)
-          run_y<T>(false, ya, b, ctx, smem.data());
-        auto xa = make_x_args<T>(*maps, ax, p, planes.data(), nullptr, out);
-        for (int b = 0; b < xa.numRowTiles * xa.numPlanes; ++b)
-          run_x<T>(false, xa, b, ctx, smem.data());
-      }
+      auto ya = make_y_args<T>(*maps, t, ax, p, sticks.data(), planes.data());
+      for (int b = 0; b < ya.numXTiles * ya.numPlanes; ++b)
+        run_y<T>(false, ya, b, ctx, smem.data());
+      auto xa = make_x_args<T>(*maps, ax, p, planes.data(), nullptr, out);
+      for (int b = 0; b < xa.numRowTiles * xa.numPlanes; ++b)
+        run_x<T>(false, xa, b, ctx, smem.data());
     } else {
-      if (fused) {
-        run_xy<T>(true, make_xy(in, nullptr), smem.data());
-      } else {
-        auto xa = make_x_args<T>(*maps, ax, p, planes.data(), in, nullptr);
-        for (int b = 0; b < xa.numRowTiles * xa.numPlanes; ++b)
-          run_x<T>(true, xa, b, ctx, smem.data());
-        auto ya = make_y_args<T>(*maps, t, ax, p, sticks.data(), planes.data());
-        for (int b = 0; b < ya.numXTiles * ya.numPlanes; ++b)
-          run_y<T>(true, ya, b, ctx, smem.data());
-      }
+      auto xa = make_x_args<T>(*maps, ax, p, planes.data(), in, nullptr);
+      for (int b = 0; b < xa.numRowTiles * xa.numPlanes; ++b)
+        run_x<T>(true, xa, b, ctx, smem.data());
+      auto ya = make_y_args<T>(*maps, t, ax, p, sticks.data(), planes.data());
+      for (int b = 0; b < ya.numXTiles * ya.numPlanes; ++b)
+        run_y<T>(true, ya, b, ctx, smem.data());
       auto za = make_z_args<T>(*maps, t, ax, p, true, sticks.data(), nullptr,
                                static_cast<T*>(out), scaling != 0);
       for (int b = 0; b < za.numTiles; ++b) run_z<T>(true, za, b, ctx, smem.data());

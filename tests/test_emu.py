@@ -216,26 +216,6 @@ def test_emulated_r2c_negative_half_input(emu, gen, shape):
     assert orc.rel_l2(out, orc.dense_backward(1, nx, ny, nz, trip, vals)) < 1e-13
 
 
-# ---- tile bodies of the pipelined xy kernel (fast_pipe_kernels.hpp): staged input buffers ---------
-@pytest.mark.parametrize("shape", [(32, 32, 32), (64, 64, 9), (128, 128, 5)], ids=lambda s: "x".join(map(str, s)))
-@pytest.mark.parametrize("single", [False, True])
-def test_emulated_pipe_xy(emu, gen, shape, single, monkeypatch):
-    monkeypatch.setenv("SB_EMU_PIPE", "1")
-    nx, ny, nz = shape
-    trip, vals = gen.make(nx, ny, nz, center=True, stick_fraction=0.5, fill_fraction=0.6)
-    param = orc.Parameters(orc.SPFFT_TRANS_C2C, nx, ny, nz, trip)
-    cdt = np.complex64 if single else np.complex128
-    tol = 2e-6 if single else 1e-13
-    v = vals.astype(cdt)
-    out = np.full((nz, ny, nx), np.nan, dtype=cdt)
-    t = np.ascontiguousarray(trip.reshape(-1))
-    assert emu.sb_emu_transform(int(single), 0, nx, ny, nz, len(trip), _ptr(t), 0, _ptr(v), _ptr(out), 0, 64, -1) == 0
-    assert orc.rel_l2(out, orc.backward(param, vals)) < tol
-    back = np.zeros(len(trip), dtype=cdt)
-    assert emu.sb_emu_transform(int(single), 0, nx, ny, nz, len(trip), _ptr(t), 1, _ptr(out), _ptr(back), 1, 64, -1) == 0
-    assert orc.rel_l2(back, vals) < tol
-
-
 # ---- distributed transforms: all ranks emulated in one process, peer-store and block exchange ------
 def _emu_distributed(emu, gen, ttype, shape, world, sdist, pdist, center, single, peer, wire_f32=False):
     from conftest import hermitian_space_values

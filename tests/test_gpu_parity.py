@@ -551,29 +551,6 @@ def test_golden_fixtures(torch_cuda, lib, path):
     assert orc.rel_l2(back, g["forward"]) <= TOL[single]
 
 
-@pytest.mark.parametrize("tune", ["5", "9"], ids=["fused", "pipelined"])
-def test_fused_xy_kernel(torch_cuda, lib, gen, tune):
-    """The persistent fused y+x kernels (SPFFT_B200_TUNE bit 2: fast_xy.cu, bit 3: the TMA-staged
-    pipelined kernel of fast_pipe.cu, double precision from 128 up): same results as the default path."""
-    old = os.environ.get("SPFFT_B200_TUNE")
-    os.environ["SPFFT_B200_TUNE"] = tune
-    try:
-        for shape, single in [((64, 64, 32), False), ((128, 128, 64), False), ((32, 32, 130), True),
-                              ((256, 256, 37), False)]:
-            nx, ny, nz = shape
-            trip, vals = gen.make(nx, ny, nz, center=True, stick_fraction=0.6)
-            param = orc.Parameters(0, nx, ny, nz, trip)
-            space, back = _run_pair(torch_cuda, lib, 0, nx, ny, nz, trip, vals, single=single)
-            v = vals.astype(np.complex64).astype(np.complex128) if single else vals
-            assert orc.rel_l2(space, orc.backward(param, v)) <= TOL[single]
-            assert orc.rel_l2(back, v) <= TOL[single]
-    finally:
-        if old is None:
-            del os.environ["SPFFT_B200_TUNE"]
-        else:
-            os.environ["SPFFT_B200_TUNE"] = old
-
-
 @pytest.mark.parametrize("case", [(0, (512, 512, 3)), (0, (512, 512, 24)), (0, (512, 512, 45)), (0, (32, 32, 512)), (1, (64, 12, 512)),
                                   (0, (512, 512, 512))],
                          ids=lambda c: ("r2c" if c[0] else "c2c") + "x".join(map(str, c[1])))
