@@ -68,6 +68,11 @@ template <typename T>
 __device__ __forceinline__ void w_stcg(cx<T>* p, cx<T> v) {
   __stcg(reinterpret_cast<double2*>(p), make_double2(v.x, v.y));
 }
+// store with an L2 eviction policy (createpolicy, tma_util.hpp)
+template <typename T>
+__device__ __forceinline__ void w_st_hint(cx<T>* p, cx<T> v, uint64_t policy) {
+  asm volatile("st.global.L2::cache_hint.v2.f64 [%0], {%1, %2}, %3;" ::"l"(p), "d"(v.x), "d"(v.y), "l"(policy) : "memory");
+}
 template <typename T>
 __device__ __forceinline__ cx<T> w_ldcs(const cx<T>* p) {
   const double2 q = __ldcs(reinterpret_cast<const double2*>(p));
@@ -197,10 +202,11 @@ __device__ __forceinline__ void w512_flat_load(cx<T>* v, const cx<T>* R, int L) 
 #pragma unroll
   for (int m = 0; m < 16; ++m) v[m] = R[L + 32 * m];
 }
-// global -> shared bulk copy (contiguous bytes, multiple of 16), completes on `bar`
-__device__ __forceinline__ void w_bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(dst)),
-               "l"(src), "r"(bytes), "r"(smem_addr(bar))
+// global -> shared bulk copy (contiguous bytes, multiple of 16), completes on `bar`; L2 policy of the source lines
+__device__ __forceinline__ void w_bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint64_t policy) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+                   smem_addr(dst)),
+               "l"(src), "r"(bytes), "r"(smem_addr(bar)), "l"(policy)
                : "memory");
 }
 

@@ -205,7 +205,7 @@ __global__ void __launch_bounds__(kWThreads, 2)
 #pragma unroll
       for (int m = 0; m < 16; ++m) {
         v[m] = mk<T>(0, 0);
-        if (iv.i[m] != kWNone) v[m] = row[iv.i[m]];
+        if (iv.i[m] != kWNone) v[m] = w_ldcs(row + iv.i[m]);  // read once: evict first, the ring stays in L2
       }
     } else {
       const cx<T>* src = a.scratch + (size_t)slot * planeElems + (size_t)(it.tile * kWWarps + w) * N + L;
@@ -262,8 +262,9 @@ __global__ void __launch_bounds__(kWThreads, 2)
       W_TRACE(trRole, 11)  // group barrier before the tensor store
       if (leader) {
         const int c0 = (it.tile * kWWarps + g * W) * 2;
-        tma_store_3d(&ringMap, c0, 0, slot, S);
-        tma_store_3d(&ringMap, c0, 256, slot, S + 256 * W);
+        const uint64_t keep = l2_policy_evict_last();
+        tma_store_3d_hint(&ringMap, c0, 0, slot, S, keep);
+        tma_store_3d_hint(&ringMap, c0, 256, slot, S + 256 * W, keep);
         tma_store_commit();
       }
       W_TRACE(trRole, 12)  // tensor store issue
@@ -273,7 +274,7 @@ __global__ void __launch_bounds__(kWThreads, 2)
       cx<T>* dst = static_cast<cx<T>*>(a.x.spaceOut) + (size_t)it.plane * planeElems +
                    (size_t)(it.tile * kWWarps + w) * N + L;
 #pragma unroll
-      for (int m = 0; m < 16; ++m) dst[32 * m] = v[m];
+      for (int m = 0; m < 16; ++m) w_stcs(dst + 32 * m, v[m]);  // written once: evict first
       W_TRACE(trRole, 12)  // stores
       pend = &dep.bDone[it.plane];
       pendTma = false;
@@ -359,7 +360,7 @@ __global__ void __launch_bounds__(kWThreads, 2)
       if (it.roleA) {
         // the W rows of the group are contiguous in the space domain: one bulk copy
         w_bulk_load(S, static_cast<const cx<T>*>(a.x.spaceIn) + (size_t)it.plane * planeElems + (size_t)(it.tile * kWWarps + g * W) * N,
-                    kSubBytes, &full[g]);
+                    kSubBytes, &full[g], l2_policy_evict_first());
       } else {
         const int c0 = (it.tile * kWWarps + g * W) * 2;
         tma_load_3d(S, &ringMap, c0, 0, slot, &full[g]);
@@ -411,7 +412,7 @@ __global__ void __launch_bounds__(kWThreads, 2)
       mbar_expect_tx(&full[g], kSubBytes);
       if (nx.roleA) {
         w_bulk_load(S, static_cast<const cx<T>*>(a.x.spaceIn) + (size_t)nx.plane * planeElems + (size_t)(nx.tile * kWWarps + g * W) * N,
-                    kSubBytes, &full[g]);
+                    kSubBytes, &full[g], l2_policy_evict_first());
       } else {
         const int nslot = nx.plane % a.ring;
         const int c0 = (nx.tile * kWWarps + g * W) * 2;
@@ -422,8 +423,9 @@ __global__ void __launch_bounds__(kWThreads, 2)
     w512_tail<T, false>(v, sTw, L);
     if (it.roleA) {
       cx<T>* dst = a.scratch + (size_t)slot * planeElems + (size_t)(it.tile * kWWarps + w) * N + L;
+      const uint64_t keep = l2_policy_evict_last();
 #pragma unroll
-      for (int m = 0; m < 16; ++m) w_stcg(dst + 32 * m, v[m]);
+      for (int m = 0; m < 16; ++m) w_st_hint(dst + 32 * m, v[m], keep);  // hand-off: stays in L2 until its y part ran
       pend = &dep.aDone[it.plane];
     } else {
       cx<T>* row = a.y.sticks + (size_t)(it.plane + a.y.zRowOffset) * a.y.pitch + e0;
@@ -431,7 +433,7 @@ __global__ void __launch_bounds__(kWThreads, 2)
       const WInv16 iv = w_unpack_inv(sInv[k & 1][tid][0], sInv[k & 1][tid][1]);
 #pragma unroll
       for (int m = 0; m < 16; ++m)
-        if (iv.i[m] != kWNone) row[iv.i[m]] = v[m];
+        if (iv.i[m] != kWNone) w_stcs(row + iv.i[m], v[m]);  // written once: evict first
       pend = &dep.bDone[it.plane];
     }
     cur = nxt;

@@ -65,6 +65,10 @@ def main():
         (1, (192, 96, 32), uniform, [1.0 + r for r in range(world)], False, False),
         (0, (32, 192, 96), first, last, True, True),
         (0, (160, 32, 160), uniform, [1.0 + r for r in range(world)], True, False),
+        # length 512: warp-FFT z stage (wfft_z.cu) on the ranks' local stick buffers
+        (0, (32, 32, 512), uniform, uniform, True, False),
+        (1, (64, 12, 512), uniform, [1.0 + r for r in range(world)], False, False),
+        (0, (512, 512, 8), uniform, uniform, True, False),
     ]
     worst = 0.0
     ok = True
@@ -136,6 +140,59 @@ def main():
               f"bwd={eb:.2e} fwd={ef:.2e} {'ok' if good else 'FAIL'}", flush=True)
         t.destroy()
         grid.destroy()
+    # ---- multi-transform over DISTRIBUTED transforms (reference: tests/mpi_tests/test_multi_transform.cpp,
+    # multi_transform_internal.hpp:140-173): every transform has its own grid / exchange buffers / stream, all
+    # are enqueued before any is waited for, so the exchange of one overlaps the stages of the others
+    for mode in modes:
+        os.environ["SPFFT_B200_P2P"] = mode
+        shapes = [(0, (32, 32, 32), True), (0, (64, 32, 128), False), (1, (64, 64, 32), False), (0, (96, 96, 96), True)]
+        ts, grids, d_vs, d_ss, d_os, refs, nreals, ns = [], [], [], [], [], [], [], []
+        for ttype, (nx, ny, nz), center in shapes:
+            trips, vals = [], []
+            for r in range(world):
+                t, v = gen.make(nx, ny, nz, hermitian=bool(ttype), center=center, num_ranks=world, rank=r,
+                                stick_distribution=uniform)
+                trips.append(t)
+                vals.append(v)
+            if ttype:
+                full = hermitian_space_values(orc, nx, ny, nz, np.concatenate(trips))
+                off = 0
+                for r in range(world):
+                    vals[r] = full[off:off + len(trips[r])]
+                    off += len(trips[r])
+            planes = gen.plane_split(nz, uniform)
+            params = orc.distributed_parameters(ttype, nx, ny, nz, trips, planes)
+            slabs = orc.backward_distributed(params, vals)
+            refs.append((slabs[rank], orc.forward_distributed(params, slabs, orc.SPFFT_FULL_SCALING)[rank], ttype, (nx, ny)))
+            grid = capi.DistributedGrid(lib, comm, nx, ny, nz, max(p.num_sticks for p in params), max(planes))
+            t = grid.create_transform(capi.SPFFT_PU_GPU, ttype, nx, ny, nz, planes[rank], trips[rank])
+            n = len(trips[rank])
+            nreal = planes[rank] * ny * nx * (1 if ttype else 2)
+            grids.append(grid)
+            ts.append(t)
+            ns.append(n)
+            nreals.append((nreal, planes[rank]))
+            d_vs.append(torch.from_numpy(np.ascontiguousarray(vals[rank].astype(np.complex128)).view(np.float64).copy()).cuda()
+                        if n else torch.zeros(1, dtype=torch.float64, device="cuda"))
+            d_ss.append(torch.full((max(nreal, 1),), float("nan"), dtype=torch.float64, device="cuda"))
+            d_os.append(torch.zeros(max(2 * n, 1), dtype=torch.float64, device="cuda"))
+        capi.multi_transform_backward_ptr(ts, d_vs, d_ss)
+        capi.multi_transform_forward_ptr(ts, d_ss, d_os, [capi.SPFFT_FULL_SCALING] * len(ts))
+        for i, (ref_slab, ref_back, ttype, (nx, ny)) in enumerate(refs):
+            nreal, pl = nreals[i]
+            sdt = np.float64 if ttype else np.complex128
+            space = d_ss[i].cpu().numpy()[:nreal].view(sdt).reshape(pl, ny, nx)
+            back = d_os[i].cpu().numpy()[:2 * ns[i]].view(np.complex128)
+            eb = orc.rel_l2(space, ref_slab) if nreal else 0.0
+            ef = orc.rel_l2(back, ref_back) if ns[i] else 0.0
+            good = eb <= 1e-12 and ef <= 1e-12
+            ok = ok and good
+            worst = max(worst, eb / 1e-12, ef / 1e-12)
+            print(f"[rank {rank}] multi-transform {'peer' if mode == '1' else 'nccl'} #{i} bwd={eb:.2e} fwd={ef:.2e} {'ok' if good else 'FAIL'}", flush=True)
+        for t in ts:
+            t.destroy()
+        for g_ in grids:
+            g_.destroy()
     flag = torch.tensor([0 if ok else 1], device="cuda")
     dist.all_reduce(flag)
     dist.barrier()

@@ -551,6 +551,59 @@ def test_golden_fixtures(torch_cuda, lib, path):
     assert orc.rel_l2(back, g["forward"]) <= TOL[single]
 
 
+def test_baseline_config3_256_r2c_vs_reference_library(torch_cuda, lib, ref_lib):
+    """BASELINE.json config 3 at size: 256^3 R2C / C2R double, gamma-point half sphere, value by value against
+    the reference's own host library (SPFFT_PU_HOST) on the same exactly hermitian input."""
+    from conftest import hermitian_space_values
+    n = 256
+    trip = orc.spherical_cutoff_triplets(n, hermitian=True)
+    vals = hermitian_space_values(orc, n, n, n, trip)
+    rt = capi.Transform(ref_lib, processing_unit=capi.SPFFT_PU_HOST, transform_type=1, dim_x=n, dim_y=n, dim_z=n, indices=trip)
+    rt.backward(np.ascontiguousarray(vals), capi.SPFFT_PU_HOST)
+    ref = rt.space_domain_host_view(1).copy()
+    ref_back = np.zeros(len(trip), np.complex128)
+    rt.forward(capi.SPFFT_PU_HOST, ref_back, capi.SPFFT_FULL_SCALING)
+    rt.destroy()
+    space, back = _run_pair(torch_cuda, lib, 1, n, n, n, trip, vals, twice=False)
+    assert space.dtype == np.float64
+    assert orc.rel_l2(space, ref) <= TOL[False]
+    assert orc.rel_l2(back, ref_back) <= TOL[False]
+
+
+@pytest.mark.parametrize("single", [False, True], ids=["f64", "f32"])
+def test_baseline_config5_256_bands_192(torch_cuda, lib, single):
+    """BASELINE.json config 5 at size: a batch of 256 bands at 192^3 (spherical cutoff, centered indices,
+    out-of-place with external space-domain buffers) through spfft_multi_transform_*_ptr; sampled bands against
+    the oracle, round trip of every band."""
+    torch = torch_cuda
+    n, bands = 192, 256
+    trip = orc.spherical_cutoff_triplets(n)
+    ne = len(trip)
+    rng = np.random.default_rng(5)
+    base = rng.uniform(-1, 1, ne) + 1j * rng.uniform(-1, 1, ne)
+    cdt = np.complex64 if single else np.complex128
+    rdt = torch.float32 if single else torch.float64
+    t0 = capi.Transform(lib, transform_type=0, dim_x=n, dim_y=n, dim_z=n, indices=trip, single=single)
+    ts = [t0] + [t0.clone() for _ in range(bands - 1)]
+    d_base = _to_dev(torch, base.astype(cdt))
+    ins = [d_base * (1.0 + 0.5 * b / bands) for b in range(bands)]
+    spaces = [torch.empty(2 * n ** 3, dtype=rdt, device="cuda") for _ in range(bands)]
+    outs = [torch.empty(2 * ne, dtype=rdt, device="cuda") for _ in range(bands)]
+    capi.multi_transform_backward_ptr(ts, ins, spaces)
+    capi.multi_transform_forward_ptr(ts, spaces, outs, [capi.SPFFT_FULL_SCALING] * bands)
+    torch.cuda.synchronize()
+    param = orc.Parameters(0, n, n, n, trip)
+    v0 = base.astype(np.complex64).astype(np.complex128) if single else base
+    oracle_space = orc.backward(param, v0)
+    for b in (0, 101, bands - 1):
+        got = spaces[b].cpu().numpy().view(cdt).reshape(n, n, n)
+        assert orc.rel_l2(got, oracle_space * (1.0 + 0.5 * b / bands)) <= TOL[single]
+    for b in range(bands):
+        assert float((outs[b] - ins[b]).norm() / ins[b].norm()) <= TOL[single]
+    for t in ts:
+        t.destroy()
+
+
 @pytest.mark.parametrize("case", [(0, (512, 512, 3)), (0, (512, 512, 24)), (0, (512, 512, 45)), (0, (32, 32, 512)), (1, (64, 12, 512)),
                                   (0, (512, 512, 512))],
                          ids=lambda c: ("r2c" if c[0] else "c2c") + "x".join(map(str, c[1])))
