@@ -28,15 +28,33 @@ __global__ void __launch_bounds__(kWThreads, 2)
   __shared__ __align__(16) cx<T> sTw[4 * 32];
   w_stage_twiddles<T>(sTw, twp);
   __syncthreads();
+  // inverse-map entries and value range of the thread's NEXT tile, fetched one tile ahead (cp.async: no registers):
+  // the gather of a tile then costs one HBM round trip instead of two dependent ones
+  __shared__ __align__(16) uint4 sInv[2][kWThreads][2];
   pdl_prologue();
-  for (int tile = blockIdx.x; tile < a.numTiles; tile += gridDim.x) {
-    const cx<T>* vals = a.valuesIn + a.tileStart[tile];
-    const WInv16 iv = w_load_inv(a.inv, tile, w, L);
+  int tile = blockIdx.x;
+  int e0 = tile < a.numTiles ? a.tileStart[tile] : 0;
+  if (tile < a.numTiles) {
+    const unsigned short* p = w_inv_ptr(a.inv, tile, w, L);
+    w_cp_async16(&sInv[0][tid][0], p);
+    w_cp_async16(&sInv[0][tid][1], p + 32 * 8);
+  }
+  for (int k = 0; tile < a.numTiles; tile += gridDim.x, ++k) {
+    const cx<T>* vals = a.valuesIn + e0;
+    w_cp_async_wait();
+    const WInv16 iv = w_unpack_inv(sInv[k & 1][tid][0], sInv[k & 1][tid][1]);
     cx<T> v[16];
 #pragma unroll
     for (int m = 0; m < 16; ++m) {
       v[m] = mk<T>(0, 0);
-      if (iv.i[m] != kWNone) v[m] = vals[iv.i[m]];
+      if (iv.i[m] != kWNone) v[m] = w_ldcs(vals + iv.i[m]);
+    }
+    const int next = tile + gridDim.x;
+    if (next < a.numTiles) {
+      const unsigned short* p = w_inv_ptr(a.inv, next, w, L);
+      w_cp_async16(&sInv[(k + 1) & 1][tid][0], p);
+      w_cp_async16(&sInv[(k + 1) & 1][tid][1], p + 32 * 8);
+      e0 = a.tileStart[next];
     }
     if (tile == a.symTile && w == a.symLane) {
       // hermitian completion of stick (0,0) (reference: symmetry_host.hpp:47-58): element n also
