@@ -83,8 +83,9 @@ GridResources<T>::GridResources(int maxDimX, int maxDimY, int maxDimZ, int maxNu
   if (maxDimX <= 0 || maxDimY <= 0 || maxDimZ <= 0 || maxNumLocalZSticks < 0)
     throw InvalidParameterError();
   if (!(processingUnit & (SPFFT_PU_HOST | SPFFT_PU_GPU))) throw InvalidParameterError();
-  // this build executes on the GPU only: a grid without the GPU bit cannot serve any transform
-  if (!(processingUnit & SPFFT_PU_GPU)) throw InvalidParameterError();
+  // This build executes on the GPU only. A grid / transform requested for SPFFT_PU_HOST is served by the same
+  // device kernels with its data staged through pinned host memory (callers written against the reference's host
+  // path, e.g. its examples, keep working); the device buffers are therefore allocated for every grid.
   if (numThreads_ < 1) numThreads_ = 1;  // host threads are not used; kept for the getter
   check_gpu(cudaGetDevice(&deviceId_));  // grid_internal.cpp:83
   allocate();
@@ -110,7 +111,7 @@ GridResources<T>::GridResources(int maxDimX, int maxDimY, int maxDimZ, int maxNu
   if (static_cast<long long>(maxNumLocalZSticks) * maxDimZ > 0x7fffffffLL) throw OverflowError();
   if (maxDimX <= 0 || maxDimY <= 0 || maxDimZ <= 0 || maxNumLocalZSticks < 0 || maxLocalZLength < 0)
     throw InvalidParameterError();
-  if (!(processingUnit & SPFFT_PU_GPU)) throw InvalidParameterError();
+  if (!(processingUnit & (SPFFT_PU_HOST | SPFFT_PU_GPU))) throw InvalidParameterError();
   if (exchangeType < SPFFT_EXCH_DEFAULT || exchangeType > SPFFT_EXCH_UNBUFFERED)
     throw InvalidParameterError();
   if (numThreads_ < 1) numThreads_ = 1;
@@ -446,8 +447,8 @@ TransformEngine<T>::TransformEngine(SpfftProcessingUnitType executionUnit,
   if (!(executionUnit & grid_->processing_unit())) throw InvalidParameterError();
   if (executionUnit != SPFFT_PU_HOST && executionUnit != SPFFT_PU_GPU)
     throw InvalidParameterError();
-  // no host execution path in this build (documented deviation, include/spfft/config.h)
-  if (executionUnit != SPFFT_PU_GPU) throw InvalidParameterError();
+  // (SPFFT_PU_HOST: executed by the device kernels, data staged through host memory -- there is no CPU path;
+  //  such a transform only accepts / exposes host locations, like the reference's host transform)
 
   DeviceGuard guard(grid_->device_id());
   if (!plan_) {
@@ -509,6 +510,8 @@ T* TransformEngine<T>::device_space() const {
 
 template <typename T>
 T* TransformEngine<T>::space_domain_data(SpfftProcessingUnitType location) {
+  // transform_internal.cpp:212-232: a host transform has no device-side space domain
+  if (location == SPFFT_PU_GPU && executionUnit_ != SPFFT_PU_GPU) throw InvalidParameterError();
   if (location == SPFFT_PU_GPU) return device_space();
   if (location == SPFFT_PU_HOST) return static_cast<T*>(grid_->host_space(space_bytes()));
   throw InvalidParameterError();

@@ -108,8 +108,11 @@ def test_parameter_validation_without_device(lib):
     with pytest.raises(capi.SpfftError) as e:
         capi.Grid(lib, 4, 4, 0, 4, capi.SPFFT_PU_GPU, 1)
     assert e.value.code == capi.SPFFT_INVALID_PARAMETER_ERROR
-    with pytest.raises(capi.SpfftError) as e:  # no host execution path: grids need the GPU bit
-        capi.Grid(lib, 4, 4, 4, 4, capi.SPFFT_PU_HOST, 1)
+    with pytest.raises(capi.SpfftError) as e:  # SPFFT_PU_HOST grids are served by the device kernels: without a
+        capi.Grid(lib, 4, 4, 4, 4, capi.SPFFT_PU_HOST, 1)  # device the call fails loudly (there is no CPU path)
+    assert e.value.code in (capi.SPFFT_GPU_ERROR, capi.SPFFT_GPU_SUPPORT_ERROR, capi.SPFFT_GPU_ALLOCATION_ERROR)
+    with pytest.raises(capi.SpfftError) as e:  # neither unit bit
+        capi.Grid(lib, 4, 4, 4, 4, 0, 1)
     assert e.value.code == capi.SPFFT_INVALID_PARAMETER_ERROR
     # a valid request fails LOUDLY without a device -- there is no CPU fallback
     with pytest.raises(capi.SpfftError) as e:

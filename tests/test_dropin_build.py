@@ -5,8 +5,8 @@ spfft_b200/lib/libspfft_b200.so using nothing but gcc / g++.
   the CPU, executed on the GPU box (checked against a direct DFT inside the programs);
 * the reference's own example programs, compiled from where they lie under /root/reference (never
   copied), against OUR headers and library: proves that unmodified user code builds (skipped on the
-  GPU box, where /root/reference does not exist). They select SPFFT_PU_HOST, which this library
-  rejects by design (no CPU path), so they are built, not run."""
+  GPU box, where /root/reference does not exist). They select SPFFT_PU_HOST, which this library serves with
+  its device kernels and host staging (there is no CPU path), so the binaries built here also RUN on the GPU box."""
 import os
 import shutil
 import subprocess
@@ -46,6 +46,19 @@ def test_reference_examples_build_unmodified(built, name, compiler, std):
     if not os.path.exists(src):
         pytest.skip("/root/reference is not present on this machine")
     _build(compiler, std, src, os.path.join(OUT, "ref_" + name.replace(".", "_")))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["example.c", "example.cpp"])
+def test_reference_examples_run(name):
+    """The reference's unmodified example programs (built on the CPU box by the test above, they travel with the
+    snapshot) run against this library: they create SPFFT_PU_HOST grids / transforms and print the space domain."""
+    exe = os.path.join(OUT, "ref_" + name.replace(".", "_"))
+    if not os.path.exists(exe):
+        pytest.skip("reference example not built (needs /root/reference at build time)")
+    res = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stdout + res.stderr
+    assert len(res.stdout.splitlines()) > 4
 
 
 @pytest.fixture(scope="module")

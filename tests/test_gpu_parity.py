@@ -204,7 +204,8 @@ def test_grid_shared_by_transforms_and_smaller_transform(torch_cuda, lib, gen):
 
 def test_grid_with_both_processing_unit_bits(torch_cuda, lib, gen):
     """A Grid may be created for SPFFT_PU_HOST | SPFFT_PU_GPU (grid_internal.cpp:76-99); a transform picks
-    exactly one unit (transform_internal.cpp:71-80) -- here only the GPU one exists."""
+    exactly one unit (transform_internal.cpp:71-80). A SPFFT_PU_HOST transform is served by the same device kernels
+    with its data staged through host memory (there is no CPU path): it accepts host locations only."""
     both = capi.SPFFT_PU_HOST | capi.SPFFT_PU_GPU
     grid = capi.Grid(lib, 12, 12, 12, 144, both, -1)
     assert grid.processing_unit() == both
@@ -213,10 +214,21 @@ def test_grid_with_both_processing_unit_bits(torch_cuda, lib, gen):
     param = orc.Parameters(0, nx, ny, nz, trip)
     space, back = _run_pair(torch_cuda, lib, 0, nx, ny, nz, trip, vals, grid=grid)
     assert orc.rel_l2(space, orc.backward(param, vals)) <= TOL[False]
-    for bad in (both, capi.SPFFT_PU_HOST, 0):
+    for bad in (both, 0):
         with pytest.raises(capi.SpfftError) as e:
             grid.create_transform(bad, 0, nx, ny, nz, nz, trip)
         assert e.value.code == capi.SPFFT_INVALID_PARAMETER_ERROR
+    th = grid.create_transform(capi.SPFFT_PU_HOST, 0, nx, ny, nz, nz, trip)
+    assert th.processing_unit() == capi.SPFFT_PU_HOST
+    th.backward(np.ascontiguousarray(vals), capi.SPFFT_PU_HOST)
+    assert orc.rel_l2(th.space_domain_host_view(0), orc.backward(param, vals)) <= TOL[False]
+    back = np.zeros(len(trip), np.complex128)
+    th.forward(capi.SPFFT_PU_HOST, back, capi.SPFFT_FULL_SCALING)
+    assert orc.rel_l2(back, vals) <= TOL[False]
+    with pytest.raises(capi.SpfftError) as e:  # transform_internal.cpp:212-232: no device-side space domain
+        th.backward(np.ascontiguousarray(vals), capi.SPFFT_PU_GPU)
+    assert e.value.code == capi.SPFFT_INVALID_PARAMETER_ERROR
+    th.destroy()
 
 
 def test_empty_and_degenerate(torch_cuda, lib):
@@ -387,10 +399,12 @@ def test_error_codes_on_device(torch_cuda, lib):
     with pytest.raises(capi.SpfftError) as e:  # more values than grid points
         capi.Transform(lib, transform_type=0, dim_x=1, dim_y=1, dim_z=1, indices=np.zeros((2, 3), np.int32))
     assert e.value.code == capi.SPFFT_INVALID_PARAMETER_ERROR
-    with pytest.raises(capi.SpfftError) as e:  # host execution does not exist in this build
-        capi.Transform(lib, processing_unit=capi.SPFFT_PU_HOST, transform_type=0, dim_x=4, dim_y=4, dim_z=4,
-                       indices=np.zeros((1, 3), np.int32))
-    assert e.value.code == capi.SPFFT_INVALID_PARAMETER_ERROR
+    # a grid-less SPFFT_PU_HOST transform (what the reference's examples create) works: device kernels, host staging
+    th = capi.Transform(lib, processing_unit=capi.SPFFT_PU_HOST, transform_type=0, dim_x=4, dim_y=4, dim_z=4,
+                        indices=np.zeros((1, 3), np.int32))
+    th.backward(np.array([2.0 + 1.0j]), capi.SPFFT_PU_HOST)
+    assert np.allclose(th.space_domain_host_view(0), 2.0 + 1.0j, atol=1e-14)
+    th.destroy()
     with pytest.raises(capi.SpfftError) as e:
         capi.Grid(lib, 0, 4, 4, 4, capi.SPFFT_PU_GPU, 1)
     assert e.value.code == capi.SPFFT_INVALID_PARAMETER_ERROR
