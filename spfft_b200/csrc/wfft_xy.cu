@@ -81,29 +81,103 @@ struct WxyCounters {
   }
 };
 
-// Items of a plane: 64 y tiles + 64 x tiles (N = 512, 8 columns / rows each); xy_decode with shifts.
-template <bool BWD>
-__device__ __forceinline__ XYItem w_decode(int item, int numPlanes, int lag) {
-  constexpr int kTiles = kWN / kWWarps;  // 64
-  const int u = item / (2 * kTiles);
-  const int r = item % (2 * kTiles);
+// Items in hand-out order, valid ones only (dense index 0 .. 2 * 64 * P - 1): for step u = 0 .. P + lag - 1 the
+// 64 A tiles of plane u (if u < P), then the 64 B tiles of plane u - lag (if u >= lag) -- the order of xy_decode
+// (fast_stage_kernels.hpp) without its empty slots.
+constexpr int kWTiles = kWN / kWWarps;  // 64 tiles of 8 columns / rows per plane
+__device__ __forceinline__ XYItem w_decode_dense(int idx, int P, int lag) {
   XYItem it;
-  it.roleA = r < kTiles;
-  it.plane = it.roleA ? u : u - lag;
-  it.tile = r & (kTiles - 1);
-  it.valid = it.roleA ? (u < numPlanes) : (it.plane >= 0);
+  it.valid = true;
+  const int lead = (lag < P ? lag : P) * kWTiles;  // steps with A tiles only
+  if (idx < lead) {
+    it.roleA = true;
+    it.plane = idx / kWTiles;
+    it.tile = idx % kWTiles;
+    return it;
+  }
+  idx -= lead;
+  const int both = P > lag ? (P - lag) * 2 * kWTiles : 0;  // steps with A and B tiles
+  if (idx < both) {
+    const int u = lag + idx / (2 * kWTiles);
+    const int r = idx % (2 * kWTiles);
+    it.roleA = r < kWTiles;
+    it.plane = it.roleA ? u : u - lag;
+    it.tile = r % kWTiles;
+    return it;
+  }
+  idx -= both;
+  it.roleA = false;  // steps with B tiles only
+  it.plane = (P > lag ? P - lag : 0) + idx / kWTiles;
+  it.tile = idx % kWTiles;
   return it;
 }
 
-// first valid item of this CTA's sequence at or after `i`
-template <typename T, bool BWD>
-__device__ __forceinline__ long long w_next_valid(const XYArgs<T>& a, long long i, long long total, XYItem& it) {
-  while (i < total) {
-    it = w_decode<BWD>((int)i, a.y.numPlanes, a.lag);
-    if (it.valid) break;
-    i += gridDim.x;
+// Work distribution. The CTAs CLAIM their items in hand-out order from two interleaved global counters (even /
+// odd items; a CTA belongs to the queue blockIdx & 1): a CTA that falls behind (far L2 slices, waits) simply
+// takes fewer items, so the tiles of a plane complete together instead of waiting for the slowest CTA of a static
+// round-robin schedule (profiles/r02_summary.md: 21 % / 46 % of the parts found their dependency unsatisfied).
+// All groups of a CTA work on the same item; the k-th item of the CTA is claimed by whichever group needs it
+// first, two items ahead (the atomic's round trip hides behind a whole part), and handed to the others through
+// a small tagged ring in shared memory.
+struct WQueueShared {
+  int tag[8];      // ordinal whose item index is in val[ordinal & 7]
+  int val[8];
+  int claimed;     // ordinals requested so far
+  int prog[8];     // per group: ordinal it is working on
+};
+struct WQueue {
+  WQueueShared* q;
+  int* counter;  // this CTA's global counter
+  int stride, offset, total, groups;
+  __device__ __forceinline__ int item_of(int claim) const { return claim * stride + offset; }
+  // group leader, at the start of its part k: does ordinal k + 2 still have to be claimed (by this group)?
+  __device__ __forceinline__ bool own(int ord) const {
+    if (atomicCAS(&q->claimed, ord, ord + 1) != ord) return false;
+    // the slot still holds ordinal ord - 8: every group must be past it (a group at part k reads ordinals <= k + 1)
+    for (int g = 0; g < groups; ++g)
+      while (reinterpret_cast<volatile int*>(q->prog)[g] < ord - 8) {
+      }
+    return true;
   }
-  return i;
+  // the claim itself: the returned value is first touched in post(), a whole part later, so the round trip of
+  // the atomic never stalls the leader (inline asm: no phi / select on the result right behind the atomic)
+  __device__ __forceinline__ void claim(bool mine, unsigned& raw) const {
+    if (mine) asm volatile("atom.global.add.u32 %0, [%1], 1;" : "=r"(raw) : "l"(counter) : "memory");
+  }
+  __device__ __forceinline__ void post(int ord, int claim) const {
+    int item = item_of(claim);
+    if (item > total) item = total;
+    q->val[ord & 7] = item;
+    __threadfence_block();
+    reinterpret_cast<volatile int*>(q->tag)[ord & 7] = ord;
+  }
+  // every thread: item index of ordinal ord (>= total: no more work)
+  __device__ __forceinline__ int consume(int ord) const {
+    while (reinterpret_cast<volatile int*>(q->tag)[ord & 7] != ord) {
+    }
+    __threadfence_block();
+    return reinterpret_cast<volatile int*>(q->val)[ord & 7];
+  }
+};
+__device__ __forceinline__ void w_queue_init(WQueueShared* q, WQueue& wq, int* counters, int total, int groups) {
+  wq.q = q;
+  wq.stride = gridDim.x > 1 ? 2 : 1;
+  wq.offset = wq.stride == 2 ? (blockIdx.x & 1) : 0;
+  wq.counter = counters + wq.offset;
+  wq.total = total;
+  wq.groups = groups;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 8; ++i) {
+      q->tag[i] = -1;
+      q->prog[i] = 0;
+    }
+    q->claimed = 2;
+    for (int ord = 0; ord < 2; ++ord) {
+      int item = wq.item_of(atomicAdd(wq.counter, 1));
+      q->val[ord] = item > total ? total : item;
+      q->tag[ord] = ord;
+    }
+  }
 }
 
 __device__ __forceinline__ void w_publish(int* counter) { w_red_release(counter); }
@@ -152,18 +226,28 @@ __global__ void __launch_bounds__(kWThreads, 2)
   dep.nA = (N / kWWarps) * G::kGroups;
   dep.nB = (N / kWWarps) * G::kGroups;
   dep.ring = a.ring;
-  const long long total = xy_total_items<T, true>(a);
+  const int total = 2 * kWTiles * P;
   const size_t planeElems = (size_t)N * N;
+  __shared__ WQueueShared sQueue;
+  WQueue wq;
+  w_queue_init(&sQueue, wq, a.counters + 1 + 2 * P, total, G::kGroups);
+  __syncthreads();
 
   int* pend = nullptr;   // counter of the group's previous part, not yet published (group-uniform)
   bool pendTma = false;  // ... whose output is a bulk tensor store issued by the group leader
   XYItem it, nx;
-  long long cur = w_next_valid<T, true>(a, blockIdx.x, total, it);
+  int cur = wq.consume(0);
+  if (cur < total) it = w_decode_dense(cur, P, a.lag);
   bool invAhead = false;
   int e0 = (cur < total && it.roleA) ? a.y.xtStart[it.tile] : 0;  // first stick of the part's x tile
   W_TRACE_DECL
   for (int k = 0; cur < total; ++k) {
-    const long long nxt = w_next_valid<T, true>(a, cur + gridDim.x, total, nx);
+    if (leader) reinterpret_cast<volatile int*>(sQueue.prog)[g] = k;
+    const bool mine = leader && wq.own(k + 2);
+    unsigned claimRaw = 0;
+    wq.claim(mine, claimRaw);  // (in flight until it is posted behind the tail)
+    const int nxt = wq.consume(k + 1);
+    if (nxt < total) nx = w_decode_dense(nxt, P, a.lag);
     const int trRole = it.roleA ? 0 : 1;
     (void)trRole;
     W_TRACE(trRole, 0)  // previous part's stores issued + decode
@@ -254,6 +338,7 @@ __global__ void __launch_bounds__(kWThreads, 2)
     W_TRACE_USE(v)
     W_TRACE(trRole, 9)  // tail
     if (poller) reinterpret_cast<volatile int*>(sReadySeq)[g] = ((k + 1) << 1) | (pollSeen >= pollNeed ? 1 : 0);
+    if (mine) wq.post(k + 2, (int)claimRaw);
     if (it.roleA) {
       w512_col_store<T, W>(v, S, ad);
       fence_async_smem();
@@ -329,18 +414,28 @@ __global__ void __launch_bounds__(kWThreads, 2)
   dep.nA = (N / kWWarps) * G::kGroups;
   dep.nB = (N / kWWarps) * G::kGroups;
   dep.ring = a.ring;
-  const long long total = xy_total_items<T, false>(a);
+  const int total = 2 * kWTiles * P;
   const size_t planeElems = (size_t)N * N;
   constexpr uint32_t kSubBytes = (uint32_t)G::kSubBytes;
+  __shared__ WQueueShared sQueue;
+  WQueue wq;
+  w_queue_init(&sQueue, wq, a.counters + 1 + 2 * P, total, G::kGroups);
+  __syncthreads();
 
   int* pend = nullptr;
   uint32_t phase = 0;
   bool preloaded = false;  // the sub-tile of the current (B) part is already on its way into S
   XYItem it, nx;
-  long long cur = w_next_valid<T, false>(a, blockIdx.x, total, it);
+  int cur = wq.consume(0);
+  if (cur < total) it = w_decode_dense(cur, P, a.lag);
   int e0 = (cur < total && !it.roleA) ? a.y.xtStart[it.tile] : 0;
   for (int k = 0; cur < total; ++k) {
-    const long long nxt = w_next_valid<T, false>(a, cur + gridDim.x, total, nx);
+    if (leader) reinterpret_cast<volatile int*>(sQueue.prog)[g] = k;
+    const bool mine = leader && wq.own(k + 2);
+    unsigned claimRaw = 0;
+    wq.claim(mine, claimRaw);  // (in flight until it is posted behind the tail)
+    const int nxt = wq.consume(k + 1);
+    if (nxt < total) nx = w_decode_dense(nxt, P, a.lag);
     if (k == 0 || !sReady[g][k & 1]) {
       w_group_sync<W>(g);
       if (leader) {
@@ -421,6 +516,7 @@ __global__ void __launch_bounds__(kWThreads, 2)
       }
     }
     w512_tail<T, false>(v, sTw, L);
+    if (mine) wq.post(k + 2, (int)claimRaw);
     if (it.roleA) {
       cx<T>* dst = a.scratch + (size_t)slot * planeElems + (size_t)(it.tile * kWWarps + w) * N + L;
       const uint64_t keep = l2_policy_evict_last();
@@ -571,7 +667,7 @@ int sb_wxy_config(int isFloat, int n, int numPlanes, int* ring, int* lag, int* n
   if (numPlanes <= r) r = numPlanes > 0 ? numPlanes : 1;  // every plane has its own slot: no reuse waits
   *ring = r;
   *lag = l;
-  *numCounters = 1 + 2 * (numPlanes > 0 ? numPlanes : 0);
+  *numCounters = 3 + 2 * (numPlanes > 0 ? numPlanes : 0);  // [0] unused, 2 P completion counters, 2 queue counters
   return 0;
 }
 
@@ -586,15 +682,15 @@ int sb_launch_wxy_f64(int forward, const sb::XYArgs<double>* args, void* stream)
   int grid = 0;
   int err = wxy_grid(&grid);
   if (err) return err;
-  const long long total = forward ? xy_total_items<double, false>(a) : xy_total_items<double, true>(a);
-  if (total > 0x7fffffffLL) return (int)cudaErrorInvalidConfiguration;
+  const long long total = 2LL * (kWN / kWWarps) * a.y.numPlanes;
+  if (total > 0x3fffffffLL) return (int)cudaErrorInvalidConfiguration;
   if (grid > total) grid = (int)total;
   static const WTw4<double> tw = [] {
     WTw4<double> t;
     wfft_lane_twiddles<double>(kWN, 32, &t.w[0][0]);
     return t;
   }();
-  cudaError_t e = cudaMemsetAsync(a.counters, 0, sizeof(int) * (1 + 2 * (size_t)a.y.numPlanes), s);
+  cudaError_t e = cudaMemsetAsync(a.counters, 0, sizeof(int) * (3 + 2 * (size_t)a.y.numPlanes), s);
   if (e != cudaSuccess) return (int)e;
   sb_note_launches(1);
   switch (wxy_group(forward)) {
