@@ -174,19 +174,40 @@ void GridResources<T>::map_peers() {
   if (local()) return;
   const char* env = std::getenv("SPFFT_B200_P2P");
   int want = !(env && std::atoi(env) == 0) && comm_->size() <= sb::kMaxPeers ? 1 : 0;
+  if (want) {
+    // second copy of the buffers the peers store into (array_a(1) / array_q(1), see transform_engine.hpp); a rank
+    // that cannot allocate it votes against the peer exchange (everybody then uses NCCL)
+    try {
+      a2_.allocate(a_.bytes());
+      q2_.allocate(q_.bytes());
+    } catch (const GPUAllocationError&) {
+      want = 0;
+    }
+  }
   {
     const std::vector<int> votes = comm_->all_gather_ints(&want, 1);
     for (int v : votes) want = want && v;
   }
-  if (!want) return;
+  if (!want) {
+    a2_.allocate(0);
+    q2_.allocate(0);
+    return;
+  }
   flags_.allocate(sizeof(int) * sb::kMaxPeers);
   check_gpu(cudaMemset(flags_.get(), 0, flags_.bytes()));
   check_gpu(cudaDeviceSynchronize());
   peerA_.open(*comm_, a_.get());
   peerQ_.open(*comm_, q_.get());
+  peerA2_.open(*comm_, a2_.get());
+  peerQ2_.open(*comm_, q2_.get());
   peerFlags_.open(*comm_, flags_.get());
-  peerOk_ = peerA_.mapped() && peerQ_.mapped() && peerFlags_.mapped();
+  peerOk_ = peerA_.mapped() && peerQ_.mapped() && peerA2_.mapped() && peerQ2_.mapped() && peerFlags_.mapped();
+  if (!peerOk_) {
+    a2_.allocate(0);
+    q2_.allocate(0);
+  }
   barrierEpoch_ = 0;
+  exchangeCalls_[0] = exchangeCalls_[1] = 0;
 }
 
 template <typename T>
@@ -596,11 +617,11 @@ sb::XYArgs<T> TransformEngine<T>::make_xy_args(const TileMaps& geo, const T* spa
 }
 
 template <typename T>
-sb::YArgs<T> TransformEngine<T>::make_y_stage_args(const TileMaps& geo, bool forward) {
+sb::YArgs<T> TransformEngine<T>::make_y_stage_args(const TileMaps& geo, bool forward, int parity) {
   auto ya = make_y_args<T>(*maps_, geo, plan_->axes, plan_->ptrs, sticks(), planes());
   if (plan_->distributed && forward && peer_exchange()) {
-    // forward over peer memory: every stick goes straight into its owner's stick buffer
-    for (int r = 0; r < maps_->commSize; ++r) ya.peer[r] = static_cast<sb::cx<T>*>(grid_->peer_a(r));
+    // forward over peer memory: every stick goes straight into its owner's stick buffer (copy `parity`)
+    for (int r = 0; r < maps_->commSize; ++r) ya.peer[r] = static_cast<sb::cx<T>*>(grid_->peer_a(parity, r));
     ya.stickRank = plan_->stickRank;
     ya.fwdBase = plan_->fwdBase;
     ya.tileFwdBase = plan_->tileFwdBase;
@@ -609,7 +630,7 @@ sb::YArgs<T> TransformEngine<T>::make_y_stage_args(const TileMaps& geo, bool for
   }
   if (plan_->distributed) {
     // sticks of all ranks, read from / written to the plane-side exchange buffer
-    ya.sticks = static_cast<sb::cx<T>*>(grid_->array_q());
+    ya.sticks = static_cast<sb::cx<T>*>(grid_->array_q(forward ? 0 : parity));
     ya.srcBase = plan_->srcBase;
     ya.srcPitch = plan_->srcPitch;
     ya.tileBase = plan_->tileBase;
@@ -649,15 +670,17 @@ void TransformEngine<T>::enqueue_backward(const T* input, T* output) {
   geo.symTile = plan_->symTile;
   geo.symLane = plan_->symLane;
   const bool peer = dist && peer_exchange();
-  // peers may still read the plane-side buffer this call's z stage stores into
-  if (peer) grid_->enqueue_peer_barrier(s);
+  // Peers may still read the plane-side buffer the previous backward call filled: this call's z stages store into
+  // the other copy (no barrier at the start of the call; the copy used two calls ago is free because every rank
+  // passed the barrier of the previous call after its last read of it).
+  const int parity = peer ? grid_->next_exchange_parity(0) : 0;
   if (plan_->numStickTiles > 0) {
     auto za = make_z_args<T>(m, geo, plan_->axes, plan_->ptrs, false, sticks(), values, nullptr,
                              false);
     if (peer) {
       // the z stage stores every row straight into the plane-side buffer of the rank that owns
       // the plane: compute and exchange are one kernel
-      for (int r = 0; r < m.commSize; ++r) za.peer[r] = static_cast<sb::cx<T>*>(grid_->peer_q(r));
+      for (int r = 0; r < m.commSize; ++r) za.peer[r] = static_cast<sb::cx<T>*>(grid_->peer_q(parity, r));
       za.rowRank = plan_->rowRank;
       za.rowOff = plan_->rowOff;
     }
@@ -690,7 +713,7 @@ void TransformEngine<T>::enqueue_backward(const T* input, T* output) {
     record_stage("xy backward");
   } else {
     // ---- y stage: stick gather + plane symmetry + y-FFT (execution_gpu.cpp:371-390)
-    check_launch(Launch<T>::y(0, make_y_stage_args(geo, false), s));
+    check_launch(Launch<T>::y(0, make_y_stage_args(geo, false, parity), s));
     record_stage("y backward");
     // ---- x stage: x-FFT (C2C / C2R) into the space domain
     auto xa = make_x_args<T>(m, plan_->axes, plan_->ptrs, planes(), nullptr, outDev);
@@ -727,8 +750,9 @@ void TransformEngine<T>::enqueue_forward(const T* input, T* output, SpfftScaling
   const bool anySticks = dist ? !plan_->exchange.stickSlot.empty() : (plan_->numStickTiles > 0 && ne > 0);
 
   const bool peer = dist && peer_exchange();
-  // peers may still read the stick buffer this call's y stage stores into
-  if (peer) grid_->enqueue_peer_barrier(s);
+  // peers may still read the stick buffer the previous forward call filled: this call's y stages store into the
+  // other copy (see enqueue_backward)
+  const int parity = peer ? grid_->next_exchange_parity(1) : 0;
   // ---- x stage (execution_gpu.cpp:254-282)
   if (haveSpace) {
     const T* src = input;
@@ -749,7 +773,7 @@ void TransformEngine<T>::enqueue_forward(const T* input, T* output, SpfftScaling
       record_stage("x forward");
       if (anySticks) {
         // ---- y stage: y-FFT + scatter into the plane-major sticks / the exchange buffer
-        check_launch(Launch<T>::y(1, make_y_stage_args(geo, true), s));
+        check_launch(Launch<T>::y(1, make_y_stage_args(geo, true, parity), s));
         record_stage(peer ? "y forward + exchange" : "y forward");
       }
     }
@@ -769,7 +793,8 @@ void TransformEngine<T>::enqueue_forward(const T* input, T* output, SpfftScaling
   const bool outOnDevice = is_device_pointer(output);
   T* outDev = outOnDevice ? output : static_cast<T*>(grid_->array_b());
   {
-    auto za = make_z_args<T>(m, geo, plan_->axes, plan_->ptrs, true, sticks(), nullptr, outDev,
+    auto za = make_z_args<T>(m, geo, plan_->axes, plan_->ptrs, true,
+                             static_cast<sb::cx<T>*>(grid_->array_a(parity)), nullptr, outDev,
                              scaling == SPFFT_FULL_SCALING);
     za.wireF32 = wire_f32() ? 1 : 0;
     check_launch(plan_->wfftZ && !za.wireF32 ? Launch<T>::wz(1, za, s) : Launch<T>::z(1, za, s));
