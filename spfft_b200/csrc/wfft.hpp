@@ -262,6 +262,63 @@ inline void wfft_lane_twiddles(int n, int lanes, cx<T>* out /* [4][lanes] */) {
     }
 }
 
+// --------------------------------------------------------------------------------------------
+// Tile geometry of the stage kernels built on the length-512 plan (wfft_kernels.cuh; double precision).
+// Host + device so that tests/emu can check the address algebra against WPlan<T, 512>::xw / xr.
+// --------------------------------------------------------------------------------------------
+constexpr int kWN = 512;    // transform length of this kernel family
+constexpr int kWWarps = 8;  // transforms per tile
+// Sub-tiles. The 8 warps of a CTA form 8 / W independent groups of W warps; a group owns W adjacent columns of
+// the CTA's 8-column tile and its own sub-tile buffer [512 rows][W x 16-byte chunks] (TMA swizzle of the row
+// width: 128B / 64B / 32B), synchronises on its own named barrier and never waits for the other groups: with
+// W = 2 (pairs) four groups per CTA drift through load / fp64 / exchange / store phases independently, which is
+// what lets the SM overlap them (one 8-warp tile per CTA ran in lock step: ncu barrier stalls 29 % of all samples).
+template <int W>
+struct WGeom {
+  static_assert(W == 2 || W == 4 || W == 8, "columns per group");
+  static constexpr int kGroups = kWWarps / W;
+  static constexpr int kGroupThreads = W * 32;
+  static constexpr unsigned kRowBytes = 16u * W;
+  static constexpr size_t kSubBytes = (size_t)kWN * kRowBytes;
+  static constexpr int kLog2RowsPer128 = W == 8 ? 0 : (W == 4 ? 1 : 2);
+  // chunk permutation of row s: chunk c sits at c ^ fold(s)
+  static SB_HD constexpr unsigned fold(unsigned s) { return (s >> kLog2RowsPer128) & (W - 1); }
+  // xor pattern of the low three slot bits q
+  static SB_HD constexpr unsigned pat(unsigned q) { return (q * kRowBytes) | (fold(q) << 4); }
+};
+// Byte offsets inside the group's sub-tile of everything lane L of its warp wl touches, in a form that costs ONE
+// xor per access (RB = row bytes = 16 W):
+//   natural element n = L + 32 m of column wl        : nat + m * 32 RB
+//   exchange write, register i (slot xw(L, i))       : (xwBase ^ pat(i & 7)) + (i >> 3) * 16 RB
+//   exchange read, input r (slot xr(L, r))           : (nat ^ pat(r & 7)) + r * 32 RB
+// (slot s of column wl lives at byte s * RB + ((wl ^ fold(s)) << 4); the slots of WPlan<T, 512> differ from
+// lane-constant bases only in their low three bits q, which enter the address as the xor pattern pat(q).)
+struct WAddr {
+  unsigned nat, xwBase;
+};
+template <int W>
+SB_HD WAddr w_addr(int wl, int L) {
+  using G = WGeom<W>;
+  WAddr a;
+  a.nat = ((unsigned)L * G::kRowBytes) | ((unsigned)(wl ^ G::fold(L & 7)) << 4);
+  const unsigned j = L & 15, h = L >> 4, q = j & 7;
+  a.xwBase = ((32u * j + 8u * h) * G::kRowBytes) | (q * G::kRowBytes) | ((unsigned)(wl ^ G::fold(q)) << 4);
+  return a;
+}
+// byte offsets of the three access patterns (see above)
+template <int W>
+SB_HD unsigned w_xw_off(const WAddr& ad, int i) {
+  return (ad.xwBase ^ WGeom<W>::pat(i & 7)) + (unsigned)(i >> 3) * 16u * WGeom<W>::kRowBytes;
+}
+template <int W>
+SB_HD unsigned w_xr_off(const WAddr& ad, int r) {
+  return (ad.nat ^ WGeom<W>::pat(r & 7)) + (unsigned)r * 32u * WGeom<W>::kRowBytes;
+}
+template <int W>
+SB_HD unsigned w_nat_off(const WAddr& ad, int m) {
+  return ad.nat + (unsigned)m * 32u * WGeom<W>::kRowBytes;
+}
+
 // number of table entries / fill (host side, long double roots like make_fast_twiddles)
 inline int wfft_tw_size(int n) { return n == 512 ? 15 * 32 : (n == 256 ? 15 * 16 : 0); }
 inline bool wfft_length(int n) { return n == 512 || n == 256; }

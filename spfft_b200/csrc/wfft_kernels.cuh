@@ -23,8 +23,6 @@
 
 namespace sb {
 
-constexpr int kWN = 512;        // transform length of this kernel family
-constexpr int kWWarps = 8;      // transforms per tile
 constexpr int kWThreads = 256;
 constexpr size_t kWTileBytes = (size_t)kWN * kWWarps * sizeof(cx<double>);  // 64 KB
 
@@ -120,24 +118,6 @@ __device__ __forceinline__ void w512_head(cx<T>* v, int L) {
     P::stage_a_combine(v[i], v[8 + i], recv, L);
   }
 }
-// Sub-tiles. The 8 warps of a CTA form 8 / W independent groups of W warps; a group owns W adjacent columns of
-// the CTA's 8-column tile and its own sub-tile buffer [512 rows][W x 16-byte chunks] (TMA swizzle of the row
-// width: 128B / 64B / 32B), synchronises on its own named barrier and never waits for the other groups: with
-// W = 2 (pairs) four groups per CTA drift through load / fp64 / exchange / store phases independently, which is
-// what lets the SM overlap them (one 8-warp tile per CTA ran in lock step: ncu barrier stalls 29 % of all samples).
-template <int W>
-struct WGeom {
-  static_assert(W == 2 || W == 4 || W == 8, "columns per group");
-  static constexpr int kGroups = kWWarps / W;
-  static constexpr int kGroupThreads = W * 32;
-  static constexpr unsigned kRowBytes = 16u * W;
-  static constexpr size_t kSubBytes = (size_t)kWN * kRowBytes;
-  static constexpr int kLog2RowsPer128 = W == 8 ? 0 : (W == 4 ? 1 : 2);
-  // chunk permutation of row s: chunk c sits at c ^ fold(s)
-  __host__ __device__ static constexpr unsigned fold(unsigned s) { return (s >> kLog2RowsPer128) & (W - 1); }
-  // xor pattern of the low three slot bits q
-  __host__ __device__ static constexpr unsigned pat(unsigned q) { return (q * kRowBytes) | (fold(q) << 4); }
-};
 template <int W>
 __device__ __forceinline__ void w_group_sync(int g) {
   if constexpr (W == 8) {
@@ -147,25 +127,6 @@ __device__ __forceinline__ void w_group_sync(int g) {
   }
 }
 
-// Byte offsets inside the group's sub-tile of everything lane L of its warp wl touches, in a form that costs ONE
-// xor per access (RB = row bytes = 16 W):
-//   natural element n = L + 32 m of column wl        : nat + m * 32 RB
-//   exchange write, register i (slot xw(L, i))       : (xwBase ^ pat(i & 7)) + (i >> 3) * 16 RB
-//   exchange read, input r (slot xr(L, r))           : (nat ^ pat(r & 7)) + r * 32 RB
-// (slot s of column wl lives at byte s * RB + ((wl ^ fold(s)) << 4); the slots of WPlan<T, 512> differ from
-// lane-constant bases only in their low three bits q, which enter the address as the xor pattern pat(q).)
-struct WAddr {
-  unsigned nat, xwBase;
-};
-template <int W>
-__device__ __forceinline__ WAddr w_addr(int wl, int L) {
-  using G = WGeom<W>;
-  WAddr a;
-  a.nat = ((unsigned)L * G::kRowBytes) | ((unsigned)(wl ^ G::fold(L & 7)) << 4);
-  const unsigned j = L & 15, h = L >> 4, q = j & 7;
-  a.xwBase = ((32u * j + 8u * h) * G::kRowBytes) | (q * G::kRowBytes) | ((unsigned)(wl ^ G::fold(q)) << 4);
-  return a;
-}
 template <typename T>
 __device__ __forceinline__ cx<T>* w_at(cx<T>* S, unsigned byteOff) {
   return reinterpret_cast<cx<T>*>(reinterpret_cast<char*>(S) + byteOff);
@@ -174,12 +135,11 @@ __device__ __forceinline__ cx<T>* w_at(cx<T>* S, unsigned byteOff) {
 template <typename T, int W>
 __device__ __forceinline__ void w512_exchange(cx<T>* v, cx<T>* S, const WAddr& ad) {
   static_assert(sizeof(cx<T>) == 16, "double precision tile layout");
-  using G = WGeom<W>;
 #pragma unroll
-  for (int i = 0; i < 16; ++i) *w_at(S, (ad.xwBase ^ G::pat(i & 7)) + (unsigned)(i >> 3) * 16u * G::kRowBytes) = v[i];
+  for (int i = 0; i < 16; ++i) *w_at(S, w_xw_off<W>(ad, i)) = v[i];
   __syncwarp();
 #pragma unroll
-  for (int r = 0; r < 16; ++r) v[r] = *w_at(S, (ad.nat ^ G::pat(r & 7)) + (unsigned)r * 32u * G::kRowBytes);
+  for (int r = 0; r < 16; ++r) v[r] = *w_at(S, w_xr_off<W>(ad, r));
   __syncwarp();
 }
 // The same exchange in a FLAT private region of 512 elements (a row that a bulk copy landed in natural order):
@@ -214,12 +174,12 @@ __device__ __forceinline__ void w_bulk_load(void* dst, const void* src, uint32_t
 template <typename T, int W>
 __device__ __forceinline__ void w512_col_load(cx<T>* v, cx<T>* S, const WAddr& ad) {
 #pragma unroll
-  for (int m = 0; m < 16; ++m) v[m] = *w_at(S, ad.nat + (unsigned)m * 32u * WGeom<W>::kRowBytes);
+  for (int m = 0; m < 16; ++m) v[m] = *w_at(S, w_nat_off<W>(ad, m));
 }
 template <typename T, int W>
 __device__ __forceinline__ void w512_col_store(const cx<T>* v, cx<T>* S, const WAddr& ad) {
 #pragma unroll
-  for (int m = 0; m < 16; ++m) *w_at(S, ad.nat + (unsigned)m * 32u * WGeom<W>::kRowBytes) = v[m];
+  for (int m = 0; m < 16; ++m) *w_at(S, w_nat_off<W>(ad, m)) = v[m];
 }
 // Stage B: afterwards v[q] = X[L + 32 q].
 template <typename T, bool BWD>

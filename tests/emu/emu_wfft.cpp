@@ -83,9 +83,119 @@ int worst_conflict() {
   return worst;
 }
 
+// The transform as the stage kernels run it (wfft_kernels.cuh): exchange through the column of a [512][W] sub-tile
+// addressed in xor form (w_addr / w_xw_off / w_xr_off / w_nat_off), stage B with the four lane twiddles
+// w, w^2, w^4, w^8 and derived powers (twiddle_dft16). One warp = column `wl` of the sub-tile; the other columns
+// are poisoned and must stay untouched. Returns 0, or a code for: 1 overlapping writes, 2 foreign column touched.
+template <typename T, int W, bool BWD>
+int run_warp_tile(int wl, const T* x, T* out) {
+  using P = sb::WPlan<T, 512>;
+  using G = sb::WGeom<W>;
+  constexpr int N = 512;
+  std::vector<sb::cx<T>> tw4(4 * 32);
+  sb::wfft_lane_twiddles<T>(N, 32, tw4.data());
+  const size_t elems = G::kSubBytes / sizeof(sb::cx<T>);
+  std::vector<sb::cx<T>> S(elems, sb::mk<T>(T(7e30), T(-7e30)));
+  std::vector<int> owner(elems, -1);
+  auto at = [&](unsigned byteOff) -> size_t { return byteOff / sizeof(sb::cx<T>); };
+  std::vector<sb::cx<T>> v(32 * 16);
+  const sb::cx<T>* in = reinterpret_cast<const sb::cx<T>*>(x);
+  // tile side in: the natural-order column, as a bulk tensor load would have placed it
+  for (int L = 0; L < 32; ++L) {
+    const sb::WAddr ad = sb::w_addr<W>(wl, L);
+    for (int m = 0; m < 16; ++m) {
+      const size_t e = at(sb::w_nat_off<W>(ad, m));
+      const int n = L + 32 * m;
+      // element n of column wl must sit at chunk wl ^ fold(n) of row n (the TMA swizzle of the row width)
+      if (e != (size_t)n * W + (wl ^ G::fold(n))) return 3;
+      S[e] = in[n];
+    }
+  }
+  for (int L = 0; L < 32; ++L) {
+    const sb::WAddr ad = sb::w_addr<W>(wl, L);
+    for (int m = 0; m < 16; ++m) v[L * 16 + m] = S[at(sb::w_nat_off<W>(ad, m))];
+    P::template stage_a_local<BWD>(&v[L * 16], L);
+  }
+  std::vector<sb::cx<T>> sent(32 * 8);
+  for (int L = 0; L < 32; ++L)
+    for (int i = 0; i < 8; ++i) sent[L * 8 + i] = v[L * 16 + 8 + i];
+  for (int L = 0; L < 32; ++L)
+    for (int i = 0; i < 8; ++i) P::stage_a_combine(v[L * 16 + i], v[L * 16 + 8 + i], sent[(L ^ 16) * 8 + i], L);
+  std::vector<int> written(elems, 0);
+  for (int L = 0; L < 32; ++L) {
+    const sb::WAddr ad = sb::w_addr<W>(wl, L);
+    for (int i = 0; i < 16; ++i) {
+      const size_t e = at(sb::w_xw_off<W>(ad, i));
+      const int s = P::xw(L, i);
+      if (e != (size_t)s * W + (wl ^ G::fold(s))) return 4;  // xor form == slot of the plan in column wl
+      if (written[e]) return 1;
+      written[e] = 1;
+      S[e] = v[L * 16 + i];
+    }
+  }
+  for (int L = 0; L < 32; ++L) {
+    const sb::WAddr ad = sb::w_addr<W>(wl, L);
+    for (int r = 0; r < 16; ++r) {
+      const size_t e = at(sb::w_xr_off<W>(ad, r));
+      const int s = P::xr(L, r);
+      if (e != (size_t)s * W + (wl ^ G::fold(s))) return 5;
+      v[L * 16 + r] = S[e];
+    }
+    sb::LaneTw<T> t;
+    t.w1 = tw4[L];
+    t.w2 = tw4[32 + L];
+    t.w4 = tw4[64 + L];
+    t.w8 = tw4[96 + L];
+    sb::twiddle_dft16<T, BWD>(&v[L * 16], t);
+  }
+  // every element outside column wl is still poisoned
+  for (size_t e = 0; e < elems; ++e) {
+    const size_t row = e / W, chunk = e % W;
+    const bool mine = (chunk ^ G::fold((unsigned)row)) == (size_t)wl;
+    if (!mine && S[e].x != T(7e30)) return 2;
+  }
+  sb::cx<T>* o = reinterpret_cast<sb::cx<T>*>(out);
+  for (int L = 0; L < 32; ++L)
+    for (int q = 0; q < 16; ++q) o[L + 32 * q] = v[L * 16 + q];
+  return 0;
+}
+
+// worst number of lanes of a quarter warp (8 lanes: one 128-byte wavefront of a 128-bit access) that fall into
+// the same 16-byte bank group, over the three access patterns of the stage kernels
+template <int W>
+int worst_tile_conflict(int wl) {
+  int worst = 1;
+  for (int pass = 0; pass < 3; ++pass)
+    for (int i = 0; i < 16; ++i)
+      for (int g = 0; g < 4; ++g) {
+        int cnt[8] = {0};
+        for (int l = 0; l < 8; ++l) {
+          const int L = g * 8 + l;
+          const sb::WAddr ad = sb::w_addr<W>(wl, L);
+          const unsigned off = pass == 0 ? sb::w_xw_off<W>(ad, i) : (pass == 1 ? sb::w_xr_off<W>(ad, i) : sb::w_nat_off<W>(ad, i));
+          worst = std::max(worst, ++cnt[(off >> 4) & 7]);
+        }
+      }
+  return worst;
+}
+
 }  // namespace
 
 extern "C" {
+// the product form: column wl of a [512][W] sub-tile, xor-form addresses, derived twiddles (double precision)
+int emu_wfft_tile_f64(int W, int wl, int backward, const double* x, double* out) {
+#define SB_TILE(WW) \
+  if (W == WW) return backward ? run_warp_tile<double, WW, true>(wl, x, out) : run_warp_tile<double, WW, false>(wl, x, out);
+  SB_TILE(2) SB_TILE(4) SB_TILE(8)
+#undef SB_TILE
+  return -1;
+}
+int emu_wfft_tile_conflicts(int W, int wl) {
+  if (W == 2) return worst_tile_conflict<2>(wl);
+  if (W == 4) return worst_tile_conflict<4>(wl);
+  if (W == 8) return worst_tile_conflict<8>(wl);
+  return -1;
+}
 // dir: 0 forward (sign -), 1 backward (sign +). Returns 0 on success.
 int emu_wfft_f64(int n, int backward, const double* x, double* out) {
   if (n == 512) return backward ? run_warp<double, 512, true>(x, out) : run_warp<double, 512, false>(x, out);

@@ -474,3 +474,47 @@ def test_emulated_kernels_vs_reference_host_library(emu, gen, ref_lib, case):
     back = np.zeros(len(trip), dtype=np.complex128)
     assert emu.sb_emu_transform(0, ttype, nx, ny, nz, len(trip), _ptr(t), 1, _ptr(out), _ptr(back), 1, 64, -1) == 0
     assert orc.rel_l2(back, ref_back) <= 1e-12
+
+
+# ---- warp FFT (wfft.hpp): the arithmetic bodies, exchange slots and tile address algebra of the length-512 /
+# length-256 plans, lane by lane on the CPU (tests/emu/emu_wfft.cpp) ------------------------------------------
+@pytest.fixture(scope="module")
+def emu_wfft(built):
+    lib = C.CDLL(built.EMU_WFFT_LIB)
+    for f in ("emu_wfft_f64", "emu_wfft_f32", "emu_wfft_conflicts", "emu_wfft_tile_f64", "emu_wfft_tile_conflicts"):
+        getattr(lib, f).restype = C.c_int
+    return lib
+
+
+@pytest.mark.parametrize("n", [512, 256])
+@pytest.mark.parametrize("backward", [0, 1])
+@pytest.mark.parametrize("single", [False, True])
+def test_warp_fft_plan(emu_wfft, n, backward, single):
+    """One warp = one (n = 512) or two (n = 256) transforms: 16 values per lane, one exchange, natural order in and
+    out; the exchange slots are a bijection (checked inside) and bank-conflict free."""
+    rng = np.random.default_rng(n + backward)
+    count = 1 if n == 512 else 2
+    cdt = np.complex64 if single else np.complex128
+    x = (rng.uniform(-1, 1, (count, n)) + 1j * rng.uniform(-1, 1, (count, n))).astype(cdt)
+    out = np.zeros_like(x)
+    fn = emu_wfft.emu_wfft_f32 if single else emu_wfft.emu_wfft_f64
+    assert fn(n, backward, _ptr(x), _ptr(out)) == 0
+    ref = (np.fft.ifft(x.astype(np.complex128), axis=1) * n) if backward else np.fft.fft(x.astype(np.complex128), axis=1)
+    assert orc.rel_l2(out, ref) < (2e-6 if single else 1e-14)
+    assert emu_wfft.emu_wfft_conflicts(n, int(single)) == 1
+
+
+@pytest.mark.parametrize("W", [2, 4, 8])
+@pytest.mark.parametrize("backward", [0, 1])
+def test_warp_fft_tile_form(emu_wfft, W, backward):
+    """The form the stage kernels run (wfft_kernels.cuh): the warp's column of a [512][W] sub-tile in the TMA swizzle
+    of the row width, xor-form addresses equal to the plan's slots, lane twiddles w, w^2, w^4, w^8 with derived
+    powers; no other column is touched, no quarter warp hits a 16-byte bank group twice."""
+    rng = np.random.default_rng(10 * W + backward)
+    for wl in range(W):
+        x = rng.uniform(-1, 1, 512) + 1j * rng.uniform(-1, 1, 512)
+        out = np.zeros_like(x)
+        assert emu_wfft.emu_wfft_tile_f64(W, wl, backward, _ptr(x), _ptr(out)) == 0
+        ref = np.fft.ifft(x) * 512 if backward else np.fft.fft(x)
+        assert orc.rel_l2(out, ref) < 1e-14
+        assert emu_wfft.emu_wfft_tile_conflicts(W, wl) == 1
