@@ -706,12 +706,21 @@ void TransformEngine<T>::enqueue_backward(const T* input, T* output) {
   T* outDev = outOnDevice ? output : device_space();
   // (the warp-FFT kernels move rows with 16-byte bulk copies / vector accesses: a space pointer that is only
   // aligned to its scalar type takes the separate y and x kernels)
-  const bool fusedHere = plan_->fusedXY && !(plan_->wfftXY && (reinterpret_cast<size_t>(outDev) & 15) != 0);
+  bool fusedHere = plan_->fusedXY && !(plan_->wfftXY && (reinterpret_cast<size_t>(outDev) & 15) != 0);
   if (fusedHere) {
     // ---- fused xy stage: y tiles and x tiles in one persistent kernel, hand-off through L2
-    check_launch(Launch<T>::wxy(0, make_xy_args(geo, nullptr, outDev), s));
-    record_stage("xy backward");
-  } else {
+    const int err = Launch<T>::wxy(0, make_xy_args(geo, nullptr, outDev), s);
+    if (err == static_cast<int>(cudaErrorCooperativeLaunchTooLarge)) {
+      // the device cannot hold the whole persistent grid right now (e.g. shared with another process):
+      // the separate y and x kernels do the same work through the plane buffer
+      cudaGetLastError();
+      fusedHere = false;
+    } else {
+      check_launch(err);
+      record_stage("xy backward");
+    }
+  }
+  if (!fusedHere) {
     // ---- y stage: stick gather + plane symmetry + y-FFT (execution_gpu.cpp:371-390)
     check_launch(Launch<T>::y(0, make_y_stage_args(geo, false, parity), s));
     record_stage("y backward");
@@ -761,13 +770,18 @@ void TransformEngine<T>::enqueue_forward(const T* input, T* output, SpfftScaling
       src = device_space();
       record_stage("h2d space");
     }
-    const bool fusedHere = plan_->fusedXY && !(plan_->wfftXY && (reinterpret_cast<size_t>(src) & 15) != 0);
-    if (fusedHere) {
-      if (anySticks) {
-        check_launch(Launch<T>::wxy(1, make_xy_args(geo, src, nullptr), s));
+    bool fusedHere = plan_->fusedXY && !(plan_->wfftXY && (reinterpret_cast<size_t>(src) & 15) != 0);
+    if (fusedHere && anySticks) {
+      const int err = Launch<T>::wxy(1, make_xy_args(geo, src, nullptr), s);
+      if (err == static_cast<int>(cudaErrorCooperativeLaunchTooLarge)) {
+        cudaGetLastError();  // see enqueue_backward
+        fusedHere = false;
+      } else {
+        check_launch(err);
         record_stage("xy forward");
       }
-    } else {
+    }
+    if (!fusedHere) {
       auto xa = make_x_args<T>(m, plan_->axes, plan_->ptrs, planes(), src, nullptr);
       check_launch(Launch<T>::x(1, xa, s));
       record_stage("x forward");

@@ -8,16 +8,16 @@
 // Replaces the two passes of the reference's 2-D cuFFT plans (src/fft/transform_2d_gpu.hpp:51-140)
 // and its transposing unpack / pack kernels (src/transpose/gpu_kernels/local_transpose_kernels.cu).
 //
-// Schedule: items in the order of xy_decode (fast_stage_kernels.hpp): for step u, the A tiles of
-// plane u, then the B tiles of plane u - lag; an item = 8 columns (y tile) or 8 rows (x tile) of one
-// plane. Item i belongs to CTA i mod gridDim (static, no claim counter); the grid is launched
-// cooperatively, so every CTA is resident and waiting on an earlier item cannot deadlock. Inside a CTA
-// the 8 / W groups of W warps (WGeom) each take W columns / rows of the item and run on their own: own
-// sub-tile buffer, own named barrier, own flags. A group's B part waits until all A parts of its plane
-// are complete, an A part until the B parts of the plane that used its ring slot before are complete
-// (counters count group parts). Completion of a group's part k is published while its part k+1 runs
-// (after the group barrier that part needs anyway), and the dependency of part k+1 is polled while the
-// loads of part k are in flight, so in the steady state no warp ever waits on a flag.
+// Schedule: items in hand-out order (w_decode_dense): for step u, the A tiles of plane u, then the B tiles of plane
+// u - lag; an item = 8 columns (y tile) or 8 rows (x tile) of one plane. The CTAs CLAIM their items in that order
+// from two interleaved global counters (WQueue), two items ahead; the grid is launched cooperatively, so every CTA
+// is resident and waiting on an earlier item cannot deadlock. Inside a CTA the 8 / W groups of W warps (WGeom)
+// each take W columns / rows of the CTA's item and run on their own: own sub-tile buffer, own named barrier, own
+// flags. A group's B part waits until all A parts of its plane are complete, an A part until the B parts of the
+// plane that used its ring slot before are complete (counters count group parts). Completion of a group's part k is
+// published while its part k+1 runs (right after the group barrier that part needs anyway, by another warp than
+// the one that handles the tensor copies), and the dependency of part k+1 is polled behind the exchange of part k
+// with a relaxed load, so in the steady state no warp waits on a flag round trip.
 #include <cstdlib>
 
 #include "fast_launch.cuh"
@@ -557,14 +557,7 @@ int wxy_group(int forward) {
   return w ? w : (forward ? 8 : 4);
 }
 
-// experiment: SPFFT_B200_WPAD = extra dynamic shared memory in KB (forces fewer CTAs per SM)
-size_t wxy_smem() {
-  static const size_t pad = [] {
-    const char* e = getenv("SPFFT_B200_WPAD");
-    return e ? (size_t)atoi(e) * 1024 : (size_t)0;
-  }();
-  return kWTileBytes + pad;
-}
+size_t wxy_smem() { return kWTileBytes; }
 
 template <int W>
 int wxy_grid_w(int* gridOut) {
