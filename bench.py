@@ -513,7 +513,8 @@ def main():
     stage_bytes = {"z backward": ab["z"], "y backward": ab["y"], "x backward": ab["x"],
                    "x forward": ab["x"], "y forward": ab["y"], "z forward": ab["z"],
                    "xy backward": ab["y"] + ab["x"], "xy forward": ab["y"] + ab["x"],
-                   "z backward + exchange": ab["z"], "y forward + exchange": ab["y"]}
+                   "z backward + exchange": ab["z"], "y forward + exchange": ab["y"],
+                   "xy forward + exchange": ab["y"] + ab["x"]}
     kernels = [(nm, ms) for nm, ms in stages if nm in stage_bytes]
     roofline = None
     pair_frac = bands * 2 * ab["dir"] / (ms_per_step * 1e-3) / 1e9 / peak

@@ -366,9 +366,11 @@ std::shared_ptr<DevicePlan<T>> build_device_plan(const IndexMaps& m, long long s
   // Warp-FFT kernels (default where they exist; SPFFT_B200_WFFT=0 selects the round-1 kernels, bit 0 =
   // fused xy stage, bit 1 = z stage): one warp per transform, tiles staged by TMA, y <-> x hand-off in L2.
   const char* wEnv = std::getenv("SPFFT_B200_WFFT");
-  const int wMask = wEnv ? std::atoi(wEnv) : 3;
+  const int wMask = wEnv ? std::atoi(wEnv) : 7;
+  // (bit 2: the fused xy stage also for distributed transforms, whose y tiles read / write the exchange buffers)
   if (!plan->fusedXY && (wMask & 1) && sizeof(T) == 8 && fastX && fastY && m.dimX == m.dimY &&
-      m.type == SPFFT_TRANS_C2C && m.commSize == 1 && m.num_sticks() > 0 && ax.log2Vy == 3) {
+      m.type == SPFFT_TRANS_C2C && ax.log2Vy == 3 &&
+      (m.commSize == 1 ? m.num_sticks() > 0 : ((wMask & 4) && m.local_planes() > 0))) {
     const int err = sb_wxy_config(0, m.dimX, m.local_planes(), &plan->xyRing, &plan->xyLag, &plan->xyCounters);
     plan->fusedXY = plan->wfftXY = err == 0;
   }
@@ -428,8 +430,8 @@ std::shared_ptr<DevicePlan<T>> build_device_plan(const IndexMaps& m, long long s
     // the rotated order is the one measured on 4 and 8 GPUs, so it stays the default)
     const char* ord = std::getenv("SPFFT_B200_FWD_ORDER");
     if (ord && std::atoi(ord) == 1) plan->fwdTileOrder = upload(st, total, plan->exchange.fwdTileOrder);
-    plan->fusedXY = false;
-    plan->wfftXY = false;
+    // the fused xy stage needs the inverse map over all ranks' sticks
+    if (plan->exchange.yInv.empty() || plan->exchange.numXTiles * 8 != m.dimX) plan->fusedXY = plan->wfftXY = false;
   } else {
     p.xtStart = upload(st, total, t.xtStart);
     p.stickSlot = upload(st, total, t.stickSlot);
@@ -602,10 +604,11 @@ void TransformEngine<T>::synchronize() {
 }
 
 template <typename T>
-sb::XYArgs<T> TransformEngine<T>::make_xy_args(const TileMaps& geo, const T* spaceIn, T* spaceOut) {
+sb::XYArgs<T> TransformEngine<T>::make_xy_args(const TileMaps& geo, const T* spaceIn, T* spaceOut, bool forward,
+                                               int parity) {
   const IndexMaps& m = *maps_;
   sb::XYArgs<T> a{};
-  a.y = make_y_stage_args(geo, false);
+  a.y = make_y_stage_args(geo, forward, parity);
   a.y.planes = nullptr;
   a.x = make_x_args<T>(m, plan_->axes, plan_->ptrs, nullptr, spaceIn, spaceOut);
   a.ring = plan_->xyRing;
@@ -706,10 +709,11 @@ void TransformEngine<T>::enqueue_backward(const T* input, T* output) {
   T* outDev = outOnDevice ? output : device_space();
   // (the warp-FFT kernels move rows with 16-byte bulk copies / vector accesses: a space pointer that is only
   // aligned to its scalar type takes the separate y and x kernels)
-  bool fusedHere = plan_->fusedXY && !(plan_->wfftXY && (reinterpret_cast<size_t>(outDev) & 15) != 0);
+  bool fusedHere = plan_->fusedXY && !(plan_->wfftXY && (reinterpret_cast<size_t>(outDev) & 15) != 0) &&
+                   !(dist && wire_f32());
   if (fusedHere) {
     // ---- fused xy stage: y tiles and x tiles in one persistent kernel, hand-off through L2
-    const int err = Launch<T>::wxy(0, make_xy_args(geo, nullptr, outDev), s);
+    const int err = Launch<T>::wxy(0, make_xy_args(geo, nullptr, outDev, false, parity), s);
     if (err == static_cast<int>(cudaErrorCooperativeLaunchTooLarge)) {
       // the device cannot hold the whole persistent grid right now (e.g. shared with another process):
       // the separate y and x kernels do the same work through the plane buffer
@@ -770,15 +774,16 @@ void TransformEngine<T>::enqueue_forward(const T* input, T* output, SpfftScaling
       src = device_space();
       record_stage("h2d space");
     }
-    bool fusedHere = plan_->fusedXY && !(plan_->wfftXY && (reinterpret_cast<size_t>(src) & 15) != 0);
+    bool fusedHere = plan_->fusedXY && !(plan_->wfftXY && (reinterpret_cast<size_t>(src) & 15) != 0) &&
+                     !(dist && wire_f32());
     if (fusedHere && anySticks) {
-      const int err = Launch<T>::wxy(1, make_xy_args(geo, src, nullptr), s);
+      const int err = Launch<T>::wxy(1, make_xy_args(geo, src, nullptr, true, parity), s);
       if (err == static_cast<int>(cudaErrorCooperativeLaunchTooLarge)) {
         cudaGetLastError();  // see enqueue_backward
         fusedHere = false;
       } else {
         check_launch(err);
-        record_stage("xy forward");
+        record_stage(peer ? "xy forward + exchange" : "xy forward");
       }
     }
     if (!fusedHere) {

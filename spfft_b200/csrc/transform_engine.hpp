@@ -185,7 +185,7 @@ public:
 
 private:
   void begin_call();
-  sb::XYArgs<T> make_xy_args(const TileMaps& geo, const T* spaceIn, T* spaceOut);
+  sb::XYArgs<T> make_xy_args(const TileMaps& geo, const T* spaceIn, T* spaceOut, bool forward = false, int parity = 0);
   sb::YArgs<T> make_y_stage_args(const TileMaps& geo, bool forward, int parity = 0);
   void record_stage(const char* name);
   size_t space_bytes() const;

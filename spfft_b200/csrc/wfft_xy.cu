@@ -240,6 +240,11 @@ __global__ void __launch_bounds__(kWThreads, 2)
   if (cur < total) it = w_decode_dense(cur, P, a.lag);
   bool invAhead = false;
   int e0 = (cur < total && it.roleA) ? a.y.xtStart[it.tile] : 0;  // first stick of the part's x tile
+  int tileBase = 0, tilePitch = 0;  // distributed: block of a single-source tile in the exchange buffer
+  if (cur < total && it.roleA && a.y.srcBase) {
+    tileBase = a.y.tileBase[it.tile];
+    tilePitch = a.y.tilePitch[it.tile];
+  }
   W_TRACE_DECL
   for (int k = 0; cur < total; ++k) {
     if (leader) reinterpret_cast<volatile int*>(sQueue.prog)[g] = k;
@@ -278,7 +283,6 @@ __global__ void __launch_bounds__(kWThreads, 2)
     cx<T> v[16];
     const int slot = it.plane % a.ring;
     if (it.roleA) {
-      const cx<T>* row = a.y.sticks + (size_t)(it.plane + a.y.zRowOffset) * a.y.pitch + e0;
       WInv16 iv;
       if (invAhead) {
         w_cp_async_wait();
@@ -286,10 +290,23 @@ __global__ void __launch_bounds__(kWThreads, 2)
       } else {
         iv = w_load_inv(a.y.inv, it.tile, w, L);
       }
+      if (a.y.srcBase && tilePitch == 0) {
+        // distributed, sticks of this tile from several ranks (tiles at a rank boundary): per-stick tables
 #pragma unroll
-      for (int m = 0; m < 16; ++m) {
-        v[m] = mk<T>(0, 0);
-        if (iv.i[m] != kWNone) v[m] = w_ldcs(row + iv.i[m]);  // read once: evict first, the ring stays in L2
+        for (int m = 0; m < 16; ++m) {
+          v[m] = mk<T>(0, 0);
+          if (iv.i[m] != kWNone) v[m] = *y_dist_stick<T, false>(a.y, e0 + iv.i[m], it.plane);
+        }
+      } else {
+        // local: row of the plane-major stick buffer; distributed: the tile's block inside its source rank's part
+        // of the plane-side exchange buffer
+        const cx<T>* row = a.y.srcBase ? a.y.sticks + (size_t)tileBase + (size_t)it.plane * tilePitch
+                                       : a.y.sticks + (size_t)(it.plane + a.y.zRowOffset) * a.y.pitch + e0;
+#pragma unroll
+        for (int m = 0; m < 16; ++m) {
+          v[m] = mk<T>(0, 0);
+          if (iv.i[m] != kWNone) v[m] = w_ldcs(row + iv.i[m]);  // read once: evict first, the ring stays in L2
+        }
       }
     } else {
       const cx<T>* src = a.scratch + (size_t)slot * planeElems + (size_t)(it.tile * kWWarps + w) * N + L;
@@ -298,12 +315,16 @@ __global__ void __launch_bounds__(kWThreads, 2)
     }
     // ---- in flight behind this part's work: inverse map and first stick of the next y part, flag of the next part
     invAhead = nxt < total && nx.roleA;
-    int e0Next = 0;
+    int e0Next = 0, tileBaseNext = 0, tilePitchNext = 0;
     if (invAhead) {
       const unsigned short* p = w_inv_ptr(a.y.inv, nx.tile, w, L);
       w_cp_async16(&sInv[(k + 1) & 1][tid][0], p);
       w_cp_async16(&sInv[(k + 1) & 1][tid][1], p + 32 * 8);
       e0Next = a.y.xtStart[nx.tile];
+      if (a.y.srcBase) {
+        tileBaseNext = a.y.tileBase[nx.tile];
+        tilePitchNext = a.y.tilePitch[nx.tile];
+      }
     }
     W_TRACE(trRole, 2)  // loads issued (incl. inverse map wait)
     W_TRACE_USE(v)
@@ -368,6 +389,8 @@ __global__ void __launch_bounds__(kWThreads, 2)
     cur = nxt;
     it = nx;
     e0 = e0Next;
+    tileBase = tileBaseNext;
+    tilePitch = tilePitchNext;
   }
   // publish the group's last part (parts of other CTAs may wait for it); the bulk store of the last y
   // tile must have read the sub-tile before the CTA exits
@@ -426,8 +449,15 @@ __global__ void __launch_bounds__(kWThreads, 2)
   uint32_t phase = 0;
   bool preloaded = false;  // the sub-tile of the current (B) part is already on its way into S
   XYItem it, nx;
+  // y tiles of a plane are visited starting at tile xtRotate (distributed: every rank then stores to a different
+  // destination at any time); the ring columns, the inverse map and the sticks all follow the remapped tile
+  auto decode = [&](int idx) {
+    XYItem d = w_decode_dense(idx, P, a.lag);
+    if (!d.roleA) d.tile = y_forward_tile_at<T>(a.y, d.tile);
+    return d;
+  };
   int cur = wq.consume(0);
-  if (cur < total) it = w_decode_dense(cur, P, a.lag);
+  if (cur < total) it = decode(cur);
   int e0 = (cur < total && !it.roleA) ? a.y.xtStart[it.tile] : 0;
   for (int k = 0; cur < total; ++k) {
     if (leader) reinterpret_cast<volatile int*>(sQueue.prog)[g] = k;
@@ -435,7 +465,7 @@ __global__ void __launch_bounds__(kWThreads, 2)
     unsigned claimRaw = 0;
     wq.claim(mine, claimRaw);  // (in flight until it is posted behind the tail)
     const int nxt = wq.consume(k + 1);
-    if (nxt < total) nx = w_decode_dense(nxt, P, a.lag);
+    if (nxt < total) nx = decode(nxt);
     if (k == 0 || !sReady[g][k & 1]) {
       w_group_sync<W>(g);
       if (leader) {
@@ -524,12 +554,25 @@ __global__ void __launch_bounds__(kWThreads, 2)
       for (int m = 0; m < 16; ++m) w_st_hint(dst + 32 * m, v[m], keep);  // hand-off: stays in L2 until its y part ran
       pend = &dep.aDone[it.plane];
     } else {
-      cx<T>* row = a.y.sticks + (size_t)(it.plane + a.y.zRowOffset) * a.y.pitch + e0;
       w_cp_async_wait();
       const WInv16 iv = w_unpack_inv(sInv[k & 1][tid][0], sInv[k & 1][tid][1]);
+      if (!a.y.srcBase) {
+        cx<T>* row = a.y.sticks + (size_t)(it.plane + a.y.zRowOffset) * a.y.pitch + e0;
 #pragma unroll
-      for (int m = 0; m < 16; ++m)
-        if (iv.i[m] != kWNone) w_stcs(row + iv.i[m], v[m]);  // written once: evict first
+        for (int m = 0; m < 16; ++m)
+          if (iv.i[m] != kWNone) w_stcs(row + iv.i[m], v[m]);  // written once: evict first
+      } else if (a.y.tilePitch[it.tile] != 0) {
+        // distributed, all sticks of the tile owned by one rank: straight into its stick buffer (NVLink peer
+        // memory, or the local exchange buffer of the NCCL path) -- the y stage IS the exchange
+        cx<T>* row = y_dist_tile<T, true>(a.y, it.tile, it.plane);
+#pragma unroll
+        for (int m = 0; m < 16; ++m)
+          if (iv.i[m] != kWNone) row[iv.i[m]] = v[m];
+      } else {
+#pragma unroll
+        for (int m = 0; m < 16; ++m)
+          if (iv.i[m] != kWNone) *y_dist_stick<T, true>(a.y, e0 + iv.i[m], it.plane) = v[m];
+      }
       pend = &dep.bDone[it.plane];
     }
     cur = nxt;
@@ -669,7 +712,7 @@ int sb_launch_wxy_f64(int forward, const sb::XYArgs<double>* args, void* stream)
   const XYArgs<double>& a = *args;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (a.y.numPlanes <= 0) return 0;
-  if (a.x.nx != kWN || a.y.ny != kWN || a.y.nxf != kWN || !a.y.inv || a.y.srcBase || a.y.numXTiles != kWN / kWWarps ||
+  if (a.x.nx != kWN || a.y.ny != kWN || a.y.nxf != kWN || !a.y.inv || a.y.wireF32 || a.y.numXTiles != kWN / kWWarps ||
       a.x.numRowTiles != kWN / kWWarps)
     return (int)cudaErrorInvalidValue;
   int grid = 0;
