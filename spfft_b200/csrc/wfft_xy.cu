@@ -208,7 +208,7 @@ __global__ void __launch_bounds__(kWThreads, 2)
   __shared__ __align__(16) cx<T> sTw[4 * 32];
   // inverse-map entries of the thread's NEXT y part, fetched asynchronously one part ahead (no registers,
   // no exposed round trip in front of the gather)
-  __shared__ __align__(16) uint4 sInv[2][kWThreads][2];  // [parity of the part][thread][half]
+  __shared__ __align__(16) uint4 sInv[2][2][kWThreads];  // [parity of the part][half][thread]: conflict-free LDGSTS
   const int tid = threadIdx.x;
   const int w = tid >> 5, L = tid & 31;  // w: column / row of the item
   const int g = w / W, wl = w % W;       // group, warp inside the group
@@ -286,7 +286,7 @@ __global__ void __launch_bounds__(kWThreads, 2)
       WInv16 iv;
       if (invAhead) {
         w_cp_async_wait();
-        iv = w_unpack_inv(sInv[k & 1][tid][0], sInv[k & 1][tid][1]);
+        iv = w_unpack_inv(sInv[k & 1][0][tid], sInv[k & 1][1][tid]);
       } else {
         iv = w_load_inv(a.y.inv, it.tile, w, L);
       }
@@ -318,8 +318,8 @@ __global__ void __launch_bounds__(kWThreads, 2)
     int e0Next = 0, tileBaseNext = 0, tilePitchNext = 0;
     if (invAhead) {
       const unsigned short* p = w_inv_ptr(a.y.inv, nx.tile, w, L);
-      w_cp_async16(&sInv[(k + 1) & 1][tid][0], p);
-      w_cp_async16(&sInv[(k + 1) & 1][tid][1], p + 32 * 8);
+      w_cp_async16(&sInv[(k + 1) & 1][0][tid], p);
+      w_cp_async16(&sInv[(k + 1) & 1][1][tid], p + 32 * 8);
       e0Next = a.y.xtStart[nx.tile];
       if (a.y.srcBase) {
         tileBaseNext = a.y.tileBase[nx.tile];
@@ -415,7 +415,7 @@ __global__ void __launch_bounds__(kWThreads, 2)
   __shared__ int sReady[G::kGroups][2];
   __shared__ __align__(8) uint64_t full[G::kGroups];
   __shared__ __align__(16) cx<T> sTw[4 * 32];
-  __shared__ __align__(16) uint4 sInv[2][kWThreads][2];  // inverse-map entries of the thread's current y part, by parity
+  __shared__ __align__(16) uint4 sInv[2][2][kWThreads];  // inverse-map entries of the thread's current y part, by parity
   const int tid = threadIdx.x;
   const int w = tid >> 5, L = tid & 31;
   const int g = w / W, wl = w % W;
@@ -494,8 +494,8 @@ __global__ void __launch_bounds__(kWThreads, 2)
     }
     if (!it.roleA) {
       const unsigned short* p = w_inv_ptr(a.y.inv, it.tile, w, L);
-      w_cp_async16(&sInv[k & 1][tid][0], p);
-      w_cp_async16(&sInv[k & 1][tid][1], p + 32 * 8);
+      w_cp_async16(&sInv[k & 1][0][tid], p);
+      w_cp_async16(&sInv[k & 1][1][tid], p + 32 * 8);
     }
     // in flight behind this part's work: first stick of the next y part, flag of the next part
     const int e0Next = (nxt < total && !nx.roleA) ? a.y.xtStart[nx.tile] : 0;
@@ -555,7 +555,7 @@ __global__ void __launch_bounds__(kWThreads, 2)
       pend = &dep.aDone[it.plane];
     } else {
       w_cp_async_wait();
-      const WInv16 iv = w_unpack_inv(sInv[k & 1][tid][0], sInv[k & 1][tid][1]);
+      const WInv16 iv = w_unpack_inv(sInv[k & 1][0][tid], sInv[k & 1][1][tid]);
       if (!a.y.srcBase) {
         cx<T>* row = a.y.sticks + (size_t)(it.plane + a.y.zRowOffset) * a.y.pitch + e0;
 #pragma unroll

@@ -30,19 +30,19 @@ __global__ void __launch_bounds__(kWThreads, 2)
   __syncthreads();
   // inverse-map entries and value range of the thread's NEXT tile, fetched one tile ahead (cp.async: no registers):
   // the gather of a tile then costs one HBM round trip instead of two dependent ones
-  __shared__ __align__(16) uint4 sInv[2][kWThreads][2];
+  __shared__ __align__(16) uint4 sInv[2][2][kWThreads];
   pdl_prologue();
   int tile = blockIdx.x;
   int e0 = tile < a.numTiles ? a.tileStart[tile] : 0;
   if (tile < a.numTiles) {
     const unsigned short* p = w_inv_ptr(a.inv, tile, w, L);
-    w_cp_async16(&sInv[0][tid][0], p);
-    w_cp_async16(&sInv[0][tid][1], p + 32 * 8);
+    w_cp_async16(&sInv[0][0][tid], p);
+    w_cp_async16(&sInv[0][1][tid], p + 32 * 8);
   }
   for (int k = 0; tile < a.numTiles; tile += gridDim.x, ++k) {
     const cx<T>* vals = a.valuesIn + e0;
     w_cp_async_wait();
-    const WInv16 iv = w_unpack_inv(sInv[k & 1][tid][0], sInv[k & 1][tid][1]);
+    const WInv16 iv = w_unpack_inv(sInv[k & 1][0][tid], sInv[k & 1][1][tid]);
     cx<T> v[16];
 #pragma unroll
     for (int m = 0; m < 16; ++m) {
@@ -52,8 +52,8 @@ __global__ void __launch_bounds__(kWThreads, 2)
     const int next = tile + gridDim.x;
     if (next < a.numTiles) {
       const unsigned short* p = w_inv_ptr(a.inv, next, w, L);
-      w_cp_async16(&sInv[(k + 1) & 1][tid][0], p);
-      w_cp_async16(&sInv[(k + 1) & 1][tid][1], p + 32 * 8);
+      w_cp_async16(&sInv[(k + 1) & 1][0][tid], p);
+      w_cp_async16(&sInv[(k + 1) & 1][1][tid], p + 32 * 8);
       e0 = a.tileStart[next];
     }
     if (tile == a.symTile && w == a.symLane) {
