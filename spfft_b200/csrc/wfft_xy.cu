@@ -81,37 +81,6 @@ struct WxyCounters {
   }
 };
 
-// Items in hand-out order, valid ones only (dense index 0 .. 2 * 64 * P - 1): for step u = 0 .. P + lag - 1 the
-// 64 A tiles of plane u (if u < P), then the 64 B tiles of plane u - lag (if u >= lag) -- the order of xy_decode
-// (fast_stage_kernels.hpp) without its empty slots.
-constexpr int kWTiles = kWN / kWWarps;  // 64 tiles of 8 columns / rows per plane
-__device__ __forceinline__ XYItem w_decode_dense(int idx, int P, int lag) {
-  XYItem it;
-  it.valid = true;
-  const int lead = (lag < P ? lag : P) * kWTiles;  // steps with A tiles only
-  if (idx < lead) {
-    it.roleA = true;
-    it.plane = idx / kWTiles;
-    it.tile = idx % kWTiles;
-    return it;
-  }
-  idx -= lead;
-  const int both = P > lag ? (P - lag) * 2 * kWTiles : 0;  // steps with A and B tiles
-  if (idx < both) {
-    const int u = lag + idx / (2 * kWTiles);
-    const int r = idx % (2 * kWTiles);
-    it.roleA = r < kWTiles;
-    it.plane = it.roleA ? u : u - lag;
-    it.tile = r % kWTiles;
-    return it;
-  }
-  idx -= both;
-  it.roleA = false;  // steps with B tiles only
-  it.plane = (P > lag ? P - lag : 0) + idx / kWTiles;
-  it.tile = idx % kWTiles;
-  return it;
-}
-
 // Work distribution. The CTAs CLAIM their items in hand-out order from two interleaved global counters (even /
 // odd items; a CTA belongs to the queue blockIdx & 1): a CTA that falls behind (far L2 slices, waits) simply
 // takes fewer items, so the tiles of a plane complete together instead of waiting for the slowest CTA of a static

@@ -518,3 +518,12 @@ def test_warp_fft_tile_form(emu_wfft, W, backward):
         ref = np.fft.ifft(x) * 512 if backward else np.fft.fft(x)
         assert orc.rel_l2(out, ref) < 1e-14
         assert emu_wfft.emu_wfft_tile_conflicts(W, wl) == 1
+
+
+@pytest.mark.parametrize("planes,lag,ring", [(1, 8, 1), (3, 8, 3), (8, 8, 8), (9, 8, 9), (24, 8, 18), (64, 8, 18), (512, 8, 18),
+                                             (45, 5, 12), (20, 12, 26)])
+def test_fused_xy_hand_out_order(emu, planes, lag, ring):
+    """Item order of the fused xy stage (wfft_xy.cu): the dense decode the kernels use enumerates the valid items of
+    xy_decode in the same order, dependencies only point backwards (also when there are fewer planes than the lag)."""
+    emu.sb_emu_check_xy_order.restype = C.c_int
+    assert emu.sb_emu_check_xy_order(planes, lag, ring) == 0
