@@ -604,13 +604,46 @@ void TransformEngine<T>::synchronize() {
 }
 
 template <typename T>
+int TransformEngine<T>::host_slabs() const {
+  // SPFFT_B200_HOST_SLABS (default 4, 1 = one copy after / before the whole xy stage)
+  static const int n = [] {
+    const char* e = std::getenv("SPFFT_B200_HOST_SLABS");
+    const int v = e ? std::atoi(e) : 4;
+    return v < 1 ? 1 : (v > 16 ? 16 : v);
+  }();
+  const bool ok = !plan_->distributed && maps_->type == SPFFT_TRANS_C2C && maps_->local_planes() >= 8 * n;
+  return ok ? n : 1;
+}
+
+template <typename T>
+cudaStream_t TransformEngine<T>::copy_stream() {
+  if (!copyStream_) copyStream_.reset(new Stream());
+  return copyStream_->get();
+}
+
+template <typename T>
+cudaEvent_t TransformEngine<T>::slab_event(int i) {
+  while (static_cast<int>(slabEvents_.size()) <= i) slabEvents_.emplace_back(new Event());
+  return slabEvents_[static_cast<size_t>(i)]->get();
+}
+
+template <typename T>
 sb::XYArgs<T> TransformEngine<T>::make_xy_args(const TileMaps& geo, const T* spaceIn, T* spaceOut, bool forward,
-                                               int parity) {
+                                               int parity, int planeBegin, int planeCount) {
   const IndexMaps& m = *maps_;
   sb::XYArgs<T> a{};
   a.y = make_y_stage_args(geo, forward, parity);
   a.y.planes = nullptr;
   a.x = make_x_args<T>(m, plan_->axes, plan_->ptrs, nullptr, spaceIn, spaceOut);
+  if (planeCount >= 0) {
+    // a slab of the local planes (host-pointer calls): stick rows / space planes from planeBegin on
+    const size_t off = 2 * static_cast<size_t>(planeBegin) * static_cast<size_t>(m.dimX) * static_cast<size_t>(m.dimY);
+    a.y.zRowOffset += planeBegin;
+    a.y.numPlanes = planeCount;
+    a.x.numPlanes = planeCount;
+    if (spaceIn) a.x.spaceIn = spaceIn + off;
+    if (spaceOut) a.x.spaceOut = spaceOut + off;
+  }
   a.ring = plan_->xyRing;
   a.lag = plan_->xyLag;
   const size_t planeBytes = sizeof(sb::cx<T>) * static_cast<size_t>(m.dimX) * static_cast<size_t>(m.dimY);
@@ -711,30 +744,66 @@ void TransformEngine<T>::enqueue_backward(const T* input, T* output) {
   // aligned to its scalar type takes the separate y and x kernels)
   bool fusedHere = plan_->fusedXY && !(plan_->wfftXY && (reinterpret_cast<size_t>(outDev) & 15) != 0) &&
                    !(dist && wire_f32());
-  if (fusedHere) {
-    // ---- fused xy stage: y tiles and x tiles in one persistent kernel, hand-off through L2
-    const int err = Launch<T>::wxy(0, make_xy_args(geo, nullptr, outDev, false, parity), s);
-    if (err == static_cast<int>(cudaErrorCooperativeLaunchTooLarge)) {
-      // the device cannot hold the whole persistent grid right now (e.g. shared with another process):
-      // the separate y and x kernels do the same work through the plane buffer
-      cudaGetLastError();
-      fusedHere = false;
-    } else {
-      check_launch(err);
-      record_stage("xy backward");
+  // Host output (reference: execution_gpu.cpp:391-397 copies after the whole stage): the xy stage runs slab by slab
+  // and every finished slab leaves on a second stream while the next one is computed.
+  const int slabs = outOnDevice ? 1 : host_slabs();
+  const int P = m.local_planes();
+  const size_t planeReals = space_bytes() / sizeof(T) / static_cast<size_t>(P > 0 ? P : 1);
+  for (int c = 0; c < slabs; ++c) {
+    const int p0 = static_cast<int>(static_cast<long long>(P) * c / slabs);
+    const int p1 = static_cast<int>(static_cast<long long>(P) * (c + 1) / slabs);
+    const bool whole = slabs == 1;
+    if (fusedHere) {
+      // ---- fused xy stage: y tiles and x tiles in one persistent kernel, hand-off through L2
+      const int err = Launch<T>::wxy(0, whole ? make_xy_args(geo, nullptr, outDev, false, parity)
+                                               : make_xy_args(geo, nullptr, outDev, false, parity, p0, p1 - p0), s);
+      if (err == static_cast<int>(cudaErrorCooperativeLaunchTooLarge)) {
+        // the device cannot hold the whole persistent grid right now (e.g. shared with another process):
+        // the separate y and x kernels do the same work through the plane buffer
+        cudaGetLastError();
+        fusedHere = false;
+      } else {
+        check_launch(err);
+        record_stage("xy backward");
+      }
+    }
+    if (!fusedHere) {
+      // ---- y stage: stick gather + plane symmetry + y-FFT (execution_gpu.cpp:371-390)
+      auto ya = make_y_stage_args(geo, false, parity);
+      auto xa = make_x_args<T>(m, plan_->axes, plan_->ptrs, planes(), nullptr, outDev);
+      if (!whole) {
+        const size_t planeElems = static_cast<size_t>(m.dimY) * static_cast<size_t>(m.dimXFreq);
+        ya.zRowOffset += p0;
+        ya.numPlanes = p1 - p0;
+        ya.planes += planeElems * static_cast<size_t>(p0);
+        xa.numPlanes = p1 - p0;
+        xa.planes += planeElems * static_cast<size_t>(p0);
+        xa.spaceOut = outDev + planeReals * static_cast<size_t>(p0);
+      }
+      check_launch(Launch<T>::y(0, ya, s));
+      record_stage("y backward");
+      // ---- x stage: x-FFT (C2C / C2R) into the space domain
+      check_launch(Launch<T>::x(0, xa, s));
+      record_stage("x backward");
+    }
+    if (!outOnDevice) {
+      if (whole) {
+        check_gpu(cudaMemcpyAsync(output, outDev, space_bytes(), cudaMemcpyDeviceToHost, s));
+      } else {
+        cudaStream_t cs = copy_stream();
+        check_gpu(cudaEventRecord(slab_event(c), s));
+        check_gpu(cudaStreamWaitEvent(cs, slab_event(c), 0));
+        check_gpu(cudaMemcpyAsync(output + planeReals * static_cast<size_t>(p0), outDev + planeReals * static_cast<size_t>(p0),
+                                  planeReals * static_cast<size_t>(p1 - p0) * sizeof(T), cudaMemcpyDeviceToHost, cs));
+      }
     }
   }
-  if (!fusedHere) {
-    // ---- y stage: stick gather + plane symmetry + y-FFT (execution_gpu.cpp:371-390)
-    check_launch(Launch<T>::y(0, make_y_stage_args(geo, false, parity), s));
-    record_stage("y backward");
-    // ---- x stage: x-FFT (C2C / C2R) into the space domain
-    auto xa = make_x_args<T>(m, plan_->axes, plan_->ptrs, planes(), nullptr, outDev);
-    check_launch(Launch<T>::x(0, xa, s));
-    record_stage("x backward");
-  }
   if (!outOnDevice) {
-    check_gpu(cudaMemcpyAsync(output, outDev, space_bytes(), cudaMemcpyDeviceToHost, s));
+    if (slabs > 1) {
+      // the transform's stream is the one callers synchronise with: it waits for the last slab's copy
+      check_gpu(cudaEventRecord(slab_event(slabs), copy_stream()));
+      check_gpu(cudaStreamWaitEvent(s, slab_event(slabs), 0));
+    }
     record_stage("d2h space");
   }
 }
@@ -769,31 +838,67 @@ void TransformEngine<T>::enqueue_forward(const T* input, T* output, SpfftScaling
   // ---- x stage (execution_gpu.cpp:254-282)
   if (haveSpace) {
     const T* src = input;
-    if (!is_device_pointer(input)) {
-      check_gpu(cudaMemcpyAsync(device_space(), input, space_bytes(), cudaMemcpyHostToDevice, s));
+    const bool inOnDevice = is_device_pointer(input);
+    // Host input (reference: execution_gpu.cpp:263-276 copies before the whole stage): the space domain arrives slab
+    // by slab on a second stream, the xy stage of a slab starts as soon as it is there.
+    const int slabs = inOnDevice ? 1 : host_slabs();
+    const int P = m.local_planes();
+    const size_t planeReals = space_bytes() / sizeof(T) / static_cast<size_t>(P > 0 ? P : 1);
+    if (!inOnDevice) {
       src = device_space();
-      record_stage("h2d space");
+      if (slabs == 1) {
+        check_gpu(cudaMemcpyAsync(device_space(), input, space_bytes(), cudaMemcpyHostToDevice, s));
+        record_stage("h2d space");
+      } else {
+        // the copies may overwrite the internal space buffer only after everything enqueued so far is done with it
+        cudaStream_t cs = copy_stream();
+        check_gpu(cudaEventRecord(slab_event(slabs), s));
+        check_gpu(cudaStreamWaitEvent(cs, slab_event(slabs), 0));
+        for (int c = 0; c < slabs; ++c) {
+          const size_t r0 = planeReals * static_cast<size_t>(static_cast<long long>(P) * c / slabs);
+          const size_t r1 = planeReals * static_cast<size_t>(static_cast<long long>(P) * (c + 1) / slabs);
+          check_gpu(cudaMemcpyAsync(device_space() + r0, input + r0, (r1 - r0) * sizeof(T), cudaMemcpyHostToDevice, cs));
+          check_gpu(cudaEventRecord(slab_event(c), cs));
+        }
+      }
     }
     bool fusedHere = plan_->fusedXY && !(plan_->wfftXY && (reinterpret_cast<size_t>(src) & 15) != 0) &&
                      !(dist && wire_f32());
-    if (fusedHere && anySticks) {
-      const int err = Launch<T>::wxy(1, make_xy_args(geo, src, nullptr, true, parity), s);
-      if (err == static_cast<int>(cudaErrorCooperativeLaunchTooLarge)) {
-        cudaGetLastError();  // see enqueue_backward
-        fusedHere = false;
-      } else {
-        check_launch(err);
-        record_stage(peer ? "xy forward + exchange" : "xy forward");
+    for (int c = 0; c < slabs; ++c) {
+      const int p0 = static_cast<int>(static_cast<long long>(P) * c / slabs);
+      const int p1 = static_cast<int>(static_cast<long long>(P) * (c + 1) / slabs);
+      const bool whole = slabs == 1;
+      if (!whole) check_gpu(cudaStreamWaitEvent(s, slab_event(c), 0));
+      if (fusedHere && anySticks) {
+        const int err = Launch<T>::wxy(1, whole ? make_xy_args(geo, src, nullptr, true, parity)
+                                                 : make_xy_args(geo, src, nullptr, true, parity, p0, p1 - p0), s);
+        if (err == static_cast<int>(cudaErrorCooperativeLaunchTooLarge)) {
+          cudaGetLastError();  // see enqueue_backward
+          fusedHere = false;
+        } else {
+          check_launch(err);
+          record_stage(peer ? "xy forward + exchange" : "xy forward");
+        }
       }
-    }
-    if (!fusedHere) {
-      auto xa = make_x_args<T>(m, plan_->axes, plan_->ptrs, planes(), src, nullptr);
-      check_launch(Launch<T>::x(1, xa, s));
-      record_stage("x forward");
-      if (anySticks) {
-        // ---- y stage: y-FFT + scatter into the plane-major sticks / the exchange buffer
-        check_launch(Launch<T>::y(1, make_y_stage_args(geo, true, parity), s));
-        record_stage(peer ? "y forward + exchange" : "y forward");
+      if (!fusedHere) {
+        auto xa = make_x_args<T>(m, plan_->axes, plan_->ptrs, planes(), src, nullptr);
+        auto ya = make_y_stage_args(geo, true, parity);
+        if (!whole) {
+          const size_t planeElems = static_cast<size_t>(m.dimY) * static_cast<size_t>(m.dimXFreq);
+          xa.numPlanes = p1 - p0;
+          xa.planes += planeElems * static_cast<size_t>(p0);
+          xa.spaceIn = src + planeReals * static_cast<size_t>(p0);
+          ya.zRowOffset += p0;
+          ya.numPlanes = p1 - p0;
+          ya.planes += planeElems * static_cast<size_t>(p0);
+        }
+        check_launch(Launch<T>::x(1, xa, s));
+        record_stage("x forward");
+        if (anySticks) {
+          // ---- y stage: y-FFT + scatter into the plane-major sticks / the exchange buffer
+          check_launch(Launch<T>::y(1, ya, s));
+          record_stage(peer ? "y forward + exchange" : "y forward");
+        }
       }
     }
   }

@@ -185,7 +185,8 @@ public:
 
 private:
   void begin_call();
-  sb::XYArgs<T> make_xy_args(const TileMaps& geo, const T* spaceIn, T* spaceOut, bool forward = false, int parity = 0);
+  sb::XYArgs<T> make_xy_args(const TileMaps& geo, const T* spaceIn, T* spaceOut, bool forward = false, int parity = 0,
+                             int planeBegin = 0, int planeCount = -1);
   sb::YArgs<T> make_y_stage_args(const TileMaps& geo, bool forward, int parity = 0);
   void record_stage(const char* name);
   size_t space_bytes() const;
@@ -207,6 +208,13 @@ private:
   std::shared_ptr<DevicePlan<T>> plan_;
   std::unique_ptr<Stream> stream_;
   std::unique_ptr<Event> startEvent_, endEvent_;
+  // host-pointer calls of local C2C transforms: the space domain moves in slabs of planes on a second stream while
+  // the xy stage of the neighbouring slab runs (enqueue_backward / enqueue_forward)
+  std::unique_ptr<Stream> copyStream_;
+  std::vector<std::unique_ptr<Event>> slabEvents_;
+  int host_slabs() const;
+  cudaStream_t copy_stream();
+  cudaEvent_t slab_event(int i);
   bool profiling_ = false;
   std::vector<std::unique_ptr<Event>> profEvents_;
   std::vector<const char*> profNames_;

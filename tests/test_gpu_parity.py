@@ -678,6 +678,29 @@ def test_warp_fft_transforms_on_concurrent_streams(torch_cuda, lib, gen):
         t.destroy()
 
 
+@pytest.mark.parametrize("shape", [(64, 48, 40), (512, 512, 36), (96, 32, 64)], ids=lambda s: "x".join(map(str, s)))
+def test_host_pointer_slabs(torch_cuda, lib, gen, shape):
+    """Host-pointer calls of local C2C transforms move the space domain in slabs of planes on a second stream while
+    the xy stage of the neighbouring slab runs (enqueue_backward / enqueue_forward): same bits as the device-pointer
+    call, also when the call is repeated and through the internal host buffer."""
+    nx, ny, nz = shape
+    trip, vals = gen.make(nx, ny, nz, center=True, stick_fraction=0.6, fill_fraction=0.7)
+    space_d, back_d = _run_pair(torch_cuda, lib, 0, nx, ny, nz, trip, vals)
+    space_h, back_h = _run_pair(torch_cuda, lib, 0, nx, ny, nz, trip, vals, device_ptrs=False)
+    assert np.array_equal(space_d, space_h) and np.array_equal(back_d, back_h)
+    param = orc.Parameters(0, nx, ny, nz, trip)
+    assert orc.rel_l2(space_h, orc.backward(param, vals)) <= TOL[False]
+    # external pinned-or-not host buffers through the _ptr entry points
+    t = capi.Transform(lib, transform_type=0, dim_x=nx, dim_y=ny, dim_z=nz, indices=trip)
+    out = np.full((nz, ny, nx), np.nan + 0j, dtype=np.complex128)
+    t.backward_ptr(np.ascontiguousarray(vals), out)
+    assert np.array_equal(out, space_d)
+    back = np.zeros(len(trip), np.complex128)
+    t.forward_ptr(out, back, capi.SPFFT_FULL_SCALING)
+    assert np.array_equal(back, back_d)
+    t.destroy()
+
+
 def test_distributed_two_gpus(torch_cuda):
     """One process per GPU over NCCL (tests/dist_gpu_check.py); skipped on a single-GPU box."""
     import subprocess
