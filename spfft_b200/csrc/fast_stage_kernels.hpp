@@ -993,30 +993,32 @@ SB_HD XYItem xy_decode(const XYArgs<T>& a, int item) {
 // 64 A tiles of plane u (if u < P), then the 64 B tiles of plane u - lag (if u >= lag) -- the order of xy_decode
 // (fast_stage_kernels.hpp) without its empty slots.
 constexpr int kWTiles = 64;  // tiles of 8 columns / rows per plane (N = 512)
+// (TILES: 64, or 32 for the single-precision kernels whose items cover 16 columns / rows)
+template <int TILES = kWTiles>
 SB_HD XYItem w_decode_dense(int idx, int P, int lag) {
   XYItem it;
   it.valid = true;
-  const int lead = (lag < P ? lag : P) * kWTiles;  // steps with A tiles only
+  const int lead = (lag < P ? lag : P) * TILES;  // steps with A tiles only
   if (idx < lead) {
     it.roleA = true;
-    it.plane = idx / kWTiles;
-    it.tile = idx % kWTiles;
+    it.plane = idx / TILES;
+    it.tile = idx % TILES;
     return it;
   }
   idx -= lead;
-  const int both = P > lag ? (P - lag) * 2 * kWTiles : 0;  // steps with A and B tiles
+  const int both = P > lag ? (P - lag) * 2 * TILES : 0;  // steps with A and B tiles
   if (idx < both) {
-    const int u = lag + idx / (2 * kWTiles);
-    const int r = idx % (2 * kWTiles);
-    it.roleA = r < kWTiles;
+    const int u = lag + idx / (2 * TILES);
+    const int r = idx % (2 * TILES);
+    it.roleA = r < TILES;
     it.plane = it.roleA ? u : u - lag;
-    it.tile = r % kWTiles;
+    it.tile = r % TILES;
     return it;
   }
   idx -= both;
   it.roleA = false;  // steps with B tiles only
-  it.plane = (P > lag ? P - lag : 0) + idx / kWTiles;
-  it.tile = idx % kWTiles;
+  it.plane = (P > lag ? P - lag : 0) + idx / TILES;
+  it.tile = idx % TILES;
   return it;
 }
 

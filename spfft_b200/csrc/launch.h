@@ -24,8 +24,10 @@ int sb_launch_peer_barrier(int* const* flags, int numRanks, int me, int epoch, v
  * launch: the launcher enqueues the memset); sb_wz_available: z stage (dimZ == 512, values in stick order). */
 int sb_wxy_config(int isFloat, int n, int numPlanes, int* ring, int* lag, int* numCounters);
 int sb_launch_wxy_f64(int forward, const sb::XYArgs<double>* args, void* stream);
+int sb_launch_wxy_f32(int forward, const sb::XYArgs<float>* args, void* stream); /* local transforms only */
 int sb_wz_available(int isFloat, int nz);
 int sb_launch_wz_f64(int forward, const sb::ZArgs<double>* args, void* stream);
+int sb_launch_wz_f32(int forward, const sb::ZArgs<float>* args, void* stream); /* C2C only (symTile < 0) */
 /* Batched multi-transform (band_kernels.cu): one launch per stage over `numBands` <= sb::kMaxBands
  * transforms that share the plan in `args`; the table holds the per-band data pointers.
  * sb_band_kernel_available: does a batched kernel exist for an axis of length n (registerFft: the

@@ -38,8 +38,8 @@ struct Launch<float> {
   static int z(int f, const sb::ZArgs<float>& a, void* s) { return sb_launch_z_f32(f, &a, s); }
   static int y(int f, const sb::YArgs<float>& a, void* s) { return sb_launch_y_f32(f, &a, s); }
   static int x(int f, const sb::XArgs<float>& a, void* s) { return sb_launch_x_f32(f, &a, s); }
-  static int wxy(int, const sb::XYArgs<float>&, void*) { return static_cast<int>(cudaErrorInvalidValue); }
-  static int wz(int, const sb::ZArgs<float>&, void*) { return static_cast<int>(cudaErrorInvalidValue); }
+  static int wxy(int f, const sb::XYArgs<float>& a, void* s) { return sb_launch_wxy_f32(f, &a, s); }
+  static int wz(int f, const sb::ZArgs<float>& a, void* s) { return sb_launch_wz_f32(f, &a, s); }
 };
 
 inline void check_launch(int err) {
@@ -366,17 +366,20 @@ std::shared_ptr<DevicePlan<T>> build_device_plan(const IndexMaps& m, long long s
   // Warp-FFT kernels (default where they exist; SPFFT_B200_WFFT=0 selects the round-1 kernels, bit 0 =
   // fused xy stage, bit 1 = z stage): one warp per transform, tiles staged by TMA, y <-> x hand-off in L2.
   const char* wEnv = std::getenv("SPFFT_B200_WFFT");
-  const int wMask = wEnv ? std::atoi(wEnv) : 7;
-  // (bit 2: the fused xy stage also for distributed transforms, whose y tiles read / write the exchange buffers)
-  if (!plan->fusedXY && (wMask & 1) && sizeof(T) == 8 && fastX && fastY && m.dimX == m.dimY &&
+  const int wMask = wEnv ? std::atoi(wEnv) : 15;
+  // (bit 2: the fused xy stage also for distributed transforms, whose y tiles read / write the exchange buffers;
+  // bit 3: single precision, two transforms per warp on the packed fp32 pipe -- local C2C transforms)
+  const bool single = sizeof(T) == 4;
+  const bool wSingleOk = !single || ((wMask & 8) && m.commSize == 1 && m.type == SPFFT_TRANS_C2C);
+  if (!plan->fusedXY && (wMask & 1) && wSingleOk && fastX && fastY && m.dimX == m.dimY &&
       m.type == SPFFT_TRANS_C2C && ax.log2Vy == 3 &&
       (m.commSize == 1 ? m.num_sticks() > 0 : ((wMask & 4) && m.local_planes() > 0))) {
-    const int err = sb_wxy_config(0, m.dimX, m.local_planes(), &plan->xyRing, &plan->xyLag, &plan->xyCounters);
+    const int err = sb_wxy_config(single ? 1 : 0, m.dimX, m.local_planes(), &plan->xyRing, &plan->xyLag, &plan->xyCounters);
     plan->fusedXY = plan->wfftXY = err == 0;
   }
   if (!plan->fusedXY && fastX) ax.log2Vx = fast_path_log2_lanes_x(m.dimX);
   TileMaps t = build_tile_maps(m, ax.log2Vz, ax.log2Vy, fastZ, fastY);
-  plan->wfftZ = (wMask & 2) && fastZ && ax.log2Vz == 3 && sb_wz_available(sizeof(T) == 4, m.dimZ) && !t.zInv.empty();
+  plan->wfftZ = (wMask & 2) && wSingleOk && fastZ && ax.log2Vz == 3 && sb_wz_available(single ? 1 : 0, m.dimZ) && !t.zInv.empty();
   plan->numStickTiles = t.numStickTiles;
   plan->pitch = t.pitch;
   plan->numXTiles = t.numXTiles;
@@ -721,7 +724,10 @@ void TransformEngine<T>::enqueue_backward(const T* input, T* output) {
       za.rowOff = plan_->rowOff;
     }
     za.wireF32 = wire_f32() ? 1 : 0;
-    check_launch(plan_->wfftZ && !peer && !za.wireF32 ? Launch<T>::wz(0, za, s) : Launch<T>::z(0, za, s));
+    // (single precision: the backward warp kernel gathers two sticks per warp with 8-byte loads and is slower than
+    // the round-1 kernel, 0.390 against 0.357 ms at 512^3 -- profiles/r02_summary.md; the forward one is faster)
+    const bool warpZ = plan_->wfftZ && !peer && !za.wireF32 && sizeof(T) == 8;
+    check_launch(warpZ ? Launch<T>::wz(0, za, s) : Launch<T>::z(0, za, s));
     record_stage(peer ? "z backward + exchange" : "z backward");
   }
   // ---- exchange: every rank sends, for every peer, the rows of that peer's slab (one contiguous

@@ -32,6 +32,7 @@
 // src/fft/transform_2d_gpu.hpp:51-140): unnormalised DFT, sign + backward / - forward.
 #pragma once
 #include <cmath>
+#include <cstring>
 
 #include "cx.hpp"
 #include "fft_tile.hpp"
@@ -63,6 +64,140 @@ template <typename T>
 SB_HD cx<T> flip_sign(cx<T> v, unsigned mask) {
   return mk<T>(flip_sign<T>(v.x, mask), flip_sign<T>(v.y, mask));
 }
+
+// --------------------------------------------------------------------------------------------
+// f2: TWO single-precision values in one 64-bit register, element-wise arithmetic on the packed fp32 pipe of
+// sm_100 (FADD2 / FMUL2 / FFMA2: one instruction per pair). A warp that computes on cx<f2> runs two single-
+// precision transforms at the instruction count of one double-precision transform, and a cx<f2> is a 16-byte
+// unit like cx<double>, so the tile geometry below (TMA swizzle, exchange addresses) serves both precisions.
+// Half `lo` belongs to the first transform of the pair, `hi` to the second. On the CPU (tests/emu) the same
+// type is a plain pair of floats.
+// --------------------------------------------------------------------------------------------
+struct f2 {
+#if SB_ON_GPU
+  unsigned long long r;
+#else
+  float a, b;
+#endif
+  f2() = default;
+  SB_HD explicit f2(double c);
+};
+#if SB_ON_GPU
+SB_HD f2 f2_make(float lo, float hi) {
+  f2 v;
+#ifdef __CUDA_ARCH__
+  asm("mov.b64 %0, {%1, %2};" : "=l"(v.r) : "f"(lo), "f"(hi));  // (ptxas sees a register pair, not integer arithmetic)
+#else
+  unsigned int ul, uh;
+  memcpy(&ul, &lo, 4);
+  memcpy(&uh, &hi, 4);
+  v.r = (unsigned long long)ul | ((unsigned long long)uh << 32);
+#endif
+  return v;
+}
+SB_HD float f2_lo(f2 v) {
+#ifdef __CUDA_ARCH__
+  float lo;
+  asm("{ .reg .b32 t; mov.b64 {%0, t}, %1; }" : "=f"(lo) : "l"(v.r));
+  return lo;
+#else
+  const unsigned int u = (unsigned)(v.r & 0xffffffffULL);
+  float f;
+  memcpy(&f, &u, 4);
+  return f;
+#endif
+}
+SB_HD float f2_hi(f2 v) {
+#ifdef __CUDA_ARCH__
+  float hi;
+  asm("{ .reg .b32 t; mov.b64 {t, %0}, %1; }" : "=f"(hi) : "l"(v.r));
+  return hi;
+#else
+  const unsigned int u = (unsigned)(v.r >> 32);
+  float f;
+  memcpy(&f, &u, 4);
+  return f;
+#endif
+}
+#else
+SB_HD f2 f2_make(float lo, float hi) {
+  f2 v;
+  v.a = lo;
+  v.b = hi;
+  return v;
+}
+SB_HD float f2_lo(f2 v) { return v.a; }
+SB_HD float f2_hi(f2 v) { return v.b; }
+#endif
+SB_HD f2::f2(double c) { *this = f2_make((float)c, (float)c); }
+#if defined(__CUDA_ARCH__)
+SB_HD f2 operator+(f2 x, f2 y) {
+  f2 v;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(v.r) : "l"(x.r), "l"(y.r));
+  return v;
+}
+SB_HD f2 operator-(f2 x, f2 y) {
+  f2 v;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(v.r) : "l"(x.r), "l"(y.r));
+  return v;
+}
+SB_HD f2 operator*(f2 x, f2 y) {
+  f2 v;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(v.r) : "l"(x.r), "l"(y.r));
+  return v;
+}
+// x * y + z
+SB_HD f2 f2_fma(f2 x, f2 y, f2 z) {
+  f2 v;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(v.r) : "l"(x.r), "l"(y.r), "l"(z.r));
+  return v;
+}
+#else
+SB_HD f2 operator+(f2 x, f2 y) { return f2_make(f2_lo(x) + f2_lo(y), f2_hi(x) + f2_hi(y)); }
+SB_HD f2 operator-(f2 x, f2 y) { return f2_make(f2_lo(x) - f2_lo(y), f2_hi(x) - f2_hi(y)); }
+SB_HD f2 operator*(f2 x, f2 y) { return f2_make(f2_lo(x) * f2_lo(y), f2_hi(x) * f2_hi(y)); }
+SB_HD f2 f2_fma(f2 x, f2 y, f2 z) {
+  return f2_make(fmaf(f2_lo(x), f2_lo(y), f2_lo(z)), fmaf(f2_hi(x), f2_hi(y), f2_hi(z)));
+}
+#endif
+// (ptxas folds the two negations into the operand modifiers of the packed instruction that consumes them)
+SB_HD f2 operator-(f2 x) { return f2_make(-f2_lo(x), -f2_hi(x)); }
+// the products of the butterflies with ONE fused multiply-add per component pair (the generic cx<T> operators
+// rely on the compiler contracting a * b - c * d, which it cannot do across the packed instructions)
+SB_HD cx<f2> operator*(cx<f2> a, cx<f2> b) {
+  return mk<f2>(f2_fma(a.x, b.x, -(a.y * b.y)), f2_fma(a.x, b.y, a.y * b.x));
+}
+template <>
+SB_HD cx<f2> mul_w<true, f2>(cx<f2> v, f2 c, f2 sn) {
+  return mk<f2>(f2_fma(v.x, c, -(v.y * sn)), f2_fma(v.x, sn, v.y * c));
+}
+template <>
+SB_HD cx<f2> mul_w<false, f2>(cx<f2> v, f2 c, f2 sn) {
+  return mk<f2>(f2_fma(v.x, c, v.y * sn), f2_fma(v.y, c, -(v.x * sn)));
+}
+template <>
+SB_HD f2 flip_sign<f2>(f2 x, unsigned mask) {
+#if SB_ON_GPU
+  f2 v;
+  v.r = x.r ^ (((unsigned long long)mask << 32) | (unsigned long long)mask);
+  return v;
+#else
+  return mask ? -x : x;
+#endif
+}
+// the two complex numbers of a unit as they lie in memory, (re0, im0, re1, im1), <-> the packed form
+// ((re0, re1), (im0, im1)); the permutation is its own inverse. Identity for double precision.
+template <typename T>
+SB_HD cx<T> unit_transpose(cx<T> v) {
+  return v;
+}
+template <>
+SB_HD cx<f2> unit_transpose<f2>(cx<f2> v) {
+  return mk<f2>(f2_make(f2_lo(v.x), f2_lo(v.y)), f2_make(f2_hi(v.x), f2_hi(v.y)));
+}
+SB_HD cx<f2> unit_pack(cx<float> c0, cx<float> c1) { return mk<f2>(f2_make(c0.x, c1.x), f2_make(c0.y, c1.y)); }
+SB_HD cx<float> unit_lo(cx<f2> v) { return mk<float>(f2_lo(v.x), f2_lo(v.y)); }
+SB_HD cx<float> unit_hi(cx<f2> v) { return mk<float>(f2_hi(v.x), f2_hi(v.y)); }
 
 // 16-point DFT in registers, natural order in and out (4 x 4 decomposition, 8 radix-4 butterflies).
 template <typename T, bool BWD>
@@ -327,11 +462,14 @@ inline bool wfft_length(int n) { return n == 512 || n == 256; }
 // complex shuffle
 template <typename T>
 SB_DEV cx<T> shfl_xor_cx(cx<T> v, int mask) {
-  if constexpr (sizeof(T) == 8) {
-    return mk<T>(__shfl_xor_sync(0xffffffffu, v.x, mask), __shfl_xor_sync(0xffffffffu, v.y, mask));
-  } else {
-    return mk<T>(__shfl_xor_sync(0xffffffffu, v.x, mask), __shfl_xor_sync(0xffffffffu, v.y, mask));
-  }
+  return mk<T>(__shfl_xor_sync(0xffffffffu, v.x, mask), __shfl_xor_sync(0xffffffffu, v.y, mask));
+}
+template <>
+SB_DEV cx<f2> shfl_xor_cx<f2>(cx<f2> v, int mask) {
+  cx<f2> o;
+  o.x.r = __shfl_xor_sync(0xffffffffu, v.x.r, mask);
+  o.y.r = __shfl_xor_sync(0xffffffffu, v.y.r, mask);
+  return o;
 }
 
 // The whole transform of one warp: v[m] = x[L + T m] in, v[q] = X[L + T q] out. `X` = the warp's private

@@ -4,7 +4,8 @@
 // discard.global.L2), so the stage moves only its algorithmic bytes through HBM:
 //     backward:  sticks (sparse rows, gathered through the inverse map) -> y-FFT -> ring -> x-FFT -> space
 //     forward :  space -> x-FFT -> ring -> y-FFT -> sticks (scattered through the inverse map)
-// C2C, double precision, dimX == dimY == 512, one process-local slab of planes.
+// C2C, dimX == dimY == 512, one process-local slab of planes; double precision (also on distributed transforms) and
+// single precision (local transforms; two transforms per warp on the packed fp32 pipe, WUnit in wfft_kernels.cuh).
 // Replaces the two passes of the reference's 2-D cuFFT plans (src/fft/transform_2d_gpu.hpp:51-140)
 // and its transposing unpack / pack kernels (src/transpose/gpu_kernels/local_transpose_kernels.cu).
 //
@@ -172,31 +173,36 @@ __global__ void __launch_bounds__(kWThreads, 2)
               const __grid_constant__ WTw4<T> twp) {
   constexpr int N = kWN;
   using G = WGeom<W>;
+  using Sc = typename WUnit<T>::Sc;           // scalar of a unit: double, or two floats (two transforms per warp)
+  constexpr int kPer = WUnit<T>::kPer;        // transforms per warp
+  constexpr int kTiles = kWTiles / kPer;      // items per plane and role
+  constexpr int kRows = kWWarps * kPer;       // columns / rows per item
   extern __shared__ __align__(1024) unsigned char smemRaw[];
   __shared__ int sReadySeq[G::kGroups];  // (k << 1) | ready: dependency of the group's part k seen satisfied
-  __shared__ __align__(16) cx<T> sTw[4 * 32];
+  __shared__ __align__(16) cx<Sc> sTw[4 * 32];
   // inverse-map entries of the thread's NEXT y part, fetched asynchronously one part ahead (no registers,
   // no exposed round trip in front of the gather)
-  __shared__ __align__(16) uint4 sInv[2][2][kWThreads];  // [parity of the part][half][thread]: conflict-free LDGSTS
+  __shared__ __align__(16) uint4 sInv[2][2 * kPer][kWThreads];  // [parity of the part][column, half][thread]: conflict-free LDGSTS
   const int tid = threadIdx.x;
   const int w = tid >> 5, L = tid & 31;  // w: column / row of the item
   const int g = w / W, wl = w % W;       // group, warp inside the group
   const bool leader = L == 0 && wl == 0;
   const bool poller = L == 0 && wl == 1;
   const bool publisher = L == 0 && wl == W - 1;
-  cx<T>* S = reinterpret_cast<cx<T>*>(smemRaw + (size_t)g * G::kSubBytes);
+  cx<Sc>* S = reinterpret_cast<cx<Sc>*>(smemRaw + (size_t)g * G::kSubBytes);
   const WAddr ad = w_addr<W>(wl, L);
-  w_stage_twiddles<T>(sTw, twp);
+  w_stage_twiddles(sTw, twp);
   __syncthreads();
   const int P = a.y.numPlanes;
   WxyCounters dep;
   dep.aDone = a.counters + 1;
   dep.bDone = a.counters + 1 + P;
-  dep.nA = (N / kWWarps) * G::kGroups;
-  dep.nB = (N / kWWarps) * G::kGroups;
+  dep.nA = kTiles * G::kGroups;
+  dep.nB = kTiles * G::kGroups;
   dep.ring = a.ring;
-  const int total = 2 * kWTiles * P;
+  const int total = 2 * kTiles * P;
   const size_t planeElems = (size_t)N * N;
+  const int planLane = w_plan_lane<kPer>(w);  // the warp's (first) column inside its tile of the index plan
   __shared__ WQueueShared sQueue;
   WQueue wq;
   w_queue_init(&sQueue, wq, a.counters + 1 + 2 * P, total, G::kGroups);
@@ -206,13 +212,15 @@ __global__ void __launch_bounds__(kWThreads, 2)
   bool pendTma = false;  // ... whose output is a bulk tensor store issued by the group leader
   XYItem it, nx;
   int cur = wq.consume(0);
-  if (cur < total) it = w_decode_dense(cur, P, a.lag);
+  if (cur < total) it = w_decode_dense<kTiles>(cur, P, a.lag);
   bool invAhead = false;
-  int e0 = (cur < total && it.roleA) ? a.y.xtStart[it.tile] : 0;  // first stick of the part's x tile
+  int e0 = (cur < total && it.roleA) ? a.y.xtStart[w_plan_tile<kPer>(it.tile, w)] : 0;  // first stick of the part's x tile
   int tileBase = 0, tilePitch = 0;  // distributed: block of a single-source tile in the exchange buffer
-  if (cur < total && it.roleA && a.y.srcBase) {
-    tileBase = a.y.tileBase[it.tile];
-    tilePitch = a.y.tilePitch[it.tile];
+  if constexpr (kPer == 1) {
+    if (cur < total && it.roleA && a.y.srcBase) {
+      tileBase = a.y.tileBase[it.tile];
+      tilePitch = a.y.tilePitch[it.tile];
+    }
   }
   W_TRACE_DECL
   for (int k = 0; cur < total; ++k) {
@@ -221,7 +229,7 @@ __global__ void __launch_bounds__(kWThreads, 2)
     unsigned claimRaw = 0;
     wq.claim(mine, claimRaw);  // (in flight until it is posted behind the tail)
     const int nxt = wq.consume(k + 1);
-    if (nxt < total) nx = w_decode_dense(nxt, P, a.lag);
+    if (nxt < total) nx = w_decode_dense<kTiles>(nxt, P, a.lag);
     const int trRole = it.roleA ? 0 : 1;
     (void)trRole;
     W_TRACE(trRole, 0)  // previous part's stores issued + decode
@@ -249,62 +257,62 @@ __global__ void __launch_bounds__(kWThreads, 2)
     }
     W_TRACE(trRole, 1)  // dependency (slow path)
     // ---- loads
-    cx<T> v[16];
+    cx<Sc> v[16];
     const int slot = it.plane % a.ring;
     if (it.roleA) {
-      WInv16 iv;
+      WInvUnit<kPer> iv;
       if (invAhead) {
         w_cp_async_wait();
-        iv = w_unpack_inv(sInv[k & 1][0][tid], sInv[k & 1][1][tid]);
+        iv = w_inv_read<kPer>(sInv[k & 1], tid);
       } else {
-        iv = w_load_inv(a.y.inv, it.tile, w, L);
+        iv = w_inv_load<kPer>(a.y.inv, w_plan_tile<kPer>(it.tile, w), planLane, L);
       }
-      if (a.y.srcBase && tilePitch == 0) {
+      bool perStick = false;
+      if constexpr (kPer == 1) perStick = a.y.srcBase && tilePitch == 0;
+      if (perStick) {
         // distributed, sticks of this tile from several ranks (tiles at a rank boundary): per-stick tables
+        if constexpr (kPer == 1) {
 #pragma unroll
-        for (int m = 0; m < 16; ++m) {
-          v[m] = mk<T>(0, 0);
-          if (iv.i[m] != kWNone) v[m] = *y_dist_stick<T, false>(a.y, e0 + iv.i[m], it.plane);
+          for (int m = 0; m < 16; ++m) {
+            v[m] = mk<T>(0, 0);
+            if (iv.c[0].i[m] != kWNone) v[m] = *y_dist_stick<T, false>(a.y, e0 + iv.c[0].i[m], it.plane);
+          }
         }
       } else {
         // local: row of the plane-major stick buffer; distributed: the tile's block inside its source rank's part
-        // of the plane-side exchange buffer
-        const cx<T>* row = a.y.srcBase ? a.y.sticks + (size_t)tileBase + (size_t)it.plane * tilePitch
-                                       : a.y.sticks + (size_t)(it.plane + a.y.zRowOffset) * a.y.pitch + e0;
-#pragma unroll
-        for (int m = 0; m < 16; ++m) {
-          v[m] = mk<T>(0, 0);
-          if (iv.i[m] != kWNone) v[m] = w_ldcs(row + iv.i[m]);  // read once: evict first, the ring stays in L2
-        }
+        // of the plane-side exchange buffer (read once: evict first, the ring stays in L2)
+        const cx<T>* row = (kPer == 1 && a.y.srcBase) ? a.y.sticks + (size_t)tileBase + (size_t)it.plane * tilePitch
+                                                      : a.y.sticks + (size_t)(it.plane + a.y.zRowOffset) * a.y.pitch + e0;
+        w_gather_cs(v, row, iv);
       }
     } else {
-      const cx<T>* src = a.scratch + (size_t)slot * planeElems + (size_t)(it.tile * kWWarps + w) * N + L;
+      const cx<T>* src = a.scratch + (size_t)slot * planeElems + (size_t)(it.tile * kRows + w * kPer) * N + L;
 #pragma unroll
-      for (int m = 0; m < 16; ++m) v[m] = w_ldcg(src + 32 * m);
+      for (int m = 0; m < 16; ++m) v[m] = w_row_ldcg(src + 32 * m, N);
     }
     // ---- in flight behind this part's work: inverse map and first stick of the next y part, flag of the next part
     invAhead = nxt < total && nx.roleA;
     int e0Next = 0, tileBaseNext = 0, tilePitchNext = 0;
     if (invAhead) {
-      const unsigned short* p = w_inv_ptr(a.y.inv, nx.tile, w, L);
-      w_cp_async16(&sInv[(k + 1) & 1][0][tid], p);
-      w_cp_async16(&sInv[(k + 1) & 1][1][tid], p + 32 * 8);
-      e0Next = a.y.xtStart[nx.tile];
-      if (a.y.srcBase) {
-        tileBaseNext = a.y.tileBase[nx.tile];
-        tilePitchNext = a.y.tilePitch[nx.tile];
+      w_inv_prefetch<kPer>(sInv[(k + 1) & 1], a.y.inv, w_plan_tile<kPer>(nx.tile, w), planLane, L, tid);
+      e0Next = a.y.xtStart[w_plan_tile<kPer>(nx.tile, w)];
+      if constexpr (kPer == 1) {
+        if (a.y.srcBase) {
+          tileBaseNext = a.y.tileBase[nx.tile];
+          tilePitchNext = a.y.tilePitch[nx.tile];
+        }
       }
     }
     W_TRACE(trRole, 2)  // loads issued (incl. inverse map wait)
     W_TRACE_USE(v)
     W_TRACE(trRole, 3)  // loads arrived
-    w512_head<T, true>(v, L);
+    w512_head<Sc, true>(v, L);
     W_TRACE_USE(v)
     W_TRACE(trRole, 5)  // head
     if (!it.roleA) {
-      // the consumed hand-off row (8 KB, fully read by now) is dropped from L2, not written back
+      // the consumed hand-off row(s) of the warp (8 KB, fully read by now) are dropped from L2, not written back
       const char* rowBytes = reinterpret_cast<const char*>(a.scratch + (size_t)slot * planeElems +
-                                                           (size_t)(it.tile * kWWarps + w) * N);
+                                                           (size_t)(it.tile * kRows + w * kPer) * N);
       asm volatile("discard.global.L2 [%0], 128;" ::"l"(rowBytes + (size_t)L * 128) : "memory");
       asm volatile("discard.global.L2 [%0], 128;" ::"l"(rowBytes + (size_t)(L + 32) * 128) : "memory");
     }
@@ -315,7 +323,7 @@ __global__ void __launch_bounds__(kWThreads, 2)
     w_group_sync<W>(g);
     W_TRACE(trRole, 7)  // group barrier
     if (publisher && pend) w_publish(pend);  // all stores of the previous part precede the barrier
-    w512_exchange<T, W>(v, S, ad);
+    w512_exchange<Sc, W>(v, S, ad);
     W_TRACE_USE(v)
     W_TRACE(trRole, 8)  // exchange (+ publish)
     // flag of the next part: looked at as late as possible, the round trip hides behind the tail
@@ -324,13 +332,13 @@ __global__ void __launch_bounds__(kWThreads, 2)
       const int* c = dep.dep_counter(nx, pollNeed);
       if (c) pollSeen = w_ld_relaxed(c); else pollNeed = 0;
     }
-    w512_tail<T, true>(v, sTw, L);
+    w512_tail<Sc, true>(v, sTw, L);
     W_TRACE_USE(v)
     W_TRACE(trRole, 9)  // tail
     if (poller) reinterpret_cast<volatile int*>(sReadySeq)[g] = ((k + 1) << 1) | (pollSeen >= pollNeed ? 1 : 0);
     if (mine) wq.post(k + 2, (int)claimRaw);
     if (it.roleA) {
-      w512_col_store<T, W>(v, S, ad);
+      w512_col_store<Sc, W>(v, S, ad);
       fence_async_smem();
       W_TRACE(trRole, 10)  // column store
       w_group_sync<W>(g);
@@ -347,9 +355,9 @@ __global__ void __launch_bounds__(kWThreads, 2)
       pendTma = true;
     } else {
       cx<T>* dst = static_cast<cx<T>*>(a.x.spaceOut) + (size_t)it.plane * planeElems +
-                   (size_t)(it.tile * kWWarps + w) * N + L;
+                   (size_t)(it.tile * kRows + w * kPer) * N + L;
 #pragma unroll
-      for (int m = 0; m < 16; ++m) w_stcs(dst + 32 * m, v[m]);  // written once: evict first
+      for (int m = 0; m < 16; ++m) w_row_stcs(dst + 32 * m, N, v[m]);  // written once: evict first
       W_TRACE(trRole, 12)  // stores
       pend = &dep.bDone[it.plane];
       pendTma = false;
@@ -380,20 +388,24 @@ __global__ void __launch_bounds__(kWThreads, 2)
               const __grid_constant__ WTw4<T> twp) {
   constexpr int N = kWN;
   using G = WGeom<W>;
+  using Sc = typename WUnit<T>::Sc;
+  constexpr int kPer = WUnit<T>::kPer;
+  constexpr int kTiles = kWTiles / kPer;
+  constexpr int kRows = kWWarps * kPer;
   extern __shared__ __align__(1024) unsigned char smemRaw[];
   __shared__ int sReady[G::kGroups][2];
   __shared__ __align__(8) uint64_t full[G::kGroups];
-  __shared__ __align__(16) cx<T> sTw[4 * 32];
-  __shared__ __align__(16) uint4 sInv[2][2][kWThreads];  // inverse-map entries of the thread's current y part, by parity
+  __shared__ __align__(16) cx<Sc> sTw[4 * 32];
+  __shared__ __align__(16) uint4 sInv[2][2 * kPer][kWThreads];  // inverse-map entries of the thread's current y part, by parity
   const int tid = threadIdx.x;
   const int w = tid >> 5, L = tid & 31;
   const int g = w / W, wl = w % W;
   const bool leader = L == 0 && wl == 0;
   const bool poller = L == 0 && wl == 1;
   const bool publisher = L == 0 && wl == W - 1;
-  cx<T>* S = reinterpret_cast<cx<T>*>(smemRaw + (size_t)g * G::kSubBytes);
+  cx<Sc>* S = reinterpret_cast<cx<Sc>*>(smemRaw + (size_t)g * G::kSubBytes);
   const WAddr ad = w_addr<W>(wl, L);
-  w_stage_twiddles<T>(sTw, twp);
+  w_stage_twiddles(sTw, twp);
   if (leader) {
     mbar_init(&full[g], 1);
     mbar_fence_init();
@@ -403,11 +415,12 @@ __global__ void __launch_bounds__(kWThreads, 2)
   WxyCounters dep;
   dep.aDone = a.counters + 1;
   dep.bDone = a.counters + 1 + P;
-  dep.nA = (N / kWWarps) * G::kGroups;
-  dep.nB = (N / kWWarps) * G::kGroups;
+  dep.nA = kTiles * G::kGroups;
+  dep.nB = kTiles * G::kGroups;
   dep.ring = a.ring;
-  const int total = 2 * kWTiles * P;
+  const int total = 2 * kTiles * P;
   const size_t planeElems = (size_t)N * N;
+  const int planLane = w_plan_lane<kPer>(w);
   constexpr uint32_t kSubBytes = (uint32_t)G::kSubBytes;
   __shared__ WQueueShared sQueue;
   WQueue wq;
@@ -421,13 +434,15 @@ __global__ void __launch_bounds__(kWThreads, 2)
   // y tiles of a plane are visited starting at tile xtRotate (distributed: every rank then stores to a different
   // destination at any time); the ring columns, the inverse map and the sticks all follow the remapped tile
   auto decode = [&](int idx) {
-    XYItem d = w_decode_dense(idx, P, a.lag);
-    if (!d.roleA) d.tile = y_forward_tile_at<T>(a.y, d.tile);
+    XYItem d = w_decode_dense<kTiles>(idx, P, a.lag);
+    if constexpr (kPer == 1) {
+      if (!d.roleA) d.tile = y_forward_tile_at<T>(a.y, d.tile);
+    }
     return d;
   };
   int cur = wq.consume(0);
   if (cur < total) it = decode(cur);
-  int e0 = (cur < total && !it.roleA) ? a.y.xtStart[it.tile] : 0;
+  int e0 = (cur < total && !it.roleA) ? a.y.xtStart[w_plan_tile<kPer>(it.tile, w)] : 0;
   for (int k = 0; cur < total; ++k) {
     if (leader) reinterpret_cast<volatile int*>(sQueue.prog)[g] = k;
     const bool mine = leader && wq.own(k + 2);
@@ -444,16 +459,16 @@ __global__ void __launch_bounds__(kWThreads, 2)
       pend = nullptr;
       w_group_sync<W>(g);
     }
-    cx<T> v[16];
+    cx<Sc> v[16];
     const int slot = it.plane % a.ring;
-    cx<T>* R = S + (size_t)wl * N;  // x parts: the warp's flat private region of the sub-tile
+    cx<Sc>* R = S + (size_t)wl * N;  // x parts: the warp's flat private region of the sub-tile (its row, or its two rows)
     // every warp of the group is past the barrier of the previous part, i.e. past its last access of S
     if (!preloaded && leader) {
       w_fence_proxy_async();
       mbar_expect_tx(&full[g], kSubBytes);
       if (it.roleA) {
         // the W rows of the group are contiguous in the space domain: one bulk copy
-        w_bulk_load(S, static_cast<const cx<T>*>(a.x.spaceIn) + (size_t)it.plane * planeElems + (size_t)(it.tile * kWWarps + g * W) * N,
+        w_bulk_load(S, static_cast<const cx<T>*>(a.x.spaceIn) + (size_t)it.plane * planeElems + (size_t)(it.tile * kWWarps + g * W) * kPer * N,
                     kSubBytes, &full[g], l2_policy_evict_first());
       } else {
         const int c0 = (it.tile * kWWarps + g * W) * 2;
@@ -461,13 +476,9 @@ __global__ void __launch_bounds__(kWThreads, 2)
         tma_load_3d(S + 256 * W, &ringMap, c0, 256, slot, &full[g]);
       }
     }
-    if (!it.roleA) {
-      const unsigned short* p = w_inv_ptr(a.y.inv, it.tile, w, L);
-      w_cp_async16(&sInv[k & 1][0][tid], p);
-      w_cp_async16(&sInv[k & 1][1][tid], p + 32 * 8);
-    }
+    if (!it.roleA) w_inv_prefetch<kPer>(sInv[k & 1], a.y.inv, w_plan_tile<kPer>(it.tile, w), planLane, L, tid);
     // in flight behind this part's work: first stick of the next y part, flag of the next part
-    const int e0Next = (nxt < total && !nx.roleA) ? a.y.xtStart[nx.tile] : 0;
+    const int e0Next = (nxt < total && !nx.roleA) ? a.y.xtStart[w_plan_tile<kPer>(nx.tile, w)] : 0;
     int pollNeed = 0, pollSeen = 0;
     if (poller && nxt < total) {
       const int* c = dep.dep_counter(nx, pollNeed);
@@ -476,25 +487,25 @@ __global__ void __launch_bounds__(kWThreads, 2)
     mbar_wait(&full[g], phase);
     phase ^= 1;
     if (it.roleA) {
-      w512_flat_load<T>(v, R, L);
+      w512_flat_load(v, R, L);
       __syncwarp();
     } else {
-      w512_col_load<T, W>(v, S, ad);
+      w512_col_load<Sc, W>(v, S, ad);
       __syncwarp();
       // the consumed column segments are dropped from L2 where the group consumes whole 128-byte lines
       // (W == 8); narrower groups share their lines with the other groups of the CTA
       if constexpr (W == 8) {
-        const char* tileBytes = reinterpret_cast<const char*>(a.scratch + (size_t)slot * planeElems + (size_t)it.tile * kWWarps);
+        const char* tileBytes = reinterpret_cast<const char*>(a.scratch + (size_t)slot * planeElems + (size_t)it.tile * kRows);
         asm volatile("discard.global.L2 [%0], 128;" ::"l"(tileBytes + (size_t)tid * N * sizeof(cx<T>)) : "memory");
         asm volatile("discard.global.L2 [%0], 128;" ::"l"(tileBytes + (size_t)(tid + 256) * N * sizeof(cx<T>)) : "memory");
       }
     }
-    w512_head<T, false>(v, L);
+    w512_head<Sc, false>(v, L);
     if (poller) sReady[g][(k + 1) & 1] = pollSeen >= pollNeed;
     if (it.roleA)
-      w512_exchange_flat<T>(v, R, L);
+      w512_exchange_flat<Sc>(v, R, L);
     else
-      w512_exchange<T, W>(v, S, ad);
+      w512_exchange<Sc, W>(v, S, ad);
     // ---- every warp of the group is done with S; all stores of the previous part were issued before this point
     w_group_sync<W>(g);
     if (publisher && pend) w_publish(pend);
@@ -505,7 +516,7 @@ __global__ void __launch_bounds__(kWThreads, 2)
       w_fence_proxy_async();
       mbar_expect_tx(&full[g], kSubBytes);
       if (nx.roleA) {
-        w_bulk_load(S, static_cast<const cx<T>*>(a.x.spaceIn) + (size_t)nx.plane * planeElems + (size_t)(nx.tile * kWWarps + g * W) * N,
+        w_bulk_load(S, static_cast<const cx<T>*>(a.x.spaceIn) + (size_t)nx.plane * planeElems + (size_t)(nx.tile * kWWarps + g * W) * kPer * N,
                     kSubBytes, &full[g], l2_policy_evict_first());
       } else {
         const int nslot = nx.plane % a.ring;
@@ -514,33 +525,30 @@ __global__ void __launch_bounds__(kWThreads, 2)
         tma_load_3d(S + 256 * W, &ringMap, c0, 256, nslot, &full[g]);
       }
     }
-    w512_tail<T, false>(v, sTw, L);
+    w512_tail<Sc, false>(v, sTw, L);
     if (mine) wq.post(k + 2, (int)claimRaw);
     if (it.roleA) {
-      cx<T>* dst = a.scratch + (size_t)slot * planeElems + (size_t)(it.tile * kWWarps + w) * N + L;
+      cx<T>* dst = a.scratch + (size_t)slot * planeElems + (size_t)(it.tile * kRows + w * kPer) * N + L;
       const uint64_t keep = l2_policy_evict_last();
 #pragma unroll
-      for (int m = 0; m < 16; ++m) w_st_hint(dst + 32 * m, v[m], keep);  // hand-off: stays in L2 until its y part ran
+      for (int m = 0; m < 16; ++m) w_row_st_hint(dst + 32 * m, N, v[m], keep);  // hand-off: stays in L2 until its y part ran
       pend = &dep.aDone[it.plane];
     } else {
       w_cp_async_wait();
-      const WInv16 iv = w_unpack_inv(sInv[k & 1][0][tid], sInv[k & 1][1][tid]);
-      if (!a.y.srcBase) {
-        cx<T>* row = a.y.sticks + (size_t)(it.plane + a.y.zRowOffset) * a.y.pitch + e0;
+      const WInvUnit<kPer> iv = w_inv_read<kPer>(sInv[k & 1], tid);
+      if (kPer == 2 || !a.y.srcBase) {
+        // (written once: evict first)
+        w_scatter_cs(a.y.sticks + (size_t)(it.plane + a.y.zRowOffset) * a.y.pitch + e0, v, iv);
+      } else if constexpr (kPer == 1) {
+        if (a.y.tilePitch[it.tile] != 0) {
+          // distributed, all sticks of the tile owned by one rank: straight into its stick buffer (NVLink peer
+          // memory, or the local exchange buffer of the NCCL path) -- the y stage IS the exchange
+          w_scatter_plain(y_dist_tile<T, true>(a.y, it.tile, it.plane), v, iv);
+        } else {
 #pragma unroll
-        for (int m = 0; m < 16; ++m)
-          if (iv.i[m] != kWNone) w_stcs(row + iv.i[m], v[m]);  // written once: evict first
-      } else if (a.y.tilePitch[it.tile] != 0) {
-        // distributed, all sticks of the tile owned by one rank: straight into its stick buffer (NVLink peer
-        // memory, or the local exchange buffer of the NCCL path) -- the y stage IS the exchange
-        cx<T>* row = y_dist_tile<T, true>(a.y, it.tile, it.plane);
-#pragma unroll
-        for (int m = 0; m < 16; ++m)
-          if (iv.i[m] != kWNone) row[iv.i[m]] = v[m];
-      } else {
-#pragma unroll
-        for (int m = 0; m < 16; ++m)
-          if (iv.i[m] != kWNone) *y_dist_stick<T, true>(a.y, e0 + iv.i[m], it.plane) = v[m];
+          for (int m = 0; m < 16; ++m)
+            if (iv.c[0].i[m] != kWNone) *y_dist_stick<T, true>(a.y, e0 + iv.c[0].i[m], it.plane) = v[m];
+        }
       }
       pend = &dep.bDone[it.plane];
     }
@@ -571,21 +579,21 @@ int wxy_group(int forward) {
 
 size_t wxy_smem() { return kWTileBytes; }
 
-template <int W>
+template <typename T, int W>
 int wxy_grid_w(int* gridOut) {
   static int cached = 0;
   if (cached > 0) {
     *gridOut = cached;
     return 0;
   }
-  cudaError_t e = cudaFuncSetAttribute(k_wxy_bwd<double, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wxy_smem());
+  cudaError_t e = cudaFuncSetAttribute(k_wxy_bwd<T, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wxy_smem());
   if (e != cudaSuccess) return (int)e;
-  e = cudaFuncSetAttribute(k_wxy_fwd<double, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wxy_smem());
+  e = cudaFuncSetAttribute(k_wxy_fwd<T, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wxy_smem());
   if (e != cudaSuccess) return (int)e;
   int b0 = 0, b1 = 0, dev = 0, sms = 0;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b0, k_wxy_bwd<double, W>, kWThreads, wxy_smem());
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b0, k_wxy_bwd<T, W>, kWThreads, wxy_smem());
   if (e != cudaSuccess) return (int)e;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b1, k_wxy_fwd<double, W>, kWThreads, wxy_smem());
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b1, k_wxy_fwd<T, W>, kWThreads, wxy_smem());
   if (e != cudaSuccess) return (int)e;
   e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return (int)e;
@@ -600,23 +608,23 @@ int wxy_grid_w(int* gridOut) {
   *gridOut = cached;
   return 0;
 }
+template <typename T>
 int wxy_grid(int* gridOut) {
   // (same launch bounds and shared memory for every W: one occupancy figure)
   int ga = 0, gb = 0;
-  int err = wxy_grid_w<8>(&ga);
+  int err = wxy_grid_w<T, 8>(&ga);
   if (err) return err;
-  err = wxy_grid_w<4>(&gb);
+  err = wxy_grid_w<T, 4>(&gb);
   if (err) return err;
   int gc = 0;
-  err = wxy_grid_w<2>(&gc);
+  err = wxy_grid_w<T, 2>(&gc);
   if (err) return err;
   *gridOut = ga < gb ? (ga < gc ? ga : gc) : (gb < gc ? gb : gc);
   return 0;
 }
 
-template <typename Kernel>
-int wxy_launch(Kernel kernel, int grid, const XYArgs<double>& a, const TensorMap& map, const WTw4<double>& tw,
-               cudaStream_t s) {
+template <typename T, typename Kernel>
+int wxy_launch(Kernel kernel, int grid, const XYArgs<T>& a, const TensorMap& map, const WTw4<T>& tw, cudaStream_t s) {
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)grid);
   cfg.blockDim = dim3(kWThreads);
@@ -630,12 +638,46 @@ int wxy_launch(Kernel kernel, int grid, const XYArgs<double>& a, const TensorMap
   return (int)cudaLaunchKernelEx(&cfg, kernel, a, map, tw);
 }
 
-template <int W>
-int wxy_launch_w(int forward, int grid, const XYArgs<double>& a, const WTw4<double>& tw, cudaStream_t s) {
+template <typename T, int W>
+int wxy_launch_w(int forward, int grid, const XYArgs<T>& a, const WTw4<T>& tw, cudaStream_t s) {
+  // the hand-off ring as planes of 16-byte units (one complex double / two complex floats): the same box of
+  // W units x 256 rows in both precisions
+  constexpr int kPer = WUnit<T>::kPer;
   TensorMap map;
-  const int err = make_tile_map(&map, a.scratch, sizeof(cx<double>), kWN, kWN, kWN, a.ring, (long long)kWN * kWN, W, 256);
+  const int err = make_tile_map(&map, a.scratch, 16, kWN / kPer, kWN, kWN / kPer, a.ring, (long long)kWN * kWN / kPer, W, 256);
   if (err) return err;
-  return forward ? wxy_launch(k_wxy_fwd<double, W>, grid, a, map, tw, s) : wxy_launch(k_wxy_bwd<double, W>, grid, a, map, tw, s);
+  return forward ? wxy_launch<T>(k_wxy_fwd<T, W>, grid, a, map, tw, s) : wxy_launch<T>(k_wxy_bwd<T, W>, grid, a, map, tw, s);
+}
+
+template <typename T>
+int wxy_run(int forward, const XYArgs<T>& a, cudaStream_t s) {
+  constexpr int kPer = WUnit<T>::kPer;
+  if (a.y.numPlanes <= 0) return 0;
+  // (the index plan's tiles have 8 columns / rows in both precisions; a single-precision item takes two of them)
+  if (a.x.nx != kWN || a.y.ny != kWN || a.y.nxf != kWN || !a.y.inv || a.y.wireF32 || a.y.numXTiles != kWN / kWWarps ||
+      a.x.numRowTiles != kWN / kWWarps)
+    return (int)cudaErrorInvalidValue;
+  if (kPer == 2 && (a.y.srcBase || (a.y.pitch & 1) || (reinterpret_cast<size_t>(a.y.sticks) & 15)))
+    return (int)cudaErrorInvalidValue;  // single precision: local transforms only
+  int grid = 0;
+  int err = wxy_grid<T>(&grid);
+  if (err) return err;
+  const long long total = 2LL * (kWN / kWWarps / kPer) * a.y.numPlanes;
+  if (total > 0x3fffffffLL) return (int)cudaErrorInvalidConfiguration;
+  if (grid > total) grid = (int)total;
+  static const WTw4<T> tw = [] {
+    WTw4<T> t;
+    wfft_lane_twiddles<T>(kWN, 32, &t.w[0][0]);
+    return t;
+  }();
+  cudaError_t e = cudaMemsetAsync(a.counters, 0, sizeof(int) * (3 + 2 * (size_t)a.y.numPlanes), s);
+  if (e != cudaSuccess) return (int)e;
+  sb_note_launches(1);
+  switch (wxy_group(forward)) {
+    case 8: return wxy_launch_w<T, 8>(forward, grid, a, tw, s);
+    case 4: return wxy_launch_w<T, 4>(forward, grid, a, tw, s);
+    default: return wxy_launch_w<T, 2>(forward, grid, a, tw, s);
+  }
 }
 
 }  // namespace
@@ -655,14 +697,14 @@ __attribute__((visibility("default"))) int sb_wxy_trace_read(unsigned long long*
 #endif
 
 int sb_wxy_config(int isFloat, int n, int numPlanes, int* ring, int* lag, int* numCounters) {
-  if (isFloat || n != sb::kWN) return (int)cudaErrorInvalidValue;
+  if (n != sb::kWN) return (int)cudaErrorInvalidValue;
   int grid = 0;
-  const int err = sb::wxy_grid(&grid);
+  const int err = isFloat ? sb::wxy_grid<float>(&grid) : sb::wxy_grid<double>(&grid);
   if (err) return err;
-  const int perStep = 2 * (n / sb::kWWarps);
+  const int perStep = 2 * (n / sb::kWWarps) / (isFloat ? 2 : 1);  // items per plane (single precision: 16 columns / rows each)
   // A part is published one part later than it ran and polled one part before it is needed, and the CTAs drift
   // apart by about one part: the B parts of a plane follow its A parts by the parts in flight (grid / perStep
-  // steps) + 5 steps. Measured at 512^3 (profiles/r02_wfft_summary.md): lag 6 / 8 / 10 / 12 = 1.29+1.36 /
+  // steps) + 5 steps. Measured at 512^3 double (profiles/r02_summary.md): lag 6 / 8 / 10 / 12 = 1.29+1.36 /
   // 1.33+1.31 / 1.38+1.37 / 1.39+1.44 ms (backward + forward), ring = 2 lag + 2; a ring of lag + 4 makes the A
   // parts wait for their slot (1.46+1.44 ms at lag 8).
   int l = (grid + perStep - 1) / perStep + 5;
@@ -677,31 +719,9 @@ int sb_wxy_config(int isFloat, int n, int numPlanes, int* ring, int* lag, int* n
 }
 
 int sb_launch_wxy_f64(int forward, const sb::XYArgs<double>* args, void* stream) {
-  using namespace sb;
-  const XYArgs<double>& a = *args;
-  cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (a.y.numPlanes <= 0) return 0;
-  if (a.x.nx != kWN || a.y.ny != kWN || a.y.nxf != kWN || !a.y.inv || a.y.wireF32 || a.y.numXTiles != kWN / kWWarps ||
-      a.x.numRowTiles != kWN / kWWarps)
-    return (int)cudaErrorInvalidValue;
-  int grid = 0;
-  int err = wxy_grid(&grid);
-  if (err) return err;
-  const long long total = 2LL * (kWN / kWWarps) * a.y.numPlanes;
-  if (total > 0x3fffffffLL) return (int)cudaErrorInvalidConfiguration;
-  if (grid > total) grid = (int)total;
-  static const WTw4<double> tw = [] {
-    WTw4<double> t;
-    wfft_lane_twiddles<double>(kWN, 32, &t.w[0][0]);
-    return t;
-  }();
-  cudaError_t e = cudaMemsetAsync(a.counters, 0, sizeof(int) * (3 + 2 * (size_t)a.y.numPlanes), s);
-  if (e != cudaSuccess) return (int)e;
-  sb_note_launches(1);
-  switch (wxy_group(forward)) {
-    case 8: return wxy_launch_w<8>(forward, grid, a, tw, s);
-    case 4: return wxy_launch_w<4>(forward, grid, a, tw, s);
-    default: return wxy_launch_w<2>(forward, grid, a, tw, s);
-  }
+  return sb::wxy_run<double>(forward, *args, static_cast<cudaStream_t>(stream));
+}
+int sb_launch_wxy_f32(int forward, const sb::XYArgs<float>* args, void* stream) {
+  return sb::wxy_run<float>(forward, *args, static_cast<cudaStream_t>(stream));
 }
 }

@@ -1,4 +1,5 @@
-// wfft_z.cu -- z stage on the warp FFT (wfft.hpp, wfft_kernels.cuh), double precision, dimZ == 512,
+// wfft_z.cu -- z stage on the warp FFT (wfft.hpp, wfft_kernels.cuh), dimZ == 512; double precision, and single
+// precision with two sticks per warp (WUnit: an item = 16 sticks = two tiles of the index plan, C2C only);
 // values given in stick order (inverse-map form, index_plan.cpp):
 //   backward: every warp gathers the values of ONE stick through the inverse map straight into
 //             registers (absent = 0; stick (0,0) of an R2C transform completed by conjugation on the
@@ -20,61 +21,67 @@ __global__ void __launch_bounds__(kWThreads, 2)
     k_wz_bwd(const __grid_constant__ ZArgs<T> a, const __grid_constant__ TensorMap stickMap,
              const __grid_constant__ WTw4<T> twp) {
   constexpr int N = kWN;
+  using Sc = typename WUnit<T>::Sc;
+  constexpr int kPer = WUnit<T>::kPer;  // sticks per warp; an item = 8 kPer sticks = kPer tiles of the index plan
   extern __shared__ __align__(1024) unsigned char smemRaw[];
-  cx<T>* S = reinterpret_cast<cx<T>*>(smemRaw);
+  cx<Sc>* S = reinterpret_cast<cx<Sc>*>(smemRaw);
   const int tid = threadIdx.x;
   const int w = tid >> 5, L = tid & 31;
   const WAddr ad = w_addr<8>(w, L);
-  __shared__ __align__(16) cx<T> sTw[4 * 32];
-  w_stage_twiddles<T>(sTw, twp);
+  __shared__ __align__(16) cx<Sc> sTw[4 * 32];
+  w_stage_twiddles(sTw, twp);
   __syncthreads();
   // inverse-map entries and value range of the thread's NEXT tile, fetched one tile ahead (cp.async: no registers):
   // the gather of a tile then costs one HBM round trip instead of two dependent ones
-  __shared__ __align__(16) uint4 sInv[2][2][kWThreads];
+  __shared__ __align__(16) uint4 sInv[2][2 * kPer][kWThreads];
   pdl_prologue();
+  const int numItems = (a.numTiles + kPer - 1) / kPer;
+  const int planLane = w_plan_lane<kPer>(w);
   int tile = blockIdx.x;
-  int e0 = tile < a.numTiles ? a.tileStart[tile] : 0;
-  if (tile < a.numTiles) {
-    const unsigned short* p = w_inv_ptr(a.inv, tile, w, L);
-    w_cp_async16(&sInv[0][0][tid], p);
-    w_cp_async16(&sInv[0][1][tid], p + 32 * 8);
-  }
-  for (int k = 0; tile < a.numTiles; tile += gridDim.x, ++k) {
+  // (single precision, odd number of plan tiles: the upper half of the last item has no sticks)
+  bool have = tile < numItems && w_plan_tile<kPer>(tile, w) < a.numTiles;
+  int e0 = have ? a.tileStart[w_plan_tile<kPer>(tile, w)] : 0;
+  if (have) w_inv_prefetch<kPer>(sInv[0], a.inv, w_plan_tile<kPer>(tile, w), planLane, L, tid);
+  for (int k = 0; tile < numItems; tile += gridDim.x, ++k) {
     const cx<T>* vals = a.valuesIn + e0;
     w_cp_async_wait();
-    const WInv16 iv = w_unpack_inv(sInv[k & 1][0][tid], sInv[k & 1][1][tid]);
-    cx<T> v[16];
+    cx<Sc> v[16];
+    if (have) {
+      const WInvUnit<kPer> iv = w_inv_read<kPer>(sInv[k & 1], tid);
+      w_gather_cs(v, vals, iv);
+    } else {
 #pragma unroll
-    for (int m = 0; m < 16; ++m) {
-      v[m] = mk<T>(0, 0);
-      if (iv.i[m] != kWNone) v[m] = w_ldcs(vals + iv.i[m]);
+      for (int m = 0; m < 16; ++m) v[m] = w_zero<Sc>();
     }
     const int next = tile + gridDim.x;
-    if (next < a.numTiles) {
-      const unsigned short* p = w_inv_ptr(a.inv, next, w, L);
-      w_cp_async16(&sInv[(k + 1) & 1][0][tid], p);
-      w_cp_async16(&sInv[(k + 1) & 1][1][tid], p + 32 * 8);
-      e0 = a.tileStart[next];
+    const bool haveNext = next < numItems && w_plan_tile<kPer>(next, w) < a.numTiles;
+    if (haveNext) {
+      w_inv_prefetch<kPer>(sInv[(k + 1) & 1], a.inv, w_plan_tile<kPer>(next, w), planLane, L, tid);
+      e0 = a.tileStart[w_plan_tile<kPer>(next, w)];
     }
-    if (tile == a.symTile && w == a.symLane) {
-      // hermitian completion of stick (0,0) (reference: symmetry_host.hpp:47-58): element n also
-      // looks at the given value at N - n
-      const unsigned short* invCol = a.inv + ((size_t)tile * 512 + (size_t)w * 64) * 8;
+    have = haveNext;
+    if constexpr (kPer == 1) {
+      // (double precision only; single-precision R2C transforms keep the round-1 z kernels)
+      if (tile == a.symTile && w == a.symLane) {
+        // hermitian completion of stick (0,0) (reference: symmetry_host.hpp:47-58): element n also
+        // looks at the given value at N - n
+        const unsigned short* invCol = a.inv + ((size_t)tile * 512 + (size_t)w * 64) * 8;
 #pragma unroll
-      for (int m = 0; m < 16; ++m) {
-        const int n = L + 32 * m;
-        const int n2 = (N - n) & (N - 1);
-        const unsigned short i2 = invCol[(size_t)(n2 & 63) * 8 + (n2 >> 6)];
-        const cx<T> q = i2 != kWNone ? vals[i2] : mk<T>(0, 0);
-        v[m] = hermitian_combine<T>(n, N, v[m], q);
+        for (int m = 0; m < 16; ++m) {
+          const int n = L + 32 * m;
+          const int n2 = (N - n) & (N - 1);
+          const unsigned short i2 = invCol[(size_t)(n2 & 63) * 8 + (n2 >> 6)];
+          const cx<T> q = i2 != kWNone ? vals[i2] : mk<T>(0, 0);
+          v[m] = hermitian_combine<T>(n, N, v[m], q);
+        }
       }
     }
-    w512_head<T, true>(v, L);
+    w512_head<Sc, true>(v, L);
     if (tid == 0) tma_store_wait_read();  // the previous tile's store has read S
     __syncthreads();
-    w512_exchange<T, 8>(v, S, ad);
-    w512_tail<T, true>(v, sTw, L);
-    w512_col_store<T, 8>(v, S, ad);
+    w512_exchange<Sc, 8>(v, S, ad);
+    w512_tail<Sc, true>(v, sTw, L);
+    w512_col_store<Sc, 8>(v, S, ad);
     fence_async_smem();
     __syncthreads();
     if (tid == 0) {
@@ -90,14 +97,16 @@ template <typename T>
 __global__ void __launch_bounds__(kWThreads, 2)
     k_wz_fwd(const __grid_constant__ ZArgs<T> a, const __grid_constant__ TensorMap stickMap,
              const __grid_constant__ WTw4<T> twp) {
+  using Sc = typename WUnit<T>::Sc;
+  constexpr int kPer = WUnit<T>::kPer;
   extern __shared__ __align__(1024) unsigned char smemRaw[];
-  cx<T>* S = reinterpret_cast<cx<T>*>(smemRaw);
+  cx<Sc>* S = reinterpret_cast<cx<Sc>*>(smemRaw);
   __shared__ __align__(8) uint64_t full;
   const int tid = threadIdx.x;
   const int w = tid >> 5, L = tid & 31;
   const WAddr ad = w_addr<8>(w, L);
-  __shared__ __align__(16) cx<T> sTw[4 * 32];
-  w_stage_twiddles<T>(sTw, twp);
+  __shared__ __align__(16) cx<Sc> sTw[4 * 32];
+  w_stage_twiddles(sTw, twp);
   __syncthreads();
   if (tid == 0) {
     mbar_init(&full, 1);
@@ -106,55 +115,63 @@ __global__ void __launch_bounds__(kWThreads, 2)
   __syncthreads();
   pdl_prologue();
   uint32_t phase = 0;
+  const int numItems = (a.numTiles + kPer - 1) / kPer;
+  const int planLane = w_plan_lane<kPer>(w);
   int tile = blockIdx.x;
-  if (tile < a.numTiles && tid == 0) {
+  if (tile < numItems && tid == 0) {
     mbar_expect_tx(&full, (uint32_t)kWTileBytes);
     tma_load_3d(S, &stickMap, tile * 16, 0, 0, &full);
     tma_load_3d(S + 256 * 8, &stickMap, tile * 16, 256, 0, &full);
   }
-  for (; tile < a.numTiles; tile += gridDim.x) {
-    const WInv16 iv = w_load_inv(a.inv, tile, w, L);
-    cx<T>* out = a.valuesOut + a.tileStart[tile];
+  for (; tile < numItems; tile += gridDim.x) {
+    const int planTile = w_plan_tile<kPer>(tile, w);
+    const bool have = planTile < a.numTiles;  // (single precision: the last item may cover one plan tile only)
+    WInvUnit<kPer> iv;
+    cx<T>* out = a.valuesOut;
+    if (have) {
+      iv = w_inv_load<kPer>(a.inv, planTile, planLane, L);
+      out += a.tileStart[planTile];
+    }
     mbar_wait(&full, phase);
     phase ^= 1;
-    cx<T> v[16];
-    w512_col_load<T, 8>(v, S, ad);
+    cx<Sc> v[16];
+    w512_col_load<Sc, 8>(v, S, ad);
     __syncwarp();
-    w512_head<T, false>(v, L);
-    w512_exchange<T, 8>(v, S, ad);
+    w512_head<Sc, false>(v, L);
+    w512_exchange<Sc, 8>(v, S, ad);
     __syncthreads();  // every warp is done with S
     const int next = tile + gridDim.x;
-    if (next < a.numTiles && tid == 0) {
+    if (next < numItems && tid == 0) {
       mbar_expect_tx(&full, (uint32_t)kWTileBytes);
       tma_load_3d(S, &stickMap, next * 16, 0, 0, &full);
       tma_load_3d(S + 256 * 8, &stickMap, next * 16, 256, 0, &full);
     }
-    w512_tail<T, false>(v, sTw, L);
+    w512_tail<Sc, false>(v, sTw, L);
     if (a.useScale) {
+      const Sc sc = Sc((double)a.scale);
 #pragma unroll
-      for (int m = 0; m < 16; ++m) v[m] = a.scale * v[m];
+      for (int m = 0; m < 16; ++m) v[m] = sc * v[m];
     }
-#pragma unroll
-    for (int m = 0; m < 16; ++m)
-      if (iv.i[m] != kWNone) out[iv.i[m]] = v[m];
+    if (have) w_scatter_plain(out, v, iv);
   }
 }
 
 namespace {
+template <typename T>
 int wz_grid(int* gridOut) {
   static int cached = 0;
   if (cached > 0) {
     *gridOut = cached;
     return 0;
   }
-  cudaError_t e = cudaFuncSetAttribute(k_wz_bwd<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWTileBytes);
+  cudaError_t e = cudaFuncSetAttribute(k_wz_bwd<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWTileBytes);
   if (e != cudaSuccess) return (int)e;
-  e = cudaFuncSetAttribute(k_wz_fwd<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWTileBytes);
+  e = cudaFuncSetAttribute(k_wz_fwd<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWTileBytes);
   if (e != cudaSuccess) return (int)e;
   int b0 = 0, b1 = 0, dev = 0, sms = 0;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b0, k_wz_bwd<double>, kWThreads, kWTileBytes);
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b0, k_wz_bwd<T>, kWThreads, kWTileBytes);
   if (e != cudaSuccess) return (int)e;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b1, k_wz_fwd<double>, kWThreads, kWTileBytes);
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b1, k_wz_fwd<T>, kWThreads, kWTileBytes);
   if (e != cudaSuccess) return (int)e;
   e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return (int)e;
@@ -166,34 +183,44 @@ int wz_grid(int* gridOut) {
   *gridOut = cached;
   return 0;
 }
+
+template <typename T>
+int wz_run(int forward, const ZArgs<T>& a, cudaStream_t s) {
+  constexpr int kPer = WUnit<T>::kPer;
+  if (a.numTiles <= 0) return 0;
+  if (a.nz != kWN || !a.inv || a.rowRank || a.wireF32 || a.log2V != 3) return (int)cudaErrorInvalidValue;
+  // single precision: C2C (no stick to complete), stick rows of whole 16-byte units
+  if (kPer == 2 && (a.symTile >= 0 || (a.pitch & 1) || (reinterpret_cast<size_t>(a.sticks) & 15))) return (int)cudaErrorInvalidValue;
+  int grid = 0;
+  int err = wz_grid<T>(&grid);
+  if (err) return err;
+  const int numItems = (a.numTiles + kPer - 1) / kPer;
+  if (grid > numItems) grid = numItems;
+  static const WTw4<T> tw = [] {
+    WTw4<T> t;
+    wfft_lane_twiddles<T>(kWN, 32, &t.w[0][0]);
+    return t;
+  }();
+  // the stick buffer [z][pitch] as rows of 16-byte units: box = 8 units x 256 rows in both precisions
+  TensorMap map;
+  err = make_tile_map(&map, a.sticks, 16, a.pitch / kPer, kWN, a.pitch / kPer, 1, 0, 8, 256);
+  if (err) return err;
+  sb_note_launches(1);
+  if (forward) return launch_stage_kernel(k_wz_fwd<T>, dim3((unsigned)grid), kWThreads, kWTileBytes, s, a, map, tw);
+  return launch_stage_kernel(k_wz_bwd<T>, dim3((unsigned)grid), kWThreads, kWTileBytes, s, a, map, tw);
+}
 }  // namespace
 }  // namespace sb
 
 extern "C" {
 
-/* Is the warp-FFT z stage applicable (double, nz == 512, inverse-map form, local row layout)? */
-int sb_wz_available(int isFloat, int nz) { return !isFloat && nz == sb::kWN; }
+/* Is the warp-FFT z stage applicable (nz == 512, inverse-map form, local row layout)? */
+int sb_wz_available(int /*isFloat*/, int nz) { return nz == sb::kWN; }
 
 int sb_launch_wz_f64(int forward, const sb::ZArgs<double>* args, void* stream) {
-  using namespace sb;
-  const ZArgs<double>& a = *args;
-  cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (a.numTiles <= 0) return 0;
-  if (a.nz != kWN || !a.inv || a.rowRank || a.wireF32 || a.log2V != 3) return (int)cudaErrorInvalidValue;
-  int grid = 0;
-  int err = wz_grid(&grid);
-  if (err) return err;
-  if (grid > a.numTiles) grid = a.numTiles;
-  static const WTw4<double> tw = [] {
-    WTw4<double> t;
-    wfft_lane_twiddles<double>(kWN, 32, &t.w[0][0]);
-    return t;
-  }();
-  TensorMap map;
-  err = make_tile_map(&map, a.sticks, sizeof(cx<double>), a.pitch, kWN, a.pitch, 1, 0, 8, 256);
-  if (err) return err;
-  sb_note_launches(1);
-  if (forward) return launch_stage_kernel(k_wz_fwd<double>, dim3((unsigned)grid), kWThreads, kWTileBytes, s, a, map, tw);
-  return launch_stage_kernel(k_wz_bwd<double>, dim3((unsigned)grid), kWThreads, kWTileBytes, s, a, map, tw);
+  return sb::wz_run<double>(forward, *args, static_cast<cudaStream_t>(stream));
+}
+int sb_launch_wz_f32(int forward, const sb::ZArgs<float>* args, void* stream) {
+  return sb::wz_run<float>(forward, *args, static_cast<cudaStream_t>(stream));
 }
 }

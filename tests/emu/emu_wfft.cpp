@@ -87,8 +87,10 @@ int worst_conflict() {
 // addressed in xor form (w_addr / w_xw_off / w_xr_off / w_nat_off), stage B with the four lane twiddles
 // w, w^2, w^4, w^8 and derived powers (twiddle_dft16). One warp = column `wl` of the sub-tile; the other columns
 // are poisoned and must stay untouched. Returns 0, or a code for: 1 overlapping writes, 2 foreign column touched.
+inline bool operator!=(sb::f2 a, sb::f2 b) { return sb::f2_lo(a) != sb::f2_lo(b) || sb::f2_hi(a) != sb::f2_hi(b); }
+
 template <typename T, int W, bool BWD>
-int run_warp_tile(int wl, const T* x, T* out) {
+int run_warp_tile(int wl, const sb::cx<T>* in, sb::cx<T>* o) {
   using P = sb::WPlan<T, 512>;
   using G = sb::WGeom<W>;
   constexpr int N = 512;
@@ -99,7 +101,6 @@ int run_warp_tile(int wl, const T* x, T* out) {
   std::vector<int> owner(elems, -1);
   auto at = [&](unsigned byteOff) -> size_t { return byteOff / sizeof(sb::cx<T>); };
   std::vector<sb::cx<T>> v(32 * 16);
-  const sb::cx<T>* in = reinterpret_cast<const sb::cx<T>*>(x);
   // tile side in: the natural-order column, as a bulk tensor load would have placed it
   for (int L = 0; L < 32; ++L) {
     const sb::WAddr ad = sb::w_addr<W>(wl, L);
@@ -154,7 +155,6 @@ int run_warp_tile(int wl, const T* x, T* out) {
     const bool mine = (chunk ^ G::fold((unsigned)row)) == (size_t)wl;
     if (!mine && S[e].x != T(7e30)) return 2;
   }
-  sb::cx<T>* o = reinterpret_cast<sb::cx<T>*>(out);
   for (int L = 0; L < 32; ++L)
     for (int q = 0; q < 16; ++q) o[L + 32 * q] = v[L * 16 + q];
   return 0;
@@ -184,11 +184,41 @@ int worst_tile_conflict(int wl) {
 extern "C" {
 // the product form: column wl of a [512][W] sub-tile, xor-form addresses, derived twiddles (double precision)
 int emu_wfft_tile_f64(int W, int wl, int backward, const double* x, double* out) {
+  const sb::cx<double>* in = reinterpret_cast<const sb::cx<double>*>(x);
+  sb::cx<double>* o = reinterpret_cast<sb::cx<double>*>(out);
 #define SB_TILE(WW) \
-  if (W == WW) return backward ? run_warp_tile<double, WW, true>(wl, x, out) : run_warp_tile<double, WW, false>(wl, x, out);
+  if (W == WW) return backward ? run_warp_tile<double, WW, true>(wl, in, o) : run_warp_tile<double, WW, false>(wl, in, o);
   SB_TILE(2) SB_TILE(4) SB_TILE(8)
 #undef SB_TILE
   return -1;
+}
+// the same with the packed single-precision pair type (sb::f2): x / out = [2][512] interleaved complex floats, the
+// two transforms a warp of the single-precision stage kernels runs at once; also checks the memory <-> packed
+// permutation of a unit (unit_transpose / unit_pack / unit_lo / unit_hi)
+int emu_wfft_tile_f32x2(int W, int wl, int backward, const float* x, float* out) {
+  const sb::cx<float>* xc = reinterpret_cast<const sb::cx<float>*>(x);
+  sb::cx<float>* oc = reinterpret_cast<sb::cx<float>*>(out);
+  std::vector<sb::cx<sb::f2>> in(512), o(512);
+  for (int n = 0; n < 512; ++n) {
+    in[n] = sb::unit_pack(xc[n], xc[512 + n]);
+    // a unit as it lies in memory: (re0, im0, re1, im1)
+    const sb::cx<sb::f2> mem = sb::mk<sb::f2>(sb::f2_make(xc[n].x, xc[n].y), sb::f2_make(xc[512 + n].x, xc[512 + n].y));
+    const sb::cx<sb::f2> t = sb::unit_transpose<sb::f2>(mem);
+    if (t.x != in[n].x || t.y != in[n].y) return 6;
+    const sb::cx<sb::f2> back = sb::unit_transpose<sb::f2>(t);
+    if (back.x != mem.x || back.y != mem.y) return 6;
+  }
+  int err = -1;
+#define SB_TILE(WW) \
+  if (W == WW) err = backward ? run_warp_tile<sb::f2, WW, true>(wl, in.data(), o.data()) : run_warp_tile<sb::f2, WW, false>(wl, in.data(), o.data());
+  SB_TILE(2) SB_TILE(4) SB_TILE(8)
+#undef SB_TILE
+  if (err) return err;
+  for (int n = 0; n < 512; ++n) {
+    oc[n] = sb::unit_lo(o[n]);
+    oc[512 + n] = sb::unit_hi(o[n]);
+  }
+  return 0;
 }
 int emu_wfft_tile_conflicts(int W, int wl) {
   if (W == 2) return worst_tile_conflict<2>(wl);

@@ -481,7 +481,8 @@ def test_emulated_kernels_vs_reference_host_library(emu, gen, ref_lib, case):
 @pytest.fixture(scope="module")
 def emu_wfft(built):
     lib = C.CDLL(built.EMU_WFFT_LIB)
-    for f in ("emu_wfft_f64", "emu_wfft_f32", "emu_wfft_conflicts", "emu_wfft_tile_f64", "emu_wfft_tile_conflicts"):
+    for f in ("emu_wfft_f64", "emu_wfft_f32", "emu_wfft_conflicts", "emu_wfft_tile_f64", "emu_wfft_tile_conflicts",
+              "emu_wfft_tile_f32x2"):
         getattr(lib, f).restype = C.c_int
     return lib
 
@@ -518,6 +519,21 @@ def test_warp_fft_tile_form(emu_wfft, W, backward):
         ref = np.fft.ifft(x) * 512 if backward else np.fft.fft(x)
         assert orc.rel_l2(out, ref) < 1e-14
         assert emu_wfft.emu_wfft_tile_conflicts(W, wl) == 1
+
+
+@pytest.mark.parametrize("W", [4, 8])
+@pytest.mark.parametrize("backward", [0, 1])
+def test_warp_fft_tile_form_single_pairs(emu_wfft, W, backward):
+    """Single precision in the stage kernels: a warp runs TWO transforms packed into 16-byte units (sb::f2, wfft.hpp)
+    through the same tile geometry; both come out right and independent of each other."""
+    rng = np.random.default_rng(77 * W + backward)
+    for wl in range(W):
+        x = (rng.uniform(-1, 1, (2, 512)) + 1j * rng.uniform(-1, 1, (2, 512))).astype(np.complex64)
+        out = np.zeros_like(x)
+        assert emu_wfft.emu_wfft_tile_f32x2(W, wl, backward, _ptr(x), _ptr(out)) == 0
+        x64 = x.astype(np.complex128)
+        ref = np.fft.ifft(x64, axis=1) * 512 if backward else np.fft.fft(x64, axis=1)
+        assert orc.rel_l2(out[0], ref[0]) < 2e-6 and orc.rel_l2(out[1], ref[1]) < 2e-6
 
 
 @pytest.mark.parametrize("planes,lag,ring", [(1, 8, 1), (3, 8, 3), (8, 8, 8), (9, 8, 9), (24, 8, 18), (64, 8, 18), (512, 8, 18),

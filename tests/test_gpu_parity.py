@@ -652,6 +652,39 @@ def test_warp_fft_kernels(torch_cuda, lib, ref_lib, gen, case):
     assert orc.rel_l2(back, orc.forward(param, ref, orc.SPFFT_FULL_SCALING)) <= TOL[False]
 
 
+@pytest.mark.parametrize("shape,device_ptrs", [((512, 512, 3), True), ((512, 512, 24), True), ((512, 512, 45), True),
+                                               ((32, 32, 512), True), ((64, 12, 512), True), ((512, 512, 512), True),
+                                               ((512, 512, 36), False)],
+                         ids=lambda v: "x".join(map(str, v)) if isinstance(v, tuple) else ("dev" if v else "host"))
+def test_warp_fft_kernels_single_precision(torch_cuda, lib, gen, monkeypatch, shape, device_ptrs):
+    """Single precision on the warp-FFT kernels (SPFFT_B200_WFFT bit 3): a warp runs two transforms packed into
+    16-byte units on the packed fp32 pipe (sb::f2, wfft.hpp). Against the numpy oracle, against the round-1 kernels on
+    the same inputs, and the launch count proves which kernels ran (4 per pair: z, fused xy, fused xy, z)."""
+    nx, ny, nz = shape
+    if nx * ny * nz >= 512 ** 3:
+        trip = orc.spherical_cutoff_triplets(nx)
+        rng = np.random.default_rng(43)
+        vals = rng.uniform(-1, 1, len(trip)) + 1j * rng.uniform(-1, 1, len(trip))
+    else:
+        trip, vals = gen.make(nx, ny, nz, center=True, stick_fraction=0.6, fill_fraction=0.7)
+    monkeypatch.setenv("SPFFT_B200_WFFT", "7")
+    space_r1, back_r1 = _run_pair(torch_cuda, lib, 0, nx, ny, nz, trip, vals, single=True, device_ptrs=device_ptrs)
+    monkeypatch.setenv("SPFFT_B200_WFFT", "15")
+    l0 = capi.kernel_launch_count(lib)
+    space, back = _run_pair(torch_cuda, lib, 0, nx, ny, nz, trip, vals, single=True, device_ptrs=device_ptrs, twice=False)
+    launches = capi.kernel_launch_count(lib) - l0
+    warp_z, warp_xy = nz == 512, nx == 512
+    if device_ptrs:
+        assert launches == (2 if warp_xy else 4) + 2
+    assert np.isfinite(space).all()
+    assert orc.rel_l2(space, space_r1) <= 2e-6 and orc.rel_l2(back, back_r1) <= 2e-6
+    assert orc.rel_l2(back, vals) <= TOL[True]
+    if nx * ny * nz < 512 ** 3:
+        param = orc.Parameters(0, nx, ny, nz, trip)
+        assert orc.rel_l2(space, orc.backward(param, vals)) <= TOL[True]
+    assert warp_z or warp_xy
+
+
 def test_warp_fft_transforms_on_concurrent_streams(torch_cuda, lib, gen):
     """Several transforms that take the warp-FFT kernels, enqueued together on their own streams through
     spfft_multi_transform_* (asynchronous execution inside the call): the fused xy stage is a cooperative persistent
