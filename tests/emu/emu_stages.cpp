@@ -458,11 +458,12 @@ int sb_emu_tile_fft(int isFloat, int n, int log2V, int backward, int swizzle, vo
 // Hand-out order of the fused xy stage (wfft_xy.cu): the dense decode enumerates exactly the valid items of
 // xy_decode (fast_stage_kernels.hpp) in the same order; every B tile comes after all A tiles of its plane and
 // every A tile after the B tiles of the plane that used its ring slot (ring > lag). Returns 0 or an error code.
-extern "C" int sb_emu_check_xy_order(int numPlanes, int lag, int ring) {
+template <int TILES>
+static int check_xy_order(int numPlanes, int lag, int ring) {
   sb::XYArgs<double> a{};
   a.y.numPlanes = numPlanes;
-  a.y.numXTiles = 64;
-  a.x.numRowTiles = 64;
+  a.y.numXTiles = TILES;
+  a.x.numRowTiles = TILES;
   a.lag = lag;
   a.ring = ring;
   const long long total = sb::xy_total_items<double, true>(a);
@@ -471,20 +472,24 @@ extern "C" int sb_emu_check_xy_order(int numPlanes, int lag, int ring) {
   for (long long item = 0; item < total; ++item) {
     const sb::XYItem it = sb::xy_decode<double, true>(a, (int)item);
     if (!it.valid) continue;
-    const sb::XYItem d = sb::w_decode_dense(dense, numPlanes, lag);
+    const sb::XYItem d = sb::w_decode_dense<TILES>(dense, numPlanes, lag);
     if (d.roleA != it.roleA || d.plane != it.plane || d.tile != it.tile) return 1;
-    if (d.plane < 0 || d.plane >= numPlanes || d.tile < 0 || d.tile >= 64) return 2;
+    if (d.plane < 0 || d.plane >= numPlanes || d.tile < 0 || d.tile >= TILES) return 2;
     if (d.roleA) {
-      if (d.plane >= ring && bSeen[d.plane - ring] != 64) return 3;  // slot not yet consumed
+      if (d.plane >= ring && bSeen[d.plane - ring] != TILES) return 3;  // slot not yet consumed
       ++aSeen[d.plane];
     } else {
-      if (aSeen[d.plane] != 64) return 4;  // plane not yet complete
+      if (aSeen[d.plane] != TILES) return 4;  // plane not yet complete
       ++bSeen[d.plane];
     }
     ++dense;
   }
-  if (dense != 2 * 64 * numPlanes) return 5;
+  if (dense != 2 * TILES * numPlanes) return 5;
   for (int p = 0; p < numPlanes; ++p)
-    if (aSeen[p] != 64 || bSeen[p] != 64) return 6;
+    if (aSeen[p] != TILES || bSeen[p] != TILES) return 6;
   return 0;
+}
+// tiles: items per plane and role, 64 (double precision) or 32 (single precision: 16 columns / rows per item)
+extern "C" int sb_emu_check_xy_order(int numPlanes, int lag, int ring, int tiles) {
+  return tiles == 64 ? check_xy_order<64>(numPlanes, lag, ring) : (tiles == 32 ? check_xy_order<32>(numPlanes, lag, ring) : -1);
 }

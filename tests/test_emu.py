@@ -537,9 +537,11 @@ def test_warp_fft_tile_form_single_pairs(emu_wfft, W, backward):
 
 
 @pytest.mark.parametrize("planes,lag,ring", [(1, 8, 1), (3, 8, 3), (8, 8, 8), (9, 8, 9), (24, 8, 18), (64, 8, 18), (512, 8, 18),
-                                             (45, 5, 12), (20, 12, 26)])
-def test_fused_xy_hand_out_order(emu, planes, lag, ring):
+                                             (45, 5, 12), (20, 12, 26), (512, 10, 22), (36, 10, 22)])
+@pytest.mark.parametrize("tiles", [64, 32])
+def test_fused_xy_hand_out_order(emu, planes, lag, ring, tiles):
     """Item order of the fused xy stage (wfft_xy.cu): the dense decode the kernels use enumerates the valid items of
-    xy_decode in the same order, dependencies only point backwards (also when there are fewer planes than the lag)."""
+    xy_decode in the same order, dependencies only point backwards (also when there are fewer planes than the lag).
+    tiles = items per plane and role: 64 in double precision, 32 in single precision (16 columns / rows per item)."""
     emu.sb_emu_check_xy_order.restype = C.c_int
-    assert emu.sb_emu_check_xy_order(planes, lag, ring) == 0
+    assert emu.sb_emu_check_xy_order(planes, lag, ring, tiles) == 0
