@@ -97,13 +97,6 @@ __device__ __forceinline__ uint64_t l2_policy_evict_first() {
   asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
   return p;
 }
-__device__ __forceinline__ void tma_load_3d_hint(void* dst, const TensorMap* map, int c0, int c1, int c2, uint64_t* bar, uint64_t policy) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3, %4}], [%5], %6;" ::"r"(
-          smem_addr(dst)),
-      "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(smem_addr(bar)), "l"(policy)
-      : "memory");
-}
 __device__ __forceinline__ void tma_store_3d_hint(const TensorMap* map, int c0, int c1, int c2, const void* src, uint64_t policy) {
   asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%1, %2, %3}], [%4], %5;" ::"l"(map), "r"(c0),
                "r"(c1), "r"(c2), "r"(smem_addr(src)), "l"(policy)

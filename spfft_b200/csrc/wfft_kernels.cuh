@@ -83,11 +83,6 @@ __device__ __forceinline__ LaneTw<T> w_lane_twiddles(const cx<T>* sTw, int L) {
   return t;
 }
 
-__device__ __forceinline__ int w_ld_acquire(const int* p) {
-  int v;
-  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
 __device__ __forceinline__ void w_fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
 __device__ __forceinline__ void w_tma_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
@@ -95,10 +90,6 @@ template <typename T>
 __device__ __forceinline__ cx<T> w_ldcg(const cx<T>* p) {
   const double2 q = __ldcg(reinterpret_cast<const double2*>(p));
   return mk<T>(q.x, q.y);
-}
-template <typename T>
-__device__ __forceinline__ void w_stcg(cx<T>* p, cx<T> v) {
-  __stcg(reinterpret_cast<double2*>(p), make_double2(v.x, v.y));
 }
 // store with an L2 eviction policy (createpolicy, tma_util.hpp)
 template <typename T>
@@ -146,21 +137,6 @@ __device__ __forceinline__ void w_row_st_hint(cx<double>* p, int, cx<double> v, 
 __device__ __forceinline__ void w_row_st_hint(cx<float>* p, int n, cx<f2> v, uint64_t policy) {
   w_st_hint(p, unit_lo(v), policy);
   w_st_hint(p + n, unit_hi(v), policy);
-}
-
-// L2 prefetch of [base, base + bytes) by the CTA (no registers held, no wait): the inputs of the CTA's NEXT
-// item, so that its demand loads pay the L2 latency instead of the HBM latency (16 warps per SM hide neither).
-__device__ __forceinline__ void w_prefetch_l2(const void* base, size_t bytes) {
-  const char* p = static_cast<const char*>(base);
-  const size_t mis = reinterpret_cast<size_t>(p) & 127;
-  p -= mis;
-  bytes += mis;
-  for (size_t off = (size_t)threadIdx.x * 128; off < bytes; off += (size_t)blockDim.x * 128)
-    asm volatile("prefetch.global.L2 [%0];" ::"l"(p + off));
-}
-// L2 prefetch of a tile of a tensor map (one thread)
-__device__ __forceinline__ void w_prefetch_tile(const TensorMap* map, int c0, int c1, int c2) {
-  asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global [%0, {%1, %2, %3}];" ::"l"(map), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
 
 // 16-byte asynchronous copy global -> shared (LDGSTS): no register holds the data while it is in flight
