@@ -40,8 +40,10 @@ __device__ unsigned long long g_wtrace[2][16];
   }
 #define W_TRACE_COUNT(role) if (tr_on) atomicAdd(&g_wtrace[role][15], 1ULL);
 #define W_TRACE_SLOW(role) if (tr_on) atomicAdd(&g_wtrace[role][14], 1ULL);
-#define W_TRACE_USE(v)                                                          \
-  _Pragma("unroll") for (int m_ = 0; m_ < 16; ++m_) asm volatile("" ::"d"((v)[m_].x), "d"((v)[m_].y));
+__device__ __forceinline__ void w_trace_use(const cx<double>& v) { asm volatile("" ::"d"(v.x), "d"(v.y)); }
+__device__ __forceinline__ void w_trace_use(const cx<f2>& v) { asm volatile("" ::"l"(v.x.r), "l"(v.y.r)); }
+#define W_TRACE_USE(v) \
+  _Pragma("unroll") for (int m_ = 0; m_ < 16; ++m_) w_trace_use((v)[m_]);
 #else
 #define W_TRACE_DECL
 #define W_TRACE(role, ph)

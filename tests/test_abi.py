@@ -157,3 +157,16 @@ def test_fortran_module_matches_the_c_api(built):
     # structure: balanced blocks, no line beyond the free-form limit
     assert committed.count("end function") == count and committed.count("\ninterface\n") == 1
     assert max(len(l) for l in committed.splitlines()) <= 132
+
+
+def test_trace_variant_of_the_fused_xy_kernels_compiles():
+    """The experiment build with phase timers (-DSB_WTRACE, tools/build_variant.py + tools/r02/wtrace.py) must keep
+    compiling for every instantiation of the fused xy kernels, single precision included (front end + PTX only)."""
+    import __graft_entry__ as g
+    if not os.path.exists(g.NVCC):
+        pytest.skip("no nvcc")
+    src = os.path.join(g.CSRC, "wfft_xy.cu")
+    cmd = [g.NVCC, "-DSB_WTRACE", "-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "--expt-relaxed-constexpr",
+           "-ccbin", g.HOST_CXX] + g.INCLUDES + ["-ptx", "-o", os.devnull, src]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr[-2000:]
