@@ -170,3 +170,39 @@ def test_trace_variant_of_the_fused_xy_kernels_compiles():
            "-ccbin", g.HOST_CXX] + g.INCLUDES + ["-ptx", "-o", os.devnull, src]
     res = subprocess.run(cmd, capture_output=True, text=True)
     assert res.returncode == 0, res.stderr[-2000:]
+
+
+def test_default_512_kernels_use_tma_and_packed_fp32(built):
+    """SASS of the warp-FFT objects that go into the library (cuobjdump, no GPU needed): the double- and single-
+    precision stage kernels of the headline shape move their tiles with bulk tensor copies / bulk copies, prefetch
+    the inverse maps with LDGSTS, exchange across lanes with SHFL, and the single-precision instantiations compute
+    on the packed fp32 pipe (FADD2 / FMUL2 / FFMA2) -- the evidence summarised in profiles/r02_sass_summary.txt."""
+    import shutil
+    import __graft_entry__ as g
+    cuobjdump = os.path.join(g.CUDA_HOME, "bin", "cuobjdump")
+    if not os.path.exists(cuobjdump) or shutil.which("c++filt") is None:
+        pytest.skip("no cuobjdump / c++filt")
+    ops = {}
+    for obj in ("wfft_xy.cu.o", "wfft_z.cu.o"):
+        out = subprocess.run([cuobjdump, "-sass", os.path.join(g.OBJDIR, obj)], capture_output=True, text=True, check=True).stdout
+        name = None
+        for line in out.splitlines():
+            m = re.search(r"Function : (\S+)", line)
+            if m:
+                name = subprocess.run(["c++filt", m.group(1)], capture_output=True, text=True).stdout.split("(")[0].replace("void sb::", "")
+                ops[name] = set()
+                continue
+            m = re.match(r"\s+/\*[0-9a-f]{4}\*/\s+(?:@!?U?P\d\s+)?([A-Z0-9_]+)", line)
+            if m and name:
+                ops[name].add(m.group(1))
+    for prec in ("double", "float"):
+        assert {"UTMASTG", "LDGSTS", "SHFL"} <= ops[f"k_wz_bwd<{prec}>"]
+        assert {"UTMALDG", "SHFL"} <= ops[f"k_wz_fwd<{prec}>"]
+        for W in (2, 4, 8):
+            assert {"UTMASTG", "LDGSTS", "SHFL"} <= ops[f"k_wxy_bwd<{prec}, {W}>"]
+            assert {"UTMALDG", "UBLKCP", "LDGSTS", "SHFL"} <= ops[f"k_wxy_fwd<{prec}, {W}>"]
+    for k, v in ops.items():
+        if "<float" in k:
+            assert {"FADD2", "FMUL2", "FFMA2"} <= v and "DFMA" not in v, k
+        else:
+            assert "DFMA" in v, k
