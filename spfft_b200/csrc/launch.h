@@ -18,7 +18,7 @@ int sb_launch_x_f32(int forward, const sb::XArgs<float>* args, void* stream);
 /* Barrier over the ranks of a distributed transform through peer-mapped flag arrays
  * (flags[r] = rank r's array of numRanks ints, zero-initialised; epoch increases by one per call). */
 int sb_launch_peer_barrier(int* const* flags, int numRanks, int me, int epoch, void* stream);
-/* Warp-FFT kernels (wfft_xy.cu, wfft_z.cu: one warp per transform, TMA-staged tiles; double precision,
+/* Warp-FFT kernels (wfft_xy.cu, wfft_z.cu: one warp per transform -- two in single precision --, TMA-staged tiles,
  * transform length 512). sb_wxy_config: plan-time query of the fused xy stage (C2C, dimX == dimY == 512,
  * local slab): scratch ring (planes), item lag and number of int counters the kernel needs (which must be zero at
  * launch: the launcher enqueues the memset); sb_wz_available: z stage (dimZ == 512, values in stick order). */

@@ -398,7 +398,8 @@ inline void wfft_lane_twiddles(int n, int lanes, cx<T>* out /* [4][lanes] */) {
 }
 
 // --------------------------------------------------------------------------------------------
-// Tile geometry of the stage kernels built on the length-512 plan (wfft_kernels.cuh; double precision).
+// Tile geometry of the stage kernels built on the length-512 plan (wfft_kernels.cuh): 16-byte units, i.e. one
+// complex double or two complex floats (f2 above).
 // Host + device so that tests/emu can check the address algebra against WPlan<T, 512>::xw / xr.
 // --------------------------------------------------------------------------------------------
 constexpr int kWN = 512;    // transform length of this kernel family

@@ -177,7 +177,7 @@ __device__ __forceinline__ cx<T>* w_at(cx<T>* S, unsigned byteOff) {
 // The exchange inside the warp's column of the sub-tile (private to the warp).
 template <typename T, int W>
 __device__ __forceinline__ void w512_exchange(cx<T>* v, cx<T>* S, const WAddr& ad) {
-  static_assert(sizeof(cx<T>) == 16, "double precision tile layout");
+  static_assert(sizeof(cx<T>) == 16, "tiles are made of 16-byte units (cx<double> / cx<f2>)");
 #pragma unroll
   for (int i = 0; i < 16; ++i) *w_at(S, w_xw_off<W>(ad, i)) = v[i];
   __syncwarp();
